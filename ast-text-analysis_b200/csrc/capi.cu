@@ -1,0 +1,412 @@
+// capi.cu -- the C ABI of libeast_b200.so (declared in include/east_b200.h).
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "../../include/east_b200.h"
+#include "sa_build.h"
+
+namespace east {
+
+thread_local int64_t g_launches = 0;
+static thread_local std::string g_error;
+static thread_local std::vector<float> g_stage_ms;
+static thread_local std::vector<std::string> g_stage_names;
+
+static std::mutex g_opt_mutex;
+static std::map<std::string, int64_t> g_options;
+
+static int64_t get_option(const char *name, int64_t dflt) {
+    std::lock_guard<std::mutex> g(g_opt_mutex);
+    auto it = g_options.find(name);
+    return (it == g_options.end() || it->second == 0) ? dflt : it->second;
+}
+
+void *dev_alloc(size_t bytes, cudaStream_t s) {
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes, s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        throw Error(e == cudaErrorMemoryAllocation ? -3 : -2,
+                    std::string("cudaMallocAsync(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
+    return p;
+}
+void dev_free(void *p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+
+void StageTimer::mark(const char *name) {
+    cudaEvent_t e;
+    EAST_CUDA(cudaEventCreate(&e));
+    EAST_CUDA(cudaEventRecord(e, s));
+    ev.push_back(e);
+    names.push_back(name);
+}
+void StageTimer::finish() { mark(""); }
+void StageTimer::collect() {
+    g_stage_ms.clear();
+    g_stage_names.clear();
+    for (size_t i = 0; i + 1 < ev.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) != cudaSuccess) { cudaGetLastError(); ms = -1.f; }
+        g_stage_ms.push_back(ms);
+        g_stage_names.push_back(names[i]);
+    }
+}
+StageTimer::~StageTimer() { for (auto e : ev) cudaEventDestroy(e); }
+
+static void use_device(int device) {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        throw Error(-2, "no CUDA device available (libeast_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= cnt) throw Error(-1, "bad device ordinal");
+    EAST_CUDA(cudaSetDevice(device));
+    static std::mutex m;
+    static std::map<int, bool> tuned;
+    std::lock_guard<std::mutex> g(m);
+    if (!tuned[device]) {
+        cudaMemPool_t pool;
+        EAST_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = ~0ull;  // keep freed blocks in the pool: build/score steps reuse them
+        EAST_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        tuned[device] = true;
+    }
+}
+
+}  // namespace east
+
+using namespace east;
+
+struct east_index {
+    int device = 0;
+    int32_t n_docs = 0;
+    int32_t n = 0;
+    int64_t m_total = 0;
+    std::vector<int32_t> doc_off;  // host copies
+    std::vector<int32_t> doc_m;
+    bool owns_text = false;
+    uint32_t *text = nullptr;
+    int32_t *d_doc_off = nullptr, *d_doc_m = nullptr;
+    int32_t *sa = nullptr, *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
+    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0;
+    uint32_t active_after_round0 = 0;
+};
+
+static int fail(const Error &e) { g_error = e.what(); return e.status; }
+static int fail(int st, const char *msg) { g_error = msg; return st; }
+
+#define EAST_API_BEGIN try {
+#define EAST_API_END                                                        \
+    }                                                                       \
+    catch (const Error &e) { return fail(e); }                              \
+    catch (const std::bad_alloc &) { return fail(EAST_ERR_NOMEM, "host out of memory"); } \
+    catch (const std::exception &e) { return fail(EAST_ERR_INVALID, e.what()); }           \
+    return EAST_OK;
+
+extern "C" {
+
+const char *east_last_error(void) { return g_error.c_str(); }
+const char *east_version(void) { return "east_b200 0.1 (sm_100a)"; }
+
+int east_device_count(void) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return cnt;
+}
+
+int east_set_option(const char *name, int64_t value) {
+    if (!name) return fail(EAST_ERR_INVALID, "option name is NULL");
+    std::lock_guard<std::mutex> g(g_opt_mutex);
+    g_options[name] = value;
+    return EAST_OK;
+}
+
+int64_t east_launch_count(int reset) {
+    int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int east_last_timings(float *ms, char *names, int32_t cap, int32_t names_cap) {
+    int n = (int)g_stage_ms.size();
+    int32_t w = 0;
+    for (int i = 0; i < n; ++i) {
+        if (ms && i < cap) ms[i] = g_stage_ms[i];
+        if (names) {
+            const std::string &s = g_stage_names[i];
+            if (w + (int32_t)s.size() + 1 <= names_cap) {
+                memcpy(names + w, s.c_str(), s.size() + 1);
+                w += (int32_t)s.size() + 1;
+            }
+        }
+    }
+    return n;
+}
+
+static void free_index(east_index *idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    if (idx->owns_text && idx->text) cudaFree(idx->text);
+    for (void *p : {(void *)idx->d_doc_off, (void *)idx->d_doc_m, (void *)idx->sa, (void *)idx->lcp,
+                    (void *)idx->up, (void *)idx->down, (void *)idx->next, (void *)idx->ann})
+        if (p) cudaFreeAsync(p, 0);
+    delete idx;
+}
+
+static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t *doc_off, const int32_t *doc_m,
+                        int32_t n_docs, int device, cudaStream_t s, east_index **out) {
+    std::unique_ptr<east_index, void (*)(east_index *)> idx(new east_index(), free_index);
+    idx->device = device;
+    idx->n_docs = n_docs;
+    idx->text = const_cast<uint32_t *>(text_dev);
+    idx->owns_text = owns_text;
+    const int64_t n64 = doc_off[n_docs];
+    idx->n = (int32_t)n64;
+    const int32_t n = idx->n;
+    idx->doc_off.resize(n_docs + 1);
+    idx->doc_m.assign(doc_m, doc_m + n_docs);
+    for (int i = 0; i <= n_docs; ++i) idx->doc_off[i] = (int32_t)doc_off[i];
+    for (int i = 0; i < n_docs; ++i) idx->m_total += doc_m[i];
+
+    idx->d_doc_off = (int32_t *)dev_alloc(sizeof(int32_t) * (n_docs + 1), s);
+    idx->d_doc_m = (int32_t *)dev_alloc(sizeof(int32_t) * n_docs, s);
+    EAST_CUDA(cudaMemcpyAsync(idx->d_doc_off, idx->doc_off.data(), sizeof(int32_t) * (n_docs + 1),
+                              cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(idx->d_doc_m, idx->doc_m.data(), sizeof(int32_t) * n_docs, cudaMemcpyHostToDevice, s));
+    idx->sa = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
+    idx->lcp = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
+    idx->up = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
+    idx->down = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
+    idx->next = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
+    idx->ann = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
+
+    StageTimer tm(s);
+    {
+        DevBuf<uint32_t> rank(n, s);
+        SaInput in;
+        in.text = idx->text; in.doc_off = idx->d_doc_off; in.doc_m = idx->d_doc_m;
+        in.n = n; in.n_docs = n_docs; in.m_total = idx->m_total;
+        in.key_chars = (int)get_option("key_chars", 0);
+        in.force_general = (int)get_option("force_general", 0);
+        SaOutput so;
+        so.sa = idx->sa; so.rank = rank.p;
+        build_suffix_array(in, so, tm, s);
+        idx->rounds = so.rounds; idx->fast_path = so.fast_path; idx->key_chars = so.key_chars;
+        idx->key_bits = so.key_bits; idx->active_after_round0 = so.active_after_round0;
+        tm.mark("lcp");
+        build_lcp(idx->text, idx->sa, idx->d_doc_off, n_docs, n, idx->lcp, s);
+        tm.mark("child_ann");
+        build_child_ann(idx->lcp, idx->d_doc_off, idx->d_doc_m, n_docs, n, idx->up, idx->down, idx->next,
+                        idx->ann, s);
+        tm.finish();
+    }
+    EAST_CUDA(cudaStreamSynchronize(s));
+    tm.collect();
+    *out = idx.release();
+    return EAST_OK;
+}
+
+static void check_build_args(const void *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                             east_index **out) {
+    if (!text || !doc_off || !doc_m || !out) throw Error(EAST_ERR_INVALID, "NULL argument");
+    if (n_docs <= 0) throw Error(EAST_ERR_INVALID, "n_docs must be positive");
+    if (doc_off[0] != 0) throw Error(EAST_ERR_INVALID, "doc_off[0] must be 0");
+    for (int i = 0; i < n_docs; ++i) {
+        if (doc_off[i + 1] <= doc_off[i]) throw Error(EAST_ERR_INVALID, "empty document (a packed document has at least one terminator)");
+        if (doc_m[i] <= 0) throw Error(EAST_ERR_INVALID, "document without strings (EmptyStringsCollectionException in the reference)");
+        if (doc_m[i] > doc_off[i + 1] - doc_off[i]) throw Error(EAST_ERR_INVALID, "doc_m larger than the document");
+    }
+    if (doc_off[n_docs] >= (1ll << 30)) throw Error(EAST_ERR_RANGE, "more than 2^30 code points in one index; split the batch");
+}
+
+int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                    int device, east_index **out) {
+    EAST_API_BEGIN
+    check_build_args(text, doc_off, doc_m, n_docs, out);
+    use_device(device);
+    const size_t bytes = sizeof(uint32_t) * (size_t)doc_off[n_docs];
+    uint32_t *d_text = nullptr;
+    EAST_CUDA(cudaMalloc(&d_text, bytes));
+    cudaError_t e = cudaMemcpy(d_text, text, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_text); throw Error(EAST_ERR_CUDA, cudaGetErrorString(e)); }
+    try {
+        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out);
+    } catch (...) {
+        // build_common's unique_ptr already released everything it owned, including the text
+        throw;
+    }
+    EAST_API_END
+}
+
+int east_build_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                   int device, void *stream, east_index **out) {
+    EAST_API_BEGIN
+    check_build_args(text_dev, doc_off, doc_m, n_docs, out);
+    use_device(device);
+    build_common(text_dev, false, doc_off, doc_m, n_docs, device, (cudaStream_t)stream, out);
+    EAST_API_END
+}
+
+void east_free(east_index *idx) { free_index(idx); }
+
+int east_index_info(const east_index *idx, int32_t *n_docs, int64_t *n_total, int32_t *device, int32_t *rounds,
+                    int32_t *fast_path) {
+    if (!idx) return fail(EAST_ERR_INVALID, "NULL index");
+    if (n_docs) *n_docs = idx->n_docs;
+    if (n_total) *n_total = idx->n;
+    if (device) *device = idx->device;
+    if (rounds) *rounds = idx->rounds;
+    if (fast_path) *fast_path = idx->fast_path;
+    return EAST_OK;
+}
+
+int east_index_doc(const east_index *idx, int32_t doc, int64_t *offset, int64_t *n, int32_t *m) {
+    if (!idx || doc < 0 || doc >= idx->n_docs) return fail(EAST_ERR_INVALID, "bad index/doc");
+    if (offset) *offset = idx->doc_off[doc];
+    if (n) *n = idx->doc_off[doc + 1] - idx->doc_off[doc];
+    if (m) *m = idx->doc_m[doc];
+    return EAST_OK;
+}
+
+static const int32_t *array_of(const east_index *idx, int which) {
+    switch (which) {
+        case EAST_SUFTAB: return idx->sa;
+        case EAST_LCPTAB: return idx->lcp;
+        case EAST_CHILDTAB_UP: return idx->up;
+        case EAST_CHILDTAB_DOWN: return idx->down;
+        case EAST_CHILDTAB_NEXT_L_INDEX: return idx->next;
+        case EAST_ANNTAB: return idx->ann;
+        default: return nullptr;
+    }
+}
+
+int east_index_copy(const east_index *idx, int32_t doc, int which, int32_t *dst_host) {
+    EAST_API_BEGIN
+    if (!idx || !dst_host || doc < 0 || doc >= idx->n_docs) throw Error(EAST_ERR_INVALID, "bad index/doc/destination");
+    const int32_t *src = array_of(idx, which);
+    if (!src) throw Error(EAST_ERR_INVALID, "unknown array id");
+    EAST_CUDA(cudaSetDevice(idx->device));
+    const int32_t off = idx->doc_off[doc], n = idx->doc_off[doc + 1] - off;
+    EAST_CUDA(cudaMemcpy(dst_host, src + off, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (which == EAST_SUFTAB)
+        for (int32_t i = 0; i < n; ++i) dst_host[i] -= off;  // global text position -> position in the document
+    EAST_API_END
+}
+
+int east_index_devptr(const east_index *idx, int which, const void **ptr) {
+    if (!idx || !ptr) return fail(EAST_ERR_INVALID, "NULL argument");
+    if (which == 100) { *ptr = idx->text; return EAST_OK; }
+    const int32_t *p = array_of(idx, which);
+    if (!p) return fail(EAST_ERR_INVALID, "unknown array id");
+    *ptr = p;
+    return EAST_OK;
+}
+
+// ---- scoring ----------------------------------------------------------------------------
+static void score_common(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
+                         int normalized, double *out_dev, int32_t doc_begin, int32_t doc_count, cudaStream_t s,
+                         double *suffix_out_dev /* optional: per-suffix results of the doc range */) {
+    const int64_t total = kp_off[K];
+    if (total >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "keyphrase buffer too large");
+    std::vector<int32_t> off32(K + 1), suf_kp((size_t)total);
+    for (int32_t k = 0; k <= K; ++k) off32[k] = (int32_t)kp_off[k];
+    for (int32_t k = 0; k < K; ++k) {
+        if (kp_off[k + 1] <= kp_off[k]) throw Error(EAST_ERR_ZERODIV, "empty query: float division by zero");
+        for (int64_t p = kp_off[k]; p < kp_off[k + 1]; ++p) suf_kp[(size_t)p] = k;
+    }
+    DevBuf<int32_t> d_off(K + 1, s), d_suf((size_t)total, s);
+    EAST_CUDA(cudaMemcpyAsync(d_off.p, off32.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(d_suf.p, suf_kp.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    DevBuf<double> tmp_own;
+    double *tmp = suffix_out_dev;
+    if (!tmp) {
+        tmp_own = DevBuf<double>((size_t)doc_count * (size_t)total, s);
+        tmp = tmp_own.p;
+    }
+    ScoreInput in;
+    in.text = idx->text; in.sa = idx->sa;
+    in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
+    in.kp = kp_dev; in.kp_off = d_off.p; in.suf_kp = d_suf.p; in.K = K; in.total_suffixes = (int32_t)total;
+    in.normalized = normalized ? 1 : 0;
+    StageTimer tm(s);
+    tm.mark("score");
+    score_table(in, tmp, out_dev, s);
+    tm.finish();
+    EAST_CUDA(cudaStreamSynchronize(s));  // host staging vectors above must outlive the copies
+    tm.collect();
+}
+
+int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
+                         int normalized, double *out_DxK_dev, void *stream) {
+    EAST_API_BEGIN
+    if (!idx || !kp_dev || !kp_off || !out_DxK_dev || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    EAST_CUDA(cudaSetDevice(idx->device));
+    score_common(idx, kp_dev, kp_off, K, normalized, out_DxK_dev, 0, idx->n_docs, (cudaStream_t)stream, nullptr);
+    EAST_API_END
+}
+
+int east_score_table_host(const east_index *idx, const uint32_t *kp, const int64_t *kp_off, int32_t K,
+                          int normalized, double *out_DxK) {
+    EAST_API_BEGIN
+    if (!idx || !kp || !kp_off || !out_DxK || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    EAST_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t s = 0;
+    DevBuf<uint32_t> d_kp((size_t)kp_off[K], s);
+    DevBuf<double> d_out((size_t)idx->n_docs * K, s);
+    EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, s));
+    score_common(idx, d_kp.p, kp_off, K, normalized, d_out.p, 0, idx->n_docs, s, nullptr);
+    EAST_CUDA(cudaMemcpy(out_DxK, d_out.p, sizeof(double) * (size_t)idx->n_docs * K, cudaMemcpyDeviceToHost));
+    EAST_API_END
+}
+
+int east_score_one(const east_index *idx, int32_t doc, const uint32_t *q, int32_t len, int normalized,
+                   double *score, double *suffix_scores) {
+    EAST_API_BEGIN
+    if (!idx || !score || doc < 0 || doc >= idx->n_docs) throw Error(EAST_ERR_INVALID, "bad argument");
+    if (len <= 0 || !q) throw Error(EAST_ERR_ZERODIV, "empty query: float division by zero");
+    EAST_CUDA(cudaSetDevice(idx->device));
+    cudaStream_t s = 0;
+    int64_t off[2] = {0, len};
+    DevBuf<uint32_t> d_q(len, s);
+    DevBuf<double> d_out(1, s), d_suf(len, s);
+    EAST_CUDA(cudaMemcpyAsync(d_q.p, q, sizeof(uint32_t) * len, cudaMemcpyHostToDevice, s));
+    score_common(idx, d_q.p, off, 1, normalized, d_out.p, doc, 1, s, d_suf.p);
+    EAST_CUDA(cudaMemcpy(score, d_out.p, sizeof(double), cudaMemcpyDeviceToHost));
+    if (suffix_scores) EAST_CUDA(cudaMemcpy(suffix_scores, d_suf.p, sizeof(double) * len, cudaMemcpyDeviceToHost));
+    EAST_API_END
+}
+
+// ---- graph ------------------------------------------------------------------------------
+int east_cooc_dev(const double *S_DxK_dev, int64_t D, int32_t K, double threshold, int32_t *C_KxK_dev, int device,
+                  void *stream) {
+    EAST_API_BEGIN
+    if (!S_DxK_dev || !C_KxK_dev || D <= 0 || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    use_device(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    StageTimer tm(s);
+    tm.mark("cooc");
+    cooc_counts(S_DxK_dev, D, K, threshold, C_KxK_dev, s);
+    tm.finish();
+    EAST_CUDA(cudaStreamSynchronize(s));
+    tm.collect();
+    EAST_API_END
+}
+
+int east_cooc_host(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C_KxK, int device) {
+    EAST_API_BEGIN
+    if (!S_DxK || !C_KxK || D <= 0 || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    use_device(device);
+    cudaStream_t s = 0;
+    DevBuf<double> d_S((size_t)D * K, s);
+    DevBuf<int32_t> d_C((size_t)K * K, s);
+    EAST_CUDA(cudaMemcpyAsync(d_S.p, S_DxK, sizeof(double) * (size_t)D * K, cudaMemcpyHostToDevice, s));
+    cooc_counts(d_S.p, D, K, threshold, d_C.p, s);
+    EAST_CUDA(cudaMemcpy(C_KxK, d_C.p, sizeof(int32_t) * (size_t)K * K, cudaMemcpyDeviceToHost));
+    EAST_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// common.cuh -- shared host/device helpers for libeast_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#define EAST_TERM_BASE 0x0A00u  // east/consts.py:24 UNICODE_SPECIAL_SYMBOLS_START
+#define EAST_NUM_SMS 148        // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+namespace east {
+
+struct Error : public std::runtime_error {
+    int status;
+    Error(int st, const std::string &m) : std::runtime_error(m), status(st) {}
+};
+
+#define EAST_CUDA(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            throw ::east::Error(-2, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+extern thread_local int64_t g_launches;
+
+// every kernel launch of the library goes through this macro so bench.py can report
+// "gpu_launches" from a real count
+#define EAST_LAUNCH(kernel, grid, block, smem, stream, ...)                                  \
+    do {                                                                                     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+        ++::east::g_launches;                                                                \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess)                                                               \
+            throw ::east::Error(-2, std::string(#kernel) + " launch: " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// stream-ordered allocations from the device's default pool (release threshold raised once)
+void *dev_alloc(size_t bytes, cudaStream_t s);
+void dev_free(void *p, cudaStream_t s);
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = 0;
+    DevBuf() {}
+    DevBuf(size_t n_, cudaStream_t s_) : n(n_), s(s_) { p = (T *)dev_alloc(sizeof(T) * (n_ ? n_ : 1), s_); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; }
+        return *this;
+    }
+    void release() { if (p) { dev_free(p, s); p = nullptr; } }
+    ~DevBuf() { release(); }
+};
+
+// per-stage device timing with CUDA events on the launching stream
+struct StageTimer {
+    cudaStream_t s;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> names;
+    explicit StageTimer(cudaStream_t s_) : s(s_) {}
+    void mark(const char *name);  // closes the previous stage, opens `name`
+    void finish();                // closes the last stage
+    void collect();               // after stream sync: publish to the thread-local table
+    ~StageTimer();
+};
+
+static inline int bits_for(uint64_t v) {  // number of bits needed to represent v (0 -> 0)
+    int b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+static inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {
+    int64_t g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    int64_t cap = (int64_t)EAST_NUM_SMS * max_waves;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+}  // namespace east
+
+// ---------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace east {
+
+// largest d with doc_off[d] <= x   (doc_off has D+1 entries, doc_off[0]==0, x < doc_off[D])
+__device__ __forceinline__ int doc_of(const int32_t *__restrict__ doc_off, int D, int32_t x) {
+    int lo = 0, hi = D - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(doc_off + mid) <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+}  // namespace east
+#endif

@@ -1,0 +1,246 @@
+// radix_sort.cuh -- hand-written one-sweep LSD radix sort of (uint64 key, uint32 value) pairs.
+//
+// This is the sorting engine of the prefix-doubling suffix-array construction that replaces
+// east/asts/easa.py:141-245 (_compute_suftab/_kark_sort/_radixpass).
+//
+// Structure (one launch per 8-bit digit, least significant first):
+//   * the digit histograms of ALL passes are accumulated up-front by whoever generates the
+//     keys (shared-memory histograms, flushed with global atomics) -- see rs_hist_add();
+//   * k_rs_scan_hist turns them into exclusive bin offsets;
+//   * k_rs_onesweep: each CTA takes the next tile (ticket from an atomic counter, so tile
+//     order == scheduling order and look-back cannot deadlock), ranks its 4096 keys with
+//     warp-level match_any multi-split + per-warp shared-memory counters, publishes its
+//     per-digit counts, resolves the counts of the preceding tiles by decoupled look-back,
+//     stages keys and values through shared memory so every digit run leaves as one
+//     coalesced burst, and scatters.  Stable by construction.
+#pragma once
+#include "common.cuh"
+
+namespace east {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 pairs per CTA
+constexpr int RS_MAX_PASSES = 8;
+
+constexpr uint32_t RS_FLAG_AGG = 1u << 30;
+constexpr uint32_t RS_FLAG_PREFIX = 2u << 30;
+constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
+
+static inline int rs_num_passes(int nbits) { return (nbits + 7) / 8; }
+static inline int rs_num_tiles(int64_t n) { return (int)((n + RS_TILE - 1) / RS_TILE); }
+// bytes of scratch (status words + tile tickets) for sorting n pairs with `passes` passes
+static inline size_t rs_scratch_bytes(int64_t n, int passes) {
+    return ((size_t)rs_num_tiles(n) * 256 * passes + 64) * sizeof(uint32_t);
+}
+
+#ifdef __CUDACC__
+
+// Accumulate the digits of one key into a CTA-private histogram s_hist[passes][256].
+// Warp-uniform digits (document id bits, high rank bits) are folded into one atomic.
+__device__ __forceinline__ void rs_hist_add(uint32_t *s_hist, uint64_t key, int passes, bool valid) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int p = 0; p < passes; ++p) {
+        unsigned d = (unsigned)(key >> (8 * p)) & 255u;
+        unsigned d0 = __shfl_sync(full, d, 0);
+        if (__all_sync(full, valid && d == d0)) {
+            if (lane == 0) atomicAdd(&s_hist[p * 256 + d0], 32u);
+        } else if (valid) {
+            atomicAdd(&s_hist[p * 256 + d], 1u);
+        }
+    }
+}
+
+// flush a CTA-private histogram to the global one
+__device__ __forceinline__ void rs_hist_flush(const uint32_t *s_hist, uint32_t *g_hist, int passes) {
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) {
+        uint32_t v = s_hist[i];
+        if (v) atomicAdd(&g_hist[i], v);
+    }
+}
+
+// exclusive scan of each pass' 256 bins, in place.  grid = passes, block = 256
+__global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t *hist) {
+    __shared__ uint32_t s_warp[8];
+    uint32_t *h = hist + blockIdx.x * 256;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    uint32_t v = h[t], x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int i = 0; i < w; ++i) base += s_warp[i];
+    h[t] = base + x - v;
+}
+
+// standalone histogram (used when keys were not produced by a fused generator)
+__global__ void __launch_bounds__(256) k_rs_hist(const uint64_t *__restrict__ keys, int32_t n,
+                                                 int passes, uint32_t *g_hist) {
+    __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = ((int64_t)n + 31) & ~31ll;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool valid = i < n;
+        uint64_t k = valid ? keys[i] : 0;
+        rs_hist_add(s_hist, k, passes, valid);
+    }
+    __syncthreads();
+    rs_hist_flush(s_hist, g_hist, passes);
+}
+
+// One LSD pass.  hist_excl: this pass' 256 exclusive bin offsets.  status: tiles*256 words,
+// zero-initialised.  ticket: zero-initialised tile counter.
+__global__ void __launch_bounds__(RS_THREADS)
+k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
+              const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout, int32_t n, int shift,
+              const uint32_t *__restrict__ hist_excl, volatile uint32_t *status, uint32_t *ticket) {
+    __shared__ uint32_t s_cnt[RS_WARPS][256];
+    __shared__ uint32_t s_dstart[256];
+    __shared__ uint32_t s_gbase[256];
+    __shared__ uint32_t s_wsum[8];
+    __shared__ uint64_t s_keys[RS_TILE];
+    __shared__ uint32_t s_tile;
+    uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_keys);
+
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_cnt[w][lane + 32 * i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t tile_base = (int64_t)tile * RS_TILE;
+    const int tile_n = (int)min((int64_t)RS_TILE, (int64_t)n - tile_base);
+
+    // ---- load (warp-striped: item j of lane l is element w*512 + j*32 + l of the tile)
+    uint64_t key[RS_ITEMS];
+    uint32_t val[RS_ITEMS];
+    const int wbase = w * (32 * RS_ITEMS) + lane;
+    if (tile_n == RS_TILE) {
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) key[j] = kin[tile_base + wbase + j * 32];
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) val[j] = vin[tile_base + wbase + j * 32];
+    } else {
+#pragma unroll
+        for (int j = 0; j < RS_ITEMS; ++j) {
+            int o = wbase + j * 32;
+            key[j] = (o < tile_n) ? kin[tile_base + o] : ~0ull;
+            val[j] = (o < tile_n) ? vin[tile_base + o] : 0u;
+        }
+    }
+
+    // ---- rank inside the warp (stable: items are visited in element order)
+    uint32_t pos[RS_ITEMS];
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        unsigned d = (unsigned)(key[j] >> shift) & 255u;
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader) {
+            old = s_cnt[w][d];
+            s_cnt[w][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        pos[j] = old + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-digit exclusive prefix over warps, digit totals (thread t owns digit t)
+    uint32_t total = 0;
+#pragma unroll
+    for (int i = 0; i < RS_WARPS; ++i) {
+        uint32_t c = s_cnt[i][t];
+        s_cnt[i][t] = total;
+        total += c;
+    }
+    // publish the tile aggregate as early as possible
+    volatile uint32_t *my_status = status + (size_t)tile * 256 + t;
+    if (tile == 0) *my_status = RS_FLAG_PREFIX | total;
+    else *my_status = RS_FLAG_AGG | total;
+
+    // ---- exclusive scan of totals over the 256 digits -> local start of each digit run
+    {
+        uint32_t x = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_wsum[w] = x;
+        __syncthreads();
+        uint32_t base = 0;
+#pragma unroll
+        for (int i = 0; i < RS_WARPS; ++i) base += (i < w) ? s_wsum[i] : 0u;
+        s_dstart[t] = base + x - total;
+    }
+
+    // ---- decoupled look-back: how many keys with digit t precede this tile
+    uint32_t excl = 0;
+    if (tile > 0) {
+        int64_t prev = (int64_t)tile - 1;
+        while (true) {
+            uint32_t sv = status[(size_t)prev * 256 + t];
+            uint32_t flag = sv & ~RS_VALUE_MASK;
+            if (flag == 0) continue;  // predecessor not there yet
+            excl += sv & RS_VALUE_MASK;
+            if (flag == RS_FLAG_PREFIX) break;
+            --prev;
+        }
+        *my_status = RS_FLAG_PREFIX | (excl + total);
+    }
+    s_gbase[t] = hist_excl[t] + excl - s_dstart[t];
+    __syncthreads();
+
+    // ---- keys: scatter into shared memory at their tile-sorted position, then stream out
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+        unsigned d = (unsigned)(key[j] >> shift) & 255u;
+        pos[j] += s_dstart[d] + s_cnt[w][d];
+        s_keys[pos[j]] = key[j];
+    }
+    __syncthreads();
+    uint32_t dig[RS_ITEMS / 4];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS / 4; ++i) dig[i] = 0;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        int p = t + i * RS_THREADS;
+        uint64_t k = s_keys[p];
+        unsigned d = (unsigned)(k >> shift) & 255u;
+        dig[i >> 2] |= d << (8 * (i & 3));
+        if (p < tile_n) kout[s_gbase[d] + p] = k;
+    }
+    __syncthreads();
+    // ---- values follow the same permutation
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) s_vals[pos[j]] = val[j];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        int p = t + i * RS_THREADS;
+        unsigned d = (dig[i >> 2] >> (8 * (i & 3))) & 255u;
+        if (p < tile_n) vout[s_gbase[d] + p] = s_vals[p];
+    }
+}
+
+#endif  // __CUDACC__
+
+// Host driver.  Sorts n pairs on bits [0, nbits) of the key.  `hist` holds passes*256 counters
+// that are either already accumulated (hist_ready) or computed here.  scratch: rs_scratch_bytes.
+// Returns 0 if the result is in (ka, va), 1 if in (kb, vb).
+int radix_sort_pairs(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int32_t n, int nbits,
+                     uint32_t *hist, bool hist_ready, void *scratch, cudaStream_t s);
+
+}  // namespace east

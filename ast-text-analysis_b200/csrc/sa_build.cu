@@ -1,0 +1,525 @@
+// sa_build.cu -- generalized suffix array of a batch of packed documents by prefix doubling.
+//
+// Replaces east/asts/easa.py:141-245 (_compute_suftab: DC3 in the reference).  The suffix
+// array under code point order is unique, so a different construction gives the same array.
+//
+// One global problem for the whole batch: the document id is the most significant part of
+// every sort key, so the result is doc-major and rank r of the batch is rank r - doc_off[d]
+// of document d.
+//
+// Round 0  sorts all suffixes by a packed window of `kc` symbols (b bits each) under the
+//          document id.  On the fast path (every code point >= 0x0A00 is one of the unique,
+//          position-ordered terminators 0x0A00+i, east/asts/utils.py:25-40) symbols are dense
+//          8-bit codes, all terminators share the top code and the window is cut after the
+//          first terminator: two suffixes with equal windows that contain a terminator differ
+//          only in WHICH terminator, i.e. in string index == text position, and the stable LSD
+//          sort has already left them in position order.  They are final after round 0.
+//          On the general path (text code points collide or interleave with the terminator
+//          range, a reference quirk) symbols are raw code points and nothing is special-cased.
+// Round r  (h = kc, 2kc, ...) re-sorts only the suffixes that still share their rank with
+//          another one, by (own rank, rank[i+h]), and re-ranks; the active set shrinks fast.
+#include "radix_sort.cuh"
+#include "sa_build.h"
+
+namespace east {
+
+// ------------------------------------------------------------------------------------------
+// radix sort host driver
+// ------------------------------------------------------------------------------------------
+int radix_sort_pairs(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int32_t n, int nbits,
+                     uint32_t *hist, bool hist_ready, void *scratch, cudaStream_t s) {
+    if (n <= 0) return 0;
+    int passes = rs_num_passes(nbits);
+    if (passes < 1) passes = 1;
+    if (passes > RS_MAX_PASSES) throw Error(-1, "radix_sort_pairs: too many key bits");
+    int tiles = rs_num_tiles(n);
+    if (!hist_ready) {
+        EAST_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 256 * passes, s));
+        EAST_LAUNCH(k_rs_hist, grid_for(n, 256 * 8, 4), 256, 0, s, ka, n, passes, hist);
+    }
+    EAST_LAUNCH(k_rs_scan_hist, passes, 256, 0, s, hist);
+    EAST_CUDA(cudaMemsetAsync(scratch, 0, rs_scratch_bytes(n, passes), s));
+    uint32_t *status = (uint32_t *)scratch;
+    uint32_t *tickets = status + (size_t)tiles * 256 * passes;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const uint64_t *kin = cur ? kb : ka;
+        uint64_t *kout = cur ? ka : kb;
+        const uint32_t *vin = cur ? vb : va;
+        uint32_t *vout = cur ? va : vb;
+        EAST_LAUNCH(k_rs_onesweep, tiles, RS_THREADS, 0, s, kin, kout, vin, vout, n, 8 * p,
+                    hist + 256 * p, status + (size_t)tiles * 256 * p, tickets + p);
+        cur ^= 1;
+    }
+    return cur;
+}
+
+// ------------------------------------------------------------------------------------------
+// text scan: alphabet, maximum code point, validation of the terminator layout
+// ------------------------------------------------------------------------------------------
+struct ScanResult {
+    uint32_t present[EAST_TERM_BASE / 32];  // bitmap of code points < 0x0A00
+    uint32_t max_code;
+    uint32_t n_term;   // positions with code >= 0x0A00
+    uint32_t bad;      // terminator layout violated
+};
+
+__global__ void __launch_bounds__(256)
+k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict__ doc_off,
+            const int32_t *__restrict__ doc_m, int D, ScanResult *res) {
+    __shared__ uint32_t s_present[EAST_TERM_BASE / 32];
+    __shared__ uint32_t s_max, s_nterm, s_bad;
+    for (int i = threadIdx.x; i < EAST_TERM_BASE / 32; i += blockDim.x) s_present[i] = 0;
+    if (threadIdx.x == 0) { s_max = 0; s_nterm = 0; s_bad = 0; }
+    __syncthreads();
+    uint32_t mx = 0, nt = 0, bad = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t c = T[i];
+        mx = max(mx, c);
+        if (c < EAST_TERM_BASE) {
+            atomicOr(&s_present[c >> 5], 1u << (c & 31));
+        } else {
+            ++nt;
+            // must be 0x0A00 + (index of this string inside its document): walk back to the
+            // previous terminator of the same document
+            int d = doc_of(doc_off, D, (int32_t)i);
+            int32_t start = doc_off[d];
+            int64_t j = i - 1;
+            while (j >= start && T[j] < EAST_TERM_BASE) --j;
+            uint32_t expect = (j >= start) ? T[j] + 1u : EAST_TERM_BASE;
+            if (c != expect) bad = 1;
+            // the last code point of a document is its last terminator
+            if (i == doc_off[d + 1] - 1 && c != EAST_TERM_BASE + (uint32_t)doc_m[d] - 1u) bad = 1;
+        }
+    }
+    // every document must end with a terminator
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D; d += stride) {
+        int32_t e = doc_off[d + 1];
+        if (e <= doc_off[d] || T[e - 1] < EAST_TERM_BASE) bad = 1;
+    }
+    atomicMax(&s_max, mx);
+    atomicAdd(&s_nterm, nt);
+    if (bad) atomicOr(&s_bad, 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < EAST_TERM_BASE / 32; i += blockDim.x)
+        if (s_present[i]) atomicOr(&res->present[i], s_present[i]);
+    if (threadIdx.x == 0) {
+        atomicMax(&res->max_code, s_max);
+        atomicAdd(&res->n_term, s_nterm);
+        if (s_bad) atomicOr(&res->bad, 1u);
+    }
+}
+
+// dense byte codes: 1..sigma for present code points < 0x0A00, sigma+1 for every terminator
+__global__ void __launch_bounds__(256)
+k_encode_text(const uint32_t *__restrict__ T, int32_t n, const uint8_t *__restrict__ code_table,
+              uint8_t term_code, uint8_t *__restrict__ T8) {
+    __shared__ uint8_t s_code[EAST_TERM_BASE];
+    for (int i = threadIdx.x; i < (int)EAST_TERM_BASE; i += blockDim.x) s_code[i] = code_table[i];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        uint32_t c[4];
+        if (i + 3 < n) {
+            uint4 v = *reinterpret_cast<const uint4 *>(T + i);  // 128-bit load
+            c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+        } else {
+            for (int q = 0; q < 4; ++q) c[q] = (i + q < n) ? T[i + q] : 0u;
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t e = (c[q] < EAST_TERM_BASE) ? s_code[c[q]] : term_code;
+            packed |= e << (8 * q);
+        }
+        if (i + 3 < n) *reinterpret_cast<uint32_t *>(T8 + i) = packed;
+        else for (int q = 0; q < 4 && i + q < n; ++q) T8[i + q] = (uint8_t)(packed >> (8 * q));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// round 0 key generation (+ fused digit histograms of all passes)
+// ------------------------------------------------------------------------------------------
+constexpr int KG_THREADS = 256;
+constexpr int KG_ITEMS = 8;
+constexpr int KG_TILE = KG_THREADS * KG_ITEMS;
+constexpr int KG_HALO = 32;
+
+struct KeyParams {
+    int kc;          // symbols per window
+    int b;           // bits per symbol
+    int passes;      // radix passes over the key
+    uint32_t term;   // fast path: terminator class code; general: 0xffffffff
+};
+
+// fast path: byte codes
+__global__ void __launch_bounds__(KG_THREADS)
+k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, const int32_t *__restrict__ doc_off, int D,
+               KeyParams kp, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+               uint32_t *g_hist) {
+    __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
+    __shared__ __align__(16) uint8_t s_t[KG_TILE + KG_HALO];
+    __shared__ int s_dlo, s_dhi;
+    for (int i = threadIdx.x; i < kp.passes * 256; i += blockDim.x) s_hist[i] = 0;
+    const int num_tiles = (n + KG_TILE - 1) / KG_TILE;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int32_t base = tile * KG_TILE;
+        __syncthreads();
+        // stage the tile (+halo) of byte codes; 128-bit loads where fully in range
+        for (int o = threadIdx.x * 16; o < KG_TILE + KG_HALO; o += blockDim.x * 16) {
+            int64_t g = (int64_t)base + o;
+            if (g + 16 <= n) {
+                *reinterpret_cast<uint4 *>(s_t + o) = *reinterpret_cast<const uint4 *>(T8 + g);
+            } else {
+                for (int q = 0; q < 16; ++q) s_t[o + q] = (g + q < n) ? T8[g + q] : 0;
+            }
+        }
+        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, base);
+        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, min(base + KG_TILE, n) - 1);
+        __syncthreads();
+        const int dlo = s_dlo, dhi = s_dhi;
+#pragma unroll 1
+        for (int it = 0; it < KG_ITEMS; ++it) {
+            const int o = it * KG_THREADS + threadIdx.x;
+            const int32_t i = base + o;
+            const bool valid = i < n;
+            uint64_t key = 0;
+            if (valid) {
+                int lo = dlo, hi = dhi;  // document of position i (tile spans [dlo, dhi])
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if (__ldg(doc_off + mid) <= i) lo = mid; else hi = mid - 1;
+                }
+                key = (uint64_t)lo;
+                bool cut = false;
+                for (int c = 0; c < kp.kc; ++c) {
+                    uint32_t sym = cut ? 0u : (uint32_t)s_t[o + c];
+                    key = (key << kp.b) | sym;
+                    if (sym == kp.term) cut = true;
+                }
+                keys[i] = key;
+                vals[i] = (uint32_t)i;
+            }
+            rs_hist_add(s_hist, key, kp.passes, valid);
+        }
+    }
+    __syncthreads();
+    rs_hist_flush(s_hist, g_hist, kp.passes);
+}
+
+// general path: raw code points + 1, window cut at the end of the document (pad 0)
+__global__ void __launch_bounds__(KG_THREADS)
+k_keygen0_general(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict__ doc_off,
+                  int D, KeyParams kp, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                  uint32_t *g_hist) {
+    __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
+    for (int i = threadIdx.x; i < kp.passes * 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = ((int64_t)n + 31) & ~31ll;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < n;
+        uint64_t key = 0;
+        if (valid) {
+            int d = doc_of(doc_off, D, (int32_t)i);
+            int32_t end = doc_off[d + 1];
+            key = (uint64_t)d;
+            for (int c = 0; c < kp.kc; ++c) {
+                uint64_t sym = (i + c < end) ? (uint64_t)T[i + c] + 1ull : 0ull;
+                key = (key << kp.b) | sym;
+            }
+            keys[i] = key;
+            vals[i] = (uint32_t)i;
+        }
+        rs_hist_add(s_hist, key, kp.passes, valid);
+    }
+    __syncthreads();
+    rs_hist_flush(s_hist, g_hist, kp.passes);
+}
+
+// ------------------------------------------------------------------------------------------
+// doubling-round key generation: key = own rank (primary) . rank[i+h] (secondary)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_keygen_h(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ prim, int32_t n_act,
+           const uint32_t *__restrict__ rank, int32_t h, int sb, int passes, int general,
+           const int32_t *__restrict__ doc_off, int D, uint64_t *__restrict__ keys, uint32_t *g_hist) {
+    __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
+    for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = ((int64_t)n_act + 31) & ~31ll;
+    for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_round; a += stride) {
+        const bool valid = a < n_act;
+        uint64_t key = 0;
+        if (valid) {
+            uint32_t i = vals[a];
+            uint32_t sec;
+            if (general) {
+                int d = doc_of(doc_off, D, (int32_t)i);
+                int64_t j = (int64_t)i + h;
+                sec = (j < doc_off[d + 1]) ? rank[j] + 1u : 0u;
+            } else {
+                sec = rank[i + h];  // stays inside the string: the group shares h terminator-free symbols
+            }
+            key = ((uint64_t)prim[a] << sb) | sec;
+            keys[a] = key;
+        }
+        rs_hist_add(s_hist, key, passes, valid);
+    }
+    __syncthreads();
+    rs_hist_flush(s_hist, g_hist, passes);
+}
+
+// ------------------------------------------------------------------------------------------
+// re-rank + compaction after a sort: single pass, decoupled look-back over the pair
+// (index of the last group head, number of elements kept so far).
+// ------------------------------------------------------------------------------------------
+constexpr int RR_THREADS = 256;
+constexpr int RR_ITEMS = 8;
+constexpr int RR_TILE = RR_THREADS * RR_ITEMS;
+constexpr uint64_t RR_FLAG_AGG = 1ull << 62;
+constexpr uint64_t RR_FLAG_PREFIX = 2ull << 62;
+constexpr uint64_t RR_FIELD = (1ull << 31) - 1;
+
+struct RRState { uint32_t mx, sum; };
+__device__ __forceinline__ RRState rr_op(RRState a, RRState b) { return RRState{max(a.mx, b.mx), a.sum + b.sum}; }
+__device__ __forceinline__ uint64_t rr_pack(RRState s, uint64_t flag) { return flag | ((uint64_t)s.mx << 31) | s.sum; }
+__device__ __forceinline__ RRState rr_unpack(uint64_t w) { return RRState{(uint32_t)((w >> 31) & RR_FIELD), (uint32_t)(w & RR_FIELD)}; }
+
+template <bool ROUND0>
+__global__ void __launch_bounds__(RR_THREADS)
+k_rerank(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+         const uint32_t *__restrict__ slots, int32_t n_act, uint64_t sym_mask, uint64_t term,
+         int32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ new_vals,
+         uint32_t *__restrict__ new_slots, uint32_t *__restrict__ new_prim,
+         volatile uint64_t *status, uint32_t *ticket, uint32_t *out_counts /*[0]=kept*/) {
+    __shared__ RRState s_warp[RR_THREADS / 32];
+    __shared__ RRState s_prefix;
+    __shared__ uint32_t s_tile;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t base = (int64_t)tile * RR_TILE + (int64_t)t * RR_ITEMS;
+
+    uint64_t k[RR_ITEMS + 2];  // k[0] = predecessor, k[RR_ITEMS+1] = successor
+    bool head[RR_ITEMS + 1];
+#pragma unroll
+    for (int j = 0; j < RR_ITEMS + 2; ++j) {
+        int64_t a = base + j - 1;
+        k[j] = (a >= 0 && a < n_act) ? keys[a] : 0ull;
+    }
+    // head[j] describes element base+j (j = RR_ITEMS: the successor, for singleton detection)
+#pragma unroll
+    for (int j = 0; j <= RR_ITEMS; ++j) {
+        int64_t a = base + j;
+        bool hd = (a == 0) || (a >= n_act) || (k[j + 1] != k[j]);
+        if (ROUND0) {
+            uint64_t f = k[j + 1] & sym_mask;  // last symbol of the window: 0 = cut, term = terminator
+            hd = hd || (f == 0ull) || (f == term);
+        }
+        head[j] = hd;
+    }
+    RRState loc[RR_ITEMS];
+    RRState run{0u, 0u};
+#pragma unroll
+    for (int j = 0; j < RR_ITEMS; ++j) {
+        int64_t a = base + j;
+        bool valid = a < n_act;
+        bool keep = valid && !(head[j] && head[j + 1]);
+        RRState e{(valid && head[j]) ? (uint32_t)a : 0u, keep ? 1u : 0u};
+        run = rr_op(run, e);
+        loc[j] = run;  // inclusive within the thread
+    }
+    // warp inclusive scan of thread totals
+    RRState x = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        RRState y{__shfl_up_sync(0xffffffffu, x.mx, o), __shfl_up_sync(0xffffffffu, x.sum, o)};
+        if (lane >= o) x = rr_op(y, x);
+    }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    RRState wbase{0u, 0u};
+    for (int i = 0; i < w; ++i) wbase = rr_op(wbase, s_warp[i]);
+    RRState thread_excl{__shfl_up_sync(0xffffffffu, x.mx, 1), __shfl_up_sync(0xffffffffu, x.sum, 1)};
+    if (lane == 0) thread_excl = RRState{0u, 0u};
+    thread_excl = rr_op(wbase, thread_excl);
+
+    if (t == RR_THREADS - 1) {
+        RRState agg = rr_op(wbase, x);  // tile aggregate
+        RRState excl{0u, 0u};
+        if (tile == 0) {
+            status[tile] = rr_pack(agg, RR_FLAG_PREFIX);
+        } else {
+            status[tile] = rr_pack(agg, RR_FLAG_AGG);
+            int64_t prev = (int64_t)tile - 1;
+            while (true) {
+                uint64_t sv = status[prev];
+                uint64_t flag = sv & (3ull << 62);
+                if (flag == 0) continue;
+                excl = rr_op(rr_unpack(sv), excl);
+                if (flag == RR_FLAG_PREFIX) break;
+                --prev;
+            }
+            status[tile] = rr_pack(rr_op(excl, agg), RR_FLAG_PREFIX);
+        }
+        s_prefix = excl;
+        if ((int64_t)(tile + 1) * RR_TILE >= n_act) out_counts[0] = excl.sum + agg.sum;
+    }
+    __syncthreads();
+    const RRState pre = rr_op(s_prefix, thread_excl);
+#pragma unroll
+    for (int j = 0; j < RR_ITEMS; ++j) {
+        int64_t a = base + j;
+        if (a >= n_act) break;
+        RRState inc = rr_op(pre, loc[j]);
+        uint32_t v = vals[a];
+        uint32_t slot = ROUND0 ? (uint32_t)a : slots[a];
+        uint32_t r = ROUND0 ? inc.mx : slots[inc.mx];
+        sa[slot] = (int32_t)v;
+        rank[v] = r;
+        bool keep = !(head[j] && head[j + 1]);
+        if (keep) {
+            uint32_t dst = inc.sum - 1u;
+            new_vals[dst] = v;
+            new_slots[dst] = slot;
+            new_prim[dst] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s) {
+    const int32_t n = in.n;
+    const int D = in.n_docs;
+    tm.mark("scan_text");
+    DevBuf<ScanResult> d_scan(1, s);
+    EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
+    EAST_LAUNCH(k_scan_text, grid_for(n, 256 * 8, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p);
+    ScanResult scan;
+    EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
+    EAST_CUDA(cudaStreamSynchronize(s));
+
+    int sigma = 0;
+    std::vector<uint8_t> table(EAST_TERM_BASE, 0);
+    for (uint32_t c = 0; c < EAST_TERM_BASE; ++c)
+        if (scan.present[c >> 5] & (1u << (c & 31))) {
+            ++sigma;
+            table[c] = (uint8_t)(sigma & 0xff);
+        }
+    bool fast = !scan.bad && scan.n_term == (uint32_t)in.m_total && sigma <= 253 && !in.force_general;
+    out.fast_path = fast ? 1 : 0;
+    out.sigma = sigma;
+
+    const int dbits = bits_for((uint64_t)(D > 0 ? D - 1 : 0));
+    KeyParams kp;
+    if (fast) {
+        kp.b = bits_for((uint64_t)sigma + 1);
+        kp.term = (uint32_t)sigma + 1;
+    } else {
+        kp.b = bits_for((uint64_t)scan.max_code + 1);
+        kp.term = 0xffffffffu;
+    }
+    if (dbits + kp.b > 64) throw Error(-5, "document count x alphabet does not fit a 64-bit sort key");
+    int kc = (64 - dbits) / kp.b;
+    if (kc > KG_HALO) kc = KG_HALO;
+    if (in.key_chars > 0 && in.key_chars < kc) kc = in.key_chars;
+    kp.kc = kc;
+    const int key_bits = dbits + kc * kp.b;
+    kp.passes = rs_num_passes(key_bits);
+    out.key_chars = kc;
+    out.key_bits = key_bits;
+
+    // buffers: ping-pong keys/values, active-list side arrays, histogram + look-back scratch
+    DevBuf<uint64_t> keys_a(n, s), keys_b(n, s);
+    DevBuf<uint32_t> vals_a(n, s), vals_b(n, s);
+    DevBuf<uint32_t> hist(256 * RS_MAX_PASSES, s);
+    DevBuf<uint8_t> scratch(rs_scratch_bytes(n, RS_MAX_PASSES), s);
+    const int rr_tiles_max = (n + RR_TILE - 1) / RR_TILE;
+    DevBuf<uint64_t> rr_status((size_t)rr_tiles_max + 2, s);
+    DevBuf<uint32_t> rr_misc(8, s);  // [0] ticket, [1] kept count
+    uint32_t *rank = out.rank;
+
+    tm.mark("keygen0");
+    EAST_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 256 * RS_MAX_PASSES, s));
+    DevBuf<uint8_t> t8;
+    if (fast) {
+        DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
+        EAST_CUDA(cudaMemcpyAsync(d_table.p, table.data(), EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
+        t8 = DevBuf<uint8_t>((size_t)n + 64, s);
+        EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_table.p,
+                    (uint8_t)kp.term, t8.p);
+        EAST_LAUNCH(k_keygen0_fast, grid_for(n, KG_TILE, 4), KG_THREADS, 0, s, t8.p, n, in.doc_off, D, kp,
+                    keys_a.p, vals_a.p, hist.p);
+        EAST_CUDA(cudaStreamSynchronize(s));  // d_table goes out of scope (stream-ordered free is safe, host table too)
+    } else {
+        EAST_LAUNCH(k_keygen0_general, grid_for(n, 256 * 8, 4), 256, 0, s, in.text, n, in.doc_off, D, kp,
+                    keys_a.p, vals_a.p, hist.p);
+    }
+
+    tm.mark("sort0");
+    int cur = radix_sort_pairs(keys_a.p, keys_b.p, vals_a.p, vals_b.p, n, key_bits, hist.p, true, scratch.p, s);
+
+    tm.mark("rerank0");
+    DevBuf<uint32_t> act_vals(n, s), act_slots(n, s), act_prim(n, s);
+    DevBuf<uint32_t> nxt_vals, nxt_slots, nxt_prim;
+    EAST_CUDA(cudaMemsetAsync(rr_status.p, 0, sizeof(uint64_t) * ((size_t)rr_tiles_max + 2), s));
+    EAST_CUDA(cudaMemsetAsync(rr_misc.p, 0, sizeof(uint32_t) * 8, s));
+    {
+        const uint64_t sym_mask = (kp.b >= 64) ? ~0ull : ((1ull << kp.b) - 1ull);
+        const uint64_t term = fast ? (uint64_t)kp.term : ~0ull;
+        EAST_LAUNCH(k_rerank<true>, rr_tiles_max, RR_THREADS, 0, s, cur ? keys_b.p : keys_a.p,
+                    cur ? vals_b.p : vals_a.p, (const uint32_t *)nullptr, n, sym_mask, term, out.sa, rank,
+                    act_vals.p, act_slots.p, act_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1);
+    }
+    uint32_t n_act = 0;
+    EAST_CUDA(cudaMemcpyAsync(&n_act, rr_misc.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    EAST_CUDA(cudaStreamSynchronize(s));
+    out.active_after_round0 = n_act;
+
+    const int sb = bits_for((uint64_t)n);          // secondary: rank (+1 on the general path) <= n
+    const int pbits = bits_for((uint64_t)n - 1);   // primary: a rank
+    int rounds = 1;
+    int64_t h = kc;
+    tm.mark("doubling");
+    if (n_act > 0) {
+        nxt_vals = DevBuf<uint32_t>(n_act, s);
+        nxt_slots = DevBuf<uint32_t>(n_act, s);
+        nxt_prim = DevBuf<uint32_t>(n_act, s);
+    }
+    while (n_act > 0) {
+        if (rounds > 64) throw Error(-2, "prefix doubling did not converge");
+        if (h >= n) throw Error(-2, "prefix doubling ran past the text (malformed input?)");
+        const int nbits = sb + pbits;
+        const int passes = rs_num_passes(nbits);
+        EAST_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 256 * RS_MAX_PASSES, s));
+        EAST_LAUNCH(k_keygen_h, grid_for(n_act, 256 * 4, 8), 256, 0, s, act_vals.p, act_prim.p, (int32_t)n_act,
+                    rank, (int32_t)h, sb, passes, fast ? 0 : 1, in.doc_off, D, keys_a.p, hist.p);
+        // values to sort along: the suffix index
+        int c2 = radix_sort_pairs(keys_a.p, keys_b.p, act_vals.p, vals_b.p, (int32_t)n_act, nbits, hist.p, true,
+                                  scratch.p, s);
+        const uint64_t *sk = c2 ? keys_b.p : keys_a.p;
+        const uint32_t *sv = c2 ? vals_b.p : act_vals.p;
+        const int rr_tiles = ((int)n_act + RR_TILE - 1) / RR_TILE;
+        EAST_CUDA(cudaMemsetAsync(rr_status.p, 0, sizeof(uint64_t) * ((size_t)rr_tiles + 2), s));
+        EAST_CUDA(cudaMemsetAsync(rr_misc.p, 0, sizeof(uint32_t) * 8, s));
+        EAST_LAUNCH(k_rerank<false>, rr_tiles, RR_THREADS, 0, s, sk, sv, act_slots.p, (int32_t)n_act, 0ull, 0ull,
+                    out.sa, rank, nxt_vals.p, nxt_slots.p, nxt_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1);
+        EAST_CUDA(cudaMemcpyAsync(&n_act, rr_misc.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        EAST_CUDA(cudaStreamSynchronize(s));
+        std::swap(act_vals, nxt_vals);
+        std::swap(act_slots, nxt_slots);
+        std::swap(act_prim, nxt_prim);
+        h *= 2;
+        ++rounds;
+    }
+    out.rounds = rounds;
+    out.t8 = std::move(t8);
+}
+
+}  // namespace east

@@ -1,0 +1,58 @@
+// sa_build.h -- internal interfaces between the build stages of libeast_b200.
+#pragma once
+#include "common.cuh"
+
+namespace east {
+
+struct SaInput {
+    const uint32_t *text;     // device, n code points (packed documents, concatenated)
+    const int32_t *doc_off;   // device, n_docs + 1
+    const int32_t *doc_m;     // device, n_docs
+    int32_t n;
+    int32_t n_docs;
+    int64_t m_total;
+    int key_chars;            // 0 = as many symbols as fit the 64-bit key
+    int force_general;        // testing: never take the terminator-class fast path
+};
+
+struct SaOutput {
+    int32_t *sa;              // device, n  (global text positions, doc-major rank order)
+    uint32_t *rank;           // device, n  (inverse permutation when done)
+    DevBuf<uint8_t> t8;       // fast path: dense byte codes of the text (kept for later stages)
+    int fast_path = 0;
+    int sigma = 0;
+    int key_chars = 0;
+    int key_bits = 0;
+    int rounds = 0;
+    uint32_t active_after_round0 = 0;
+};
+
+void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s);
+
+// Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
+// (easa.py:306-331) of the whole batch
+void build_lcp(const uint32_t *text, const int32_t *sa, const int32_t *doc_off, int n_docs, int32_t n,
+               int32_t *lcp, cudaStream_t s);
+void build_child_ann(const int32_t *lcp, const int32_t *doc_off, const int32_t *doc_m, int n_docs,
+                     int32_t n, int32_t *up, int32_t *down, int32_t *next, int32_t *ann, cudaStream_t s);
+
+// batched scorer (easa.py:91-139)
+struct ScoreInput {
+    const uint32_t *text;
+    const int32_t *sa;
+    const int32_t *doc_off;
+    const int32_t *doc_m;
+    int n_docs;
+    const uint32_t *kp;        // device, concatenated queries
+    const int32_t *kp_off;     // device, K + 1
+    const int32_t *suf_kp;     // device, total_suffixes: owning keyphrase of each suffix
+    int32_t K;
+    int32_t total_suffixes;
+    int normalized;
+};
+void score_table(const ScoreInput &in, double *suffix_tmp /*n_docs x total_suffixes*/, double *out_DxK,
+                 cudaStream_t s);
+
+void cooc_counts(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s);
+
+}  // namespace east

@@ -1,0 +1,177 @@
+// score.cu -- batched keyphrase x document scorer.
+//
+// Replaces EnhancedAnnotatedSuffixArray._score (east/asts/easa.py:91-139) together with
+// _get_child_interval (:379-400), _lcp_value (:349-356) and _annotation (:340-344) for every
+// (document, keyphrase) pair of applications.keyphrases_table (applications.py:43-52).
+//
+// The reference walks the child table; the set of suffixes below the node reached after
+// matching d characters is exactly the SA interval of suffixes that start with those d
+// characters, and the node frequency is the interval size (root: n - m).  So one query suffix
+// is scored by narrowing an SA interval one character at a time:
+//     entering a NEW node (d == 0, or the interval got smaller)   frac += |child| / |parent|
+// and the suffix result is ((frac + d) - nodes) [/ d], accumulated in the reference's order
+// in IEEE fp64 (only +, -, / : nothing can be contracted into an FMA).
+//
+//   k_score_suffixes  one thread per (document, query suffix)   -> tmp[doc][suffix]
+//   k_score_combine   one thread per (document, keyphrase)      -> out[doc][k] = (sum in suffix order) / len
+#include "sa_build.h"
+
+namespace east {
+
+constexpr int SC_THREADS = 128;
+
+// character of suffix rank r at depth d as a comparable value: 0 = "no character" (sorts first)
+__device__ __forceinline__ uint64_t sym_at(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa,
+                                           int32_t r, int32_t d, int32_t end) {
+    int32_t p = sa[r] + d;
+    return (p < end) ? (uint64_t)T[p] + 1ull : 0ull;
+}
+
+__device__ __forceinline__ double score_one_suffix(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa,
+                                                   int32_t start, int32_t end, int32_t m,
+                                                   const uint32_t *__restrict__ q, int32_t len, int normalized) {
+    int32_t lo = start, hi = end - 1;
+    int32_t parent_f = (end - start) - m;
+    int32_t d = 0, nodes = 0;
+    double frac = 0.0;
+    while (d < len) {
+        const uint64_t c = (uint64_t)q[d] + 1ull;
+        int32_t nlo, nhi;
+        if (lo == hi) {
+            if (sym_at(T, sa, lo, d, end) != c) break;
+            nlo = lo; nhi = hi;
+        } else {
+            const uint64_t clo = sym_at(T, sa, lo, d, end);
+            const uint64_t chi = sym_at(T, sa, hi, d, end);
+            if (c < clo || c > chi) break;
+            // lower bound: first rank in [lo, hi] whose symbol is >= c
+            if (clo == c) {
+                nlo = lo;
+            } else {
+                int32_t a = lo, b = hi;  // sym(a) < c <= sym(b)
+                while (b - a > 1) {
+                    int32_t mid = a + ((b - a) >> 1);
+                    if (sym_at(T, sa, mid, d, end) < c) a = mid; else b = mid;
+                }
+                nlo = b;
+                if (b != hi && sym_at(T, sa, b, d, end) != c) break;
+                if (b == hi && chi != c) break;
+            }
+            // upper bound: last rank in [nlo, hi] whose symbol is <= c
+            if (chi == c) {
+                nhi = hi;
+            } else {
+                int32_t a = nlo, b = hi;  // sym(a) == c < sym(b)
+                while (b - a > 1) {
+                    int32_t mid = a + ((b - a) >> 1);
+                    if (sym_at(T, sa, mid, d, end) <= c) a = mid; else b = mid;
+                }
+                nhi = a;
+            }
+        }
+        const int32_t size = nhi - nlo + 1;
+        if (d == 0 || size != hi - lo + 1) {
+            ++nodes;
+            frac = frac + (double)size / (double)parent_f;
+        }
+        lo = nlo; hi = nhi; parent_f = size; ++d;
+    }
+    if (d == 0) return 0.0;
+    double r = (frac + (double)d) - (double)nodes;
+    if (normalized) r = r / (double)d;
+    return r;
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_score_suffixes(ScoreInput in, double *__restrict__ tmp) {
+    const int64_t total = (int64_t)in.n_docs * in.total_suffixes;
+    const int64_t stride = (int64_t)gridDim.x * SC_THREADS;
+    for (int64_t idx = (int64_t)blockIdx.x * SC_THREADS + threadIdx.x; idx < total; idx += stride) {
+        const int32_t doc = (int32_t)(idx / in.total_suffixes);
+        const int32_t sidx = (int32_t)(idx - (int64_t)doc * in.total_suffixes);
+        const int32_t k = __ldg(in.suf_kp + sidx);
+        const int32_t qend = __ldg(in.kp_off + k + 1);
+        const int32_t start = __ldg(in.doc_off + doc), end = __ldg(in.doc_off + doc + 1);
+        tmp[idx] = score_one_suffix(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx,
+                                    qend - sidx, in.normalized);
+    }
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+k_score_combine(ScoreInput in, const double *__restrict__ tmp, double *__restrict__ out) {
+    const int64_t total = (int64_t)in.n_docs * in.K;
+    const int64_t stride = (int64_t)gridDim.x * SC_THREADS;
+    for (int64_t idx = (int64_t)blockIdx.x * SC_THREADS + threadIdx.x; idx < total; idx += stride) {
+        const int32_t doc = (int32_t)(idx / in.K);
+        const int32_t k = (int32_t)(idx - (int64_t)doc * in.K);
+        const int32_t b = __ldg(in.kp_off + k), e = __ldg(in.kp_off + k + 1);
+        const double *row = tmp + (int64_t)doc * in.total_suffixes;
+        double result = 0.0;
+        for (int32_t s = b; s < e; ++s) result = result + row[s];
+        out[idx] = result / (double)(e - b);
+    }
+}
+
+void score_table(const ScoreInput &in, double *suffix_tmp, double *out_DxK, cudaStream_t s) {
+    const int64_t work = (int64_t)in.n_docs * in.total_suffixes;
+    if (work > 0)
+        EAST_LAUNCH(k_score_suffixes, grid_for(work, SC_THREADS, 64), SC_THREADS, 0, s, in, suffix_tmp);
+    const int64_t cells = (int64_t)in.n_docs * in.K;
+    if (cells > 0)
+        EAST_LAUNCH(k_score_combine, grid_for(cells, SC_THREADS, 64), SC_THREADS, 0, s, in, suffix_tmp, out_DxK);
+}
+
+// ------------------------------------------------------------------------------------------
+// Co-occurrence counts of the keyphrase graph (applications.py:111-113, 136-147):
+//   B[k][d] = S[d][k] >= threshold, C = B * B^T.  First version: bit-packed rows, AND + POPC.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_threshold_pack(const double *__restrict__ S, int64_t D, int32_t K, double thr, uint32_t *__restrict__ bits,
+                 int64_t words) {
+    // bits[k][w]: bit j of word w = (S[(32 w + j)][k] >= thr).  thread per (w, k), k fastest (coalesced S rows)
+    const int64_t total = words * K;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = idx / K;
+        const int32_t k = (int32_t)(idx - w * K);
+        uint32_t v = 0;
+        for (int j = 0; j < 32; ++j) {
+            int64_t d = w * 32 + j;
+            if (d < D && S[d * K + k] >= thr) v |= 1u << j;
+        }
+        bits[(int64_t)k * words + w] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_cooc_popc(const uint32_t *__restrict__ bits, int32_t K, int64_t words, int32_t *__restrict__ C) {
+    // 16x16 output tile per CTA, words streamed through shared memory
+    __shared__ uint32_t sa_[16][33], sb_[16][33];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
+    int32_t acc = 0;
+    for (int64_t w0 = 0; w0 < words; w0 += 32) {
+        for (int e = threadIdx.x; e < 16 * 32; e += 256) {
+            int r = e >> 5, c = e & 31;
+            int64_t w = w0 + c;
+            int ri = blockIdx.y * 16 + r, rj = blockIdx.x * 16 + r;
+            sa_[r][c] = (ri < K && w < words) ? bits[(int64_t)ri * words + w] : 0u;
+            sb_[r][c] = (rj < K && w < words) ? bits[(int64_t)rj * words + w] : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc += __popc(sa_[ty][c] & sb_[tx][c]);
+        __syncthreads();
+    }
+    if (i < K && j < K) C[(int64_t)i * K + j] = acc;
+}
+
+void cooc_counts(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s) {
+    const int64_t words = (D + 31) / 32;
+    DevBuf<uint32_t> bits((size_t)words * K, s);
+    EAST_LAUNCH(k_threshold_pack, grid_for(words * K, 256, 32), 256, 0, s, S_DxK, D, K, threshold, bits.p, words);
+    dim3 grid((K + 15) / 16, (K + 15) / 16);
+    EAST_LAUNCH(k_cooc_popc, grid, 256, 0, s, bits.p, K, words, C);
+}
+
+}  // namespace east

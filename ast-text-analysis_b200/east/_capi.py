@@ -1,0 +1,240 @@
+# -*- coding: utf-8 -*-
+"""ctypes binding of libeast_b200.so (C ABI in include/east_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible,
+every entry point raises east.exceptions.DeviceError.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from east import exceptions
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("EAST_B200_LIB",
+                          os.path.join(os.path.dirname(_HERE), "lib", "libeast_b200.so"))
+
+# east_array ids (include/east_b200.h)
+SUFTAB, LCPTAB, CHILDTAB_UP, CHILDTAB_DOWN, CHILDTAB_NEXT_L_INDEX, ANNTAB = range(6)
+TEXT_DEVPTR = 100
+
+EAST_ERR_ZERODIV = -4
+
+EXPORTED_SYMBOLS = [
+    "east_last_error", "east_device_count", "east_version", "east_build_host", "east_build_dev",
+    "east_free", "east_index_info", "east_index_doc", "east_index_copy", "east_index_devptr",
+    "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
+    "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option",
+]
+
+_lib = None
+
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_f32p = ctypes.POINTER(ctypes.c_float)
+_vp = ctypes.c_void_p
+
+
+def load():
+    """dlopen the engine and declare prototypes; raises DeviceError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise exceptions.DeviceError(
+            reason="%s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                   "or `make -C ast-text-analysis_b200`" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    L.east_last_error.restype = ctypes.c_char_p
+    L.east_version.restype = ctypes.c_char_p
+    L.east_device_count.restype = ctypes.c_int
+    L.east_build_host.argtypes = [_u32p, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, ctypes.POINTER(_vp)]
+    L.east_build_dev.argtypes = [_vp, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _vp, ctypes.POINTER(_vp)]
+    L.east_free.argtypes = [_vp]
+    L.east_free.restype = None
+    L.east_index_info.argtypes = [_vp, _i32p, _i64p, _i32p, _i32p, _i32p]
+    L.east_index_doc.argtypes = [_vp, ctypes.c_int32, _i64p, _i64p, _i32p]
+    L.east_index_copy.argtypes = [_vp, ctypes.c_int32, ctypes.c_int, _i32p]
+    L.east_index_devptr.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp)]
+    L.east_score_table_host.argtypes = [_vp, _u32p, _i64p, ctypes.c_int32, ctypes.c_int, _f64p]
+    L.east_score_table_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, _vp, _vp]
+    L.east_score_one.argtypes = [_vp, ctypes.c_int32, _u32p, ctypes.c_int32, ctypes.c_int, _f64p, _f64p]
+    L.east_cooc_dev.argtypes = [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, _vp, ctypes.c_int, _vp]
+    L.east_cooc_host.argtypes = [_f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, _i32p, ctypes.c_int]
+    L.east_last_timings.argtypes = [_f32p, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32]
+    L.east_launch_count.argtypes = [ctypes.c_int]
+    L.east_launch_count.restype = ctypes.c_int64
+    L.east_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    msg = load().east_last_error().decode("utf-8", "replace")
+    if rc == EAST_ERR_ZERODIV:
+        raise ZeroDivisionError(msg or "float division by zero")  # easa.py:134 on an empty query
+    if rc == -3:
+        raise MemoryError(msg)
+    if rc == -1 or rc == -5:
+        raise ValueError(msg)
+    raise exceptions.DeviceError(reason=msg)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+def device_count():
+    return load().east_device_count()
+
+
+def set_option(name, value):
+    _check(load().east_set_option(name.encode(), int(value)))
+
+
+def launch_count(reset=False):
+    return int(load().east_launch_count(1 if reset else 0))
+
+
+def last_timings():
+    """[(stage name, device ms)] of the last build/score/cooc call of this thread."""
+    L = load()
+    ms = (ctypes.c_float * 64)()
+    names = ctypes.create_string_buffer(4096)
+    n = L.east_last_timings(ms, names, 64, 4096)
+    parts = names.raw.split(b"\0")
+    return [(parts[i].decode(), float(ms[i])) for i in range(min(n, 64))]
+
+
+def pack_keyphrases(queries):
+    """Space-stripped queries (easa.py:36 query.replace(" ", "")) -> (uint32 codes, int64 offsets)."""
+    from east.asts.utils import codepoints
+    stripped = [q.replace(" ", "") for q in queries]
+    off = np.zeros(len(stripped) + 1, dtype=np.int64)
+    np.cumsum([len(q) for q in stripped], out=off[1:])
+    codes = np.ascontiguousarray(codepoints("".join(stripped)), dtype=np.uint32)
+    if codes.size != off[-1]:
+        raise ValueError("keyphrases contain lone surrogates")
+    return codes, off
+
+
+class DeviceIndex(object):
+    """A batch of documents indexed on one GPU (opaque east_index handle)."""
+
+    def __init__(self, packed_docs, doc_m, device=0):
+        """packed_docs: list of uint32 arrays (east.asts.utils.pack_strings_collection),
+        doc_m: number of strings of each document."""
+        L = load()
+        if len(packed_docs) == 0:
+            raise exceptions.EmptyStringsCollectionException()
+        self.n_docs = len(packed_docs)
+        self.doc_off = np.zeros(self.n_docs + 1, dtype=np.int64)
+        np.cumsum([len(p) for p in packed_docs], out=self.doc_off[1:])
+        self.doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
+        text = np.ascontiguousarray(np.concatenate(packed_docs) if self.n_docs > 1 else packed_docs[0],
+                                    dtype=np.uint32)
+        self.device = int(device)
+        self._h = _vp()
+        _check(L.east_build_host(_ptr(text, _u32p), _ptr(self.doc_off, _i64p), _ptr(self.doc_m, _i32p),
+                                 self.n_docs, self.device, ctypes.byref(self._h)))
+        self.build_timings = last_timings()
+
+    @classmethod
+    def from_handle(cls, handle, doc_off, doc_m, device):
+        self = cls.__new__(cls)
+        self._h = handle
+        self.doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
+        self.doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
+        self.n_docs = len(self.doc_m)
+        self.device = device
+        self.build_timings = last_timings()
+        return self
+
+    @classmethod
+    def build_dev(cls, text_devptr, doc_off, doc_m, device=0, stream=0):
+        """Build from a device-resident packed text (bench: inputs already in HBM)."""
+        L = load()
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
+        doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
+        h = _vp()
+        _check(L.east_build_dev(_vp(text_devptr), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m),
+                                int(device), _vp(stream), ctypes.byref(h)))
+        return cls.from_handle(h, doc_off, doc_m, int(device))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().east_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        n_docs, n_total, dev, rounds, fast = (ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int32(),
+                                              ctypes.c_int32(), ctypes.c_int32())
+        _check(load().east_index_info(self._h, ctypes.byref(n_docs), ctypes.byref(n_total), ctypes.byref(dev),
+                                      ctypes.byref(rounds), ctypes.byref(fast)))
+        return {"n_docs": n_docs.value, "n_total": n_total.value, "device": dev.value,
+                "rounds": rounds.value, "fast_path": bool(fast.value)}
+
+    def array(self, doc, which):
+        n = int(self.doc_off[doc + 1] - self.doc_off[doc])
+        out = np.empty(n, dtype=np.int32)
+        _check(load().east_index_copy(self._h, int(doc), int(which), _ptr(out, _i32p)))
+        return out
+
+    def devptr(self, which):
+        p = _vp()
+        _check(load().east_index_devptr(self._h, int(which), ctypes.byref(p)))
+        return p.value
+
+    def score_table(self, kp_codes, kp_off, normalized=True):
+        """-> float64 array [n_docs, K] (doc-major)."""
+        K = len(kp_off) - 1
+        kp_codes = np.ascontiguousarray(kp_codes, dtype=np.uint32)
+        kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
+        out = np.empty((self.n_docs, K), dtype=np.float64)
+        if kp_codes.size == 0:
+            kp_codes = np.zeros(1, dtype=np.uint32)
+        _check(load().east_score_table_host(self._h, _ptr(kp_codes, _u32p), _ptr(kp_off, _i64p), K,
+                                            1 if normalized else 0, _ptr(out, _f64p)))
+        self.score_timings = last_timings()
+        return out
+
+    def score_table_dev(self, kp_devptr, kp_off, out_devptr, normalized=True, stream=0):
+        kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
+        _check(load().east_score_table_dev(self._h, _vp(kp_devptr), _ptr(kp_off, _i64p), len(kp_off) - 1,
+                                           1 if normalized else 0, _vp(out_devptr), _vp(stream)))
+        self.score_timings = last_timings()
+
+    def score_one(self, doc, q_codes, normalized=True, want_suffix_scores=False):
+        q_codes = np.ascontiguousarray(q_codes, dtype=np.uint32)
+        L = int(q_codes.size)
+        score = ctypes.c_double(0.0)
+        ss = np.zeros(max(L, 1), dtype=np.float64)
+        qp = _ptr(q_codes, _u32p) if L else None
+        _check(load().east_score_one(self._h, int(doc), qp, L, 1 if normalized else 0, ctypes.byref(score),
+                                     _ptr(ss, _f64p) if want_suffix_scores else None))
+        return (score.value, ss[:L]) if want_suffix_scores else score.value
+
+
+def cooc_host(S, threshold, device=0):
+    """C = B B^T with B[k][d] = S[d][k] >= threshold; S float64 [D, K] -> int32 [K, K]."""
+    S = np.ascontiguousarray(S, dtype=np.float64)
+    D, K = S.shape
+    C = np.empty((K, K), dtype=np.int32)
+    _check(load().east_cooc_host(_ptr(S, _f64p), D, K, float(threshold), _ptr(C, _i32p), int(device)))
+    return C
+
+
+def cooc_dev(S_devptr, D, K, threshold, C_devptr, device=0, stream=0):
+    _check(load().east_cooc_dev(_vp(S_devptr), int(D), int(K), float(threshold), _vp(C_devptr), int(device),
+                                _vp(stream)))

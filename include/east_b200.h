@@ -1,0 +1,113 @@
+/*
+ * east_b200.h -- C ABI of libeast_b200.so, the B200 (sm_100a) engine behind EAST's
+ * `east.asts` "easa" algorithm.
+ *
+ * The reference (mikhaildubov/AST-text-analysis, pure Python) has no FFI; its boundary for
+ * this path is the Python class east.asts.easa.EnhancedAnnotatedSuffixArray
+ * (east/asts/easa.py:12-400) reached through east.asts.base.AST.get_ast
+ * (east/asts/base.py:13-18).  Each entry point below names the reference code it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes, no C++/torch types;
+ *   - every function returns 0 on success, a negative east_status on failure, and leaves a
+ *     message retrievable with east_last_error() (thread-local);
+ *   - "text" is the packed document: the code points of string 0, then 0x0A00+0, the code
+ *     points of string 1, then 0x0A00+1, ... (east/asts/utils.py:25-40 + east/asts/easa.py:19);
+ *     several documents are concatenated and delimited by doc_off[n_docs+1];
+ *   - *_host entry points take host buffers and do their own H<->D copies;
+ *     *_dev entry points take device pointers that live on the index's device;
+ *   - there is no CPU fallback: without a usable CUDA device every entry point fails.
+ */
+#ifndef EAST_B200_H
+#define EAST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct east_index east_index; /* opaque, immutable after build */
+
+typedef enum east_status {
+    EAST_OK = 0,
+    EAST_ERR_INVALID = -1, /* bad argument (NULL, negative size, empty document, ...) */
+    EAST_ERR_CUDA = -2,    /* CUDA runtime error or no device */
+    EAST_ERR_NOMEM = -3,
+    EAST_ERR_ZERODIV = -4, /* empty query: the reference raises ZeroDivisionError (easa.py:134) */
+    EAST_ERR_RANGE = -5    /* size exceeds the int32/2^30 limits of one index */
+} east_status;
+
+/* which array east_index_copy() exports; names follow east/asts/easa.py:18-24 */
+typedef enum east_array {
+    EAST_SUFTAB = 0,             /* easa.py:141-245  _compute_suftab (values local to the doc) */
+    EAST_LCPTAB = 1,             /* easa.py:247-266  _compute_lcptab */
+    EAST_CHILDTAB_UP = 2,        /* easa.py:268-287  _compute_childtab */
+    EAST_CHILDTAB_DOWN = 3,      /* easa.py:268-287 */
+    EAST_CHILDTAB_NEXT_L_INDEX = 4, /* easa.py:289-304 _compute_childtab_next_l_index */
+    EAST_ANNTAB = 5              /* easa.py:306-331  _compute_anntab */
+} east_array;
+
+const char *east_last_error(void);
+int east_device_count(void);
+const char *east_version(void);
+
+/* ---- build: replaces EnhancedAnnotatedSuffixArray.__init__ (easa.py:16-24) for a batch of
+ * documents, i.e. the loop of ASTRelevanceMeasure.set_text_collection (relevance.py:41-47).
+ *   text      : concatenated packed documents, doc_off[n_docs] code points
+ *   doc_off   : n_docs+1 offsets into text (doc_off[0] == 0)
+ *   doc_m     : number of strings (= terminators) of each document
+ * Limits: doc_off[n_docs] < 2^30 per index. */
+int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m,
+                    int32_t n_docs, int device, east_index **out);
+int east_build_dev(const uint32_t *text_dev, const int64_t *doc_off_host, const int32_t *doc_m_host,
+                   int32_t n_docs, int device, void *stream, east_index **out);
+void east_free(east_index *idx);
+
+/* ---- introspection (parity checks; the reference exposes these as numpy attributes) */
+int east_index_info(const east_index *idx, int32_t *n_docs, int64_t *n_total, int32_t *device,
+                    int32_t *rounds, int32_t *fast_path);
+int east_index_doc(const east_index *idx, int32_t doc, int64_t *offset, int64_t *n, int32_t *m);
+/* copy one array of one document to a host int32 buffer of n entries */
+int east_index_copy(const east_index *idx, int32_t doc, int which, int32_t *dst_host);
+/* device pointer to the whole-batch array (global ranks/positions); for tests and benches */
+int east_index_devptr(const east_index *idx, int which, const void **ptr);
+
+/* ---- scoring: replaces EnhancedAnnotatedSuffixArray.score/_score (easa.py:26-36, 91-139)
+ * for every (document, keyphrase) pair, i.e. the K x D loop of
+ * applications.keyphrases_table (applications.py:43-52).
+ *   kp      : concatenated code points of the K queries AFTER query.replace(" ", "")
+ *   kp_off  : K+1 offsets
+ *   out     : doc-major table out[d * K + k], IEEE double
+ * A zero-length query makes the call fail with EAST_ERR_ZERODIV. */
+int east_score_table_host(const east_index *idx, const uint32_t *kp, const int64_t *kp_off,
+                          int32_t K, int normalized, double *out_DxK);
+int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
+                         int32_t K, int normalized, double *out_DxK_dev, void *stream);
+/* single query against one document, with the per-suffix results of
+ * return_suffix_scores=True (easa.py:132-137); suffix_scores may be NULL, else len doubles */
+int east_score_one(const east_index *idx, int32_t doc, const uint32_t *q, int32_t len,
+                   int normalized, double *score, double *suffix_scores);
+
+/* ---- keyphrase graph support: replaces the pair loop of applications.keyphrases_graph
+ * (applications.py:111-113, 136-147).  B[k][d] = S[d][k] >= threshold; C = B * B^T (int32);
+ * support[k] = C[k][k]. */
+int east_cooc_dev(const double *S_DxK_dev, int64_t D, int32_t K, double threshold,
+                  int32_t *C_KxK_dev, int device, void *stream);
+int east_cooc_host(const double *S_DxK, int64_t D, int32_t K, double threshold,
+                   int32_t *C_KxK, int device);
+
+/* ---- measurement hooks (bench.py): per-stage device time of the last build/score call on
+ * this thread, measured with CUDA events on the launching stream.
+ * names: NUL-separated list written to buf; returns the number of stages. */
+int east_last_timings(float *ms, char *names, int32_t cap, int32_t names_cap);
+/* number of kernel launches issued by the library on this thread since the last reset */
+int64_t east_launch_count(int reset);
+/* tuning knobs (0 = default): "key_chars" (round-0 window), "score_block", ... */
+int east_set_option(const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAST_B200_H */

@@ -1,0 +1,280 @@
+"""GPU: the CUDA path (through the C ABI / the east package) against the oracle and the goldens.
+
+Bit-exact for suftab / lcptab / childtab_* / anntab; scores must be bit-exact too (the
+acceptance floor of the task is 1e-9 relative, asserted separately).
+"""
+import numpy as np
+import pytest
+
+from conftest import ARRAY_NAMES
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9  # north_star tolerance for scores
+
+
+def _capi():
+    from east import _capi
+    return _capi
+
+
+def _build(strings_collections, device=0):
+    from east.asts import utils
+    packed = [utils.pack_strings_collection(c) for c in strings_collections]
+    return _capi().DeviceIndex(packed, [len(c) for c in strings_collections], device=device)
+
+
+def _check_arrays(idx, doc, oracle_ast, tag):
+    capi = _capi()
+    for which, name in zip((capi.SUFTAB, capi.LCPTAB, capi.CHILDTAB_UP, capi.CHILDTAB_DOWN,
+                            capi.CHILDTAB_NEXT_L_INDEX, capi.ANNTAB), ARRAY_NAMES):
+        got = idx.array(doc, which)
+        exp = getattr(oracle_ast, name)
+        assert np.array_equal(got, exp), (tag, name, np.nonzero(got != exp)[0][:5])
+
+
+def test_golden_arrays_and_scores(golden):
+    import east  # noqa: F401
+    from east.asts import base
+    for c in golden["cases"]:
+        ast = base.AST.get_ast(c["strings"], "easa")
+        if c.get("arrays"):
+            for name in ARRAY_NAMES:
+                got = getattr(ast, name)
+                assert got.dtype == np.int64
+                assert np.array_equal(got, golden["arrays"]["%s/%s" % (c["name"], name)]), (c["name"], name)
+        for q in c["queries"]:
+            if q.get("raises"):
+                with pytest.raises(ZeroDivisionError):
+                    ast.score(q["q"])
+                continue
+            for normalized, key, skey in ((True, "norm", "suffix_norm"), (False, "denorm", "suffix_denorm")):
+                exp = float.fromhex(q[key])
+                got = ast.score(q["q"], normalized=normalized)
+                assert abs(got - exp) <= REL_TOL * abs(exp)
+                assert float(got).hex() == q[key], (c["name"], q["q"], normalized)
+                got2, per_suffix = ast.score(q["q"], normalized=normalized, return_suffix_scores=True)
+                assert float(got2).hex() == q[key]
+                assert {k: float(v).hex() for k, v in per_suffix.items()} == q[skey]
+
+
+def test_readme_known_answer():
+    import east  # noqa: F401
+    from east.asts import base
+    ast = base.AST.get_ast(["XABXAC", "HI"])
+    assert ast.score("ABCI") == 0.1875
+    assert ast.score("NOPE") == 0
+    assert ast.string == "XABXAC਀HIਁ"
+    assert ast.suftab.tolist() == [1, 4, 2, 5, 7, 8, 0, 3, 6, 9]
+    assert ast.anntab.tolist() == [8, 2, 0, 0, 0, 0, 0, 2, 0, 0]
+
+
+def test_reference_cross_engine_fixture():
+    # tests/asts/test_base.py:13-24: the GPU engine must give the value all three reference engines share
+    import east  # noqa: F401
+    from east.asts import base
+    ast = base.AST.get_ast(["abcd efg ops", "xyzq", "test"])
+    assert float(ast.score("aqcb")).hex() == "0x1.99999999999a0p-5"
+    assert float(ast.score("aqcb", normalized=False)).hex() == "0x1.99999999999a0p-5"
+    assert float(ast.score("efgp")).hex() == "0x1.2888888888888p-2"
+    assert ast.score("efgp", normalized=False) == 0.6875
+    assert ast.score("mn4") == 0
+
+
+@pytest.mark.parametrize("force_general", [0, 1])
+def test_random_collections_vs_oracle(oracle_mod, force_general):
+    capi = _capi()
+    capi.set_option("force_general", force_general)
+    try:
+        rng = np.random.default_rng(11 + force_general)
+        for trial in range(40):
+            sigma = int(rng.choice([2, 3, 4, 7, 27]))
+            alpha = list("ABCDEFGHIJKLMNOPQRSTUVWXYZ ")[:sigma]
+            n_docs = int(rng.integers(1, 6))
+            cols = []
+            for _ in range(n_docs):
+                m = int(rng.integers(1, 12))
+                cols.append(["".join(rng.choice(alpha, size=int(rng.integers(1, 40)))) for _ in range(m)])
+            idx = _build(cols)
+            assert idx.info()["fast_path"] == (not force_general)
+            oracles = [oracle_mod.OracleEASA(c) for c in cols]
+            for d, o in enumerate(oracles):
+                _check_arrays(idx, d, o, (trial, d))
+            letters = [a for a in alpha if a != " "] or ["A"]
+            queries = ["".join(rng.choice(letters, size=int(rng.integers(1, 12)))) for _ in range(9)]
+            codes, off = capi.pack_keyphrases(queries)
+            for normalized in (True, False):
+                table = idx.score_table(codes, off, normalized)
+                assert table.shape == (n_docs, len(queries))
+                for d, o in enumerate(oracles):
+                    exp = o.score_many(codes, off, normalized)
+                    assert np.array_equal(table[d].view(np.uint64), exp.view(np.uint64)), (trial, d, normalized)
+            idx.close()
+    finally:
+        capi.set_option("force_general", 0)
+
+
+def test_zipf_documents_vs_oracle(oracle_mod):
+    import synth
+    capi = _capi()
+    packed, ms, cols = synth.packed_collection(6, 10000)
+    idx = capi.DeviceIndex(packed, ms)
+    info = idx.info()
+    assert info["fast_path"] and info["rounds"] <= 6
+    oracles = [oracle_mod.OracleEASA(text=p, m=m) for p, m in zip(packed, ms)]
+    for d, o in enumerate(oracles):
+        _check_arrays(idx, d, o, d)
+    from east import utils
+    kps = [utils.prepare_text(k) for k in synth.keyphrases(50)]
+    codes, off = capi.pack_keyphrases(kps)
+    for normalized in (True, False):
+        table = idx.score_table(codes, off, normalized)
+        for d, o in enumerate(oracles):
+            exp = o.score_many(codes, off, normalized)
+            assert np.allclose(table[d], exp, rtol=REL_TOL, atol=0)
+            assert np.array_equal(table[d].view(np.uint64), exp.view(np.uint64))
+
+
+def test_key_window_sizes_give_the_same_arrays(oracle_mod):
+    # the round-0 window only changes how many doubling rounds follow, never the result
+    import synth
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(2, 6000, first_seed=40)
+    oracles = [oracle_mod.OracleEASA(text=p, m=m) for p, m in zip(packed, ms)]
+    try:
+        for kc in (1, 2, 3, 5, 8):
+            capi.set_option("key_chars", kc)
+            idx = capi.DeviceIndex(packed, ms)
+            for d, o in enumerate(oracles):
+                _check_arrays(idx, d, o, (kc, d))
+            idx.close()
+    finally:
+        capi.set_option("key_chars", 0)
+
+
+def test_deep_lcp_and_degenerate_inputs(oracle_mod):
+    rng = np.random.default_rng(3)
+    s = "".join(rng.choice(list("AB"), size=700))
+    cols = [[s] * 5,            # analysis/utils.py:5-9 worst case: identical strings
+            ["A" * 300],         # one run
+            [" "],               # empty text (utils.py:76-78)
+            ["A"], ["AB", "AB", "AB", "B", "A"]]
+    idx = _build(cols)
+    for d, c in enumerate(cols):
+        _check_arrays(idx, d, oracle_mod.OracleEASA(c), d)
+    assert idx.info()["rounds"] >= 5
+    # [" "].score("AB") == 0
+    assert idx.score_one(2, np.array([65, 66], dtype=np.uint32)) == 0.0
+
+
+def test_unicode_and_terminator_range_collisions(oracle_mod):
+    # CJK / Gurmukhi code points sort among or above the terminators 0x0A00+i: general path
+    cols = [["中中", "文中文", "ਅਆਇ"], ["ਁਂ", "A"], ["\U0001F600\U0001F600!", "ok"]]
+    idx = _build(cols)
+    assert not idx.info()["fast_path"]
+    for d, c in enumerate(cols):
+        o = oracle_mod.OracleEASA(c)
+        capi = _capi()
+        for which, name in ((capi.SUFTAB, "suftab"), (capi.LCPTAB, "lcptab")):
+            assert np.array_equal(idx.array(d, which), getattr(o, name)), (d, name)
+    # Cyrillic stays on the fast path
+    idx2 = _build([["ЖУК", "ЖУРНАЛ", "ЁЖ"]])
+    assert idx2.info()["fast_path"]
+    _check_arrays(idx2, 0, oracle_mod.OracleEASA(["ЖУК", "ЖУРНАЛ", "ЁЖ"]), "cyr")
+
+
+def test_hse_table_and_graph(golden):
+    from east import applications, relevance
+    hse = golden["hse"]
+    texts = {d["name"]: " ".join(d["strings"]) for d in hse["docs"]}
+    # rebuild texts whose strings collection equals the golden one: join 3-word groups is lossy, so
+    # feed the collections straight to the measure instead
+    measure = relevance.ASTRelevanceMeasure("easa", normalized=True)
+    from east import _capi
+    from east.asts import utils as au
+    cols = [d["strings"] for d in hse["docs"]]
+    idx = _capi.DeviceIndex([au.pack_strings_collection(c) for c in cols], [len(c) for c in cols])
+    kps = hse["keyphrases"]
+    from east import utils
+    codes, off = _capi.pack_keyphrases([utils.prepare_text(k) for k in kps])
+    for normalized, key in ((True, "table_norm"), (False, "table_denorm")):
+        table = idx.score_table(codes, off, normalized)
+        for k, kp in enumerate(kps):
+            for j, d in enumerate(hse["docs"]):
+                assert float(table[j, k]).hex() == hse[key][kp][d["name"]], (kp, d["name"])
+    # graph: co-occurrence counts on device, edges/confidences as in applications.py:111-147
+    table = idx.score_table(codes, off, True)
+    for g in hse["graphs"]:
+        cooc = _capi.cooc_host(table, g["r"])
+        B = table >= g["r"]
+        assert np.array_equal(cooc, (B.T.astype(np.int64) @ B.astype(np.int64)).astype(np.int32))
+        support = np.diag(cooc)
+        assert [n["support"] for n in g["nodes"]] == [int(support[n["id"]]) for n in g["nodes"]]
+    del measure, texts
+
+
+def test_applications_api_end_to_end(golden, oracle_mod):
+    from east import applications, relevance, utils
+    import synth
+    docs = synth.documents(5, 4000, first_seed=100)
+    texts = {"doc%d.txt" % i: d for i, d in enumerate(docs)}
+    kps = synth.keyphrases(20) + [""]
+    table = applications.keyphrases_table(kps, texts, relevance.ASTRelevanceMeasure("easa", normalized=True))
+    assert "" not in table and set(table.keys()) == set(k for k in kps if k)
+    for name, text in texts.items():
+        o = oracle_mod.OracleEASA(utils.text_to_strings_collection(text))
+        for kp in kps:
+            if kp:
+                exp = o.score(utils.prepare_text(kp), True)
+                assert float(table[kp][name]) == float(exp), (kp, name)
+    graph = applications.keyphrases_graph([k for k in kps if k], texts, referral_confidence=0.5,
+                                          relevance_threshold=0.1, support_threshold=1)
+    # the same graph from the table with the reference's set arithmetic (applications.py:111-147)
+    import itertools
+    keys = [k for k in kps if k]
+    kt = {k: set(t for t in texts if table[k][t] >= 0.1) for k in keys}
+    nodes = [{"id": i, "label": k, "support": len(kt[k])} for i, k in enumerate(keys) if len(kt[k]) >= 1]
+    edges = []
+    for a, b in itertools.permutations(range(len(nodes)), 2):
+        conf = float(len(kt[nodes[a]["label"]] & kt[nodes[b]["label"]])) / max(len(kt[nodes[a]["label"]]), 1)
+        if conf >= 0.5:
+            edges.append({"source": nodes[a]["id"], "target": nodes[b]["id"], "confidence": conf})
+    assert graph["nodes"] == nodes
+    assert graph["edges"] == edges
+
+
+def test_traversals_cover_all_intervals(oracle_mod):
+    import east  # noqa: F401
+    from east.asts import base
+    ast = base.AST.get_ast(["XABXAC", "HI"])
+    seen = []
+    ast.traverse(lambda node: seen.append((node[0], node[1], node[2])), "depth-first|post-order")
+    assert seen == [(1, 0, 1), (2, 6, 7), (0, 0, 9)]
+    pre = []
+    ast.traverse(lambda node: pre.append((node[1], node[2])), "depth-first|pre-order")
+    assert pre[0] == (0, 9) and (0, 1) in pre and (6, 7) in pre and len(pre) == 1 + 8 + 4
+    with pytest.raises(NotImplementedError):
+        ast.traverse(lambda node: None, "breadth-first")
+
+
+def test_error_paths():
+    capi = _capi()
+    idx = _build([["AB"]])
+    with pytest.raises(ZeroDivisionError):
+        idx.score_one(0, np.zeros(0, dtype=np.uint32))
+    with pytest.raises(ZeroDivisionError):
+        codes, off = capi.pack_keyphrases(["AB", " "])
+        idx.score_table(codes, off)
+    with pytest.raises(ValueError):
+        idx.array(5, capi.SUFTAB)
+    assert capi.launch_count() > 0
+
+
+def test_determinism_two_builds_identical():
+    import synth
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(3, 8000, first_seed=7)
+    a, b = capi.DeviceIndex(packed, ms), capi.DeviceIndex(packed, ms)
+    for d in range(3):
+        for which in range(6):
+            assert np.array_equal(a.array(d, which), b.array(d, which))

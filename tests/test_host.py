@@ -1,0 +1,115 @@
+"""CPU: host-side mirror of the EAST API and the C-ABI surface (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, have_gpu
+
+
+def test_tokenize_reference_known_answer(golden):
+    from east import utils
+    # tests/test_utils.py:10-13
+    assert utils.tokenize("Well, what a sunny day!") == ["Well", "what", "a", "sunny", "day"]
+    assert utils.tokenize(golden["prep"]["tokenize"]["in"]) == golden["prep"]["tokenize"]["out"]
+
+
+def test_text_to_strings_collection_matches_reference(golden):
+    from east import utils
+    for item in golden["prep"]["collections"]:
+        assert utils.text_to_strings_collection(item["in"]) == item["out"]
+    assert utils.text_to_strings_collection("") == [" "]
+    assert utils.prepare_text(b"caf\xc3\xa9 \xff") == "CAFÉ �"  # upper-case, errors=replace
+
+
+def test_asts_utils_known_answers():
+    from east.asts import utils
+    # tests/asts/test_utils.py:10-30
+    assert utils.match_strings("", "") == 0 and utils.match_strings("a", "") == 0
+    assert utils.match_strings("a", "ab") == 1 and utils.match_strings("abc", "abd") == 2
+    assert utils.match_strings("abc", "abc") == 3 and utils.match_strings("abcd", "abc") == 3
+    assert utils.index([1, 2, 3, 2], 2) == 1 and utils.index([1, 2, 3, 2], 2, 2) == 3
+    assert utils.index("abcabc", "c", 3) == 5
+    assert utils.make_unique_endings(["ab", "c"]) == ["ab਀", "cਁ"]
+
+
+def test_pack_strings_collection(oracle_mod):
+    from east.asts import utils
+    for strings in (["XABXAC", "HI"], [" "], ["", "A", ""], ["Жук", "x" * 50, "\U0001F600!"]):
+        packed = utils.pack_strings_collection(strings)
+        assert packed.dtype == np.uint32
+        expect = [ord(ch) for s in utils.make_unique_endings(strings) for ch in s]
+        assert packed.tolist() == expect
+        assert np.array_equal(packed, oracle_mod.pack(strings))
+    # no 0x110000 cap on the number of strings
+    many = utils.pack_strings_collection(["A"] * 1200000)
+    assert many[-1] == 0x0A00 + 1199999
+
+
+def test_registry_and_exceptions(golden):
+    import east  # noqa: F401  (registers engines)
+    from east import consts, exceptions
+    from east.asts import base, easa
+    assert golden["errors"] == {"empty_collection": "EmptyStringsCollectionException",
+                                "unknown_algorithm": "NoSuchASTAlgorithm"}
+    with pytest.raises(exceptions.EmptyStringsCollectionException):
+        base.AST.get_ast([])
+    with pytest.raises(exceptions.NoSuchASTAlgorithm) as ei:
+        base.AST.get_ast(["A"], "nope")
+    assert "nope" in str(ei.value)
+    assert easa.EnhancedAnnotatedSuffixArray.__algorithm__ == consts.ASTAlgorithm.EASA == "easa"
+    assert consts.String.UNICODE_SPECIAL_SYMBOLS_START == 0x0A00
+    with pytest.raises(TypeError):
+        consts.String.UNICODE_SPECIAL_SYMBOLS_START = 1
+    assert sorted(consts.ASTAlgorithm) == ["ast_linear", "ast_naive", "easa"]
+
+
+def test_capi_library_exports_every_declared_symbol():
+    from east import _capi
+    header = open(os.path.join(ROOT, "include", "east_b200.h")).read()
+    declared = set(re.findall(r"\b(east_[a-z_0-9]+)\s*\(", header))
+    declared.discard("east_index")
+    assert declared == set(_capi.EXPORTED_SYMBOLS)
+    assert os.path.exists(_capi.LIB_PATH), "build the engine first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), sym
+    assert b"sm_100a" in ctypes.c_char_p(ctypes.cast(lib.east_version, ctypes.CFUNCTYPE(ctypes.c_char_p))()).value
+
+
+@pytest.mark.skipif(have_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    from east import exceptions
+    from east.asts import base
+    with pytest.raises(exceptions.DeviceError):
+        base.AST.get_ast(["XABXAC", "HI"])
+    from east import applications
+    with pytest.raises(exceptions.DeviceError):
+        applications.keyphrases_table(["abc"], {"t": "some text here"})
+
+
+def test_argument_validation_needs_no_gpu():
+    from east import _capi
+    L = _capi.load()
+    h = ctypes.c_void_p()
+    text = np.array([65, 0x0A00], dtype=np.uint32)
+    off = np.array([0, 0], dtype=np.int64)  # empty document
+    m = np.array([1], dtype=np.int32)
+    rc = L.east_build_host(text.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                           off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                           m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 1, 0, ctypes.byref(h))
+    assert rc == -1 and b"empty document" in L.east_last_error()
+
+
+def test_synthetic_generator_is_deterministic():
+    import synth
+    d1, d2 = synth.document(10000, 1), synth.document(10000, 1)
+    assert d1 == d2 and len(d1) == 10000 and d1 != synth.document(10000, 2)
+    kps = synth.keyphrases(50)
+    assert kps == synth.keyphrases(50) and all(1 <= len(k.split(" ")) <= 3 for k in kps)
+    from east import utils
+    col = utils.text_to_strings_collection(d1)
+    n = sum(len(s) for s in col) + len(col)
+    assert 0.85 < n / 10000.0 < 0.97  # n ~ 0.911 x bytes
