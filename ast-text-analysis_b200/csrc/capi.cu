@@ -11,6 +11,41 @@
 namespace east {
 
 thread_local int64_t g_launches = 0;
+thread_local int g_time_kernels = 0;
+thread_local double g_next_bytes = 0.0;
+
+struct KernelStat { int64_t launches = 0; double ms = 0.0; double bytes = 0.0; };
+struct PendingLaunch { std::string name; cudaEvent_t a, b; double bytes; };
+static thread_local std::map<std::string, KernelStat> g_kstats;
+static thread_local std::vector<PendingLaunch> g_pending;
+static thread_local std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t pool_event() {
+    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    EAST_CUDA(cudaEventCreate(&e));
+    return e;
+}
+void ktime_begin(const char *name, cudaStream_t s) {
+    PendingLaunch p{name, pool_event(), pool_event(), g_next_bytes};
+    EAST_CUDA(cudaEventRecord(p.a, s));
+    g_pending.push_back(p);
+}
+void ktime_end(cudaStream_t s) { EAST_CUDA(cudaEventRecord(g_pending.back().b, s)); }
+void ktime_collect() {
+    for (auto &p : g_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            KernelStat &k = g_kstats[p.name];
+            k.launches += 1; k.ms += ms; k.bytes += p.bytes;
+        } else {
+            cudaGetLastError();
+        }
+        g_event_pool.push_back(p.a);
+        g_event_pool.push_back(p.b);
+    }
+    g_pending.clear();
+}
 static thread_local std::string g_error;
 static thread_local std::vector<float> g_stage_ms;
 static thread_local std::vector<std::string> g_stage_names;
@@ -45,6 +80,7 @@ void StageTimer::mark(const char *name) {
 }
 void StageTimer::finish() { mark(""); }
 void StageTimer::collect() {
+    ktime_collect();
     g_stage_ms.clear();
     g_stage_names.clear();
     for (size_t i = 0; i + 1 < ev.size(); ++i) {
@@ -120,6 +156,11 @@ int east_device_count(void) {
 
 int east_set_option(const char *name, int64_t value) {
     if (!name) return fail(EAST_ERR_INVALID, "option name is NULL");
+    if (!strcmp(name, "time_kernels")) {  // per-thread: events around every launch; value 0 also clears the table
+        g_time_kernels = value ? 1 : 0;
+        if (!value) g_kstats.clear();
+        return EAST_OK;
+    }
     std::lock_guard<std::mutex> g(g_opt_mutex);
     g_options[name] = value;
     return EAST_OK;
@@ -145,6 +186,24 @@ int east_last_timings(float *ms, char *names, int32_t cap, int32_t names_cap) {
         }
     }
     return n;
+}
+
+int east_kernel_stats(char *names, int32_t names_cap, double *ms, int64_t *launches, double *bytes, int32_t cap) {
+    int i = 0;
+    int32_t w = 0;
+    for (auto &kv : g_kstats) {
+        if (i < cap) {
+            if (ms) ms[i] = kv.second.ms;
+            if (launches) launches[i] = kv.second.launches;
+            if (bytes) bytes[i] = kv.second.bytes;
+            if (names && w + (int32_t)kv.first.size() + 1 <= names_cap) {
+                memcpy(names + w, kv.first.c_str(), kv.first.size() + 1);
+                w += (int32_t)kv.first.size() + 1;
+            }
+        }
+        ++i;
+    }
+    return i;
 }
 
 static void free_index(east_index *idx) {
@@ -309,7 +368,8 @@ int east_index_devptr(const east_index *idx, int which, const void **ptr) {
 // ---- scoring ----------------------------------------------------------------------------
 static void score_common(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
                          int normalized, double *out_dev, int32_t doc_begin, int32_t doc_count, cudaStream_t s,
-                         double *suffix_out_dev /* optional: per-suffix results of the doc range */) {
+                         double *suffix_out_dev /* optional: per-suffix results of the doc range */,
+                         int64_t *probes_out = nullptr /* optional: run the probe-counting scorer */) {
     const int64_t total = kp_off[K];
     if (total >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "keyphrase buffer too large");
     std::vector<int32_t> off32(K + 1), suf_kp((size_t)total);
@@ -332,10 +392,23 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
     in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
     in.kp = kp_dev; in.kp_off = d_off.p; in.suf_kp = d_suf.p; in.K = K; in.total_suffixes = (int32_t)total;
     in.normalized = normalized ? 1 : 0;
+    in.algorithmic_bytes = (double)get_option("score_bytes", 0);
+    DevBuf<unsigned long long> d_probes;
+    if (probes_out) {
+        d_probes = DevBuf<unsigned long long>(1, s);
+        EAST_CUDA(cudaMemsetAsync(d_probes.p, 0, sizeof(unsigned long long), s));
+        in.probe_count = d_probes.p;
+    }
     StageTimer tm(s);
     tm.mark("score");
     score_table(in, tmp, out_dev, s);
     tm.finish();
+    if (probes_out) {
+        unsigned long long h = 0;
+        EAST_CUDA(cudaMemcpyAsync(&h, d_probes.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+        EAST_CUDA(cudaStreamSynchronize(s));
+        *probes_out = (int64_t)h;
+    }
     EAST_CUDA(cudaStreamSynchronize(s));  // host staging vectors above must outlive the copies
     tm.collect();
 }
@@ -346,6 +419,15 @@ int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const in
     if (!idx || !kp_dev || !kp_off || !out_DxK_dev || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
     EAST_CUDA(cudaSetDevice(idx->device));
     score_common(idx, kp_dev, kp_off, K, normalized, out_DxK_dev, 0, idx->n_docs, (cudaStream_t)stream, nullptr);
+    EAST_API_END
+}
+
+int east_score_probes_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
+                          double *out_DxK_dev, void *stream, int64_t *probes) {
+    EAST_API_BEGIN
+    if (!idx || !kp_dev || !kp_off || !out_DxK_dev || !probes || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    EAST_CUDA(cudaSetDevice(idx->device));
+    score_common(idx, kp_dev, kp_off, K, 1, out_DxK_dev, 0, idx->n_docs, (cudaStream_t)stream, nullptr, probes);
     EAST_API_END
 }
 

@@ -24,17 +24,26 @@ struct Error : public std::runtime_error {
     } while (0)
 
 extern thread_local int64_t g_launches;
+extern thread_local int g_time_kernels;     // option "time_kernels": CUDA events around every launch
+extern thread_local double g_next_bytes;    // algorithmic bytes of the next launch (roofline numerator)
+void ktime_begin(const char *name, cudaStream_t s);
+void ktime_end(cudaStream_t s);
+void ktime_collect();  // after a stream sync: fold the pending event pairs into the per-kernel table
 
 // every kernel launch of the library goes through this macro so bench.py can report
-// "gpu_launches" from a real count
+// "gpu_launches" from a real count and per-kernel device time measured live with CUDA events
 #define EAST_LAUNCH(kernel, grid, block, smem, stream, ...)                                  \
     do {                                                                                     \
+        if (::east::g_time_kernels) ::east::ktime_begin(#kernel, (stream));                  \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+        if (::east::g_time_kernels) ::east::ktime_end((stream));                             \
         ++::east::g_launches;                                                                \
+        ::east::g_next_bytes = 0.0;                                                          \
         cudaError_t _e = cudaGetLastError();                                                 \
         if (_e != cudaSuccess)                                                               \
             throw ::east::Error(-2, std::string(#kernel) + " launch: " + cudaGetErrorString(_e)); \
     } while (0)
+#define EAST_BYTES(b) (::east::g_next_bytes = (double)(b))
 
 // stream-ordered allocations from the device's default pool (release threshold raised once)
 void *dev_alloc(size_t bytes, cudaStream_t s);

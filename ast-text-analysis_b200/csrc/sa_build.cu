@@ -47,6 +47,7 @@ int radix_sort_pairs(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int
         uint64_t *kout = cur ? ka : kb;
         const uint32_t *vin = cur ? vb : va;
         uint32_t *vout = cur ? va : vb;
+        EAST_BYTES(24.0 * n);  // read + write of an 8-byte key and a 4-byte value per element
         EAST_LAUNCH(k_rs_onesweep, tiles, RS_THREADS, 0, s, kin, kout, vin, vout, n, 8 * p,
                     hist + 256 * p, status + (size_t)tiles * 256 * p, tickets + p);
         cur ^= 1;
@@ -400,6 +401,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     tm.mark("scan_text");
     DevBuf<ScanResult> d_scan(1, s);
     EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
+    EAST_BYTES(4.0 * n);
     EAST_LAUNCH(k_scan_text, grid_for(n, 256 * 8, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p);
     ScanResult scan;
     EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
@@ -452,12 +454,15 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
         EAST_CUDA(cudaMemcpyAsync(d_table.p, table.data(), EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
         t8 = DevBuf<uint8_t>((size_t)n + 64, s);
+        EAST_BYTES(5.0 * n);
         EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_table.p,
                     (uint8_t)kp.term, t8.p);
+        EAST_BYTES(13.0 * n);
         EAST_LAUNCH(k_keygen0_fast, grid_for(n, KG_TILE, 4), KG_THREADS, 0, s, t8.p, n, in.doc_off, D, kp,
                     keys_a.p, vals_a.p, hist.p);
         EAST_CUDA(cudaStreamSynchronize(s));  // d_table goes out of scope (stream-ordered free is safe, host table too)
     } else {
+        EAST_BYTES(16.0 * n);
         EAST_LAUNCH(k_keygen0_general, grid_for(n, 256 * 8, 4), 256, 0, s, in.text, n, in.doc_off, D, kp,
                     keys_a.p, vals_a.p, hist.p);
     }
@@ -473,6 +478,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     {
         const uint64_t sym_mask = (kp.b >= 64) ? ~0ull : ((1ull << kp.b) - 1ull);
         const uint64_t term = fast ? (uint64_t)kp.term : ~0ull;
+        EAST_BYTES(20.0 * n);  // keys + values in, SA + rank out (active-list output is data dependent)
         EAST_LAUNCH(k_rerank<true>, rr_tiles_max, RR_THREADS, 0, s, cur ? keys_b.p : keys_a.p,
                     cur ? vals_b.p : vals_a.p, (const uint32_t *)nullptr, n, sym_mask, term, out.sa, rank,
                     act_vals.p, act_slots.p, act_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1);
@@ -498,6 +504,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         const int nbits = sb + pbits;
         const int passes = rs_num_passes(nbits);
         EAST_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 256 * RS_MAX_PASSES, s));
+        EAST_BYTES(20.0 * n_act);  // value + primary in, one rank gather, key out
         EAST_LAUNCH(k_keygen_h, grid_for(n_act, 256 * 4, 8), 256, 0, s, act_vals.p, act_prim.p, (int32_t)n_act,
                     rank, (int32_t)h, sb, passes, fast ? 0 : 1, in.doc_off, D, keys_a.p, hist.p);
         // values to sort along: the suffix index
@@ -508,6 +515,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         const int rr_tiles = ((int)n_act + RR_TILE - 1) / RR_TILE;
         EAST_CUDA(cudaMemsetAsync(rr_status.p, 0, sizeof(uint64_t) * ((size_t)rr_tiles + 2), s));
         EAST_CUDA(cudaMemsetAsync(rr_misc.p, 0, sizeof(uint32_t) * 8, s));
+        EAST_BYTES(24.0 * n_act);
         EAST_LAUNCH(k_rerank<false>, rr_tiles, RR_THREADS, 0, s, sk, sv, act_slots.p, (int32_t)n_act, 0ull, 0ull,
                     out.sa, rank, nxt_vals.p, nxt_slots.p, nxt_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1);
         EAST_CUDA(cudaMemcpyAsync(&n_act, rr_misc.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -49,6 +49,8 @@ struct ScoreInput {
     int32_t K;
     int32_t total_suffixes;
     int normalized;
+    unsigned long long *probe_count = nullptr;  // device counter: run the probe-counting variant
+    double algorithmic_bytes = 0.0;             // 8 B x probes of this workload, if known (roofline numerator)
 };
 void score_table(const ScoreInput &in, double *suffix_tmp /*n_docs x total_suffixes*/, double *out_DxK,
                  cudaStream_t s);

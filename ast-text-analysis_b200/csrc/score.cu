@@ -21,15 +21,19 @@ namespace east {
 constexpr int SC_THREADS = 128;
 
 // character of suffix rank r at depth d as a comparable value: 0 = "no character" (sorts first)
-__device__ __forceinline__ uint64_t sym_at(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa,
+__device__ __forceinline__ uint64_t sym_at_(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa,
                                            int32_t r, int32_t d, int32_t end) {
     int32_t p = sa[r] + d;
     return (p < end) ? (uint64_t)T[p] + 1ull : 0ull;
 }
 
+// PROBES: also count the (SA word, text word) pairs read -- the byte model of SURVEY 8(d)
+#define sym_at(T, sa, r, d, end) (PROBES ? (++probes, sym_at_(T, sa, r, d, end)) : sym_at_(T, sa, r, d, end))
+template <bool PROBES>
 __device__ __forceinline__ double score_one_suffix(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa,
                                                    int32_t start, int32_t end, int32_t m,
-                                                   const uint32_t *__restrict__ q, int32_t len, int normalized) {
+                                                   const uint32_t *__restrict__ q, int32_t len, int normalized,
+                                                   unsigned long long &probes) {
     int32_t lo = start, hi = end - 1;
     int32_t parent_f = (end - start) - m;
     int32_t d = 0, nodes = 0;
@@ -81,9 +85,12 @@ __device__ __forceinline__ double score_one_suffix(const uint32_t *__restrict__ 
     if (normalized) r = r / (double)d;
     return r;
 }
+#undef sym_at
 
+template <bool PROBES>
 __global__ void __launch_bounds__(SC_THREADS)
-k_score_suffixes(ScoreInput in, double *__restrict__ tmp) {
+k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *probe_count) {
+    unsigned long long probes = 0;
     const int64_t total = (int64_t)in.n_docs * in.total_suffixes;
     const int64_t stride = (int64_t)gridDim.x * SC_THREADS;
     for (int64_t idx = (int64_t)blockIdx.x * SC_THREADS + threadIdx.x; idx < total; idx += stride) {
@@ -92,8 +99,12 @@ k_score_suffixes(ScoreInput in, double *__restrict__ tmp) {
         const int32_t k = __ldg(in.suf_kp + sidx);
         const int32_t qend = __ldg(in.kp_off + k + 1);
         const int32_t start = __ldg(in.doc_off + doc), end = __ldg(in.doc_off + doc + 1);
-        tmp[idx] = score_one_suffix(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx,
-                                    qend - sidx, in.normalized);
+        tmp[idx] = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx,
+                                            qend - sidx, in.normalized, probes);
+    }
+    if (PROBES) {
+        for (int o = 16; o > 0; o >>= 1) probes += __shfl_down_sync(0xffffffffu, probes, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(probe_count, probes);
     }
 }
 
@@ -114,8 +125,16 @@ k_score_combine(ScoreInput in, const double *__restrict__ tmp, double *__restric
 
 void score_table(const ScoreInput &in, double *suffix_tmp, double *out_DxK, cudaStream_t s) {
     const int64_t work = (int64_t)in.n_docs * in.total_suffixes;
-    if (work > 0)
-        EAST_LAUNCH(k_score_suffixes, grid_for(work, SC_THREADS, 64), SC_THREADS, 0, s, in, suffix_tmp);
+    if (work > 0) {
+        if (in.probe_count) {
+            EAST_LAUNCH(k_score_suffixes<true>, grid_for(work, SC_THREADS, 64), SC_THREADS, 0, s, in, suffix_tmp,
+                        in.probe_count);
+        } else {
+            EAST_BYTES(in.algorithmic_bytes);
+            EAST_LAUNCH(k_score_suffixes<false>, grid_for(work, SC_THREADS, 64), SC_THREADS, 0, s, in, suffix_tmp,
+                        (unsigned long long *)nullptr);
+        }
+    }
     const int64_t cells = (int64_t)in.n_docs * in.K;
     if (cells > 0)
         EAST_LAUNCH(k_score_combine, grid_for(cells, SC_THREADS, 64), SC_THREADS, 0, s, in, suffix_tmp, out_DxK);

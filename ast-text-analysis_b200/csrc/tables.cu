@@ -55,6 +55,7 @@ k_lcp(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa, const int3
 
 void build_lcp(const uint32_t *text, const int32_t *sa, const int32_t *doc_off, int n_docs, int32_t n,
                int32_t *lcp, cudaStream_t s) {
+    EAST_BYTES(16.0 * n);  // SA in, LCP out, >= one text word per suffix of each compared pair
     EAST_LAUNCH(k_lcp, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, text, sa, doc_off, n_docs, n, lcp);
 }
 
@@ -107,6 +108,7 @@ void build_child_ann(const int32_t *lcp, const int32_t *doc_off, const int32_t *
     EAST_CUDA(cudaMemsetAsync(down, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_CUDA(cudaMemsetAsync(next, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_CUDA(cudaMemsetAsync(ann, 0, sizeof(int32_t) * (size_t)n, s));
+    EAST_BYTES(8.0 * n);   // LCP in; annotation + child entries out (sparse)
     EAST_LAUNCH(k_child_ann, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, lcp, doc_off, doc_m, n_docs, n,
                 up, down, next, ann);
 }

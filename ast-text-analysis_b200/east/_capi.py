@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = [
     "east_last_error", "east_device_count", "east_version", "east_build_host", "east_build_dev",
     "east_free", "east_index_info", "east_index_doc", "east_index_copy", "east_index_devptr",
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
-    "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option",
+    "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
+    "east_score_probes_dev",
 ]
 
 _lib = None
@@ -61,6 +62,7 @@ def load():
     L.east_index_devptr.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp)]
     L.east_score_table_host.argtypes = [_vp, _u32p, _i64p, ctypes.c_int32, ctypes.c_int, _f64p]
     L.east_score_table_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, _vp, _vp]
+    L.east_score_probes_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, _vp, _vp, _i64p]
     L.east_score_one.argtypes = [_vp, ctypes.c_int32, _u32p, ctypes.c_int32, ctypes.c_int, _f64p, _f64p]
     L.east_cooc_dev.argtypes = [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, _vp, ctypes.c_int, _vp]
     L.east_cooc_host.argtypes = [_f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, _i32p, ctypes.c_int]
@@ -68,6 +70,7 @@ def load():
     L.east_launch_count.argtypes = [ctypes.c_int]
     L.east_launch_count.restype = ctypes.c_int64
     L.east_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+    L.east_kernel_stats.argtypes = [ctypes.c_char_p, ctypes.c_int32, _f64p, _i64p, _f64p, ctypes.c_int32]
     _lib = L
     return L
 
@@ -109,6 +112,20 @@ def last_timings():
     n = L.east_last_timings(ms, names, 64, 4096)
     parts = names.raw.split(b"\0")
     return [(parts[i].decode(), float(ms[i])) for i in range(min(n, 64))]
+
+
+def kernel_stats():
+    """{kernel name: {"launches", "ms", "bytes"}} accumulated while option time_kernels == 1."""
+    L = load()
+    cap = 64
+    names = ctypes.create_string_buffer(8192)
+    ms = (ctypes.c_double * cap)()
+    launches = (ctypes.c_int64 * cap)()
+    nbytes = (ctypes.c_double * cap)()
+    n = L.east_kernel_stats(names, 8192, ms, launches, nbytes, cap)
+    parts = names.raw.split(b"\0")
+    return {parts[i].decode(): {"launches": int(launches[i]), "ms": float(ms[i]), "bytes": float(nbytes[i])}
+            for i in range(min(n, cap))}
 
 
 def pack_keyphrases(queries):
@@ -156,6 +173,29 @@ class DeviceIndex(object):
         return self
 
     @classmethod
+    def build_host(cls, text, doc_off, doc_m, device=0):
+        """Build from an already concatenated host buffer (uint32, may be pinned)."""
+        L = load()
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
+        doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
+        assert text.dtype == np.uint32 and text.flags["C_CONTIGUOUS"]
+        h = _vp()
+        _check(L.east_build_host(_ptr(text, _u32p), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m),
+                                 int(device), ctypes.byref(h)))
+        return cls.from_handle(h, doc_off, doc_m, int(device))
+
+    def score_table_into(self, kp_codes, kp_off, out, normalized=True):
+        """score_table() into a caller-provided float64 [n_docs, K] host array (may be pinned)."""
+        K = len(kp_off) - 1
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == self.n_docs * K
+        kp_codes = np.ascontiguousarray(kp_codes, dtype=np.uint32)
+        kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
+        _check(load().east_score_table_host(self._h, _ptr(kp_codes, _u32p), _ptr(kp_off, _i64p), K,
+                                            1 if normalized else 0, _ptr(out, _f64p)))
+        self.score_timings = last_timings()
+        return out
+
+    @classmethod
     def build_dev(cls, text_devptr, doc_off, doc_m, device=0, stream=0):
         """Build from a device-resident packed text (bench: inputs already in HBM)."""
         L = load()
@@ -186,6 +226,8 @@ class DeviceIndex(object):
                 "rounds": rounds.value, "fast_path": bool(fast.value)}
 
     def array(self, doc, which):
+        if not 0 <= doc < self.n_docs:
+            raise ValueError("document %r out of range" % (doc,))
         n = int(self.doc_off[doc + 1] - self.doc_off[doc])
         out = np.empty(n, dtype=np.int32)
         _check(load().east_index_copy(self._h, int(doc), int(which), _ptr(out, _i32p)))
@@ -214,6 +256,14 @@ class DeviceIndex(object):
         _check(load().east_score_table_dev(self._h, _vp(kp_devptr), _ptr(kp_off, _i64p), len(kp_off) - 1,
                                            1 if normalized else 0, _vp(out_devptr), _vp(stream)))
         self.score_timings = last_timings()
+
+    def score_probes_dev(self, kp_devptr, kp_off, out_devptr, stream=0):
+        """Normalized table via the probe-counting scorer; returns the number of probes."""
+        kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
+        probes = ctypes.c_int64(0)
+        _check(load().east_score_probes_dev(self._h, _vp(kp_devptr), _ptr(kp_off, _i64p), len(kp_off) - 1,
+                                            _vp(out_devptr), _vp(stream), ctypes.byref(probes)))
+        return probes.value
 
     def score_one(self, doc, q_codes, normalized=True, want_suffix_scores=False):
         q_codes = np.ascontiguousarray(q_codes, dtype=np.uint32)

@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the EASA hot path on B200.
+
+Metric (BASELINE.json): AST keyphrase x document scores per second.  One "step" is one pass of the
+whole hot path over one batch of synthetic documents: build the annotated suffix structure of every
+document (suffix array, LCP, child table, annotation) and score every keyphrase against every
+document -- i.e. what east.applications.keyphrases_table does (applications.py:11-56).
+
+Workload at N=1: BASELINE.json configs[1]: 1 000 keyphrases x 1 000 synthetic Zipf documents of
+~50 KB (SURVEY 8(d) generator, synth.py).  N>1: weak scaling, every rank indexes and scores its own
+1 000 documents against the same 1 000 keyphrases and the per-rank [D_r, K] fp64 score slices are
+joined with one NCCL all-gather inside the timed step.
+
+  value      device-timed (CUDA events), inputs resident in HBM, max over ranks
+  e2e        same step through the host-buffer C-ABI calls (east_build_host / east_score_table_host):
+             pinned host text -> device, table -> host, inside the timed region
+  roofline   dominant kernel of the step: algorithmic bytes / its event-timed duration vs measured HBM peak
+  cpu_baseline  the reference's own Python code (or the C port when oracle/_ref is absent) on a bounded sample
+
+`--impl reference` times only the CPU implementation (rank 0) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "ast-text-analysis_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "keyphrase_x_doc_scores_per_sec"
+UNIT = "scores/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--docs", type=int, default=1000, help="documents per GPU")
+    ap.add_argument("--doc-bytes", type=int, default=50000)
+    ap.add_argument("--keyphrases", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-docs", type=int, default=0, help="0 = 2 documents per host core (max 64)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(n_docs, doc_bytes, n_kps, procs):
+    """Run oracle/run_reference.py in a subprocess (the reference's `east` package must not share an
+    interpreter with the product's `east` package)."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_reference.py"), "--docs", str(n_docs),
+           "--doc-bytes", str(doc_bytes), "--kps", str(n_kps), "--procs", str(procs)]
+    out = subprocess.check_output(cmd, stderr=subprocess.DEVNULL, timeout=1500)
+    return json.loads(out.decode().strip().splitlines()[-1])
+
+
+def cpu_sample_size(args):
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    docs = args.cpu_sample_docs or 2 * procs
+    return docs, procs
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    docs, procs = cpu_sample_size(args)
+    times, last = [], None
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample(docs, args.doc_bytes, args.keyphrases, procs)
+        if i >= args.warmup:
+            times.append(r["wall_s"])
+        last = r
+    mean_s = sum(times) / len(times)
+    value = docs * args.keyphrases / mean_s
+    sample = "%d docs x %d B x %d keyphrases per step, %d processes (one task per document)" % (
+        docs, args.doc_bytes, args.keyphrases, procs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": last["kind"], "sample": sample,
+                         "build_MB_per_s_per_core": last["build_MB_per_s"] / max(procs, 1)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "keyphrases_table: %d keyphrases x %d synthetic Zipf docs x ~%d KB per GPU (BASELINE configs[1]), "
+                        "build (SA+LCP+child+annotation) + score, normalized" % (args.keyphrases, args.docs, args.doc_bytes // 1000),
+            "keyphrases": args.keyphrases, "docs_per_gpu": args.docs, "doc_bytes": args.doc_bytes,
+            "parallelism": "documents sharded over %d GPU(s), all-gather of score slices" % n_gpus,
+            "l2": "inputs larger than L2: packed text + sort buffers of a step are > 1 GB"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smmax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import synth
+    from east import _capi, utils
+    from east.asts import utils as asts_utils
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    # ---- host preprocessing (untimed, reported): generate, upper/tokenize/group, pack
+    t0 = time.perf_counter()
+    docs = synth.documents(args.docs, args.doc_bytes, first_seed=1 + rank * args.docs)
+    t1 = time.perf_counter()
+    cols = [utils.text_to_strings_collection(d) for d in docs]
+    packed = [asts_utils.pack_strings_collection(c) for c in cols]
+    doc_m = np.array([len(c) for c in cols], dtype=np.int32)
+    doc_off = np.zeros(args.docs + 1, dtype=np.int64)
+    np.cumsum([len(p) for p in packed], out=doc_off[1:])
+    n_total = int(doc_off[-1])
+    host_text = torch.empty(n_total, dtype=torch.int32).pin_memory()
+    host_text_np = host_text.numpy().view(np.uint32)
+    host_text_np[:] = np.concatenate(packed)
+    kps = [utils.prepare_text(k) for k in synth.keyphrases(args.keyphrases)]
+    kp_codes, kp_off = _capi.pack_keyphrases(kps)
+    t2 = time.perf_counter()
+    K, D = args.keyphrases, args.docs
+
+    stream = torch.cuda.current_stream()
+    text_dev = host_text.to(dev)
+    kp_dev = torch.from_numpy(kp_codes.view(np.int32).copy()).to(dev)
+    out_dev = torch.empty(D * K, dtype=torch.float64, device=dev)
+    gathered = torch.empty(world * D * K, dtype=torch.float64, device=dev) if world > 1 else None
+    host_out = torch.empty(D * K, dtype=torch.float64).pin_memory()
+    host_out_np = host_out.numpy().reshape(D, K)
+    torch.cuda.synchronize()
+
+    def step_device():
+        idx = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank,
+                                          stream=stream.cuda_stream)
+        idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_dev)
+        timings = idx.build_timings + idx.score_timings
+        info = idx.info()
+        idx.close()
+        return timings, info
+
+    def step_e2e():
+        idx = _capi.DeviceIndex.build_host(host_text_np, doc_off, doc_m, device=local_rank)
+        idx.score_table_into(kp_codes, kp_off, host_out_np, True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_dev)  # same exchange volume as the device-timed step
+        idx.close()
+
+    # ---- algorithmic bytes of the scorer for this workload: counted once by the instrumented scorer
+    idx0 = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream)
+    probes = idx0.score_probes_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), stream=stream.cuda_stream)
+    info0 = idx0.info()
+    idx0.close()
+    _capi.set_option("score_bytes", 8 * probes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-timed arm
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    _capi.set_option("time_kernels", 0)
+    _capi.set_option("time_kernels", 1)
+    _capi.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    stage_ms = {}
+    for _ in range(args.steps):
+        timings, info = step_device()
+        for name, ms in timings:
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+    e1.record(stream)
+    barrier()
+    launches = _capi.launch_count()
+    kstats = _capi.kernel_stats()
+    _capi.set_option("time_kernels", 0)
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+
+    # ---- end-to-end arm (host buffers through the C ABI)
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    checksum = float(host_out_np.sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peak, peak_kind = load_peaks()
+    dom_name, dom = max(kstats.items(), key=lambda kv: kv[1]["ms"])
+    per_launch_ms = dom["ms"] / max(dom["launches"], 1)
+    per_launch_bytes = dom["bytes"] / max(dom["launches"], 1)
+    achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    kernel_table = {k: {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps,
+                        "GBps": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None}
+                    for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}
+    build_ms = sum(ms for name, ms in stage_ms.items() if name != "score") / args.steps
+    score_ms = stage_ms.get("score", 0.0) / args.steps
+    text_mb = args.docs * args.doc_bytes / 1e6
+
+    line = {
+        "metric": METRIC, "value": n_gpus * D * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_gpus),
+        "e2e": {"value": n_gpus * D * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(n_total * 4 + doc_off.nbytes + doc_m.nbytes + kp_codes.nbytes + kp_off.nbytes),
+                "d2h_bytes_per_step": int(D * K * 8)},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "launches_per_step": dom["launches"] / args.steps, "ms_per_launch": per_launch_ms,
+                     "algorithmic_bytes_per_launch": per_launch_bytes,
+                     "share_of_step": dom["ms"] / args.steps / dev_ms},
+        "breakdown": {"build_ms": build_ms, "score_ms": score_ms,
+                      "sa_build_MB_per_s": text_mb / (build_ms * 1e-3) if build_ms > 0 else None,
+                      "build_codepoints_per_s": n_total / (build_ms * 1e-3) if build_ms > 0 else None,
+                      "score_only_scores_per_s": D * K / (score_ms * 1e-3) if score_ms > 0 else None,
+                      "stages_ms": {k: v / args.steps for k, v in stage_ms.items()},
+                      "kernels": kernel_table, "scorer_probes": probes,
+                      "index": info0, "n_codepoints": n_total, "checksum": checksum,
+                      "host_prep_s": {"generate": t1 - t0, "tokenize_pack": t2 - t1}},
+    }
+    if not args.no_cpu_baseline and n_gpus == 1:
+        try:
+            docs_s, procs = cpu_sample_size(args)
+            r = cpu_sample(docs_s, args.doc_bytes, args.keyphrases, procs)
+            r1 = cpu_sample(2, args.doc_bytes, args.keyphrases, 1)
+            line["cpu_baseline"] = {
+                "value": r["scores_per_s"], "unit": UNIT, "cores": procs, "kind": r["kind"],
+                "sample": "%d docs x %d B x %d keyphrases, %d processes, one task per document (build + score); "
+                          "single process on 2 docs: %.1f scores/s" % (docs_s, args.doc_bytes, args.keyphrases, procs,
+                                                                         r1["scores_per_s"]),
+                "single_process_value": r1["scores_per_s"], "wall_s": r["wall_s"],
+                "build_MB_per_s_per_core": r["build_MB_per_s"] / max(procs, 1)}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,10 @@ int east_score_table_host(const east_index *idx, const uint32_t *kp, const int64
                           int32_t K, int normalized, double *out_DxK);
 int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
                          int32_t K, int normalized, double *out_DxK_dev, void *stream);
+/* same table through an instrumented scorer that also counts the (SA word, text word) probe
+ * pairs it reads: the algorithmic-byte model of the scorer is 8 bytes x probes */
+int east_score_probes_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
+                          int32_t K, double *out_DxK_dev, void *stream, int64_t *probes);
 /* single query against one document, with the per-suffix results of
  * return_suffix_scores=True (easa.py:132-137); suffix_scores may be NULL, else len doubles */
 int east_score_one(const east_index *idx, int32_t doc, const uint32_t *q, int32_t len,
@@ -102,6 +106,11 @@ int east_cooc_host(const double *S_DxK, int64_t D, int32_t K, double threshold,
  * this thread, measured with CUDA events on the launching stream.
  * names: NUL-separated list written to buf; returns the number of stages. */
 int east_last_timings(float *ms, char *names, int32_t cap, int32_t names_cap);
+/* per-kernel device time, measured with a CUDA event pair around every launch while the
+ * per-thread option "time_kernels" is 1 (set it to 0 to stop and clear).  names: NUL-separated.
+ * bytes: algorithmic bytes moved by those launches (roofline numerator).  Returns #kernels. */
+int east_kernel_stats(char *names, int32_t names_cap, double *ms, int64_t *launches, double *bytes,
+                      int32_t cap);
 /* number of kernel launches issued by the library on this thread since the last reset */
 int64_t east_launch_count(int reset);
 /* tuning knobs (0 = default): "key_chars" (round-0 window), "score_block", ... */
