@@ -128,6 +128,10 @@ struct east_index {
     uint32_t *text = nullptr;
     int32_t *d_doc_off = nullptr, *d_doc_m = nullptr;
     int32_t *sa = nullptr, *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
+    uint8_t *t8 = nullptr;          // fast path: dense byte codes of the text
+    uint32_t *bkt = nullptr;        // fast path: 2-gram bucket table
+    std::vector<uint8_t> code_table;
+    int sym_bits = 0, term_code = 0;
     int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0;
     uint32_t active_after_round0 = 0;
 };
@@ -211,7 +215,8 @@ static void free_index(east_index *idx) {
     cudaSetDevice(idx->device);
     if (idx->owns_text && idx->text) cudaFree(idx->text);
     for (void *p : {(void *)idx->d_doc_off, (void *)idx->d_doc_m, (void *)idx->sa, (void *)idx->lcp,
-                    (void *)idx->up, (void *)idx->down, (void *)idx->next, (void *)idx->ann})
+                    (void *)idx->up, (void *)idx->down, (void *)idx->next, (void *)idx->ann, (void *)idx->t8,
+                    (void *)idx->bkt})
         if (p) cudaFreeAsync(p, 0);
     delete idx;
 }
@@ -256,11 +261,11 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         build_suffix_array(in, so, tm, s);
         idx->rounds = so.rounds; idx->fast_path = so.fast_path; idx->key_chars = so.key_chars;
         idx->key_bits = so.key_bits; idx->active_after_round0 = so.active_after_round0;
-        tm.mark("lcp");
-        build_lcp(idx->text, idx->sa, idx->d_doc_off, n_docs, n, idx->lcp, s);
-        tm.mark("child_ann");
-        build_child_ann(idx->lcp, idx->d_doc_off, idx->d_doc_m, n_docs, n, idx->up, idx->down, idx->next,
-                        idx->ann, s);
+        idx->t8 = so.t8.p; so.t8.p = nullptr;      // ownership moves to the index
+        idx->bkt = so.bkt.p; so.bkt.p = nullptr;
+        idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
+        build_lcp_tables(idx->text, idx->sa, idx->d_doc_off, idx->d_doc_m, n_docs, n, idx->lcp, idx->up,
+                         idx->down, idx->next, idx->ann, tm, s);
         tm.finish();
     }
     EAST_CUDA(cudaStreamSynchronize(s));
@@ -392,6 +397,29 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
     in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
     in.kp = kp_dev; in.kp_off = d_off.p; in.suf_kp = d_suf.p; in.K = K; in.total_suffixes = (int32_t)total;
     in.normalized = normalized ? 1 : 0;
+    // fast path: dense byte codes of the queries + per-suffix "contains a code point >= 0x0A00" flag
+    DevBuf<uint8_t> d_q8, d_generic;
+    std::vector<uint8_t> q8, generic;
+    if (idx->bkt && idx->t8 && !get_option("score_generic", 0)) {
+        std::vector<uint32_t> kp_host((size_t)total);
+        EAST_CUDA(cudaMemcpyAsync(kp_host.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+        EAST_CUDA(cudaStreamSynchronize(s));
+        q8.resize((size_t)total); generic.resize((size_t)total);
+        for (int32_t k = 0; k < K; ++k) {
+            uint8_t weird = 0;
+            for (int64_t p = kp_off[k + 1] - 1; p >= kp_off[k]; --p) {
+                const uint32_t c = kp_host[(size_t)p];
+                if (c >= EAST_TERM_BASE) { weird = 1; q8[(size_t)p] = 0; }
+                else q8[(size_t)p] = idx->code_table[c];
+                generic[(size_t)p] = weird;
+            }
+        }
+        d_q8 = DevBuf<uint8_t>((size_t)total, s); d_generic = DevBuf<uint8_t>((size_t)total, s);
+        EAST_CUDA(cudaMemcpyAsync(d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));
+        EAST_CUDA(cudaMemcpyAsync(d_generic.p, generic.data(), (size_t)total, cudaMemcpyHostToDevice, s));
+        in.t8 = idx->t8; in.q8 = d_q8.p; in.suf_generic = d_generic.p; in.sym_bits = idx->sym_bits;
+        in.bkt = idx->bkt + ((size_t)doc_begin << (2 * idx->sym_bits));
+    }
     in.algorithmic_bytes = (double)get_option("score_bytes", 0);
     DevBuf<unsigned long long> d_probes;
     if (probes_out) {

@@ -79,7 +79,10 @@ k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict
         uint32_t c = T[i];
         mx = max(mx, c);
         if (c < EAST_TERM_BASE) {
-            atomicOr(&s_present[c >> 5], 1u << (c & 31));
+            // a stale read only costs a redundant atomic; after the first few hundred characters
+            // every bit of the alphabet is set and the loop is atomic-free
+            if (!(((volatile uint32_t *)s_present)[c >> 5] & (1u << (c & 31))))
+                atomicOr(&s_present[c >> 5], 1u << (c & 31));
         } else {
             ++nt;
             // must be 0x0A00 + (index of this string inside its document): walk back to the
@@ -295,7 +298,8 @@ k_rerank(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
          const uint32_t *__restrict__ slots, int32_t n_act, uint64_t sym_mask, uint64_t term,
          int32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ new_vals,
          uint32_t *__restrict__ new_slots, uint32_t *__restrict__ new_prim,
-         volatile uint64_t *status, uint32_t *ticket, uint32_t *out_counts /*[0]=kept*/) {
+         volatile uint64_t *status, uint32_t *ticket, uint32_t *out_counts /*[0]=kept*/,
+         uint32_t *__restrict__ bkt, int bkt_shift) {
     __shared__ RRState s_warp[RR_THREADS / 32];
     __shared__ RRState s_prefix;
     __shared__ uint32_t s_tile;
@@ -322,6 +326,11 @@ k_rerank(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
             hd = hd || (f == 0ull) || (f == term);
         }
         head[j] = hd;
+        // 2-gram bucket table of the scorer: first rank of every (document, symbol 0, symbol 1)
+        if (ROUND0 && bkt != nullptr && j < RR_ITEMS && a < n_act) {
+            const uint64_t pre = k[j + 1] >> bkt_shift;
+            if (a == 0 || pre != (k[j] >> bkt_shift)) bkt[pre] = (uint32_t)a;
+        }
     }
     RRState loc[RR_ITEMS];
     RRState run{0u, 0u};
@@ -389,6 +398,39 @@ k_rerank(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
             new_slots[dst] = slot;
             new_prim[dst] = r;
         }
+    }
+}
+
+// Buckets that do not occur keep 0xffffffff after the re-rank; give every entry the first rank of
+// the next existing bucket (suffix minimum), so that [bkt[x], bkt[x+1]) is the SA interval of
+// 2-gram x and [bkt[c << b], bkt[(c+1) << b]) that of first symbol c.  One CTA per document.
+__global__ void __launch_bounds__(256)
+k_bucket_fill(uint32_t *__restrict__ bkt, int entries, const int32_t *__restrict__ doc_off) {
+    __shared__ uint32_t s_carry;
+    uint32_t *row = bkt + (size_t)blockIdx.x * entries;
+    if (threadIdx.x == 0) s_carry = (uint32_t)doc_off[blockIdx.x + 1];
+    __syncthreads();
+    for (int hi = entries; hi > 0; hi -= 256) {  // chunks of 256 from the end
+        const int x = hi - 256 + (int)threadIdx.x;
+        uint32_t v = (x >= 0) ? row[x] : 0xffffffffu;
+        // suffix-min within the chunk (thread t needs min over t..255)
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        uint32_t m = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_down_sync(0xffffffffu, m, o);
+            if (lane + o < 32) m = min(m, y);
+        }
+        __shared__ uint32_t s_w[8];
+        if (lane == 0) s_w[w] = m;
+        __syncthreads();
+        uint32_t tail = s_carry;
+        for (int i = w + 1; i < 8; ++i) tail = min(tail, s_w[i]);
+        m = min(m, tail);
+        if (x >= 0) row[x] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = m;  // minimum of this chunk and everything after it
+        __syncthreads();
     }
 }
 
@@ -470,6 +512,16 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     tm.mark("sort0");
     int cur = radix_sort_pairs(keys_a.p, keys_b.p, vals_a.p, vals_b.p, n, key_bits, hist.p, true, scratch.p, s);
 
+    // scorer acceleration (fast path): first ranks of all (document, 2-gram) buckets
+    if (fast && kc >= 2 && ((size_t)D << (2 * kp.b)) <= (size_t)2 * n + 4096) {
+        const size_t entries = ((size_t)D << (2 * kp.b)) + 1;
+        out.bkt = DevBuf<uint32_t>(entries, s);
+        EAST_CUDA(cudaMemsetAsync(out.bkt.p, 0xff, sizeof(uint32_t) * (entries - 1), s));
+        EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        out.sym_bits = kp.b;
+    }
+    out.code_table = table;
+    out.term_code = fast ? (int)kp.term : 0;
     tm.mark("rerank0");
     DevBuf<uint32_t> act_vals(n, s), act_slots(n, s), act_prim(n, s);
     DevBuf<uint32_t> nxt_vals, nxt_slots, nxt_prim;
@@ -481,7 +533,11 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         EAST_BYTES(20.0 * n);  // keys + values in, SA + rank out (active-list output is data dependent)
         EAST_LAUNCH(k_rerank<true>, rr_tiles_max, RR_THREADS, 0, s, cur ? keys_b.p : keys_a.p,
                     cur ? vals_b.p : vals_a.p, (const uint32_t *)nullptr, n, sym_mask, term, out.sa, rank,
-                    act_vals.p, act_slots.p, act_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1);
+                    act_vals.p, act_slots.p, act_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1, out.bkt.p,
+                    (kc - 2) * kp.b);
+        if (out.bkt.p) {
+            EAST_LAUNCH(k_bucket_fill, D, 256, 0, s, out.bkt.p, 1 << (2 * kp.b), in.doc_off);
+        }
     }
     uint32_t n_act = 0;
     EAST_CUDA(cudaMemcpyAsync(&n_act, rr_misc.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -517,7 +573,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         EAST_CUDA(cudaMemsetAsync(rr_misc.p, 0, sizeof(uint32_t) * 8, s));
         EAST_BYTES(24.0 * n_act);
         EAST_LAUNCH(k_rerank<false>, rr_tiles, RR_THREADS, 0, s, sk, sv, act_slots.p, (int32_t)n_act, 0ull, 0ull,
-                    out.sa, rank, nxt_vals.p, nxt_slots.p, nxt_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1);
+                    out.sa, rank, nxt_vals.p, nxt_slots.p, nxt_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1,
+                    (uint32_t *)nullptr, 0);
         EAST_CUDA(cudaMemcpyAsync(&n_act, rr_misc.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         EAST_CUDA(cudaStreamSynchronize(s));
         std::swap(act_vals, nxt_vals);

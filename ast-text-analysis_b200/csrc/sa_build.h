@@ -19,6 +19,10 @@ struct SaOutput {
     int32_t *sa;              // device, n  (global text positions, doc-major rank order)
     uint32_t *rank;           // device, n  (inverse permutation when done)
     DevBuf<uint8_t> t8;       // fast path: dense byte codes of the text (kept for later stages)
+    DevBuf<uint32_t> bkt;     // fast path: 2-gram bucket table [n_docs << 2*sym_bits] + sentinel
+    std::vector<uint8_t> code_table;  // code point (< 0x0A00) -> dense code (0 = absent)
+    int sym_bits = 0;
+    int term_code = 0;
     int fast_path = 0;
     int sigma = 0;
     int key_chars = 0;
@@ -31,10 +35,9 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
 
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch
-void build_lcp(const uint32_t *text, const int32_t *sa, const int32_t *doc_off, int n_docs, int32_t n,
-               int32_t *lcp, cudaStream_t s);
-void build_child_ann(const int32_t *lcp, const int32_t *doc_off, const int32_t *doc_m, int n_docs,
-                     int32_t n, int32_t *up, int32_t *down, int32_t *next, int32_t *ann, cudaStream_t s);
+void build_lcp_tables(const uint32_t *text, const int32_t *sa, const int32_t *doc_off, const int32_t *doc_m,
+                      int n_docs, int32_t n, int32_t *lcp, int32_t *up, int32_t *down, int32_t *next,
+                      int32_t *ann, StageTimer &tm, cudaStream_t s);
 
 // batched scorer (easa.py:91-139)
 struct ScoreInput {
@@ -49,6 +52,12 @@ struct ScoreInput {
     int32_t K;
     int32_t total_suffixes;
     int normalized;
+    // fast path (terminator-class alphabet): dense byte text, byte-coded queries, 2-gram buckets
+    const uint8_t *t8 = nullptr;
+    const uint32_t *bkt = nullptr;      // [n_docs << 2*sym_bits] + 1, rows of the docs being scored
+    const uint8_t *q8 = nullptr;        // dense codes of kp (0 = symbol absent from the batch)
+    const uint8_t *suf_generic = nullptr;  // 1 = this suffix contains a code point >= 0x0A00: generic walk
+    int sym_bits = 0;
     unsigned long long *probe_count = nullptr;  // device counter: run the probe-counting variant
     double algorithmic_bytes = 0.0;             // 8 B x probes of this workload, if known (roofline numerator)
 };

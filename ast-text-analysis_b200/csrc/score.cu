@@ -27,8 +27,9 @@ __device__ __forceinline__ uint64_t sym_at_(const uint32_t *__restrict__ T, cons
     return (p < end) ? (uint64_t)T[p] + 1ull : 0ull;
 }
 
-// PROBES: also count the (SA word, text word) pairs read -- the byte model of SURVEY 8(d)
-#define sym_at(T, sa, r, d, end) (PROBES ? (++probes, sym_at_(T, sa, r, d, end)) : sym_at_(T, sa, r, d, end))
+// PROBES: also count the ALGORITHMIC BYTES read: 8 per (SA word, text word) probe,
+// 5 per (SA word, text byte) probe and 8 per bucket-table lookup on the fast path
+#define sym_at(T, sa, r, d, end) (PROBES ? (probes += 8, sym_at_(T, sa, r, d, end)) : sym_at_(T, sa, r, d, end))
 template <bool PROBES>
 __device__ __forceinline__ double score_one_suffix(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa,
                                                    int32_t start, int32_t end, int32_t m,
@@ -87,6 +88,87 @@ __device__ __forceinline__ double score_one_suffix(const uint32_t *__restrict__ 
 }
 #undef sym_at
 
+// Fast path walk: depth 0 and 1 come from the 2-gram bucket table built during round 0 of the
+// suffix sort (two table reads each instead of two binary searches over the largest intervals);
+// deeper levels narrow by binary search over (SA word, text BYTE) probes.  Query symbols are dense
+// codes (0 = absent from the batch: cannot match).  Same arithmetic, same order as the generic walk.
+template <bool PROBES>
+__device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restrict__ T8, const int32_t *__restrict__ sa,
+                                                        const uint32_t *__restrict__ row, int b,
+                                                        int32_t start, int32_t end, int32_t m,
+                                                        const uint8_t *__restrict__ q, int32_t len, int normalized,
+                                                        unsigned long long &probes) {
+#define SYM8(r, d) (PROBES ? (probes += 5, (uint32_t)T8[sa[r] + (d)]) : (uint32_t)T8[sa[r] + (d)])
+    int32_t parent_f = (end - start) - m;
+    const uint32_t c0 = q[0];
+    if (c0 == 0) return 0.0;
+    int32_t lo = (int32_t)__ldg(row + (c0 << b));
+    int32_t hi = (int32_t)__ldg(row + ((c0 + 1) << b)) - 1;
+    if (PROBES) probes += 8;
+    if (hi < lo) return 0.0;
+    int32_t size = hi - lo + 1;
+    int32_t d = 1, nodes = 1;
+    double frac = (double)size / (double)parent_f;
+    parent_f = size;
+    if (len > 1 && q[1] != 0) {
+        const uint32_t x = (c0 << b) | q[1];
+        const int32_t nlo = (int32_t)__ldg(row + x), nhi = (int32_t)__ldg(row + x + 1) - 1;
+        if (PROBES) probes += 8;
+        if (nhi >= nlo) {
+            size = nhi - nlo + 1;
+            if (size != hi - lo + 1) {
+                ++nodes;
+                frac = frac + (double)size / (double)parent_f;
+            }
+            lo = nlo; hi = nhi; parent_f = size; d = 2;
+            while (d < len) {
+                const uint32_t c = q[d];
+                if (c == 0) break;
+                int32_t nl, nh;
+                if (lo == hi) {
+                    if (SYM8(lo, d) != c) break;
+                    nl = lo; nh = hi;
+                } else {
+                    const uint32_t clo = SYM8(lo, d), chi = SYM8(hi, d);
+                    if (c < clo || c > chi) break;
+                    if (clo == c) {
+                        nl = lo;
+                    } else {
+                        int32_t a = lo, e = hi;  // sym(a) < c <= sym(e)
+                        while (e - a > 1) {
+                            const int32_t mid = a + ((e - a) >> 1);
+                            if (SYM8(mid, d) < c) a = mid; else e = mid;
+                        }
+                        nl = e;
+                        if (e != hi && SYM8(e, d) != c) break;
+                        if (e == hi && chi != c) break;
+                    }
+                    if (chi == c) {
+                        nh = hi;
+                    } else {
+                        int32_t a = nl, e = hi;  // sym(a) == c < sym(e)
+                        while (e - a > 1) {
+                            const int32_t mid = a + ((e - a) >> 1);
+                            if (SYM8(mid, d) <= c) a = mid; else e = mid;
+                        }
+                        nh = a;
+                    }
+                }
+                size = nh - nl + 1;
+                if (size != hi - lo + 1) {
+                    ++nodes;
+                    frac = frac + (double)size / (double)parent_f;
+                }
+                lo = nl; hi = nh; parent_f = size; ++d;
+            }
+        }
+    }
+    double r = (frac + (double)d) - (double)nodes;
+    if (normalized) r = r / (double)d;
+    return r;
+#undef SYM8
+}
+
 template <bool PROBES>
 __global__ void __launch_bounds__(SC_THREADS)
 k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *probe_count) {
@@ -99,8 +181,14 @@ k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *pr
         const int32_t k = __ldg(in.suf_kp + sidx);
         const int32_t qend = __ldg(in.kp_off + k + 1);
         const int32_t start = __ldg(in.doc_off + doc), end = __ldg(in.doc_off + doc + 1);
-        tmp[idx] = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx,
-                                            qend - sidx, in.normalized, probes);
+        if (in.bkt != nullptr && !__ldg(in.suf_generic + sidx)) {
+            tmp[idx] = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.bkt + ((size_t)doc << (2 * in.sym_bits)),
+                                                     in.sym_bits, start, end, __ldg(in.doc_m + doc), in.q8 + sidx,
+                                                     qend - sidx, in.normalized, probes);
+        } else {
+            tmp[idx] = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx,
+                                                qend - sidx, in.normalized, probes);
+        }
     }
     if (PROBES) {
         for (int o = 16; o > 0; o >>= 1) probes += __shfl_down_sync(0xffffffffu, probes, o);

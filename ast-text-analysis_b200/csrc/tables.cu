@@ -17,6 +17,10 @@
 //         e inside the document and lcp[q] <= lcp[e]  ->  up[e]   = p
 //         e inside the document and lcp[e] <= lcp[q]  ->  down[q] = p
 //     first rank of a document              ->  ann = n - m   (easa.py:329)
+// q and e are found with a min-pyramid over the LCP array (level k+1 = min of 32 entries of
+// level k; level 1 is produced by the LCP kernel itself): a search scans at most 32 entries per
+// level going up and 32 per level coming down, so no rank -- not even the first l-indices of the
+// root's children, whose neighbours are thousands of ranks away -- does a long linear scan.
 // Table VALUES are ranks local to the document (0 = none, as in the reference); table
 // POSITIONS are global ranks of the batch.
 #include "sa_build.h"
@@ -24,10 +28,17 @@
 namespace east {
 
 constexpr int TB_THREADS = 256;
+constexpr int MAX_LEVELS = 8;  // 32^7 > 2^30
+
+struct MinPyramid {
+    const int32_t *lv[MAX_LEVELS];  // lv[0] = lcp
+    int32_t size[MAX_LEVELS];
+    int levels;                     // number of valid entries in lv[]
+};
 
 __global__ void __launch_bounds__(TB_THREADS)
 k_lcp(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa, const int32_t *__restrict__ doc_off,
-      int D, int32_t n, int32_t *__restrict__ lcp) {
+      int D, int32_t n, int32_t *__restrict__ lcp, int32_t *__restrict__ min1) {
     __shared__ int s_dlo, s_dhi;
     const int64_t stride = (int64_t)gridDim.x * TB_THREADS;
     for (int64_t base = (int64_t)blockIdx.x * TB_THREADS; base < n; base += stride) {
@@ -36,41 +47,103 @@ k_lcp(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa, const int3
         if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, (int32_t)min(base + TB_THREADS, (int64_t)n) - 1);
         __syncthreads();
         const int64_t r = base + threadIdx.x;
-        if (r >= n) continue;
-        int lo = s_dlo, hi = s_dhi;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (__ldg(doc_off + mid) <= r) lo = mid; else hi = mid - 1;
+        int32_t h = 0x7fffffff;
+        if (r < n) {
+            int lo = s_dlo, hi = s_dhi;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (__ldg(doc_off + mid) <= r) lo = mid; else hi = mid - 1;
+            }
+            const int32_t start = __ldg(doc_off + lo), end = __ldg(doc_off + lo + 1);
+            h = 0;
+            if (r > start) {
+                const int32_t i = sa[r - 1], j = sa[r];
+                const int32_t lim = end - max(i, j);
+                while (h < lim && T[i + h] == T[j + h]) ++h;
+            }
+            lcp[r] = h;
         }
-        const int32_t start = __ldg(doc_off + lo), end = __ldg(doc_off + lo + 1);
-        int32_t h = 0;
-        if (r > start) {
-            const int32_t i = sa[r - 1], j = sa[r];
-            const int32_t lim = end - max(i, j);
-            while (h < lim && T[i + h] == T[j + h]) ++h;
-        }
-        lcp[r] = h;
+        // level 1 of the min pyramid: one entry per 32 consecutive ranks (one warp)
+        const int32_t wmin = __reduce_min_sync(0xffffffffu, h);
+        if ((threadIdx.x & 31) == 0 && base + (threadIdx.x & ~31) < n) min1[(base + threadIdx.x) >> 5] = wmin;
     }
 }
 
-void build_lcp(const uint32_t *text, const int32_t *sa, const int32_t *doc_off, int n_docs, int32_t n,
-               int32_t *lcp, cudaStream_t s) {
-    EAST_BYTES(16.0 * n);  // SA in, LCP out, >= one text word per suffix of each compared pair
-    EAST_LAUNCH(k_lcp, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, text, sa, doc_off, n_docs, n, lcp);
+__global__ void __launch_bounds__(256)
+k_min32(const int32_t *__restrict__ in, int32_t n_in, int32_t *__restrict__ out, int32_t n_out) {
+    // one warp per output: coalesced read of its 32 inputs
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n_out) return;
+    const int64_t i = warp * 32 + lane;
+    int32_t v = (i < n_in) ? in[i] : 0x7fffffff;
+    v = __reduce_min_sync(0xffffffffu, v);
+    if (lane == 0) out[warp] = v;
+}
+
+// largest q < p with lcp[q] <= l.  Exists: the first rank of the document has lcp 0.
+__device__ __forceinline__ int32_t prev_le(const MinPyramid &M, int32_t p, int32_t l) {
+    int32_t idx = p;
+    int level = 0;
+    int32_t j;
+    while (true) {
+        const int32_t gs = idx & ~31;
+        const int32_t *a = M.lv[level];
+        for (j = idx - 1; j >= gs; --j)
+            if (a[j] <= l) goto found;
+        idx >>= 5;
+        ++level;
+        if (level >= M.levels) return 0;  // unreachable for well-formed input
+    }
+found:
+    while (level > 0) {
+        --level;
+        const int32_t *a = M.lv[level];
+        int32_t c = min(j * 32 + 31, M.size[level] - 1);
+        while (a[c] > l) --c;  // the group minimum is <= l, so this stops inside the group
+        j = c;
+    }
+    return j;
+}
+
+// smallest e > p with lcp[e] < l, or n if there is none
+__device__ __forceinline__ int32_t next_lt(const MinPyramid &M, int32_t p, int32_t l, int32_t n) {
+    int32_t idx = p;
+    int level = 0;
+    int32_t j;
+    while (true) {
+        const int32_t ge = min((idx | 31) + 1, M.size[level]);
+        const int32_t *a = M.lv[level];
+        for (j = idx + 1; j < ge; ++j)
+            if (a[j] < l) goto found;
+        idx >>= 5;
+        ++level;
+        if (level >= M.levels) return n;
+    }
+found:
+    while (level > 0) {
+        --level;
+        const int32_t *a = M.lv[level];
+        int32_t c = j * 32;
+        while (a[c] >= l) ++c;
+        j = c;
+    }
+    return j;
 }
 
 __global__ void __launch_bounds__(TB_THREADS)
-k_child_ann(const int32_t *__restrict__ lcp, const int32_t *__restrict__ doc_off,
-            const int32_t *__restrict__ doc_m, int D, int32_t n, int32_t *__restrict__ up,
-            int32_t *__restrict__ down, int32_t *__restrict__ next, int32_t *__restrict__ ann) {
+k_child_ann(MinPyramid M, const int32_t *__restrict__ doc_off, const int32_t *__restrict__ doc_m, int D,
+            int32_t n, int32_t *__restrict__ up, int32_t *__restrict__ down, int32_t *__restrict__ next,
+            int32_t *__restrict__ ann) {
     __shared__ int s_dlo, s_dhi;
+    const int32_t *__restrict__ lcp = M.lv[0];
     const int64_t stride = (int64_t)gridDim.x * TB_THREADS;
     for (int64_t base = (int64_t)blockIdx.x * TB_THREADS; base < n; base += stride) {
         __syncthreads();
         if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, (int32_t)base);
         if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, (int32_t)min(base + TB_THREADS, (int64_t)n) - 1);
         __syncthreads();
-        const int64_t p = base + threadIdx.x;
+        const int32_t p = (int32_t)(base + threadIdx.x);
         if (p >= n) continue;
         int lo = s_dlo, hi = s_dhi;
         while (lo < hi) {
@@ -83,17 +156,16 @@ k_child_ann(const int32_t *__restrict__ lcp, const int32_t *__restrict__ doc_off
             continue;
         }
         const int32_t l = lcp[p];
-        int64_t q = p - 1;
-        while (lcp[q] > l) --q;  // stops at `start` at the latest: lcp[start] == 0
+        const int32_t q = prev_le(M, p, l);
         const int32_t lq = lcp[q];
-        const int32_t p_local = (int32_t)(p - start);
+        const int32_t p_local = p - start;
         if (lq == l) {
             next[q] = p_local;
             continue;
         }
-        int64_t e = p + 1;
-        while (e < end && lcp[e] >= l) ++e;
-        ann[p] = (int32_t)(e - q);
+        // here l > lq >= 0; the first rank of the next document has lcp 0 < l, so e <= end
+        const int32_t e = next_lt(M, p, l, n);
+        ann[p] = e - q;
         if (e < end) {
             const int32_t le = lcp[e];
             if (lq <= le) up[e] = p_local;
@@ -102,14 +174,43 @@ k_child_ann(const int32_t *__restrict__ lcp, const int32_t *__restrict__ doc_off
     }
 }
 
-void build_child_ann(const int32_t *lcp, const int32_t *doc_off, const int32_t *doc_m, int n_docs,
-                     int32_t n, int32_t *up, int32_t *down, int32_t *next, int32_t *ann, cudaStream_t s) {
+void build_lcp_tables(const uint32_t *text, const int32_t *sa, const int32_t *doc_off, const int32_t *doc_m,
+                      int n_docs, int32_t n, int32_t *lcp, int32_t *up, int32_t *down, int32_t *next,
+                      int32_t *ann, StageTimer &tm, cudaStream_t s) {
+    // pyramid storage: sizes n/32, n/1024, ...
+    MinPyramid M;
+    M.lv[0] = lcp;
+    M.size[0] = n;
+    size_t total = 0;
+    int levels = 1;
+    for (int32_t sz = n; sz > 1 && levels < MAX_LEVELS; ++levels) {
+        sz = (sz + 31) / 32;
+        M.size[levels] = sz;
+        total += (size_t)sz;
+    }
+    DevBuf<int32_t> pyr(total + 1, s);
+    {
+        size_t off = 0;
+        for (int k = 1; k < levels; ++k) { M.lv[k] = pyr.p + off; off += (size_t)M.size[k]; }
+        for (int k = levels; k < MAX_LEVELS; ++k) { M.lv[k] = nullptr; M.size[k] = 0; }
+    }
+    M.levels = levels;
+
+    tm.mark("lcp");
+    EAST_BYTES(16.0 * n);  // SA in, LCP out, >= one text word per suffix of each compared pair
+    EAST_LAUNCH(k_lcp, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, text, sa, doc_off, n_docs, n, lcp,
+                levels > 1 ? const_cast<int32_t *>(M.lv[1]) : pyr.p);
+    for (int k = 2; k < levels; ++k)
+        EAST_LAUNCH(k_min32, (int)(((int64_t)M.size[k] * 32 + 255) / 256), 256, 0, s, M.lv[k - 1], M.size[k - 1],
+                    const_cast<int32_t *>(M.lv[k]), M.size[k]);
+
+    tm.mark("child_ann");
     EAST_CUDA(cudaMemsetAsync(up, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_CUDA(cudaMemsetAsync(down, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_CUDA(cudaMemsetAsync(next, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_CUDA(cudaMemsetAsync(ann, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_BYTES(8.0 * n);   // LCP in; annotation + child entries out (sparse)
-    EAST_LAUNCH(k_child_ann, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, lcp, doc_off, doc_m, n_docs, n,
+    EAST_LAUNCH(k_child_ann, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, M, doc_off, doc_m, n_docs, n,
                 up, down, next, ann);
 }
 

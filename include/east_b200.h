@@ -85,8 +85,9 @@ int east_score_table_host(const east_index *idx, const uint32_t *kp, const int64
                           int32_t K, int normalized, double *out_DxK);
 int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
                          int32_t K, int normalized, double *out_DxK_dev, void *stream);
-/* same table through an instrumented scorer that also counts the (SA word, text word) probe
- * pairs it reads: the algorithmic-byte model of the scorer is 8 bytes x probes */
+/* same table through an instrumented scorer that also counts the algorithmic bytes it reads:
+ * 8 per (SA word, text word) probe; on the fast path 5 per (SA word, text byte)
+ * probe and 8 per 2-gram bucket lookup.  *probes receives that byte count. */
 int east_score_probes_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
                           int32_t K, double *out_DxK_dev, void *stream, int64_t *probes);
 /* single query against one document, with the per-suffix results of
