@@ -65,43 +65,83 @@ struct ScanResult {
     uint32_t bad;      // terminator layout violated
 };
 
+constexpr int ST_TILE = 4096;
+constexpr int ST_HALO = 256;
+
+// One streaming pass over the packed text, staged through shared memory: alphabet bitmap of the
+// code points below 0x0A00, maximum code point, and validation that the code points >= 0x0A00
+// are exactly the terminators 0x0A00+i of string i of each document, in order.  A terminator
+// checks itself against the previous terminator of its document by walking back through the
+// staged tile (strings are ~20 symbols), falling back to global memory for very long strings.
 __global__ void __launch_bounds__(256)
 k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict__ doc_off,
             const int32_t *__restrict__ doc_m, int D, ScanResult *res) {
     __shared__ uint32_t s_present[EAST_TERM_BASE / 32];
     __shared__ uint32_t s_max, s_nterm, s_bad;
+    __shared__ __align__(16) uint32_t s_t[ST_HALO + ST_TILE];
+    __shared__ int s_dlo, s_dhi;
     for (int i = threadIdx.x; i < EAST_TERM_BASE / 32; i += blockDim.x) s_present[i] = 0;
     if (threadIdx.x == 0) { s_max = 0; s_nterm = 0; s_bad = 0; }
-    __syncthreads();
     uint32_t mx = 0, nt = 0, bad = 0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint32_t c = T[i];
-        mx = max(mx, c);
-        if (c < EAST_TERM_BASE) {
-            // a stale read only costs a redundant atomic; after the first few hundred characters
-            // every bit of the alphabet is set and the loop is atomic-free
-            if (!(((volatile uint32_t *)s_present)[c >> 5] & (1u << (c & 31))))
-                atomicOr(&s_present[c >> 5], 1u << (c & 31));
-        } else {
-            ++nt;
-            // must be 0x0A00 + (index of this string inside its document): walk back to the
-            // previous terminator of the same document
-            int d = doc_of(doc_off, D, (int32_t)i);
-            int32_t start = doc_off[d];
-            int64_t j = i - 1;
-            while (j >= start && T[j] < EAST_TERM_BASE) --j;
-            uint32_t expect = (j >= start) ? T[j] + 1u : EAST_TERM_BASE;
-            if (c != expect) bad = 1;
-            // the last code point of a document is its last terminator
-            if (i == doc_off[d + 1] - 1 && c != EAST_TERM_BASE + (uint32_t)doc_m[d] - 1u) bad = 1;
+    const int num_tiles = (n + ST_TILE - 1) / ST_TILE;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t base = (int64_t)tile * ST_TILE;
+        const int64_t win = base - ST_HALO;  // global position of s_t[0]
+        __syncthreads();
+        for (int o = threadIdx.x * 4; o < ST_HALO + ST_TILE; o += 256 * 4) {
+            const int64_t g = win + o;
+            if (g >= 0 && g + 4 <= n) {
+                *reinterpret_cast<uint4 *>(s_t + o) = *reinterpret_cast<const uint4 *>(T + g);  // 128-bit
+            } else {
+                for (int q = 0; q < 4; ++q) s_t[o + q] = (g + q >= 0 && g + q < n) ? T[g + q] : 0u;
+            }
+        }
+        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, (int32_t)base);
+        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, (int32_t)min(base + ST_TILE, (int64_t)n) - 1);
+        __syncthreads();
+        const int dlo = s_dlo, dhi = s_dhi;
+#pragma unroll 4
+        for (int it = 0; it < ST_TILE / 256; ++it) {
+            const int o = it * 256 + threadIdx.x;
+            const int64_t i = base + o;
+            if (i >= n) break;
+            const uint32_t c = s_t[ST_HALO + o];
+            mx = max(mx, c);
+            if (c < EAST_TERM_BASE) {
+                if (!(((volatile uint32_t *)s_present)[c >> 5] & (1u << (c & 31))))
+                    atomicOr(&s_present[c >> 5], 1u << (c & 31));
+            } else {
+                ++nt;
+                int lo = dlo, hi = dhi;
+                while (lo < hi) {
+                    int mid = (lo + hi + 1) >> 1;
+                    if (__ldg(doc_off + mid) <= i) lo = mid; else hi = mid - 1;
+                }
+                const int64_t start = __ldg(doc_off + lo);
+                const int64_t floor_ = max(start, win < 0 ? (int64_t)0 : win);
+                int64_t j = i - 1;
+                while (j >= floor_ && s_t[j - win] < EAST_TERM_BASE) --j;
+                uint32_t prev;
+                bool have_prev;
+                if (j >= floor_) { have_prev = true; prev = s_t[j - win]; }
+                else {
+                    while (j >= start && T[j] < EAST_TERM_BASE) --j;  // string longer than the halo
+                    have_prev = j >= start;
+                    prev = have_prev ? T[j] : 0u;
+                }
+                const uint32_t expect = have_prev ? prev + 1u : EAST_TERM_BASE;
+                if (c != expect) bad = 1;
+                if (i == __ldg(doc_off + lo + 1) - 1 && c != EAST_TERM_BASE + (uint32_t)__ldg(doc_m + lo) - 1u) bad = 1;
+            }
         }
     }
     // every document must end with a terminator
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D; d += stride) {
         int32_t e = doc_off[d + 1];
         if (e <= doc_off[d] || T[e - 1] < EAST_TERM_BASE) bad = 1;
     }
+    __syncthreads();
     atomicMax(&s_max, mx);
     atomicAdd(&s_nterm, nt);
     if (bad) atomicOr(&s_bad, 1u);
@@ -444,7 +484,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     DevBuf<ScanResult> d_scan(1, s);
     EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
     EAST_BYTES(4.0 * n);
-    EAST_LAUNCH(k_scan_text, grid_for(n, 256 * 8, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p);
+    EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p);
     ScanResult scan;
     EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
     EAST_CUDA(cudaStreamSynchronize(s));

@@ -36,8 +36,23 @@ struct MinPyramid {
     int levels;                     // number of valid entries in lv[]
 };
 
+// 8 text bytes starting at an arbitrary address: two aligned 64-bit loads + funnel shift
+// (the byte text is allocated with 64 bytes of slack, so the second load never faults)
+__device__ __forceinline__ uint64_t load8(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint64_t *q = (const uint64_t *)(a & ~(uintptr_t)7);
+    const int sh = (int)(a & 7) * 8;
+    const uint64_t lo = q[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (q[1] << (64 - sh));
+}
+
+// FAST: compare dense byte codes 8 at a time.  All terminators share one byte code, so the
+// common prefix also ends at the first terminator of either suffix (distinct terminators differ).
+template <bool FAST>
 __global__ void __launch_bounds__(TB_THREADS)
-k_lcp(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa, const int32_t *__restrict__ doc_off,
+k_lcp(const uint32_t *__restrict__ T, const uint8_t *__restrict__ T8, uint64_t term8,
+      const int32_t *__restrict__ sa, const int32_t *__restrict__ doc_off,
       int D, int32_t n, int32_t *__restrict__ lcp, int32_t *__restrict__ min1) {
     __shared__ int s_dlo, s_dhi;
     const int64_t stride = (int64_t)gridDim.x * TB_THREADS;
@@ -58,8 +73,20 @@ k_lcp(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa, const int3
             h = 0;
             if (r > start) {
                 const int32_t i = sa[r - 1], j = sa[r];
-                const int32_t lim = end - max(i, j);
-                while (h < lim && T[i + h] == T[j + h]) ++h;
+                if (FAST) {
+                    while (true) {
+                        const uint64_t x = load8(T8 + i + h), y = load8(T8 + j + h);
+                        const uint64_t diff = x ^ y;
+                        const uint64_t t = x ^ term8;  // zero byte <=> terminator in suffix i
+                        const uint64_t tz = (t - 0x0101010101010101ull) & ~t & 0x8080808080808080ull;
+                        const uint64_t stop = diff | tz;
+                        if (stop) { h += (__ffsll((long long)stop) - 1) >> 3; break; }
+                        h += 8;
+                    }
+                } else {
+                    const int32_t lim = end - max(i, j);
+                    while (h < lim && T[i + h] == T[j + h]) ++h;
+                }
             }
             lcp[r] = h;
         }
@@ -174,7 +201,7 @@ k_child_ann(MinPyramid M, const int32_t *__restrict__ doc_off, const int32_t *__
     }
 }
 
-void build_lcp_tables(const uint32_t *text, const int32_t *sa, const int32_t *doc_off, const int32_t *doc_m,
+void build_lcp_tables(const uint32_t *text, const uint8_t *t8, int term_code, const int32_t *sa, const int32_t *doc_off, const int32_t *doc_m,
                       int n_docs, int32_t n, int32_t *lcp, int32_t *up, int32_t *down, int32_t *next,
                       int32_t *ann, StageTimer &tm, cudaStream_t s) {
     // pyramid storage: sizes n/32, n/1024, ...
@@ -197,9 +224,17 @@ void build_lcp_tables(const uint32_t *text, const int32_t *sa, const int32_t *do
     M.levels = levels;
 
     tm.mark("lcp");
-    EAST_BYTES(16.0 * n);  // SA in, LCP out, >= one text word per suffix of each compared pair
-    EAST_LAUNCH(k_lcp, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, text, sa, doc_off, n_docs, n, lcp,
-                levels > 1 ? const_cast<int32_t *>(M.lv[1]) : pyr.p);
+    int32_t *min1 = levels > 1 ? const_cast<int32_t *>(M.lv[1]) : pyr.p;
+    if (t8) {
+        const uint64_t term8 = 0x0101010101010101ull * (uint64_t)(term_code & 0xff);
+        EAST_BYTES(10.0 * n);  // SA in, LCP out, >= one text byte per suffix of each compared pair
+        EAST_LAUNCH(k_lcp<true>, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, text, t8, term8, sa, doc_off,
+                    n_docs, n, lcp, min1);
+    } else {
+        EAST_BYTES(16.0 * n);  // SA in, LCP out, >= one text word per suffix of each compared pair
+        EAST_LAUNCH(k_lcp<false>, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, text, t8, 0ull, sa, doc_off,
+                    n_docs, n, lcp, min1);
+    }
     for (int k = 2; k < levels; ++k)
         EAST_LAUNCH(k_min32, (int)(((int64_t)M.size[k] * 32 + 255) / 256), 256, 0, s, M.lv[k - 1], M.size[k - 1],
                     const_cast<int32_t *>(M.lv[k]), M.size[k]);

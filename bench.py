@@ -40,7 +40,7 @@ UNIT = "scores/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--docs", type=int, default=1000, help="documents per GPU")
@@ -139,9 +139,10 @@ class ClockSampler(object):
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """Summary of the samples that arrived in [t_from, t_to] (perf_counter clock)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -151,7 +152,9 @@ class ClockSampler(object):
             self.proc.kill()
         sm, smmax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for stamp, line in self.lines:
+            if (t_from is not None and stamp < t_from) or (t_to is not None and stamp > t_to):
+                continue
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -256,12 +259,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-timed arm
+    # ---- device-timed arm (nvidia-smi needs ~100 ms to deliver its first sample: start it before the warm-up)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_device()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    t_timed0 = time.perf_counter()
     _capi.set_option("time_kernels", 0)
     _capi.set_option("time_kernels", 1)
     _capi.launch_count(reset=True)
@@ -277,7 +281,6 @@ def run_b200(args):
     launches = _capi.launch_count()
     kstats = _capi.kernel_stats()
     _capi.set_option("time_kernels", 0)
-    clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -293,6 +296,8 @@ def run_b200(args):
         step_e2e()
     barrier()
     e2e_ms = (time.perf_counter() - w0) * 1e3 / args.steps
+    # clocks under load: samples taken between the start of the device-timed region and the end of the e2e one
+    clocks = sampler.stop(t_timed0, time.perf_counter())
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
