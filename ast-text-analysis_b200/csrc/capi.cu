@@ -1,4 +1,7 @@
 // capi.cu -- the C ABI of libeast_b200.so (declared in include/east_b200.h).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -71,7 +74,12 @@ void *dev_alloc(size_t bytes, cudaStream_t s) {
 }
 void dev_free(void *p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
 
+static double host_now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 void StageTimer::mark(const char *name) {
+    static const bool debug = getenv("EAST_DEBUG_TIMING") != nullptr;
+    if (debug) fprintf(stderr, "[east] host %.3f ms  -> %s\n", host_now_ms(), name);
     cudaEvent_t e;
     EAST_CUDA(cudaEventCreate(&e));
     EAST_CUDA(cudaEventRecord(e, s));
@@ -256,6 +264,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.n = n; in.n_docs = n_docs; in.m_total = idx->m_total;
         in.key_chars = (int)get_option("key_chars", 0);
         in.force_general = (int)get_option("force_general", 0);
+        in.rs_variant = (int)get_option("rs_variant", 0);
         SaOutput so;
         so.sa = idx->sa; so.rank = rank.p;
         build_suffix_array(in, so, tm, s);
@@ -399,7 +408,9 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
     in.normalized = normalized ? 1 : 0;
     // fast path: dense byte codes of the queries + per-suffix "contains a code point >= 0x0A00" flag
     DevBuf<uint8_t> d_q8, d_generic;
+    DevBuf<int32_t> d_order;
     std::vector<uint8_t> q8, generic;
+    std::vector<int32_t> order;
     if (idx->bkt && idx->t8 && !get_option("score_generic", 0)) {
         std::vector<uint32_t> kp_host((size_t)total);
         EAST_CUDA(cudaMemcpyAsync(kp_host.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
@@ -413,6 +424,28 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
                 else q8[(size_t)p] = idx->code_table[c];
                 generic[(size_t)p] = weird;
             }
+        }
+        // visit order of the suffixes: counting sort by their first three dense symbols, so the
+        // threads of a warp walk neighbouring SA intervals (cache locality, less divergence)
+        {
+            const int b = idx->sym_bits;
+            const int nsym = (3 * b <= 18) ? 3 : ((2 * b <= 18) ? 2 : 1);
+            std::vector<uint32_t> bin((size_t)total);
+            std::vector<uint32_t> count(((size_t)1 << (nsym * b)) + 1, 0u);
+            for (int32_t k = 0; k < K; ++k)
+                for (int64_t p = kp_off[k]; p < kp_off[k + 1]; ++p) {
+                    uint32_t key = 0;
+                    for (int c = 0; c < nsym; ++c)
+                        key = (key << b) | ((p + c < kp_off[k + 1]) ? q8[(size_t)(p + c)] : 0u);
+                    bin[(size_t)p] = key;
+                    ++count[key + 1];
+                }
+            for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
+            order.resize((size_t)total);
+            for (int64_t p = 0; p < total; ++p) order[count[bin[(size_t)p]]++] = (int32_t)p;
+            d_order = DevBuf<int32_t>((size_t)total, s);
+            EAST_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+            in.order = d_order.p;
         }
         d_q8 = DevBuf<uint8_t>((size_t)total, s); d_generic = DevBuf<uint8_t>((size_t)total, s);
         EAST_CUDA(cudaMemcpyAsync(d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));

@@ -18,18 +18,16 @@
 
 namespace east {
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 4096 pairs per CTA
+constexpr int RS_MIN_TILE = 2048;  // smallest tile of any kernel variant (sizes the look-back scratch)
 constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_LOOKBACK = 8;   // predecessor status words fetched per look-back round trip
 
 constexpr uint32_t RS_FLAG_AGG = 1u << 30;
 constexpr uint32_t RS_FLAG_PREFIX = 2u << 30;
 constexpr uint32_t RS_VALUE_MASK = (1u << 30) - 1;
 
 static inline int rs_num_passes(int nbits) { return (nbits + 7) / 8; }
-static inline int rs_num_tiles(int64_t n) { return (int)((n + RS_TILE - 1) / RS_TILE); }
+static inline int rs_num_tiles(int64_t n, int tile = RS_MIN_TILE) { return (int)((n + tile - 1) / tile); }
 // bytes of scratch (status words + tile tickets) for sorting n pairs with `passes` passes
 static inline size_t rs_scratch_bytes(int64_t n, int passes) {
     return ((size_t)rs_num_tiles(n) * 256 * passes + 64) * sizeof(uint32_t);
@@ -99,124 +97,151 @@ __global__ void __launch_bounds__(256) k_rs_hist(const uint64_t *__restrict__ ke
 
 // One LSD pass.  hist_excl: this pass' 256 exclusive bin offsets.  status: tiles*256 words,
 // zero-initialised.  ticket: zero-initialised tile counter.
-__global__ void __launch_bounds__(RS_THREADS)
+// THREADS x ITEMS pairs per CTA; MINB = CTAs per SM the register allocation must allow.
+template <int THREADS, int ITEMS>
+struct RsCfg {
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr int TILE = THREADS * ITEMS;
+    // s_cnt[WARPS][256] | s_dstart[256] | s_gbase[256] | s_wsum[8] | s_tile (+pad) | s_keys[TILE]
+    static constexpr int SMEM = (WARPS * 256 + 256 + 256 + 8 + 8) * 4 + TILE * 8;
+};
+
+template <int THREADS, int ITEMS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
               const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout, int32_t n, int shift,
               const uint32_t *__restrict__ hist_excl, volatile uint32_t *status, uint32_t *ticket) {
-    __shared__ uint32_t s_cnt[RS_WARPS][256];
-    __shared__ uint32_t s_dstart[256];
-    __shared__ uint32_t s_gbase[256];
-    __shared__ uint32_t s_wsum[8];
-    __shared__ uint64_t s_keys[RS_TILE];
-    __shared__ uint32_t s_tile;
+    using Cfg = RsCfg<THREADS, ITEMS>;
+    constexpr int WARPS = Cfg::WARPS, TILE = Cfg::TILE;
+    extern __shared__ __align__(16) uint32_t rs_smem[];
+    uint32_t(*s_cnt)[256] = reinterpret_cast<uint32_t(*)[256]>(rs_smem);
+    uint32_t *s_dstart = rs_smem + WARPS * 256;
+    uint32_t *s_gbase = s_dstart + 256;
+    uint32_t *s_wsum = s_gbase + 256;
+    uint32_t *s_tile = s_wsum + 8;
+    uint64_t *s_keys = reinterpret_cast<uint64_t *>(s_tile + 8);
     uint32_t *s_vals = reinterpret_cast<uint32_t *>(s_keys);
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    if (t == 0) s_tile = atomicAdd(ticket, 1u);
+    if (t == 0) *s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s_cnt[w][lane + 32 * i] = 0;
     __syncthreads();
-    const uint32_t tile = s_tile;
-    const int64_t tile_base = (int64_t)tile * RS_TILE;
-    const int tile_n = (int)min((int64_t)RS_TILE, (int64_t)n - tile_base);
+    const uint32_t tile = *s_tile;
+    const int64_t tile_base = (int64_t)tile * TILE;
+    const int tile_n = (int)min((int64_t)TILE, (int64_t)n - tile_base);
 
-    // ---- load (warp-striped: item j of lane l is element w*512 + j*32 + l of the tile)
-    uint64_t key[RS_ITEMS];
-    uint32_t val[RS_ITEMS];
-    const int wbase = w * (32 * RS_ITEMS) + lane;
-    if (tile_n == RS_TILE) {
+    // ---- load (warp-striped: item j of lane l is element w*32*ITEMS + j*32 + l of the tile)
+    uint64_t key[ITEMS];
+    uint32_t val[ITEMS];
+    const int wbase = w * (32 * ITEMS) + lane;
+    if (tile_n == TILE) {
 #pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) key[j] = kin[tile_base + wbase + j * 32];
+        for (int j = 0; j < ITEMS; ++j) key[j] = kin[tile_base + wbase + j * 32];
 #pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) val[j] = vin[tile_base + wbase + j * 32];
+        for (int j = 0; j < ITEMS; ++j) val[j] = vin[tile_base + wbase + j * 32];
     } else {
 #pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) {
+        for (int j = 0; j < ITEMS; ++j) {
             int o = wbase + j * 32;
             key[j] = (o < tile_n) ? kin[tile_base + o] : ~0ull;
             val[j] = (o < tile_n) ? vin[tile_base + o] : 0u;
         }
     }
 
-    // ---- rank inside the warp (stable: items are visited in element order)
-    uint32_t pos[RS_ITEMS];
+    // ---- rank inside the warp (stable: items are visited in element order).
+    // All lanes holding the same digit read the running counter, the HIGHEST of them writes it
+    // back (its own rank + 1 is the group size): one MATCH and one POPC per key.
+    uint32_t pos[ITEMS];
     const unsigned lt = lanemask_lt();
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-        unsigned d = (unsigned)(key[j] >> shift) & 255u;
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader) {
-            old = s_cnt[w][d];
-            s_cnt[w][d] = old + __popc(peers);
-        }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        pos[j] = old + __popc(peers & lt);
+    for (int j = 0; j < ITEMS; ++j) {
+        const unsigned d = (unsigned)(key[j] >> shift) & 255u;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t below = __popc(peers & lt);
+        const uint32_t old = s_cnt[w][d];
         __syncwarp();
+        if ((peers >> lane) == 1u) s_cnt[w][d] = old + below + 1u;  // no peer above this lane
+        __syncwarp();
+        pos[j] = old + below;
     }
     __syncthreads();
 
-    // ---- per-digit exclusive prefix over warps, digit totals (thread t owns digit t)
+    // ---- per-digit exclusive prefix over warps, digit totals (thread t < 256 owns digit t)
     uint32_t total = 0;
+    volatile uint32_t *my_status = status + (size_t)tile * 256 + (t & 255);
+    if (t < 256) {
 #pragma unroll
-    for (int i = 0; i < RS_WARPS; ++i) {
-        uint32_t c = s_cnt[i][t];
-        s_cnt[i][t] = total;
-        total += c;
+        for (int i = 0; i < WARPS; ++i) {
+            uint32_t c = s_cnt[i][t];
+            s_cnt[i][t] = total;
+            total += c;
+        }
+        // publish the tile aggregate as early as possible
+        if (tile == 0) *my_status = RS_FLAG_PREFIX | total;
+        else *my_status = RS_FLAG_AGG | total;
     }
-    // publish the tile aggregate as early as possible
-    volatile uint32_t *my_status = status + (size_t)tile * 256 + t;
-    if (tile == 0) *my_status = RS_FLAG_PREFIX | total;
-    else *my_status = RS_FLAG_AGG | total;
-
     // ---- exclusive scan of totals over the 256 digits -> local start of each digit run
-    {
-        uint32_t x = total;
+    uint32_t x = total;
+    if (t < 256) {
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += y;
         }
         if (lane == 31) s_wsum[w] = x;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (t < 256) {
         uint32_t base = 0;
 #pragma unroll
-        for (int i = 0; i < RS_WARPS; ++i) base += (i < w) ? s_wsum[i] : 0u;
+        for (int i = 0; i < 8; ++i) base += (i < w) ? s_wsum[i] : 0u;
         s_dstart[t] = base + x - total;
-    }
 
-    // ---- decoupled look-back: how many keys with digit t precede this tile
-    uint32_t excl = 0;
-    if (tile > 0) {
-        int64_t prev = (int64_t)tile - 1;
-        while (true) {
-            uint32_t sv = status[(size_t)prev * 256 + t];
-            uint32_t flag = sv & ~RS_VALUE_MASK;
-            if (flag == 0) continue;  // predecessor not there yet
-            excl += sv & RS_VALUE_MASK;
-            if (flag == RS_FLAG_PREFIX) break;
-            --prev;
+        // ---- decoupled look-back: how many keys with digit t precede this tile.  The status
+        // words of RS_LOOKBACK predecessors are fetched together (independent loads, one L2 round
+        // trip) and consumed in order; a word that is not published yet restarts the fetch there.
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int64_t prev = (int64_t)tile - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t sv[RS_LOOKBACK];
+#pragma unroll
+                for (int u = 0; u < RS_LOOKBACK; ++u) {
+                    sv[u] = 2u << 30;  // before the first tile: an empty inclusive prefix
+                    if (prev - u >= 0) sv[u] = status[(size_t)(prev - u) * 256 + t];
+                }
+#pragma unroll
+                for (int u = 0; u < RS_LOOKBACK; ++u) {
+                    if (done) break;
+                    const uint32_t flag = sv[u] & ~RS_VALUE_MASK;
+                    if (flag == 0) break;  // not there yet: refetch starting at this predecessor
+                    excl += sv[u] & RS_VALUE_MASK;
+                    --prev;
+                    if (flag == RS_FLAG_PREFIX) done = true;
+                }
+            }
+            *my_status = RS_FLAG_PREFIX | (excl + total);
         }
-        *my_status = RS_FLAG_PREFIX | (excl + total);
+        s_gbase[t] = hist_excl[t] + excl - s_dstart[t];
     }
-    s_gbase[t] = hist_excl[t] + excl - s_dstart[t];
     __syncthreads();
 
     // ---- keys: scatter into shared memory at their tile-sorted position, then stream out
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
+    for (int j = 0; j < ITEMS; ++j) {
         unsigned d = (unsigned)(key[j] >> shift) & 255u;
         pos[j] += s_dstart[d] + s_cnt[w][d];
         s_keys[pos[j]] = key[j];
     }
     __syncthreads();
-    uint32_t dig[RS_ITEMS / 4];
+    uint32_t dig[(ITEMS + 3) / 4];
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS / 4; ++i) dig[i] = 0;
+    for (int i = 0; i < (ITEMS + 3) / 4; ++i) dig[i] = 0;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        int p = t + i * RS_THREADS;
+    for (int i = 0; i < ITEMS; ++i) {
+        int p = t + i * THREADS;
         uint64_t k = s_keys[p];
         unsigned d = (unsigned)(k >> shift) & 255u;
         dig[i >> 2] |= d << (8 * (i & 3));
@@ -225,11 +250,11 @@ k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     __syncthreads();
     // ---- values follow the same permutation
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) s_vals[pos[j]] = val[j];
+    for (int j = 0; j < ITEMS; ++j) s_vals[pos[j]] = val[j];
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        int p = t + i * RS_THREADS;
+    for (int i = 0; i < ITEMS; ++i) {
+        int p = t + i * THREADS;
         unsigned d = (dig[i >> 2] >> (8 * (i & 3))) & 255u;
         if (p < tile_n) vout[s_gbase[d] + p] = s_vals[p];
     }
@@ -241,6 +266,6 @@ k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
 // that are either already accumulated (hist_ready) or computed here.  scratch: rs_scratch_bytes.
 // Returns 0 if the result is in (ka, va), 1 if in (kb, vb).
 int radix_sort_pairs(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int32_t n, int nbits,
-                     uint32_t *hist, bool hist_ready, void *scratch, cudaStream_t s);
+                     uint32_t *hist, bool hist_ready, void *scratch, cudaStream_t s, int variant = 0);
 
 }  // namespace east

@@ -26,13 +26,35 @@ namespace east {
 // ------------------------------------------------------------------------------------------
 // radix sort host driver
 // ------------------------------------------------------------------------------------------
+template <int THREADS, int ITEMS, int MINB>
+static void launch_onesweep(const uint64_t *kin, uint64_t *kout, const uint32_t *vin, uint32_t *vout, int32_t n,
+                            int shift, const uint32_t *hist_excl, uint32_t *status, uint32_t *ticket,
+                            cudaStream_t s) {
+    using Cfg = RsCfg<THREADS, ITEMS>;
+    static bool configured = false;
+    auto kern = k_rs_onesweep<THREADS, ITEMS, MINB>;
+    if (!configured) {
+        EAST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        configured = true;
+    }
+    const int tiles = rs_num_tiles(n, Cfg::TILE);
+    EAST_BYTES(24.0 * n);  // read + write of an 8-byte key and a 4-byte value per element
+    if (g_time_kernels) ktime_begin("k_rs_onesweep", s);
+    kern<<<tiles, THREADS, Cfg::SMEM, s>>>(kin, kout, vin, vout, n, shift, hist_excl, status, ticket);
+    if (g_time_kernels) ktime_end(s);
+    ++g_launches;
+    g_next_bytes = 0.0;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(-2, std::string("k_rs_onesweep launch: ") + cudaGetErrorString(e));
+}
+
 int radix_sort_pairs(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int32_t n, int nbits,
-                     uint32_t *hist, bool hist_ready, void *scratch, cudaStream_t s) {
+                     uint32_t *hist, bool hist_ready, void *scratch, cudaStream_t s, int variant) {
     if (n <= 0) return 0;
     int passes = rs_num_passes(nbits);
     if (passes < 1) passes = 1;
     if (passes > RS_MAX_PASSES) throw Error(-1, "radix_sort_pairs: too many key bits");
-    int tiles = rs_num_tiles(n);
+    const int tiles = rs_num_tiles(n);  // scratch stride: the smallest tile of any variant
     if (!hist_ready) {
         EAST_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 256 * passes, s));
         EAST_LAUNCH(k_rs_hist, grid_for(n, 256 * 8, 4), 256, 0, s, ka, n, passes, hist);
@@ -47,9 +69,21 @@ int radix_sort_pairs(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int
         uint64_t *kout = cur ? ka : kb;
         const uint32_t *vin = cur ? vb : va;
         uint32_t *vout = cur ? va : vb;
-        EAST_BYTES(24.0 * n);  // read + write of an 8-byte key and a 4-byte value per element
-        EAST_LAUNCH(k_rs_onesweep, tiles, RS_THREADS, 0, s, kin, kout, vin, vout, n, 8 * p,
-                    hist + 256 * p, status + (size_t)tiles * 256 * p, tickets + p);
+        uint32_t *st = status + (size_t)tiles * 256 * p;
+#define RS_CASE(id, T, I, B) case id: launch_onesweep<T, I, B>(kin, kout, vin, vout, n, 8 * p, hist + 256 * p, st, tickets + p, s); break;
+        switch (variant) {
+            RS_CASE(1, 256, 16, 2)
+            RS_CASE(2, 256, 12, 4)
+            RS_CASE(3, 256, 8, 5)
+            RS_CASE(4, 384, 12, 2)
+            RS_CASE(5, 512, 8, 2)
+            RS_CASE(6, 512, 12, 1)
+            RS_CASE(7, 384, 16, 2)
+            RS_CASE(8, 256, 20, 2)
+            RS_CASE(9, 512, 16, 1)
+            default: launch_onesweep<256, 16, 3>(kin, kout, vin, vout, n, 8 * p, hist + 256 * p, st, tickets + p, s); break;
+        }
+#undef RS_CASE
         cur ^= 1;
     }
     return cur;
@@ -550,7 +584,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     }
 
     tm.mark("sort0");
-    int cur = radix_sort_pairs(keys_a.p, keys_b.p, vals_a.p, vals_b.p, n, key_bits, hist.p, true, scratch.p, s);
+    int cur = radix_sort_pairs(keys_a.p, keys_b.p, vals_a.p, vals_b.p, n, key_bits, hist.p, true, scratch.p, s,
+                               in.rs_variant);
 
     // scorer acceleration (fast path): first ranks of all (document, 2-gram) buckets
     if (fast && kc >= 2 && ((size_t)D << (2 * kp.b)) <= (size_t)2 * n + 4096) {
@@ -605,7 +640,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                     rank, (int32_t)h, sb, passes, fast ? 0 : 1, in.doc_off, D, keys_a.p, hist.p);
         // values to sort along: the suffix index
         int c2 = radix_sort_pairs(keys_a.p, keys_b.p, act_vals.p, vals_b.p, (int32_t)n_act, nbits, hist.p, true,
-                                  scratch.p, s);
+                                  scratch.p, s, in.rs_variant);
         const uint64_t *sk = c2 ? keys_b.p : keys_a.p;
         const uint32_t *sv = c2 ? vals_b.p : act_vals.p;
         const int rr_tiles = ((int)n_act + RR_TILE - 1) / RR_TILE;

@@ -13,6 +13,7 @@ struct SaInput {
     int64_t m_total;
     int key_chars;            // 0 = as many symbols as fit the 64-bit key
     int force_general;        // testing: never take the terminator-class fast path
+    int rs_variant = 0;       // tuning: radix-sort kernel shape (see radix_sort_pairs)
 };
 
 struct SaOutput {
@@ -57,6 +58,7 @@ struct ScoreInput {
     const uint32_t *bkt = nullptr;      // [n_docs << 2*sym_bits] + 1, rows of the docs being scored
     const uint8_t *q8 = nullptr;        // dense codes of kp (0 = symbol absent from the batch)
     const uint8_t *suf_generic = nullptr;  // 1 = this suffix contains a code point >= 0x0A00: generic walk
+    const int32_t *order = nullptr;     // optional visit order of the suffixes (a permutation)
     int sym_bits = 0;
     unsigned long long *probe_count = nullptr;  // device counter: run the probe-counting variant
     double algorithmic_bytes = 0.0;             // 8 B x probes of this workload, if known (roofline numerator)

@@ -177,16 +177,17 @@ k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *pr
     const int64_t stride = (int64_t)gridDim.x * SC_THREADS;
     for (int64_t idx = (int64_t)blockIdx.x * SC_THREADS + threadIdx.x; idx < total; idx += stride) {
         const int32_t doc = (int32_t)(idx / in.total_suffixes);
-        const int32_t sidx = (int32_t)(idx - (int64_t)doc * in.total_suffixes);
+        int32_t sidx = (int32_t)(idx - (int64_t)doc * in.total_suffixes);
+        if (in.order) sidx = __ldg(in.order + sidx);
         const int32_t k = __ldg(in.suf_kp + sidx);
         const int32_t qend = __ldg(in.kp_off + k + 1);
         const int32_t start = __ldg(in.doc_off + doc), end = __ldg(in.doc_off + doc + 1);
         if (in.bkt != nullptr && !__ldg(in.suf_generic + sidx)) {
-            tmp[idx] = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.bkt + ((size_t)doc << (2 * in.sym_bits)),
+            tmp[(int64_t)doc * in.total_suffixes + sidx] = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.bkt + ((size_t)doc << (2 * in.sym_bits)),
                                                      in.sym_bits, start, end, __ldg(in.doc_m + doc), in.q8 + sidx,
                                                      qend - sidx, in.normalized, probes);
         } else {
-            tmp[idx] = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx,
+            tmp[(int64_t)doc * in.total_suffixes + sidx] = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx,
                                                 qend - sidx, in.normalized, probes);
         }
     }

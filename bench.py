@@ -118,57 +118,70 @@ def workload_config(args, n_gpus):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons through NVML from a background thread
+    (nvidia_ml_py; a polling nvidia-smi process measurably perturbs the step being timed)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4), ("hw_power_brake", 0x80))
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period_s=0.02):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.period = period_s
+        self.samples = []
+        self.thread = None
+        self.error = None
+        self._stop = threading.Event()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical GPUs; map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.gpu
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                    phys = int(ids[self.gpu])
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.error = repr(e)
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+    def _run(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:  # noqa: BLE001
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                self.samples.append((time.perf_counter(), sm, reasons, power))
+            except Exception as e:  # noqa: BLE001
+                self.error = repr(e)
+                return
+            self._stop.wait(self.period)
 
     def stop(self, t_from=None, t_to=None):
-        """Summary of the samples that arrived in [t_from, t_to] (perf_counter clock)."""
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, smmax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for stamp, line in self.lines:
-            if (t_from is not None and stamp < t_from) or (t_to is not None and stamp > t_to):
-                continue
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smmax.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        """Summary of the samples taken in [t_from, t_to] (perf_counter clock)."""
+        self._stop.set()
+        if self.thread:
+            self.thread.join(timeout=2)
+        rows = [s for s in self.samples if (t_from is None or s[0] >= t_from) and (t_to is None or s[0] <= t_to)]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples: %s" % self.error], "samples": 0}
+        sm = sorted(r[1] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max,
+                "reasons": [name for name, bit in self.REASONS if bits & bit],
+                "power_w_max": max(r[3] for r in rows), "samples": len(rows), "source": "nvml"}
 
 
 # ------------------------------------------------------------------------------------------------
