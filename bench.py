@@ -40,7 +40,7 @@ UNIT = "scores/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--docs", type=int, default=1000, help="documents per GPU")
@@ -123,7 +123,7 @@ class ClockSampler(object):
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
                ("sw_power_cap", 0x4), ("hw_power_brake", 0x80))
 
-    def __init__(self, gpu_index, period_s=0.02):
+    def __init__(self, gpu_index, period_s=0.25):
         self.gpu = gpu_index
         self.period = period_s
         self.samples = []
@@ -151,21 +151,28 @@ class ClockSampler(object):
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
-    def _run(self):
+    def sample(self):
+        """One sample (also called from the main thread right before/after a timed region)."""
+        if self.error or not hasattr(self, "handle"):
+            return
         nv = self.nvml
-        while not self._stop.is_set():
+        try:
+            sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
             try:
-                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
-                try:
-                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                except Exception:  # noqa: BLE001
-                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
-                self.samples.append((time.perf_counter(), sm, reasons, power))
-            except Exception as e:  # noqa: BLE001
-                self.error = repr(e)
-                return
+                reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception:  # noqa: BLE001
+                reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            power = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+            self.samples.append((time.perf_counter(), sm, reasons, power))
+        except Exception as e:  # noqa: BLE001
+            self.error = repr(e)
+
+    def _run(self):
+        # NVML queries contend with CUDA API calls for driver locks: a fast poll slows the step
+        # being measured several-fold, so the background poll is slow (4 Hz)
+        while not self._stop.is_set() and not self.error:
             self._stop.wait(self.period)
+            self.sample()
 
     def stop(self, t_from=None, t_to=None):
         """Summary of the samples taken in [t_from, t_to] (perf_counter clock)."""
@@ -279,6 +286,7 @@ def run_b200(args):
         step_device()
     barrier()
     t_timed0 = time.perf_counter()
+    sampler.sample()
     _capi.set_option("time_kernels", 0)
     _capi.set_option("time_kernels", 1)
     _capi.launch_count(reset=True)
@@ -291,6 +299,7 @@ def run_b200(args):
             stage_ms[name] = stage_ms.get(name, 0.0) + ms
     e1.record(stream)
     barrier()
+    sampler.sample()
     launches = _capi.launch_count()
     kstats = _capi.kernel_stats()
     _capi.set_option("time_kernels", 0)

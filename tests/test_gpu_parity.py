@@ -278,3 +278,51 @@ def test_determinism_two_builds_identical():
     for d in range(3):
         for which in range(6):
             assert np.array_equal(a.array(d, which), b.array(d, which))
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    from conftest import PKG, ROOT
+    for p in (PKG, ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import synth
+        from east import distributed, utils
+        docs = [synth.document(3000 + 1000 * (j % 4), 300 + j) for j in range(7)]
+        kps = [utils.prepare_text(k) for k in synth.keyphrases(9)]
+        full = distributed.relevance_table_sharded(docs, kps, True, device=rank)
+        np.save(os.path.join(out_dir, "rank%d.npy" % rank), full.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_multi_gpu_sharded_table_is_bit_identical(tmp_path):
+    """N > 1 (run with gpurun --gpus 2): documents sharded over ranks, one NCCL all-gather; the
+    gathered table equals the single-GPU table bit for bit (pure concatenation)."""
+    import socket
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import synth
+    from east import utils
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    docs = [synth.document(3000 + 1000 * (j % 4), 300 + j) for j in range(7)]
+    kps = [utils.prepare_text(k) for k in synth.keyphrases(9)]
+    capi = _capi()
+    cols = [utils.text_to_strings_collection(d) for d in docs]
+    idx = _build(cols)
+    codes, off = capi.pack_keyphrases(kps)
+    expect = idx.score_table(codes, off, True)
+    for r in range(2):
+        got = np.load(str(tmp_path / ("rank%d.npy" % r)))
+        assert np.array_equal(got.view(np.uint64), expect.view(np.uint64))
