@@ -221,7 +221,7 @@ int east_kernel_stats(char *names, int32_t names_cap, double *ms, int64_t *launc
 static void free_index(east_index *idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
-    if (idx->owns_text && idx->text) cudaFree(idx->text);
+    if (idx->owns_text && idx->text) cudaFreeAsync(idx->text, 0);
     for (void *p : {(void *)idx->d_doc_off, (void *)idx->d_doc_m, (void *)idx->sa, (void *)idx->lcp,
                     (void *)idx->up, (void *)idx->down, (void *)idx->next, (void *)idx->ann, (void *)idx->t8,
                     (void *)idx->bkt})
@@ -302,16 +302,11 @@ int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t 
     check_build_args(text, doc_off, doc_m, n_docs, out);
     use_device(device);
     const size_t bytes = sizeof(uint32_t) * (size_t)doc_off[n_docs];
-    uint32_t *d_text = nullptr;
-    EAST_CUDA(cudaMalloc(&d_text, bytes));
-    cudaError_t e = cudaMemcpy(d_text, text, bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d_text); throw Error(EAST_ERR_CUDA, cudaGetErrorString(e)); }
-    try {
-        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out);
-    } catch (...) {
-        // build_common's unique_ptr already released everything it owned, including the text
-        throw;
-    }
+    // stream-ordered pool allocation (cudaMalloc/cudaFree take device-wide locks and synchronise)
+    uint32_t *d_text = (uint32_t *)dev_alloc(bytes, 0);
+    cudaError_t e = cudaMemcpyAsync(d_text, text, bytes, cudaMemcpyHostToDevice, 0);
+    if (e != cudaSuccess) { dev_free(d_text, 0); throw Error(EAST_ERR_CUDA, cudaGetErrorString(e)); }
+    build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out);  // owns d_text from here on
     EAST_API_END
 }
 

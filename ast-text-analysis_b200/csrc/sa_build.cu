@@ -231,21 +231,42 @@ struct KeyParams {
     uint32_t term;   // fast path: terminator class code; general: 0xffffffff
 };
 
-// fast path: byte codes
+// 8 consecutive byte codes (first symbol in the lowest byte) -> one field of 8*b bits with the
+// first symbol most significant: three SWAR merge steps instead of eight shift-or steps.
+__device__ __forceinline__ uint64_t pack8(uint64_t x, int b) {
+    x = ((x & 0x00ff00ff00ff00ffull) << b) | ((x >> 8) & 0x00ff00ff00ff00ffull);
+    x = ((x & 0x0000ffff0000ffffull) << (2 * b)) | ((x >> 16) & 0x0000ffff0000ffffull);
+    return ((x & 0x00000000ffffffffull) << (4 * b)) | (x >> 32);
+}
+
+// 8 bytes of shared memory starting at an arbitrary byte offset (two aligned 64-bit loads)
+__device__ __forceinline__ uint64_t lds8(const uint8_t *base, int o) {
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(base + (o & ~7));
+    const int sh = (o & 7) * 8;
+    const uint64_t lo = q[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (q[1] << (64 - sh));
+}
+
+// fast path: byte codes.  The window of kc symbols is packed 8 symbols at a time; everything
+// after the first terminator of the window is cleared (SWAR zero-byte search for its position).
 __global__ void __launch_bounds__(KG_THREADS)
 k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, const int32_t *__restrict__ doc_off, int D,
                KeyParams kp, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                uint32_t *g_hist) {
     __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
-    __shared__ __align__(16) uint8_t s_t[KG_TILE + KG_HALO];
+    __shared__ __align__(16) uint8_t s_t[KG_TILE + KG_HALO + 16];
     __shared__ int s_dlo, s_dhi;
     for (int i = threadIdx.x; i < kp.passes * 256; i += blockDim.x) s_hist[i] = 0;
     const int num_tiles = (n + KG_TILE - 1) / KG_TILE;
+    const int b = kp.b, kc = kp.kc;
+    const int groups = (kc + 7) >> 3, rem = kc - 8 * (groups - 1);  // symbols taken from the last group
+    const uint64_t term8 = 0x0101010101010101ull * (uint64_t)kp.term;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int32_t base = tile * KG_TILE;
         __syncthreads();
         // stage the tile (+halo) of byte codes; 128-bit loads where fully in range
-        for (int o = threadIdx.x * 16; o < KG_TILE + KG_HALO; o += blockDim.x * 16) {
+        for (int o = threadIdx.x * 16; o < KG_TILE + KG_HALO + 16; o += blockDim.x * 16) {
             int64_t g = (int64_t)base + o;
             if (g + 16 <= n) {
                 *reinterpret_cast<uint4 *>(s_t + o) = *reinterpret_cast<const uint4 *>(T8 + g);
@@ -257,7 +278,7 @@ k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, const int32_t *__restr
         if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, min(base + KG_TILE, n) - 1);
         __syncthreads();
         const int dlo = s_dlo, dhi = s_dhi;
-#pragma unroll 1
+#pragma unroll 2
         for (int it = 0; it < KG_ITEMS; ++it) {
             const int o = it * KG_THREADS + threadIdx.x;
             const int32_t i = base + o;
@@ -269,13 +290,20 @@ k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, const int32_t *__restr
                     int mid = (lo + hi + 1) >> 1;
                     if (__ldg(doc_off + mid) <= i) lo = mid; else hi = mid - 1;
                 }
-                key = (uint64_t)lo;
-                bool cut = false;
-                for (int c = 0; c < kp.kc; ++c) {
-                    uint32_t sym = cut ? 0u : (uint32_t)s_t[o + c];
-                    key = (key << kp.b) | sym;
-                    if (sym == kp.term) cut = true;
+                int tpos = kc;  // window offset of the first terminator (kc = none)
+                for (int gq = 0; gq < groups; ++gq) {
+                    const uint64_t x = lds8(s_t, o + 8 * gq);
+                    if (tpos == kc) {
+                        const uint64_t t = x ^ term8;
+                        const uint64_t z = (t - 0x0101010101010101ull) & ~t & 0x8080808080808080ull;
+                        if (z) tpos = min(kc, 8 * gq + ((__ffsll((long long)z) - 1) >> 3));
+                    }
+                    const uint64_t f = pack8(x, b);
+                    if (gq + 1 < groups) key = (key << (8 * b)) | f;
+                    else key = (key << (rem * b)) | (f >> ((8 - rem) * b));
                 }
+                if (tpos < kc - 1) key &= ~((1ull << (b * (kc - 1 - tpos))) - 1ull);
+                if (kc * b < 64) key |= (uint64_t)lo << (kc * b);
                 keys[i] = key;
                 vals[i] = (uint32_t)i;
             }
@@ -432,26 +460,44 @@ k_rerank(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
     if (lane == 0) thread_excl = RRState{0u, 0u};
     thread_excl = rr_op(wbase, thread_excl);
 
-    if (t == RR_THREADS - 1) {
-        RRState agg = rr_op(wbase, x);  // tile aggregate
+    // ---- decoupled look-back by the LAST WARP: each lane inspects one predecessor tile, so a
+    // window of 32 status words costs one round trip (a single thread walking them one by one was
+    // 45 % of this kernel's stall samples)
+    if (w == RR_THREADS / 32 - 1) {
+        const RRState mine = rr_op(wbase, x);  // lane 31: the tile aggregate
+        const RRState agg{__shfl_sync(0xffffffffu, mine.mx, 31), __shfl_sync(0xffffffffu, mine.sum, 31)};
         RRState excl{0u, 0u};
         if (tile == 0) {
-            status[tile] = rr_pack(agg, RR_FLAG_PREFIX);
+            if (lane == 31) status[0] = rr_pack(agg, RR_FLAG_PREFIX);
         } else {
-            status[tile] = rr_pack(agg, RR_FLAG_AGG);
-            int64_t prev = (int64_t)tile - 1;
+            if (lane == 31) status[tile] = rr_pack(agg, RR_FLAG_AGG);
+            int64_t win = (int64_t)tile - 1;
             while (true) {
-                uint64_t sv = status[prev];
-                uint64_t flag = sv & (3ull << 62);
-                if (flag == 0) continue;
-                excl = rr_op(rr_unpack(sv), excl);
-                if (flag == RR_FLAG_PREFIX) break;
-                --prev;
+                const int64_t idx = win - lane;
+                uint64_t sv = 2ull << 62;  // before tile 0: an empty inclusive prefix
+                if (idx >= 0) sv = status[idx];
+                const unsigned flag = (unsigned)(sv >> 62);
+                const unsigned ready = __ballot_sync(0xffffffffu, flag != 0u);
+                const unsigned pref = __ballot_sync(0xffffffffu, flag == 2u);
+                const int first_pref = pref ? (__ffs(pref) - 1) : 31;
+                const unsigned need = (first_pref == 31) ? 0xffffffffu : ((2u << first_pref) - 1u);
+                if ((ready & need) != need) continue;  // a needed predecessor has not published yet
+                RRState r = (lane <= first_pref) ? rr_unpack(sv) : RRState{0u, 0u};
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    RRState y{__shfl_xor_sync(0xffffffffu, r.mx, o), __shfl_xor_sync(0xffffffffu, r.sum, o)};
+                    r = rr_op(r, y);
+                }
+                excl = rr_op(excl, r);
+                if (pref) break;
+                win -= 32;
             }
-            status[tile] = rr_pack(rr_op(excl, agg), RR_FLAG_PREFIX);
+            if (lane == 31) status[tile] = rr_pack(rr_op(excl, agg), RR_FLAG_PREFIX);
         }
-        s_prefix = excl;
-        if ((int64_t)(tile + 1) * RR_TILE >= n_act) out_counts[0] = excl.sum + agg.sum;
+        if (lane == 31) {
+            s_prefix = excl;
+            if ((int64_t)(tile + 1) * RR_TILE >= n_act) out_counts[0] = excl.sum + agg.sum;
+        }
     }
     __syncthreads();
     const RRState pre = rr_op(s_prefix, thread_excl);

@@ -109,9 +109,8 @@ k_min32(const int32_t *__restrict__ in, int32_t n_in, int32_t *__restrict__ out,
 }
 
 // largest q < p with lcp[q] <= l.  Exists: the first rank of the document has lcp 0.
-__device__ __forceinline__ int32_t prev_le(const MinPyramid &M, int32_t p, int32_t l) {
-    int32_t idx = p;
-    int level = 0;
+__device__ __forceinline__ int32_t prev_le(const MinPyramid &M, int32_t p, int32_t l, int level = 0) {
+    int32_t idx = p;  // index AT `level` of the group that contains the query rank
     int32_t j;
     while (true) {
         const int32_t gs = idx & ~31;
@@ -134,9 +133,8 @@ found:
 }
 
 // smallest e > p with lcp[e] < l, or n if there is none
-__device__ __forceinline__ int32_t next_lt(const MinPyramid &M, int32_t p, int32_t l, int32_t n) {
-    int32_t idx = p;
-    int level = 0;
+__device__ __forceinline__ int32_t next_lt(const MinPyramid &M, int32_t p, int32_t l, int32_t n, int level = 0) {
+    int32_t idx = p;  // index AT `level` of the group that contains the query rank
     int32_t j;
     while (true) {
         const int32_t ge = min((idx | 31) + 1, M.size[level]);
@@ -201,6 +199,110 @@ k_child_ann(MinPyramid M, const int32_t *__restrict__ doc_off, const int32_t *__
     }
 }
 
+// Warp-cooperative version: one warp owns 32 consecutive ranks = one level-0 group of the pyramid.
+// PSE/NSV inside the group are found with 32 shuffle rounds (no divergence); ranks whose neighbour
+// lies outside the group look at the 32 level-1 minima of the enclosing 1024-rank block, again by
+// shuffles over one coalesced row; only what is still unresolved falls back to the per-thread
+// pyramid search from level 2.
+__global__ void __launch_bounds__(TB_THREADS)
+k_child_ann_warp(MinPyramid M, const int32_t *__restrict__ doc_off, const int32_t *__restrict__ doc_m, int D,
+                 int32_t n, int32_t *__restrict__ up, int32_t *__restrict__ down, int32_t *__restrict__ next,
+                 int32_t *__restrict__ ann) {
+    __shared__ int s_dlo, s_dhi;
+    const int32_t *__restrict__ lcp = M.lv[0];
+    const int32_t *__restrict__ lv1 = M.lv[1];
+    const int32_t size1 = M.size[1];
+    const int lane = threadIdx.x & 31;
+    const int32_t INF = 0x7fffffff;
+    const int64_t stride = (int64_t)gridDim.x * TB_THREADS;
+    for (int64_t base = (int64_t)blockIdx.x * TB_THREADS; base < n; base += stride) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, (int32_t)base);
+        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, (int32_t)min(base + TB_THREADS, (int64_t)n) - 1);
+        __syncthreads();
+        const int32_t p = (int32_t)(base + threadIdx.x);
+        const bool valid = p < n;
+        int32_t start = 0, end = 0, dsel = 0;
+        if (valid) {
+            int lo = s_dlo, hi = s_dhi;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (__ldg(doc_off + mid) <= p) lo = mid; else hi = mid - 1;
+            }
+            dsel = lo;
+            start = __ldg(doc_off + lo); end = __ldg(doc_off + lo + 1);
+        }
+        const int32_t g = p >> 5;            // level-1 index of this warp's group (uniform in the warp)
+        const int32_t v = valid ? lcp[p] : INF;
+        // ---- inside the group
+        int pse = -1, nsv = -1;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int32_t vj = __shfl_sync(0xffffffffu, v, j);
+            if (j < lane && vj <= v) pse = j;
+            if (j > lane && nsv < 0 && vj < v) nsv = j;
+        }
+        const bool is_root = valid && p == start;
+        if (is_root) ann[p] = (end - start) - __ldg(doc_m + dsel);
+        const bool active = valid && !is_root;
+        int32_t q = (pse >= 0) ? (g << 5) + pse : -1;
+        // ---- level-1 row of the enclosing 1024-rank block (one coalesced load per warp)
+        const int32_t gs1 = g & ~31, gi = g & 31;
+        const int32_t row = (gs1 + lane < size1) ? __ldg(lv1 + gs1 + lane) : INF;
+        if (__any_sync(0xffffffffu, active && q < 0)) {
+            int cand = -1;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int32_t mj = __shfl_sync(0xffffffffu, row, j);
+                if (j < gi && mj <= v) cand = j;
+            }
+            if (active && q < 0) {
+                if (cand >= 0) {
+                    int32_t c = ((gs1 + cand) << 5) + 31;
+                    while (lcp[c] > v) --c;
+                    q = c;
+                } else {
+                    q = prev_le(M, g >> 5, v, 2);
+                }
+            }
+        }
+        int32_t lq = 0;
+        bool first = false;
+        if (active) {
+            lq = lcp[q];
+            if (lq == v) next[q] = p - start;
+            else first = true;  // p is the first l-index of [q .. e-1]
+        }
+        // ---- NSV for the first l-indices
+        int32_t e = (nsv >= 0) ? (g << 5) + nsv : -1;
+        if (__any_sync(0xffffffffu, first && e < 0)) {
+            int cand = -1;
+#pragma unroll
+            for (int j = 31; j >= 0; --j) {
+                const int32_t mj = __shfl_sync(0xffffffffu, row, j);
+                if (j > gi && mj < v) cand = j;
+            }
+            if (first && e < 0) {
+                if (cand >= 0) {
+                    int32_t c = (gs1 + cand) << 5;
+                    while (lcp[c] >= v) ++c;
+                    e = c;
+                } else {
+                    e = next_lt(M, g >> 5, v, n, 2);
+                }
+            }
+        }
+        if (first) {
+            ann[p] = e - q;
+            if (e < end) {
+                const int32_t le = lcp[e];
+                if (lq <= le) up[e] = p - start;
+                if (le <= lq) down[q] = p - start;
+            }
+        }
+    }
+}
+
 void build_lcp_tables(const uint32_t *text, const uint8_t *t8, int term_code, const int32_t *sa, const int32_t *doc_off, const int32_t *doc_m,
                       int n_docs, int32_t n, int32_t *lcp, int32_t *up, int32_t *down, int32_t *next,
                       int32_t *ann, StageTimer &tm, cudaStream_t s) {
@@ -245,8 +347,13 @@ void build_lcp_tables(const uint32_t *text, const uint8_t *t8, int term_code, co
     EAST_CUDA(cudaMemsetAsync(next, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_CUDA(cudaMemsetAsync(ann, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_BYTES(8.0 * n);   // LCP in; annotation + child entries out (sparse)
-    EAST_LAUNCH(k_child_ann, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, M, doc_off, doc_m, n_docs, n,
-                up, down, next, ann);
+    if (levels >= 3) {
+        EAST_LAUNCH(k_child_ann_warp, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, M, doc_off, doc_m, n_docs, n,
+                    up, down, next, ann);
+    } else {  // fewer than 1025 ranks: the plain per-thread pyramid search
+        EAST_LAUNCH(k_child_ann, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, M, doc_off, doc_m, n_docs, n,
+                    up, down, next, ann);
+    }
 }
 
 }  // namespace east

@@ -241,18 +241,27 @@ def run_b200(args):
     host_out_np = host_out.numpy().reshape(D, K)
     torch.cuda.synchronize()
 
+    debug = bool(os.environ.get("EAST_BENCH_DEBUG"))
+
     def step_device():
+        ta = time.perf_counter()
         idx = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank,
                                           stream=stream.cuda_stream)
+        tb = time.perf_counter()
         idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
+        tc = time.perf_counter()
         if world > 1:
             dist.all_gather_into_tensor(gathered, out_dev)
+            if debug:
+                torch.cuda.synchronize()
+        td = time.perf_counter()
         timings = idx.build_timings + idx.score_timings
         info = idx.info()
         idx.close()
+        if debug:
+            sys.stderr.write("[rank %d] dev step: build %.2f ms, score %.2f ms, gather %.2f ms, close %.2f ms\n" % (
+                rank, (tb - ta) * 1e3, (tc - tb) * 1e3, (td - tc) * 1e3, (time.perf_counter() - td) * 1e3))
         return timings, info
-
-    debug = bool(os.environ.get("EAST_BENCH_DEBUG"))
 
     def step_e2e():
         ta = time.perf_counter()
