@@ -274,7 +274,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         idx->bkt = so.bkt.p; so.bkt.p = nullptr;
         idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
         build_lcp_tables(idx->text, idx->t8, idx->term_code, idx->sa, idx->d_doc_off, idx->d_doc_m, n_docs, n, idx->lcp, idx->up,
-                         idx->down, idx->next, idx->ann, tm, s);
+                         idx->down, idx->next, idx->ann, tm, s, (int)get_option("child_variant", 0));
         tm.finish();
     }
     EAST_CUDA(cudaStreamSynchronize(s));

@@ -37,12 +37,18 @@ static inline size_t rs_scratch_bytes(int64_t n, int passes) {
 
 // Accumulate the digits of one key into a CTA-private histogram s_hist[passes][256].
 // Warp-uniform digits (document id bits, high rank bits) are folded into one atomic.
-__device__ __forceinline__ void rs_hist_add(uint32_t *s_hist, uint64_t key, int passes, bool valid) {
+// Digits below `uniform_from` are known to be spread (text symbols): plain atomics, no vote.
+__device__ __forceinline__ void rs_hist_add(uint32_t *s_hist, uint64_t key, int passes, bool valid,
+                                            int uniform_from = 0) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int p = 0; p < passes; ++p) {
         unsigned d = (unsigned)(key >> (8 * p)) & 255u;
+        if (p < uniform_from) {
+            if (valid) atomicAdd(&s_hist[p * 256 + d], 1u);
+            continue;
+        }
         unsigned d0 = __shfl_sync(full, d, 0);
         if (__all_sync(full, valid && d == d0)) {
             if (lane == 0) atomicAdd(&s_hist[p * 256 + d0], 32u);

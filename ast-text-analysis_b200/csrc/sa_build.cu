@@ -307,7 +307,7 @@ k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, const int32_t *__restr
                 keys[i] = key;
                 vals[i] = (uint32_t)i;
             }
-            rs_hist_add(s_hist, key, kp.passes, valid);
+            rs_hist_add(s_hist, key, kp.passes, valid, (kc * b) >> 3);
         }
     }
     __syncthreads();
@@ -413,10 +413,26 @@ k_rerank(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
 
     uint64_t k[RR_ITEMS + 2];  // k[0] = predecessor, k[RR_ITEMS+1] = successor
     bool head[RR_ITEMS + 1];
+    if (base + RR_ITEMS <= n_act) {
+        // full thread chunk: 128-bit loads of the 8 own keys; the neighbours' edge keys come from
+        // the adjacent lanes (only warp-edge lanes touch global memory again)
 #pragma unroll
-    for (int j = 0; j < RR_ITEMS + 2; ++j) {
-        int64_t a = base + j - 1;
-        k[j] = (a >= 0 && a < n_act) ? keys[a] : 0ull;
+        for (int j = 0; j < RR_ITEMS; j += 2) {
+            const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(keys + base + j);
+            k[j + 1] = kk.x; k[j + 2] = kk.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 1; j <= RR_ITEMS; ++j) {
+            int64_t a = base + j - 1;
+            k[j] = (a < n_act) ? keys[a] : 0ull;
+        }
+    }
+    {
+        const uint64_t from_prev = __shfl_up_sync(0xffffffffu, k[RR_ITEMS], 1);
+        const uint64_t from_next = __shfl_down_sync(0xffffffffu, k[1], 1);
+        k[0] = (lane > 0) ? from_prev : ((base - 1 >= 0 && base - 1 < n_act) ? keys[base - 1] : 0ull);
+        k[RR_ITEMS + 1] = (lane < 31) ? from_next : ((base + RR_ITEMS < n_act) ? keys[base + RR_ITEMS] : 0ull);
     }
     // head[j] describes element base+j (j = RR_ITEMS: the successor, for singleton detection)
 #pragma unroll
@@ -501,15 +517,33 @@ k_rerank(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
     }
     __syncthreads();
     const RRState pre = rr_op(s_prefix, thread_excl);
+    uint32_t vv[RR_ITEMS], ss[RR_ITEMS];
+    const bool full = base + RR_ITEMS <= n_act;
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < RR_ITEMS; j += 4) {
+            const uint4 q4 = *reinterpret_cast<const uint4 *>(vals + base + j);
+            vv[j] = q4.x; vv[j + 1] = q4.y; vv[j + 2] = q4.z; vv[j + 3] = q4.w;
+            if (!ROUND0) {
+                const uint4 s4 = *reinterpret_cast<const uint4 *>(slots + base + j);
+                ss[j] = s4.x; ss[j + 1] = s4.y; ss[j + 2] = s4.z; ss[j + 3] = s4.w;
+            }
+        }
+        if (ROUND0) {  // SA slot == position in the sorted order: two 128-bit stores per thread
+#pragma unroll
+            for (int j = 0; j < RR_ITEMS; j += 4)
+                *reinterpret_cast<int4 *>(sa + base + j) = make_int4((int)vv[j], (int)vv[j + 1], (int)vv[j + 2], (int)vv[j + 3]);
+        }
+    }
 #pragma unroll
     for (int j = 0; j < RR_ITEMS; ++j) {
         int64_t a = base + j;
         if (a >= n_act) break;
         RRState inc = rr_op(pre, loc[j]);
-        uint32_t v = vals[a];
-        uint32_t slot = ROUND0 ? (uint32_t)a : slots[a];
+        uint32_t v = full ? vv[j] : vals[a];
+        uint32_t slot = ROUND0 ? (uint32_t)a : (full ? ss[j] : slots[a]);
         uint32_t r = ROUND0 ? inc.mx : slots[inc.mx];
-        sa[slot] = (int32_t)v;
+        if (!(ROUND0 && full)) sa[slot] = (int32_t)v;
         rank[v] = r;
         bool keep = !(head[j] && head[j + 1]);
         if (keep) {

@@ -38,7 +38,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
 // (easa.py:306-331) of the whole batch
 void build_lcp_tables(const uint32_t *text, const uint8_t *t8 /*or null*/, int term_code, const int32_t *sa, const int32_t *doc_off, const int32_t *doc_m,
                       int n_docs, int32_t n, int32_t *lcp, int32_t *up, int32_t *down, int32_t *next,
-                      int32_t *ann, StageTimer &tm, cudaStream_t s);
+                      int32_t *ann, StageTimer &tm, cudaStream_t s, int child_variant = 0);
 
 // batched scorer (easa.py:91-139)
 struct ScoreInput {

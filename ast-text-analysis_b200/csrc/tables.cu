@@ -30,6 +30,21 @@ namespace east {
 constexpr int TB_THREADS = 256;
 constexpr int MAX_LEVELS = 8;  // 32^7 > 2^30
 
+// Document of rank/position x for the lanes of one warp that hold 32 consecutive x: lane 0 and
+// lane 31 binary-search the whole table once, every lane then searches only [d_first, d_last]
+// (0-1 steps for real collections).  No shared memory, no block barrier.
+__device__ __forceinline__ int warp_doc_of(const int32_t *__restrict__ doc_off, int D, int64_t x, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    int d = 0;
+    if (lane == 0 || lane == 31) d = doc_of(doc_off, D, (int32_t)min(x, n - 1));
+    int lo = __shfl_sync(0xffffffffu, d, 0), hi = __shfl_sync(0xffffffffu, d, 31);
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(doc_off + mid) <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
 struct MinPyramid {
     const int32_t *lv[MAX_LEVELS];  // lv[0] = lcp
     int32_t size[MAX_LEVELS];
@@ -54,21 +69,12 @@ __global__ void __launch_bounds__(TB_THREADS)
 k_lcp(const uint32_t *__restrict__ T, const uint8_t *__restrict__ T8, uint64_t term8,
       const int32_t *__restrict__ sa, const int32_t *__restrict__ doc_off,
       int D, int32_t n, int32_t *__restrict__ lcp, int32_t *__restrict__ min1) {
-    __shared__ int s_dlo, s_dhi;
     const int64_t stride = (int64_t)gridDim.x * TB_THREADS;
     for (int64_t base = (int64_t)blockIdx.x * TB_THREADS; base < n; base += stride) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, (int32_t)base);
-        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, (int32_t)min(base + TB_THREADS, (int64_t)n) - 1);
-        __syncthreads();
         const int64_t r = base + threadIdx.x;
         int32_t h = 0x7fffffff;
+        const int lo = warp_doc_of(doc_off, D, r, n);
         if (r < n) {
-            int lo = s_dlo, hi = s_dhi;
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if (__ldg(doc_off + mid) <= r) lo = mid; else hi = mid - 1;
-            }
             const int32_t start = __ldg(doc_off + lo), end = __ldg(doc_off + lo + 1);
             h = 0;
             if (r > start) {
@@ -160,21 +166,12 @@ __global__ void __launch_bounds__(TB_THREADS)
 k_child_ann(MinPyramid M, const int32_t *__restrict__ doc_off, const int32_t *__restrict__ doc_m, int D,
             int32_t n, int32_t *__restrict__ up, int32_t *__restrict__ down, int32_t *__restrict__ next,
             int32_t *__restrict__ ann) {
-    __shared__ int s_dlo, s_dhi;
     const int32_t *__restrict__ lcp = M.lv[0];
     const int64_t stride = (int64_t)gridDim.x * TB_THREADS;
     for (int64_t base = (int64_t)blockIdx.x * TB_THREADS; base < n; base += stride) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, (int32_t)base);
-        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, (int32_t)min(base + TB_THREADS, (int64_t)n) - 1);
-        __syncthreads();
         const int32_t p = (int32_t)(base + threadIdx.x);
+        const int lo = warp_doc_of(doc_off, D, base + threadIdx.x, n);
         if (p >= n) continue;
-        int lo = s_dlo, hi = s_dhi;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (__ldg(doc_off + mid) <= p) lo = mid; else hi = mid - 1;
-        }
         const int32_t start = __ldg(doc_off + lo), end = __ldg(doc_off + lo + 1);
         if (p == start) {
             ann[p] = (end - start) - __ldg(doc_m + lo);
@@ -208,7 +205,6 @@ __global__ void __launch_bounds__(TB_THREADS)
 k_child_ann_warp(MinPyramid M, const int32_t *__restrict__ doc_off, const int32_t *__restrict__ doc_m, int D,
                  int32_t n, int32_t *__restrict__ up, int32_t *__restrict__ down, int32_t *__restrict__ next,
                  int32_t *__restrict__ ann) {
-    __shared__ int s_dlo, s_dhi;
     const int32_t *__restrict__ lcp = M.lv[0];
     const int32_t *__restrict__ lv1 = M.lv[1];
     const int32_t size1 = M.size[1];
@@ -216,19 +212,11 @@ k_child_ann_warp(MinPyramid M, const int32_t *__restrict__ doc_off, const int32_
     const int32_t INF = 0x7fffffff;
     const int64_t stride = (int64_t)gridDim.x * TB_THREADS;
     for (int64_t base = (int64_t)blockIdx.x * TB_THREADS; base < n; base += stride) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, (int32_t)base);
-        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, (int32_t)min(base + TB_THREADS, (int64_t)n) - 1);
-        __syncthreads();
         const int32_t p = (int32_t)(base + threadIdx.x);
         const bool valid = p < n;
         int32_t start = 0, end = 0, dsel = 0;
+        const int lo = warp_doc_of(doc_off, D, base + threadIdx.x, n);
         if (valid) {
-            int lo = s_dlo, hi = s_dhi;
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if (__ldg(doc_off + mid) <= p) lo = mid; else hi = mid - 1;
-            }
             dsel = lo;
             start = __ldg(doc_off + lo); end = __ldg(doc_off + lo + 1);
         }
@@ -305,7 +293,7 @@ k_child_ann_warp(MinPyramid M, const int32_t *__restrict__ doc_off, const int32_
 
 void build_lcp_tables(const uint32_t *text, const uint8_t *t8, int term_code, const int32_t *sa, const int32_t *doc_off, const int32_t *doc_m,
                       int n_docs, int32_t n, int32_t *lcp, int32_t *up, int32_t *down, int32_t *next,
-                      int32_t *ann, StageTimer &tm, cudaStream_t s) {
+                      int32_t *ann, StageTimer &tm, cudaStream_t s, int child_variant) {
     // pyramid storage: sizes n/32, n/1024, ...
     MinPyramid M;
     M.lv[0] = lcp;
@@ -347,7 +335,7 @@ void build_lcp_tables(const uint32_t *text, const uint8_t *t8, int term_code, co
     EAST_CUDA(cudaMemsetAsync(next, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_CUDA(cudaMemsetAsync(ann, 0, sizeof(int32_t) * (size_t)n, s));
     EAST_BYTES(8.0 * n);   // LCP in; annotation + child entries out (sparse)
-    if (levels >= 3) {
+    if (levels >= 3 && child_variant == 1) {
         EAST_LAUNCH(k_child_ann_warp, grid_for(n, TB_THREADS, 16), TB_THREADS, 0, s, M, doc_off, doc_m, n_docs, n,
                     up, down, next, ann);
     } else {  // fewer than 1025 ranks: the plain per-thread pyramid search

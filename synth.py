@@ -65,3 +65,38 @@ def packed_collection(n_docs, n_bytes, first_seed=1):
     cols = [utils.text_to_strings_collection(d) for d in documents(n_docs, n_bytes, first_seed)]
     packed = [asts_utils.pack_strings_collection(c) for c in cols]
     return packed, [len(c) for c in cols], cols
+
+
+def packed_big_document(n_bytes, seed=1, v=V):
+    """Packed form (uint32 code points + terminators, string count m) of a synthetic document of
+    ~n_bytes, built with numpy only -- the same result as
+    pack_strings_collection(text_to_strings_collection(text)) for a text made of whole vocabulary
+    words (every word has 3..10 letters, so the token filter of utils.py:63 drops nothing), but
+    without materialising tens of millions of Python strings.  Returns (packed, m, text_bytes)."""
+    words, cdf, lengths = vocabulary(v)
+    rng = np.random.default_rng(seed)
+    mean_len = float((lengths * np.diff(np.concatenate([[0.0], cdf]))).sum()) + 1.0
+    count = max(1, int(n_bytes / mean_len))
+    ids = np.searchsorted(cdf, rng.random(count), side="right")
+    wl = lengths[ids].astype(np.int64)
+    # flat upper-case code points of the chosen words
+    vocab_codes = np.frombuffer("".join(words).upper().encode("ascii"), dtype=np.uint8)
+    vocab_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    total_chars = int(wl.sum())
+    word_start_out = np.concatenate([[0], np.cumsum(wl)[:-1]])
+    idx = np.arange(total_chars, dtype=np.int64)
+    word_of = np.repeat(np.arange(count, dtype=np.int64), wl)
+    src = vocab_off[ids][word_of] + (idx - word_start_out[word_of])
+    chars = vocab_codes[src].astype(np.uint32)
+    # strings = groups of 3 consecutive words (utils.py:66-73)
+    m = (count + 2) // 3
+    str_len = np.add.reduceat(wl, np.arange(0, count, 3))
+    n = total_chars + m
+    term_pos = np.cumsum(str_len + 1) - 1
+    out = np.empty(n, dtype=np.uint32)
+    is_char = np.ones(n, dtype=bool)
+    is_char[term_pos] = False
+    out[is_char] = chars
+    out[term_pos] = 0x0A00 + np.arange(m, dtype=np.uint32)
+    text_bytes = total_chars + count - 1  # words joined by single spaces
+    return out, int(m), int(text_bytes), ids
