@@ -1,0 +1,201 @@
+// cooc_tc.cu -- keyphrase co-occurrence counts C = B * B^T on the 5th-generation tensor cores.
+//
+// Replaces the K^2 Python set intersections of applications.keyphrases_graph
+// (east/applications.py:111-113, 136-147):  B[k][d] = (S[d][k] >= threshold) in {0,1},
+// C[i][j] = sum_d B[i][d] * B[j][d] = |T_i & T_j|, support[k] = C[k][k].
+//
+// The one GEMM-shaped piece of the hot path (north_star).  Hand-written tcgen05:
+//   * k_threshold_bytes  : S (fp64, doc-major) -> B as uint8 0/1, keyphrase-major (K-major operand
+//                          for both sides of B * B^T), padded to multiples of 128 with zeros;
+//   * k_cooc_umma        : one CTA per 128 x 128 tile of C.  Per 128-byte slice of the document
+//                          dimension the CTA stages the two 128 x 128-byte operand tiles in shared
+//                          memory in the canonical K-major / no-swizzle core-matrix layout
+//                          (8 rows x 16 bytes = 128 contiguous bytes; LBO = 128 B between core matrices
+//                          along K, SBO = 1024 B between 8-row groups), one elected thread issues
+//                          four tcgen05.mma.kind::i8 (M=128, N=128, K=32, u8 x u8 -> s32) that
+//                          accumulate in TMEM, and tcgen05.commit signals an mbarrier so the
+//                          two-stage shared-memory ring can be refilled while the MMAs run.
+//                          Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> int32 stores.
+// Counts are exact: u8 products accumulated in int32 (D < 2^31).
+#include "sa_build.h"
+
+namespace east {
+
+constexpr int CT_TILE = 128;      // M = N = 128
+constexpr int CT_BK = 128;        // bytes of the reduction dimension per stage
+constexpr int CT_THREADS = 128;
+constexpr int CT_STAGE_BYTES = 2 * CT_TILE * CT_BK;  // A tile + B tile = 32 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4)        // start address, 16-byte units
+           | ((uint64_t)(128 >> 4) << 16)              // leading byte offset: next core matrix along K
+           | ((uint64_t)(1024 >> 4) << 32)             // stride byte offset: next 8-row group
+           | (1ull << 46);                             // descriptor version 1 (sm_100)
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// S[d][k] >= thr  ->  Bm[k][d] (uint8), 32 x 32 transposing tiles through shared memory
+__global__ void __launch_bounds__(256)
+k_threshold_bytes(const double *__restrict__ S, int64_t D, int32_t K, double thr, uint8_t *__restrict__ Bm,
+                  int64_t Dp) {
+    __shared__ uint8_t tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t d0 = (int64_t)blockIdx.x * 32;
+    const int32_t k0 = blockIdx.y * 32;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t d = d0 + r;
+        const int32_t k = k0 + tx;
+        tile[r][tx] = (d < D && k < K && S[d * K + k] >= thr) ? 1 : 0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int32_t k = k0 + r;
+        const int64_t d = d0 + tx;
+        if (k < K && d < Dp) Bm[(int64_t)k * Dp + d] = tile[tx][r];
+    }
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 1)
+k_cooc_umma(const uint8_t *__restrict__ Bm, int64_t Dp, int32_t Kp, int32_t K, int32_t *__restrict__ C) {
+    extern __shared__ __align__(1024) uint8_t ct_smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_tmem;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int32_t i0 = blockIdx.y * CT_TILE, j0 = blockIdx.x * CT_TILE;
+
+    if (warp == 0) {
+        // 128 TMEM columns x 128 lanes of 32-bit accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (t == 32) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = s32, A = B = u8, K-major, N = 128, M = 128
+    const uint32_t idesc = (2u << 4) | ((uint32_t)(CT_TILE >> 3) << 17) | ((uint32_t)(CT_TILE >> 4) << 24);
+    const int chunks = (int)(Dp / CT_BK);
+
+    for (int c = 0; c < chunks; ++c) {
+        const int s = c & 1;
+        uint8_t *sa = ct_smem + s * CT_STAGE_BYTES;
+        uint8_t *sb = sa + CT_TILE * CT_BK;
+        if (c >= 2) {  // the MMAs that read this stage two chunks ago must have finished
+            mbar_wait(smem_u32(&s_bar[s]), (uint32_t)(((c >> 1) - 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+        }
+        // stage A (rows i0..) and B (rows j0..): 16-byte pieces into the core-matrix layout
+        const int64_t col = (int64_t)c * CT_BK;
+#pragma unroll
+        for (int q = 0; q < (CT_TILE * CT_BK / 16) / CT_THREADS; ++q) {
+            const int piece = q * CT_THREADS + t;   // 0 .. 1023
+            const int r = piece >> 3, kc = piece & 7;  // row, 16-byte chunk along K
+            const uint32_t off = (uint32_t)((r >> 3) * 1024 + kc * 128 + (r & 7) * 16);
+            const uint4 va = *reinterpret_cast<const uint4 *>(Bm + (int64_t)(i0 + r) * Dp + col + kc * 16);
+            const uint4 vb = *reinterpret_cast<const uint4 *>(Bm + (int64_t)(j0 + r) * Dp + col + kc * 16);
+            *reinterpret_cast<uint4 *>(sa + off) = va;
+            *reinterpret_cast<uint4 *>(sb + off) = vb;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+        __syncthreads();
+        if (warp == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (lane == 0) {
+                const uint32_t a_base = smem_u32(sa), b_base = smem_u32(sb);
+#pragma unroll
+                for (int k = 0; k < CT_BK / 32; ++k) {  // K = 32 bytes per instruction = 2 core matrices
+                    const uint64_t da = umma_desc(a_base + k * 256), db = umma_desc(b_base + k * 256);
+                    const uint32_t accumulate = (c > 0 || k > 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+                        "}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                        : "memory");
+                }
+                // arrives on the stage's mbarrier when every MMA issued so far has completed
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[s]))
+                             : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    // all MMAs complete in order: wait for the commit of the last chunk
+    mbar_wait(smem_u32(&s_bar[(chunks - 1) & 1]), (uint32_t)(((chunks - 1) >> 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;");
+
+    // ---- epilogue: warp w owns TMEM lanes 32w..32w+31 = rows i0+32w.. of the tile
+    const int32_t row = i0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int cb = 0; cb < CT_TILE; cb += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < K) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int32_t colj = j0 + cb + q;
+                if (colj < K) C[(int64_t)row * K + colj] = (int32_t)v[q];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128));
+}
+
+void cooc_counts_tc(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s) {
+    const int64_t Dp = (D + CT_BK - 1) / CT_BK * CT_BK;
+    const int32_t Kp = (K + CT_TILE - 1) / CT_TILE * CT_TILE;
+    DevBuf<uint8_t> Bm((size_t)Kp * (size_t)Dp, s);
+    EAST_CUDA(cudaMemsetAsync(Bm.p, 0, (size_t)Kp * (size_t)Dp, s));  // padding rows / columns are zero
+    dim3 tg((unsigned)((Dp + 31) / 32), (unsigned)((K + 31) / 32));
+    EAST_BYTES(8.0 * (double)D * K + (double)K * Dp);
+    EAST_LAUNCH(k_threshold_bytes, tg, 256, 0, s, S_DxK, D, K, threshold, Bm.p, Dp);
+    static bool configured = false;
+    const int smem = 2 * CT_STAGE_BYTES + 1024;
+    if (!configured) {
+        EAST_CUDA(cudaFuncSetAttribute(k_cooc_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid(Kp / CT_TILE, Kp / CT_TILE);
+    EAST_LAUNCH(k_cooc_umma, grid, CT_THREADS, smem, s, Bm.p, Dp, Kp, K, C);
+}
+
+}  // namespace east

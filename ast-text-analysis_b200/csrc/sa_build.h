@@ -66,6 +66,7 @@ struct ScoreInput {
 void score_table(const ScoreInput &in, double *suffix_tmp /*n_docs x total_suffixes*/, double *out_DxK,
                  cudaStream_t s);
 
-void cooc_counts(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s);
+void cooc_counts(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s);     // AND + POPC
+void cooc_counts_tc(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s);  // tcgen05
 
 }  // namespace east

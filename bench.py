@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--doc-bytes", type=int, default=50000)
     ap.add_argument("--keyphrases", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="table", choices=["table", "single_doc"],
+                    help="table = BASELINE configs[1] (headline); single_doc = configs[2]: SA+LCP+annotation build "
+                         "throughput of ONE document of --doc-bytes (use 200000000), replicas only for N>1")
     ap.add_argument("--cpu-sample-docs", type=int, default=0, help="0 = 2 documents per host core (max 64)")
     return ap.parse_args()
 
@@ -396,8 +399,64 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_single_doc(args):
+    """BASELINE configs[2]: generalized SA + LCP + child table + annotation of one large document."""
+    import numpy as np
+    import torch
+    import synth
+    from east import _capi
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    packed, m, text_bytes, _ = synth.packed_big_document(args.doc_bytes, seed=3 + rank)
+    n = int(packed.size)
+    doc_off = np.array([0, n], dtype=np.int64)
+    doc_m = np.array([m], dtype=np.int32)
+    dev = torch.from_numpy(packed.view(np.int32)).cuda()
+    stream = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        _capi.DeviceIndex.build_dev(dev.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream).close()
+    torch.cuda.synchronize()
+    _capi.set_option("time_kernels", 0)
+    _capi.set_option("time_kernels", 1)
+    _capi.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    stage_ms = {}
+    for _ in range(args.steps):
+        idx = _capi.DeviceIndex.build_dev(dev.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream)
+        for name, ms in idx.build_timings:
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms
+        info = idx.info()
+        idx.close()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    kstats = _capi.kernel_stats()
+    launches = _capi.launch_count()
+    _capi.set_option("time_kernels", 0)
+    peak, peak_kind = load_peaks()
+    dom_name, dom = max(kstats.items(), key=lambda kv: kv[1]["ms"])
+    ach = dom["bytes"] / (dom["ms"] * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "suffix_array_build_MB_per_sec", "value": text_bytes / 1e6 / (ms_step * 1e-3), "unit": "MB/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "replicas only", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": "single document of %d text bytes: SA + LCP + child table + annotation (BASELINE configs[2])" % text_bytes,
+                   "n_codepoints": n, "strings": m},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": None, "peak_source": peak_kind, "launches_per_step": dom["launches"] / args.steps},
+        "breakdown": {"stages_ms": {k: v / args.steps for k, v in stage_ms.items()}, "index": info,
+                      "codepoints_per_s": n / (ms_step * 1e-3),
+                      "kernels": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
+                                  for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}}}))
+
+
 def main():
     args = parse_args()
+    if args.workload == "single_doc" and args.impl == "b200":
+        return run_single_doc(args)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
