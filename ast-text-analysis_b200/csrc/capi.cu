@@ -265,6 +265,8 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.key_chars = (int)get_option("key_chars", 0);
         in.force_general = (int)get_option("force_general", 0);
         in.rs_variant = (int)get_option("rs_variant", 0);
+        in.doc_off_host = idx->doc_off.data();
+        in.sort_batch_elems = get_option("sort_batch_elems", 0);
         SaOutput so;
         so.sa = idx->sa; so.rank = rank.p;
         build_suffix_array(in, so, tm, s);

@@ -251,18 +251,20 @@ __device__ __forceinline__ uint64_t lds8(const uint8_t *base, int o) {
 // fast path: byte codes.  The window of kc symbols is packed 8 symbols at a time; everything
 // after the first terminator of the window is cleared (SWAR zero-byte search for its position).
 __global__ void __launch_bounds__(KG_THREADS)
-k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, const int32_t *__restrict__ doc_off, int D,
+k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, int32_t begin, int32_t end,
+               const int32_t *__restrict__ doc_off, int D,
                KeyParams kp, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                uint32_t *g_hist) {
     __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
     __shared__ __align__(16) uint8_t s_t[KG_TILE + KG_HALO + 16];
     __shared__ int s_dlo, s_dhi;
     for (int i = threadIdx.x; i < kp.passes * 256; i += blockDim.x) s_hist[i] = 0;
-    const int num_tiles = (n + KG_TILE - 1) / KG_TILE;
+    // tiles of the global tile grid that overlap [begin, end) (tile bases stay 16-byte aligned)
+    const int tile_lo = begin / KG_TILE, tile_hi = (end + KG_TILE - 1) / KG_TILE;
     const int b = kp.b, kc = kp.kc;
     const int groups = (kc + 7) >> 3, rem = kc - 8 * (groups - 1);  // symbols taken from the last group
     const uint64_t term8 = 0x0101010101010101ull * (uint64_t)kp.term;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x) {
         const int32_t base = tile * KG_TILE;
         __syncthreads();
         // stage the tile (+halo) of byte codes; 128-bit loads where fully in range
@@ -274,15 +276,15 @@ k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, const int32_t *__restr
                 for (int q = 0; q < 16; ++q) s_t[o + q] = (g + q < n) ? T8[g + q] : 0;
             }
         }
-        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, base);
-        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, min(base + KG_TILE, n) - 1);
+        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, max(base, begin));
+        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, min(base + KG_TILE, end) - 1);
         __syncthreads();
         const int dlo = s_dlo, dhi = s_dhi;
 #pragma unroll 2
         for (int it = 0; it < KG_ITEMS; ++it) {
             const int o = it * KG_THREADS + threadIdx.x;
             const int32_t i = base + o;
-            const bool valid = i < n;
+            const bool valid = i >= begin && i < end;
             uint64_t key = 0;
             if (valid) {
                 int lo = dlo, hi = dhi;  // document of position i (tile spans [dlo, dhi])
@@ -316,16 +318,17 @@ k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, const int32_t *__restr
 
 // general path: raw code points + 1, window cut at the end of the document (pad 0)
 __global__ void __launch_bounds__(KG_THREADS)
-k_keygen0_general(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict__ doc_off,
+k_keygen0_general(const uint32_t *__restrict__ T, int32_t begin, int32_t end_, const int32_t *__restrict__ doc_off,
                   int D, KeyParams kp, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                   uint32_t *g_hist) {
     __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
     for (int i = threadIdx.x; i < kp.passes * 256; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n_round = ((int64_t)n + 31) & ~31ll;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool valid = i < n;
+    const int64_t n_round = (((int64_t)end_ - begin) + 31) & ~31ll;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += stride) {
+        const int64_t i = begin + j;
+        const bool valid = i < end_;
         uint64_t key = 0;
         if (valid) {
             int d = doc_of(doc_off, D, (int32_t)i);
@@ -626,6 +629,9 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     if (dbits + kp.b > 64) throw Error(-5, "document count x alphabet does not fit a 64-bit sort key");
     int kc = (64 - dbits) / kp.b;
     if (kc > KG_HALO) kc = KG_HALO;
+    // one symbol less when that saves a whole radix pass over all N suffixes and still leaves a
+    // window of >= 8 symbols (measured on the Zipf workload: 55-bit keys / 7 passes beat 60 / 8)
+    if (kc > 8 && rs_num_passes(dbits + (kc - 1) * kp.b) < rs_num_passes(dbits + kc * kp.b)) --kc;
     if (in.key_chars > 0 && in.key_chars < kc) kc = in.key_chars;
     kp.kc = kc;
     const int key_bits = dbits + kc * kp.b;
@@ -643,8 +649,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     DevBuf<uint32_t> rr_misc(8, s);  // [0] ticket, [1] kept count
     uint32_t *rank = out.rank;
 
-    tm.mark("keygen0");
-    EAST_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 256 * RS_MAX_PASSES, s));
+    tm.mark("encode");
     DevBuf<uint8_t> t8;
     if (fast) {
         DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
@@ -653,19 +658,44 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         EAST_BYTES(5.0 * n);
         EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_table.p,
                     (uint8_t)kp.term, t8.p);
-        EAST_BYTES(13.0 * n);
-        EAST_LAUNCH(k_keygen0_fast, grid_for(n, KG_TILE, 4), KG_THREADS, 0, s, t8.p, n, in.doc_off, D, kp,
-                    keys_a.p, vals_a.p, hist.p);
-        EAST_CUDA(cudaStreamSynchronize(s));  // d_table goes out of scope (stream-ordered free is safe, host table too)
-    } else {
-        EAST_BYTES(16.0 * n);
-        EAST_LAUNCH(k_keygen0_general, grid_for(n, 256 * 8, 4), 256, 0, s, in.text, n, in.doc_off, D, kp,
-                    keys_a.p, vals_a.p, hist.p);
     }
 
-    tm.mark("sort0");
-    int cur = radix_sort_pairs(keys_a.p, keys_b.p, vals_a.p, vals_b.p, n, key_bits, hist.p, true, scratch.p, s,
-                               in.rs_variant);
+    // Round 0 is sorted in batches of 2^g whole documents (documents are independent and the
+    // document id tops every key): inside a batch only the low g bits of the id vary, so fewer
+    // key bits need sorting, and the ping-pong buffers of a batch (~24 B per suffix) stay resident
+    // in the 126 MB L2 across all passes instead of streaming through HBM eight times.
+    tm.mark("keygen0+sort0");
+    int g = dbits;
+    {
+        // measured on B200: batching is a LOSS (every launch pays ~13 us of ramp-up/tail and the
+        // kernel is latency- not bandwidth-bound), so the default sorts the whole batch at once
+        const int64_t target = in.sort_batch_elems > 0 ? in.sort_batch_elems : (int64_t)n;
+        const int64_t avg = std::max<int64_t>(1, (int64_t)n / D);
+        int want = 0;
+        while (want < dbits && (avg << (want + 1)) <= target) ++want;
+        g = (target >= (int64_t)n) ? dbits : std::min(dbits, want);
+    }
+    const int sort_bits = kc * kp.b + g;
+    kp.passes = rs_num_passes(sort_bits);
+    out.key_bits = sort_bits;
+    int cur = 0;
+    for (int d0 = 0; d0 < D; d0 += (1 << g)) {
+        const int d1 = std::min(D, d0 + (1 << g));
+        const int32_t e0 = in.doc_off_host[d0], e1 = in.doc_off_host[d1];
+        const int32_t nb = e1 - e0;
+        EAST_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 256 * RS_MAX_PASSES, s));
+        if (fast) {
+            EAST_BYTES(13.0 * nb);
+            EAST_LAUNCH(k_keygen0_fast, grid_for(nb, KG_TILE, 4), KG_THREADS, 0, s, t8.p, n, e0, e1, in.doc_off, D, kp,
+                        keys_a.p, vals_a.p, hist.p);
+        } else {
+            EAST_BYTES(16.0 * nb);
+            EAST_LAUNCH(k_keygen0_general, grid_for(nb, 256 * 8, 4), 256, 0, s, in.text, e0, e1, in.doc_off, D, kp,
+                        keys_a.p, vals_a.p, hist.p);
+        }
+        cur = radix_sort_pairs(keys_a.p + e0, keys_b.p + e0, vals_a.p + e0, vals_b.p + e0, nb, sort_bits, hist.p, true,
+                               scratch.p, s, in.rs_variant);
+    }
 
     // scorer acceleration (fast path): first ranks of all (document, 2-gram) buckets
     if (fast && kc >= 2 && ((size_t)D << (2 * kp.b)) <= (size_t)2 * n + 4096) {

@@ -14,6 +14,8 @@ struct SaInput {
     int key_chars;            // 0 = as many symbols as fit the 64-bit key
     int force_general;        // testing: never take the terminator-class fast path
     int rs_variant = 0;       // tuning: radix-sort kernel shape (see radix_sort_pairs)
+    const int32_t *doc_off_host = nullptr;  // host copy of doc_off
+    int64_t sort_batch_elems = 0;           // round-0 sort batch in suffixes (0 = whole batch at once)
 };
 
 struct SaOutput {

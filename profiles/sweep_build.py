@@ -14,6 +14,7 @@ ap.add_argument("--docs", type=int, default=1000)
 ap.add_argument("--doc-bytes", type=int, default=50000)
 ap.add_argument("--variants", default="0,1,2,3,4,5,6,7,8,9")
 ap.add_argument("--key-chars", default="0")
+ap.add_argument("--batch", default="0", help="sort_batch_elems values (0 = default 3Mi, -1 = whole)")
 a = ap.parse_args()
 packed, ms, _ = synth.packed_collection(a.docs, a.doc_bytes)
 doc_off = np.zeros(a.docs + 1, dtype=np.int64); np.cumsum([len(p) for p in packed], out=doc_off[1:])
@@ -21,8 +22,10 @@ doc_m = np.array(ms, dtype=np.int32)
 dev = torch.from_numpy(np.concatenate(packed).view(np.int32)).cuda()
 for _ in range(3):
     _capi.DeviceIndex.build_dev(dev.data_ptr(), doc_off, doc_m).close()
-for kc in [int(x) for x in a.key_chars.split(",")]:
+import itertools
+for kc, bt in itertools.product([int(x) for x in a.key_chars.split(",")], [int(x) for x in a.batch.split(",")]):
     _capi.set_option("key_chars", kc)
+    _capi.set_option("sort_batch_elems", bt)
     for v in [int(x) for x in a.variants.split(",")]:
         _capi.set_option("rs_variant", v)
         best = None
@@ -38,5 +41,5 @@ for kc in [int(x) for x in a.key_chars.split(",")]:
             if best is None or row[0] < best[0]:
                 best = row
         _capi.set_option("time_kernels", 0)
-        print("key_chars=%d rs_variant=%d  build_wall=%.2f ms  onesweep=%.3f ms in %d launches (%.0f GB/s)  rounds=%d  stages=%s" % (
-            kc, v, best[0], best[1], best[2], best[3], best[5], {k: round(x, 2) for k, x in best[4].items()}))
+        print("batch=%d key_chars=%d rs_variant=%d  build_wall=%.2f ms  onesweep=%.3f ms in %d launches (%.0f GB/s)  rounds=%d  stages=%s" % (
+            bt, kc, v, best[0], best[1], best[2], best[3], best[5], {k: round(x, 2) for k, x in best[4].items()}))
