@@ -345,6 +345,11 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel
     peak, peak_kind = load_peaks()
+    traffic_table = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_table = json.load(f)
     dom_name, dom = max(kstats.items(), key=lambda kv: kv[1]["ms"])
     per_launch_ms = dom["ms"] / max(dom["launches"], 1)
     per_launch_bytes = dom["bytes"] / max(dom["launches"], 1)
@@ -356,6 +361,11 @@ def run_b200(args):
     score_ms = stage_ms.get("score", 0.0) / args.steps
     text_mb = args.docs * args.doc_bytes / 1e6
 
+    tinfo = traffic_table.get(dom_name, {})
+    if "dram_bytes_per_algorithmic_byte" in tinfo:   # DRAM bytes per launch from the committed ncu --set full capture
+        traffic = per_launch_bytes * tinfo["dram_bytes_per_algorithmic_byte"]
+    else:
+        traffic = tinfo.get("dram_bytes_per_launch")
     line = {
         "metric": METRIC, "value": n_gpus * D * K / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": n_gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
@@ -367,7 +377,8 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": tinfo.get("source"),
+                     "peak_source": peak_kind,
                      "launches_per_step": dom["launches"] / args.steps, "ms_per_launch": per_launch_ms,
                      "algorithmic_bytes_per_launch": per_launch_bytes,
                      "share_of_step": dom["ms"] / args.steps / dev_ms},

@@ -3,7 +3,7 @@
 import csv, sys
 rows = list(csv.reader(sys.stdin))
 hdr = rows[0]
-want = [('Kernel Name', 'kernel'), ('gpu__time_duration.sum', 'us'), ('dram__bytes_read.sum', 'rdMB'),
+want = [('Kernel Name', 'kernel'), ('gpu__time_duration.sum', 'time'), ('dram__bytes_read.sum', 'rdMB'),
         ('dram__bytes_write.sum', 'wrMB'), ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram%'),
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps%'), ('launch__registers_per_thread', 'regs'),
         ('lts__t_sector_hit_rate.pct', 'L2hit%'), ('l1tex__t_sector_hit_rate.pct', 'L1hit%'),
@@ -21,6 +21,8 @@ for r in rows[2:]:
         if n == 'kernel':
             v = v.split('(')[0].replace('east::', '')
         elif n in ('rdMB', 'wrMB') and units[i] != 'Mbyte':
+            v = v + units[i]
+        elif n == 'time':
             v = v + units[i]
         out.append('%s=%s' % (n, v))
     print(' '.join(out))
