@@ -78,21 +78,36 @@ class EnhancedAnnotatedSuffixArray(base.AST):
         return np.float64(result) if result != 0 else 0  # the reference returns int 0 on no match
 
     # ---- traversals (easa.py:38-89), host side over the downloaded tables ----
-    def _child_intervals(self, l, i, j):
-        """Child intervals (l', i', j', first char) of the lcp-interval l-[i..j]."""
-        lcp, sa, text = self.lcptab, self.suftab, self.string
-        n = len(sa)
-        # l-indices of [i..j]: positions k in (i, j] with lcp[k] == min(lcp[i+1..j])
-        seg = lcp[i + 1:j + 1]
-        depth = int(seg.min())
-        cuts = [i] + [int(k) + i + 1 for k in np.nonzero(seg == depth)[0]] + [j + 1]
+    def _lcp_value(self, i, j):
+        """lcp value of the interval [i..j] read off the child table (easa.py:349-356), including
+        the reference's treatment of the root and of singleton intervals."""
+        n = len(self.suftab)
+        if (i == 0 or i == n - 1) and j == n - 1:
+            return 0
+        up_next = self.childtab_up[j + 1]  # IndexError for j == n - 1, exactly as the reference
+        if i < up_next <= j:
+            return self.lcptab[up_next]
+        return self.lcptab[self.childtab_down[i]]
+
+    def _get_child_intervals(self, i, j):
+        """Child intervals (l, i', j', first character of the edge) of [i..j] in rank order:
+        first l-index from up[j+1] / down[i], then the next-l-index chain (easa.py:358-377)."""
+        if i == j:
+            return []
+        n = len(self.suftab)
+        depth = self._lcp_value(i, j)
+        sa, text, nxt = self.suftab, self.string, self.childtab_next_l_index
         out = []
-        for a, b in zip(cuts[:-1], cuts[1:]):
-            b -= 1
-            child_l = int(lcp[a + 1:b + 1].min()) if b > a else 0
-            if a == b:
-                child_l = 0 if (a == 0 or a == n - 1) and b == n - 1 else child_l
-            out.append((child_l, a, b, text[int(sa[a]) + depth]))
+        if i == 0 and j == n - 1:
+            cut = 0
+        else:
+            cut = self.childtab_up[j + 1] if i < self.childtab_up[j + 1] else self.childtab_down[i]
+            out.append((self._lcp_value(i, cut - 1), i, cut - 1, text[sa[i] + depth]))
+        while nxt[cut] != 0:
+            following = nxt[cut]
+            out.append((self._lcp_value(cut, following - 1), cut, following - 1, text[sa[cut] + depth]))
+            cut = following
+        out.append((self._lcp_value(cut, j), cut, j, text[sa[cut] + depth]))
         return out
 
     def traverse_depth_first_pre_order(self, callback):
@@ -101,7 +116,7 @@ class EnhancedAnnotatedSuffixArray(base.AST):
         def visit(node):
             callback(node)
             if node[1] != node[2]:
-                for child in sorted(self._child_intervals(node[0], node[1], node[2]), key=lambda c: c[3]):
+                for child in sorted(self._get_child_intervals(node[1], node[2]), key=lambda c: c[3]):
                     visit(child)
 
         visit([0, 0, n - 1, ""])
@@ -131,3 +146,18 @@ class EnhancedAnnotatedSuffixArray(base.AST):
 
     def traverse_breadth_first(self, callback):
         raise NotImplementedError
+
+
+class _TreeAlias(EnhancedAnnotatedSuffixArray):
+    """The reference's pointer-tree engines give exactly the scores of EASA (its own test,
+    tests/asts/test_base.py:16-24, asserts equality); their names resolve to the B200 engine."""
+
+    __algorithm__ = None
+
+
+class LinearAnnotatedSuffixTreeAlias(_TreeAlias):
+    __algorithm__ = consts.ASTAlgorithm.AST_LINEAR
+
+
+class NaiveAnnotatedSuffixTreeAlias(_TreeAlias):
+    __algorithm__ = consts.ASTAlgorithm.AST_NAIVE

@@ -43,7 +43,7 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         self.asts = []
         self._index = None
         total_texts = len(texts)
-        if self.ast_algorithm != consts.ASTAlgorithm.EASA:
+        if self.ast_algorithm not in tuple(consts.ASTAlgorithm):
             # other registered engines (none ship in this package) go through the registry
             for i in range(total_texts):
                 self.asts.append(base.AST.get_ast(utils.text_to_strings_collection(texts[i]),

@@ -254,9 +254,10 @@ def run_b200(args):
         idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
         tc = time.perf_counter()
         if world > 1:
+            # the step ends when the gathered [N*D, K] table is complete on this rank (without this
+            # host sync the NCCL kernel of step i overlaps the build of step i+1 and both crawl)
             dist.all_gather_into_tensor(gathered, out_dev)
-            if debug:
-                torch.cuda.synchronize()
+            torch.cuda.synchronize()
         td = time.perf_counter()
         timings = idx.build_timings + idx.score_timings
         info = idx.info()
@@ -273,7 +274,9 @@ def run_b200(args):
         idx.score_table_into(kp_codes, kp_off, host_out_np, True)
         tc = time.perf_counter()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out_dev)  # same exchange volume as the device-timed step
+            out_dev.copy_(host_out.view(-1), non_blocking=True)   # gather the table this step produced
+            dist.all_gather_into_tensor(gathered, out_dev)
+            torch.cuda.synchronize()
         idx.close()
         if debug:
             sys.stderr.write("e2e: build_host %.2f ms, score_host %.2f ms, close %.2f ms\n" % (

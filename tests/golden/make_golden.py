@@ -140,6 +140,20 @@ def main():
                                  for e in g["edges"]]})
     hse["graphs"] = graphs
 
+    # traversal callbacks (easa.py:38-85): pre-order nodes (l, i, j, char) and post-order nodes
+    # (l, i, j, [children as (l, i, j)])
+    traversals = []
+    for strings in (["XABXAC", "HI"], ["abcd efg ops", "xyzq", "test"], ["AAAAAAAA", "AAAA", "AAAAAAAA"],
+                    utils.text_to_strings_collection(doc[:600])):
+        ast = base.AST.get_ast(strings, "easa")
+        pre, post = [], []
+        ast.traverse(lambda node: pre.append([int(node[0]), int(node[1]), int(node[2]), node[3]]),
+                     "depth-first|pre-order")
+        ast.traverse(lambda node: post.append([int(node[0]), int(node[1]), int(node[2]),
+                                               [[int(c[0]), int(c[1]), int(c[2])] for c in node[3]]]),
+                     "depth-first|post-order")
+        traversals.append({"strings": strings, "pre": pre, "post": post})
+
     # host preprocessing known answers (tests/test_utils.py:10-13 and utils.py:49-79 behaviour)
     prep = {
         "tokenize": {"in": "Well, what a sunny day!", "out": utils.tokenize("Well, what a sunny day!")},
@@ -157,8 +171,8 @@ def main():
             errors[label] = type(e).__name__
 
     with open(os.path.join(HERE, "golden.json"), "w", encoding="utf-8") as f:
-        json.dump({"cases": cases, "hse": hse, "prep": prep, "errors": errors,
-                   "source": "py3-patched reference (oracle/make_ref.py), EAST 0.3.8"}, f, ensure_ascii=False, indent=0)
+        json.dump({"cases": cases, "hse": hse, "prep": prep, "errors": errors, "traversals": traversals,
+                   "source": "py3-patched reference (oracle/make_ref.py), EAST 0.3.8"}, f, ensure_ascii=False, separators=(",", ":"))
     np.savez_compressed(os.path.join(HERE, "golden_arrays.npz"), **arrays)
     print("cases:", len(cases), "arrays:", len(arrays))
 

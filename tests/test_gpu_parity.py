@@ -344,3 +344,56 @@ def test_cooccurrence_tensor_core_counts_are_exact(K, D):
         assert np.array_equal(capi.cooc_host(S, 0.25), expect)
     finally:
         capi.set_option("cooc_variant", 0)
+
+
+def test_traversal_callbacks_match_reference(golden):
+    """traverse() pre-/post-order: same nodes, same order, same callback payload as easa.py:38-85."""
+    import east  # noqa: F401
+    from east.asts import base
+    for item in golden["traversals"]:
+        ast = base.AST.get_ast(item["strings"], "easa")
+        pre, post = [], []
+        ast.traverse(lambda node: pre.append([int(node[0]), int(node[1]), int(node[2]), node[3]]),
+                     "depth-first|pre-order")
+        ast.traverse(lambda node: post.append([int(node[0]), int(node[1]), int(node[2]),
+                                               [[int(c[0]), int(c[1]), int(c[2])] for c in node[3]]]),
+                     "depth-first|post-order")
+        assert pre == item["pre"]
+        assert post == item["post"]
+
+
+def test_tree_engine_names_resolve_to_the_same_scores():
+    # tests/asts/test_base.py:16-24: all engine names give equal scores
+    import east  # noqa: F401
+    from east.asts import base
+    strings, queries = ["abcd efg ops", "xyzq", "test"], ["aqcb", "efgp", "mn4"]
+    for normalized in (True, False):
+        ref = [base.AST.get_ast(strings, "easa").score(q, normalized=normalized) for q in queries]
+        for alg in ("ast_linear", "ast_naive"):
+            assert [base.AST.get_ast(strings, alg).score(q, normalized=normalized) for q in queries] == ref
+
+
+def test_cli_table_and_graph(tmp_path, golden):
+    """The fixed thin CLI (east/main.py) on a directory of texts: csv/xml table and edges/gml graph."""
+    import io
+    from east import main as cli
+    hse = golden["hse"]
+    d = tmp_path / "texts"
+    d.mkdir()
+    for doc in hse["docs"][:6]:
+        (d / doc["name"]).write_text(" ".join(doc["strings"]), encoding="utf-8")
+    kp = tmp_path / "kp.txt"
+    kp.write_text("\n".join(hse["keyphrases"][:5]) + "\n", encoding="utf-8")
+    out = io.StringIO()
+    assert cli.main(["-f", "csv", "keyphrases", "table", str(kp), str(d)], out=out) == 0
+    lines = out.getvalue().strip().splitlines()
+    assert len(lines) == 1 + 6 and lines[0].count(",") == 5
+    out = io.StringIO()
+    assert cli.main(["keyphrases", "table", str(kp), str(d)], out=out) == 0
+    assert out.getvalue().startswith("<table>") and out.getvalue().count("<text name=") == 30
+    out = io.StringIO()
+    assert cli.main(["-f", "gml", "-r", "0.1", "-c", "0.5", "keyphrases", "graph", str(kp), str(d)], out=out) == 0
+    assert out.getvalue().startswith("graph\n[") and "referral_confidence 0.50" in out.getvalue()
+    out = io.StringIO()
+    assert cli.main(["-s", "cosine", "keyphrases", "table", str(kp), str(d)], out=out) == 1
+    assert cli.main(["keyphrases"], out=io.StringIO()) == 1
