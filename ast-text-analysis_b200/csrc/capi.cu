@@ -267,6 +267,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.rs_variant = (int)get_option("rs_variant", 0);
         in.doc_off_host = idx->doc_off.data();
         in.sort_batch_elems = get_option("sort_batch_elems", 0);
+        in.local_group_sort = get_option("doubling_radix", 0) ? 0 : 1;
         SaOutput so;
         so.sa = idx->sa; so.rank = rank.p;
         build_suffix_array(in, so, tm, s);

@@ -375,10 +375,43 @@ k_keygen_h(const uint32_t *__restrict__ vals, const uint32_t *__restrict__ prim,
             key = ((uint64_t)prim[a] << sb) | sec;
             keys[a] = key;
         }
-        rs_hist_add(s_hist, key, passes, valid);
+        if (passes > 0) rs_hist_add(s_hist, key, passes, valid);
     }
     __syncthreads();
     rs_hist_flush(s_hist, g_hist, passes);
+}
+
+// ------------------------------------------------------------------------------------------
+// doubling rounds, common case: the groups that are still ambiguous are SMALL (a few to a few
+// hundred suffixes sharing a repeated phrase), so instead of seven global radix passes every
+// element ranks itself inside its own group: it finds the group's extent in the active list
+// (equal primary = equal upper key bits), counts the members with a smaller (secondary, index)
+// pair and writes its key/value to group_start + count.  Reads are contiguous and shared by the
+// threads of the group.  A group larger than GS_MAX sets *overflow and the host redoes the round
+// with the radix sort (deep-LCP inputs: many identical strings).
+// ------------------------------------------------------------------------------------------
+constexpr int GS_MAX = 1024;
+
+__global__ void __launch_bounds__(256)
+k_group_sort(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, int32_t n_act, int sb,
+             uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t *overflow) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < n_act; a += stride) {
+        const uint64_t key = keys[a];
+        const uint64_t prim = key >> sb;
+        int64_t gs = a, ge = a + 1;
+        int steps = 0;
+        while (gs > 0 && (keys[gs - 1] >> sb) == prim && steps < GS_MAX) { --gs; ++steps; }
+        while (ge < n_act && (keys[ge] >> sb) == prim && steps < GS_MAX) { ++ge; ++steps; }
+        if (steps >= GS_MAX) { *overflow = 1u; continue; }
+        uint32_t below = 0;
+        for (int64_t b = gs; b < ge; ++b) {
+            const uint64_t kb = keys[b];
+            below += (kb < key || (kb == key && b < a)) ? 1u : 0u;
+        }
+        keys_out[gs + below] = key;
+        vals_out[gs + below] = vals[a];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -404,7 +437,8 @@ k_rerank(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
          int32_t *__restrict__ sa, uint32_t *__restrict__ rank, uint32_t *__restrict__ new_vals,
          uint32_t *__restrict__ new_slots, uint32_t *__restrict__ new_prim,
          volatile uint64_t *status, uint32_t *ticket, uint32_t *out_counts /*[0]=kept*/,
-         uint32_t *__restrict__ bkt, int bkt_shift) {
+         uint32_t *__restrict__ bkt, int bkt_shift, const uint32_t *__restrict__ abort_flag) {
+    if (abort_flag != nullptr && *abort_flag != 0u) return;  // the local group sort gave up: host redoes the round
     __shared__ RRState s_warp[RR_THREADS / 32];
     __shared__ RRState s_prefix;
     __shared__ uint32_t s_tile;
@@ -719,7 +753,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         EAST_LAUNCH(k_rerank<true>, rr_tiles_max, RR_THREADS, 0, s, cur ? keys_b.p : keys_a.p,
                     cur ? vals_b.p : vals_a.p, (const uint32_t *)nullptr, n, sym_mask, term, out.sa, rank,
                     act_vals.p, act_slots.p, act_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1, out.bkt.p,
-                    (kc - 2) * kp.b);
+                    (kc - 2) * kp.b, (const uint32_t *)nullptr);
         if (out.bkt.p) {
             EAST_LAUNCH(k_bucket_fill, D, 256, 0, s, out.bkt.p, 1 << (2 * kp.b), in.doc_off);
         }
@@ -744,24 +778,40 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         if (h >= n) throw Error(-2, "prefix doubling ran past the text (malformed input?)");
         const int nbits = sb + pbits;
         const int passes = rs_num_passes(nbits);
-        EAST_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 256 * RS_MAX_PASSES, s));
-        EAST_BYTES(20.0 * n_act);  // value + primary in, one rank gather, key out
-        EAST_LAUNCH(k_keygen_h, grid_for(n_act, 256 * 4, 8), 256, 0, s, act_vals.p, act_prim.p, (int32_t)n_act,
-                    rank, (int32_t)h, sb, passes, fast ? 0 : 1, in.doc_off, D, keys_a.p, hist.p);
-        // values to sort along: the suffix index
-        int c2 = radix_sort_pairs(keys_a.p, keys_b.p, act_vals.p, vals_b.p, (int32_t)n_act, nbits, hist.p, true,
-                                  scratch.p, s, in.rs_variant);
-        const uint64_t *sk = c2 ? keys_b.p : keys_a.p;
-        const uint32_t *sv = c2 ? vals_b.p : act_vals.p;
         const int rr_tiles = ((int)n_act + RR_TILE - 1) / RR_TILE;
-        EAST_CUDA(cudaMemsetAsync(rr_status.p, 0, sizeof(uint64_t) * ((size_t)rr_tiles + 2), s));
-        EAST_CUDA(cudaMemsetAsync(rr_misc.p, 0, sizeof(uint32_t) * 8, s));
-        EAST_BYTES(24.0 * n_act);
-        EAST_LAUNCH(k_rerank<false>, rr_tiles, RR_THREADS, 0, s, sk, sv, act_slots.p, (int32_t)n_act, 0ull, 0ull,
-                    out.sa, rank, nxt_vals.p, nxt_slots.p, nxt_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1,
-                    (uint32_t *)nullptr, 0);
-        EAST_CUDA(cudaMemcpyAsync(&n_act, rr_misc.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        EAST_CUDA(cudaStreamSynchronize(s));
+        bool local = in.local_group_sort != 0;
+        while (true) {
+            EAST_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 256 * RS_MAX_PASSES, s));
+            EAST_CUDA(cudaMemsetAsync(rr_status.p, 0, sizeof(uint64_t) * ((size_t)rr_tiles + 2), s));
+            EAST_CUDA(cudaMemsetAsync(rr_misc.p, 0, sizeof(uint32_t) * 8, s));
+            EAST_BYTES(20.0 * n_act);  // value + primary in, one rank gather, key out
+            EAST_LAUNCH(k_keygen_h, grid_for(n_act, 256 * 4, 8), 256, 0, s, act_vals.p, act_prim.p, (int32_t)n_act,
+                        rank, (int32_t)h, sb, local ? 0 : passes, fast ? 0 : 1, in.doc_off, D, keys_a.p, hist.p);
+            const uint64_t *sk;
+            const uint32_t *sv;
+            if (local) {
+                EAST_BYTES(24.0 * n_act);
+                EAST_LAUNCH(k_group_sort, grid_for(n_act, 256, 16), 256, 0, s, keys_a.p, act_vals.p, (int32_t)n_act, sb,
+                            keys_b.p, vals_b.p, rr_misc.p + 2);
+                sk = keys_b.p; sv = vals_b.p;
+            } else {
+                // values to sort along: the suffix index
+                int c2 = radix_sort_pairs(keys_a.p, keys_b.p, act_vals.p, vals_b.p, (int32_t)n_act, nbits, hist.p, true,
+                                          scratch.p, s, in.rs_variant);
+                sk = c2 ? keys_b.p : keys_a.p;
+                sv = c2 ? vals_b.p : act_vals.p;
+            }
+            EAST_BYTES(24.0 * n_act);
+            EAST_LAUNCH(k_rerank<false>, rr_tiles, RR_THREADS, 0, s, sk, sv, act_slots.p, (int32_t)n_act, 0ull, 0ull,
+                        out.sa, rank, nxt_vals.p, nxt_slots.p, nxt_prim.p, rr_status.p, rr_misc.p, rr_misc.p + 1,
+                        (uint32_t *)nullptr, 0, local ? rr_misc.p + 2 : (const uint32_t *)nullptr);
+            uint32_t res[2] = {0u, 0u};  // kept count, overflow flag
+            EAST_CUDA(cudaMemcpyAsync(res, rr_misc.p + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            EAST_CUDA(cudaStreamSynchronize(s));
+            if (local && res[1] != 0u) { local = false; ++out.radix_fallback_rounds; continue; }  // a huge group: radix this round
+            n_act = res[0];
+            break;
+        }
         std::swap(act_vals, nxt_vals);
         std::swap(act_slots, nxt_slots);
         std::swap(act_prim, nxt_prim);
