@@ -779,7 +779,10 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         const int nbits = sb + pbits;
         const int passes = rs_num_passes(nbits);
         const int rr_tiles = ((int)n_act + RR_TILE - 1) / RR_TILE;
-        bool local = in.local_group_sort != 0;
+        // rank-in-group costs O(g) reads per element: a win for the late rounds (tiny groups, and each
+        // avoided radix launch saves ~13 us of fixed cost), a loss for the first doubling round of
+        // Zipf text, where the occurrences of frequent words still form groups of several hundred
+        bool local = in.local_group_sort != 0 && n_act <= (1u << 20);
         while (true) {
             EAST_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * 256 * RS_MAX_PASSES, s));
             EAST_CUDA(cudaMemsetAsync(rr_status.p, 0, sizeof(uint64_t) * ((size_t)rr_tiles + 2), s));
