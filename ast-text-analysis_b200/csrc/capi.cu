@@ -1,4 +1,5 @@
 // capi.cu -- the C ABI of libeast_b200.so (declared in include/east_b200.h).
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -393,10 +394,15 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
     DevBuf<int32_t> d_off(K + 1, s), d_suf((size_t)total, s);
     EAST_CUDA(cudaMemcpyAsync(d_off.p, off32.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, s));
     EAST_CUDA(cudaMemcpyAsync(d_suf.p, suf_kp.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    // per-suffix results tmp[doc][suffix] are produced and consumed tile by tile over the documents,
+    // so the scratch stays <= ~1 GB however large K x D is (config 4: 1.3 M suffixes x 12 500 docs)
     DevBuf<double> tmp_own;
     double *tmp = suffix_out_dev;
+    int32_t tile_docs = doc_count;
     if (!tmp) {
-        tmp_own = DevBuf<double>((size_t)doc_count * (size_t)total, s);
+        const int64_t budget = get_option("score_tmp_doubles", (int64_t)1 << 27);
+        tile_docs = (int32_t)std::max<int64_t>(1, std::min<int64_t>(doc_count, budget / std::max<int64_t>(1, total)));
+        tmp_own = DevBuf<double>((size_t)tile_docs * (size_t)total, s);
         tmp = tmp_own.p;
     }
     ScoreInput in;
@@ -460,7 +466,15 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
     }
     StageTimer tm(s);
     tm.mark("score");
-    score_table(in, tmp, out_dev, s);
+    for (int32_t d0 = 0; d0 < doc_count; d0 += tile_docs) {
+        ScoreInput part = in;
+        part.n_docs = std::min(tile_docs, doc_count - d0);
+        part.doc_off = in.doc_off + d0;
+        part.doc_m = in.doc_m + d0;
+        if (in.bkt) part.bkt = in.bkt + ((size_t)d0 << (2 * in.sym_bits));
+        part.algorithmic_bytes = in.algorithmic_bytes * ((double)part.n_docs / (double)doc_count);
+        score_table(part, tmp, out_dev + (size_t)d0 * K, s);
+    }
     tm.finish();
     if (probes_out) {
         unsigned long long h = 0;

@@ -101,28 +101,38 @@ struct ScanResult {
 
 constexpr int ST_TILE = 4096;
 constexpr int ST_HALO = 256;
+constexpr int ST_NONE = -2;   // scan state: nothing seen
+constexpr int ST_RESET = -1;  // scan state: a document started, no terminator since
 
 // One streaming pass over the packed text, staged through shared memory: alphabet bitmap of the
 // code points below 0x0A00, maximum code point, and validation that the code points >= 0x0A00
-// are exactly the terminators 0x0A00+i of string i of each document, in order.  A terminator
-// checks itself against the previous terminator of its document by walking back through the
-// staged tile (strings are ~20 symbols), falling back to global memory for very long strings.
+// are exactly the terminators 0x0A00+i of string i of each document, in order.
+// "The previous terminator of my document" is a prefix scan with the operator "take the right
+// operand unless it is empty" over (document start -> RESET, terminator -> its value): each warp
+// scans its 512 consecutive code points 32 at a time with shuffles, warps are chained through
+// shared-memory summaries, and the state before the tile comes from the 256-code-point halo
+// (one ballot per 32 code points; global memory only for strings longer than the halo).
 __global__ void __launch_bounds__(256)
 k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict__ doc_off,
             const int32_t *__restrict__ doc_m, int D, ScanResult *res) {
     __shared__ uint32_t s_present[EAST_TERM_BASE / 32];
     __shared__ uint32_t s_max, s_nterm, s_bad;
     __shared__ __align__(16) uint32_t s_t[ST_HALO + ST_TILE];
+    __shared__ uint32_t s_ds[ST_TILE / 32];  // document-start flags of the tile
+    __shared__ int s_sum[8];
+    __shared__ int s_carry;
     __shared__ int s_dlo, s_dhi;
-    for (int i = threadIdx.x; i < EAST_TERM_BASE / 32; i += blockDim.x) s_present[i] = 0;
-    if (threadIdx.x == 0) { s_max = 0; s_nterm = 0; s_bad = 0; }
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int i = t; i < EAST_TERM_BASE / 32; i += 256) s_present[i] = 0;
+    if (t == 0) { s_max = 0; s_nterm = 0; s_bad = 0; }
     uint32_t mx = 0, nt = 0, bad = 0;
     const int num_tiles = (n + ST_TILE - 1) / ST_TILE;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int64_t base = (int64_t)tile * ST_TILE;
         const int64_t win = base - ST_HALO;  // global position of s_t[0]
+        const int tile_n = (int)min((int64_t)ST_TILE, (int64_t)n - base);
         __syncthreads();
-        for (int o = threadIdx.x * 4; o < ST_HALO + ST_TILE; o += 256 * 4) {
+        for (int o = t * 4; o < ST_HALO + ST_TILE; o += 256 * 4) {
             const int64_t g = win + o;
             if (g >= 0 && g + 4 <= n) {
                 *reinterpret_cast<uint4 *>(s_t + o) = *reinterpret_cast<const uint4 *>(T + g);  // 128-bit
@@ -130,43 +140,108 @@ k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict
                 for (int q = 0; q < 4; ++q) s_t[o + q] = (g + q >= 0 && g + q < n) ? T[g + q] : 0u;
             }
         }
-        if (threadIdx.x == 0) s_dlo = doc_of(doc_off, D, (int32_t)base);
-        if (threadIdx.x == 32) s_dhi = doc_of(doc_off, D, (int32_t)min(base + ST_TILE, (int64_t)n) - 1);
+        if (t < ST_TILE / 32) s_ds[t] = 0;
+        if (t == 0) s_dlo = doc_of(doc_off, D, (int32_t)base);
+        if (t == 32) s_dhi = doc_of(doc_off, D, (int32_t)(base + tile_n - 1));
         __syncthreads();
         const int dlo = s_dlo, dhi = s_dhi;
-#pragma unroll 4
-        for (int it = 0; it < ST_TILE / 256; ++it) {
-            const int o = it * 256 + threadIdx.x;
-            const int64_t i = base + o;
-            if (i >= n) break;
-            const uint32_t c = s_t[ST_HALO + o];
-            mx = max(mx, c);
-            if (c < EAST_TERM_BASE) {
-                if (!(((volatile uint32_t *)s_present)[c >> 5] & (1u << (c & 31))))
-                    atomicOr(&s_present[c >> 5], 1u << (c & 31));
-            } else {
-                ++nt;
-                int lo = dlo, hi = dhi;
-                while (lo < hi) {
-                    int mid = (lo + hi + 1) >> 1;
-                    if (__ldg(doc_off + mid) <= i) lo = mid; else hi = mid - 1;
+        for (int d = dlo + t; d <= dhi; d += 256) {
+            const int64_t off = (int64_t)__ldg(doc_off + d) - base;
+            if (off >= 0) atomicOr(&s_ds[off >> 5], 1u << (off & 31));
+        }
+        // ---- state before the tile (warp 0): last terminator of the halo that belongs to document dlo
+        if (w == 0) {
+            const int64_t dstart = __ldg(doc_off + dlo);
+            int carry = ST_NONE;
+            if (dstart >= base) carry = ST_RESET;  // the tile starts a document
+            else {
+                const int64_t lower = max(dstart, max(win, (int64_t)0));
+                for (int64_t hi = base - 1; hi >= lower && carry == ST_NONE; hi -= 32) {
+                    const int64_t p = hi - (31 - lane);  // lanes cover [hi-31, hi]
+                    const bool is_t = p >= lower && s_t[p - win] >= EAST_TERM_BASE;
+                    const unsigned m = __ballot_sync(0xffffffffu, is_t);
+                    if (m) {
+                        const int hl = 31 - __clz(m);
+                        carry = (int)__shfl_sync(0xffffffffu, is_t ? s_t[p - win] : 0u, hl);
+                    }
                 }
-                const int64_t start = __ldg(doc_off + lo);
-                const int64_t floor_ = max(start, win < 0 ? (int64_t)0 : win);
-                int64_t j = i - 1;
-                while (j >= floor_ && s_t[j - win] < EAST_TERM_BASE) --j;
-                uint32_t prev;
-                bool have_prev;
-                if (j >= floor_) { have_prev = true; prev = s_t[j - win]; }
-                else {
-                    while (j >= start && T[j] < EAST_TERM_BASE) --j;  // string longer than the halo
-                    have_prev = j >= start;
-                    prev = have_prev ? T[j] : 0u;
+                if (carry == ST_NONE) {
+                    if (lower == dstart) carry = ST_RESET;
+                    else {  // a string longer than the halo: walk global memory (lane 0)
+                        int64_t j = lower - 1;
+                        if (lane == 0) {
+                            while (j >= dstart && T[j] < EAST_TERM_BASE) --j;
+                            carry = (j >= dstart) ? (int)T[j] : ST_RESET;
+                        }
+                        carry = __shfl_sync(0xffffffffu, carry, 0);
+                    }
                 }
-                const uint32_t expect = have_prev ? prev + 1u : EAST_TERM_BASE;
-                if (c != expect) bad = 1;
-                if (i == __ldg(doc_off + lo + 1) - 1 && c != EAST_TERM_BASE + (uint32_t)__ldg(doc_m + lo) - 1u) bad = 1;
             }
+            if (lane == 0) s_carry = carry;
+        }
+        __syncthreads();
+        // ---- phase 1: what each warp's 512 code points leave behind
+        {
+            int summary = ST_NONE;
+            for (int r = 15; r >= 0 && summary == ST_NONE; --r) {
+                const int o = w * 512 + r * 32 + lane;
+                const uint32_t c = s_t[ST_HALO + o];
+                const bool is_t = o < tile_n && c >= EAST_TERM_BASE;
+                const bool is_d = o < tile_n && ((s_ds[o >> 5] >> (o & 31)) & 1u);
+                const unsigned m = __ballot_sync(0xffffffffu, is_t || is_d);
+                if (m) {
+                    const int hl = 31 - __clz(m);
+                    summary = __shfl_sync(0xffffffffu, is_t ? (int)c : ST_RESET, hl);
+                }
+            }
+            if (lane == 0) s_sum[w] = summary;
+        }
+        __syncthreads();
+        int state = s_carry;  // state before this warp's first code point
+        for (int i = 0; i < w; ++i) if (s_sum[i] != ST_NONE) state = s_sum[i];
+        // ---- phase 2: scan the rows, check every terminator against the state in front of it
+#pragma unroll 4
+        for (int r = 0; r < 16; ++r) {
+            const int o = w * 512 + r * 32 + lane;
+            const int64_t i = base + o;
+            const bool in = o < tile_n;
+            const uint32_t c = s_t[ST_HALO + o];
+            const bool is_t = in && c >= EAST_TERM_BASE;
+            const bool is_d = in && ((s_ds[o >> 5] >> (o & 31)) & 1u);
+            int x = is_t ? (int)c : (is_d ? ST_RESET : ST_NONE);  // what this code point leaves behind
+#pragma unroll
+            for (int sh = 1; sh < 32; sh <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, x, sh);
+                if (lane >= sh && x == ST_NONE) x = y;
+            }
+            int before = __shfl_up_sync(0xffffffffu, x, 1);   // inclusive state of the lane to the left
+            if (lane == 0 || before == ST_NONE) before = (lane == 0) ? state : before;
+            // lanes whose left neighbours saw nothing inherit the row's incoming state
+            if (before == ST_NONE) before = state;
+            if (is_d) before = ST_RESET;
+            if (in) {
+                mx = max(mx, c);
+                if (!is_t) {
+                    if (c < EAST_TERM_BASE && !(((volatile uint32_t *)s_present)[c >> 5] & (1u << (c & 31))))
+                        atomicOr(&s_present[c >> 5], 1u << (c & 31));
+                } else {
+                    ++nt;
+                    const uint32_t expect = (before >= 0) ? (uint32_t)before + 1u : EAST_TERM_BASE;
+                    if (c != expect) bad = 1;
+                    // the last code point of a document must be its last terminator
+                    const bool doc_end = (i + 1 == n) || (o + 1 < tile_n ? ((s_ds[(o + 1) >> 5] >> ((o + 1) & 31)) & 1u) : false);
+                    if (doc_end || o + 1 == tile_n) {
+                        int lo = dlo, hi = dhi;
+                        while (lo < hi) {
+                            int mid = (lo + hi + 1) >> 1;
+                            if (__ldg(doc_off + mid) <= i) lo = mid; else hi = mid - 1;
+                        }
+                        if (i == __ldg(doc_off + lo + 1) - 1 && c != EAST_TERM_BASE + (uint32_t)__ldg(doc_m + lo) - 1u) bad = 1;
+                    }
+                }
+            }
+            const int last = __shfl_sync(0xffffffffu, x, 31);
+            if (last != ST_NONE) state = last;
         }
     }
     // every document must end with a terminator
@@ -180,9 +255,9 @@ k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict
     atomicAdd(&s_nterm, nt);
     if (bad) atomicOr(&s_bad, 1u);
     __syncthreads();
-    for (int i = threadIdx.x; i < EAST_TERM_BASE / 32; i += blockDim.x)
+    for (int i = t; i < EAST_TERM_BASE / 32; i += 256)
         if (s_present[i]) atomicOr(&res->present[i], s_present[i]);
-    if (threadIdx.x == 0) {
+    if (t == 0) {
         atomicMax(&res->max_code, s_max);
         atomicAdd(&res->n_term, s_nterm);
         if (s_bad) atomicOr(&res->bad, 1u);

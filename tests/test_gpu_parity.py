@@ -398,3 +398,23 @@ def test_cli_table_and_graph(tmp_path, golden):
     out = io.StringIO()
     assert cli.main(["-s", "cosine", "keyphrases", "table", str(kp), str(d)], out=out) == 1
     assert cli.main(["keyphrases"], out=io.StringIO()) == 1
+
+
+def test_score_table_tiles_over_documents(oracle_mod):
+    """The per-suffix scratch is bounded: scoring in document tiles gives the identical table."""
+    import synth
+    from east import utils
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(9, 3000, first_seed=70)
+    idx = capi.DeviceIndex(packed, ms)
+    kps = [utils.prepare_text(k) for k in synth.keyphrases(40)]
+    codes, off = capi.pack_keyphrases(kps)
+    full = idx.score_table(codes, off, True)
+    try:
+        capi.set_option("score_tmp_doubles", int(off[-1]) * 2)  # two documents per tile
+        tiled = idx.score_table(codes, off, True)
+    finally:
+        capi.set_option("score_tmp_doubles", 0)
+    assert np.array_equal(full.view(np.uint64), tiled.view(np.uint64))
+    exp = oracle_mod.OracleEASA(text=packed[8], m=ms[8]).score_many(codes, off, True)
+    assert np.array_equal(tiled[8].view(np.uint64), exp.view(np.uint64))
