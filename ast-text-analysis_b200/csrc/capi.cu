@@ -37,9 +37,16 @@ void ktime_begin(const char *name, cudaStream_t s) {
 }
 void ktime_end(cudaStream_t s) { EAST_CUDA(cudaEventRecord(g_pending.back().b, s)); }
 void ktime_collect() {
+    std::vector<PendingLaunch> still;
     for (auto &p : g_pending) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+        cudaError_t e = cudaEventElapsedTime(&ms, p.a, p.b);
+        if (e == cudaErrorNotReady) {  // launched on the auxiliary stream and not finished yet: keep for later
+            cudaGetLastError();
+            still.push_back(p);
+            continue;
+        }
+        if (e == cudaSuccess) {
             KernelStat &k = g_kstats[p.name];
             k.launches += 1; k.ms += ms; k.bytes += p.bytes;
         } else {
@@ -48,7 +55,7 @@ void ktime_collect() {
         g_event_pool.push_back(p.a);
         g_event_pool.push_back(p.b);
     }
-    g_pending.clear();
+    g_pending.swap(still);
 }
 static thread_local std::string g_error;
 static thread_local std::vector<float> g_stage_ms;
@@ -143,7 +150,34 @@ struct east_index {
     int sym_bits = 0, term_code = 0;
     int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0;
     uint32_t active_after_round0 = 0;
+    // LCP / child / annotation tables are produced on an auxiliary stream after the suffix array is
+    // final, so a score call (which needs only SA + text) overlaps them; readers wait on ev_tables
+    std::unique_ptr<StageTimer> build_timer;
+    cudaEvent_t ev_tables = nullptr;
+    bool tables_pending = false;
 };
+
+// per-device auxiliary (non-blocking) stream for the table kernels
+static cudaStream_t aux_stream(int device) {
+    static std::mutex m;
+    static std::map<int, cudaStream_t> streams;
+    std::lock_guard<std::mutex> g(m);
+    auto it = streams.find(device);
+    if (it != streams.end()) return it->second;
+    cudaStream_t st;
+    EAST_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    streams[device] = st;
+    return st;
+}
+
+// block until the tables of `idx` are complete; publishes the build's stage timings once
+static void wait_tables(const east_index *cidx) {
+    east_index *idx = const_cast<east_index *>(cidx);
+    if (!idx->tables_pending) return;
+    EAST_CUDA(cudaEventSynchronize(idx->ev_tables));
+    idx->tables_pending = false;
+    if (idx->build_timer) idx->build_timer->collect();
+}
 
 static int fail(const Error &e) { g_error = e.what(); return e.status; }
 static int fail(int st, const char *msg) { g_error = msg; return st; }
@@ -222,6 +256,9 @@ int east_kernel_stats(char *names, int32_t names_cap, double *ms, int64_t *launc
 static void free_index(east_index *idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
+    if (idx->tables_pending) { cudaEventSynchronize(idx->ev_tables); idx->tables_pending = false; }
+    if (idx->build_timer) { try { idx->build_timer->collect(); } catch (...) {} idx->build_timer.reset(); }
+    if (idx->ev_tables) cudaEventDestroy(idx->ev_tables);
     if (idx->owns_text && idx->text) cudaFreeAsync(idx->text, 0);
     for (void *p : {(void *)idx->d_doc_off, (void *)idx->d_doc_m, (void *)idx->sa, (void *)idx->lcp,
                     (void *)idx->up, (void *)idx->down, (void *)idx->next, (void *)idx->ann, (void *)idx->t8,
@@ -257,7 +294,9 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
     idx->next = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
     idx->ann = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
 
-    StageTimer tm(s);
+    idx->build_timer.reset(new StageTimer(s));
+    StageTimer &tm = *idx->build_timer;
+    const bool overlap = get_option("sync_build", 0) == 0;
     {
         DevBuf<uint32_t> rank(n, s);
         SaInput in;
@@ -277,12 +316,30 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         idx->t8 = so.t8.p; so.t8.p = nullptr;      // ownership moves to the index
         idx->bkt = so.bkt.p; so.bkt.p = nullptr;
         idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
+        // the suffix array is final here (the doubling loop ended on a host sync)
+        cudaStream_t ts = s;
+        if (overlap) {
+            ts = aux_stream(device);
+            cudaEvent_t fork;
+            EAST_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+            EAST_CUDA(cudaEventRecord(fork, s));
+            EAST_CUDA(cudaStreamWaitEvent(ts, fork, 0));
+            EAST_CUDA(cudaEventDestroy(fork));
+            tm.s = ts;
+        }
         build_lcp_tables(idx->text, idx->t8, idx->term_code, idx->sa, idx->d_doc_off, idx->d_doc_m, n_docs, n, idx->lcp, idx->up,
-                         idx->down, idx->next, idx->ann, tm, s, (int)get_option("child_variant", 0));
+                         idx->down, idx->next, idx->ann, tm, ts, (int)get_option("child_variant", 0));
         tm.finish();
+        if (overlap) {
+            EAST_CUDA(cudaEventCreateWithFlags(&idx->ev_tables, cudaEventDisableTiming));
+            EAST_CUDA(cudaEventRecord(idx->ev_tables, ts));
+            idx->tables_pending = true;
+        }
     }
-    EAST_CUDA(cudaStreamSynchronize(s));
-    tm.collect();
+    if (!overlap) {
+        EAST_CUDA(cudaStreamSynchronize(s));
+        tm.collect();
+    }
     *out = idx.release();
     return EAST_OK;
 }
@@ -362,6 +419,7 @@ int east_index_copy(const east_index *idx, int32_t doc, int which, int32_t *dst_
     const int32_t *src = array_of(idx, which);
     if (!src) throw Error(EAST_ERR_INVALID, "unknown array id");
     EAST_CUDA(cudaSetDevice(idx->device));
+    wait_tables(idx);
     const int32_t off = idx->doc_off[doc], n = idx->doc_off[doc + 1] - off;
     EAST_CUDA(cudaMemcpy(dst_host, src + off, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
     if (which == EAST_SUFTAB)
@@ -372,6 +430,7 @@ int east_index_copy(const east_index *idx, int32_t doc, int which, int32_t *dst_
 int east_index_devptr(const east_index *idx, int which, const void **ptr) {
     if (!idx || !ptr) return fail(EAST_ERR_INVALID, "NULL argument");
     if (which == 100) { *ptr = idx->text; return EAST_OK; }
+    try { wait_tables(idx); } catch (const Error &e) { return fail(e); }
     const int32_t *p = array_of(idx, which);
     if (!p) return fail(EAST_ERR_INVALID, "unknown array id");
     *ptr = p;

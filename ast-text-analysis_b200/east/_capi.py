@@ -159,7 +159,7 @@ class DeviceIndex(object):
         self._h = _vp()
         _check(L.east_build_host(_ptr(text, _u32p), _ptr(self.doc_off, _i64p), _ptr(self.doc_m, _i32p),
                                  self.n_docs, self.device, ctypes.byref(self._h)))
-        self.build_timings = last_timings()
+        self.build_timings = []  # filled by close(): the table kernels may still be running
 
     @classmethod
     def from_handle(cls, handle, doc_off, doc_m, device):
@@ -169,7 +169,7 @@ class DeviceIndex(object):
         self.doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
         self.n_docs = len(self.doc_m)
         self.device = device
-        self.build_timings = last_timings()
+        self.build_timings = []
         return self
 
     @classmethod
@@ -207,9 +207,19 @@ class DeviceIndex(object):
         return cls.from_handle(h, doc_off, doc_m, int(device))
 
     def close(self):
+        """Free the index (waits for its table kernels); afterwards build_timings holds the per-stage
+        device times of its build."""
         if getattr(self, "_h", None):
             load().east_free(self._h)
             self._h = None
+            self.build_timings = last_timings()
+
+    def wait(self):
+        """Block until every table of the index is complete (build calls return once the suffix array
+        is final; LCP / child / annotation tables finish on an auxiliary stream)."""
+        p = _vp()
+        _check(load().east_index_devptr(self._h, LCPTAB, ctypes.byref(p)))
+        self.build_timings = last_timings()
 
     def __del__(self):
         try:

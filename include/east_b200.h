@@ -58,7 +58,11 @@ const char *east_version(void);
  *   text      : concatenated packed documents, doc_off[n_docs] code points
  *   doc_off   : n_docs+1 offsets into text (doc_off[0] == 0)
  *   doc_m     : number of strings (= terminators) of each document
- * Limits: doc_off[n_docs] < 2^30 per index. */
+ * Limits: doc_off[n_docs] < 2^30 per index.
+ * The call returns once the suffix array (all a scorer needs) is final; the LCP, child and annotation
+ * tables are completed on an auxiliary stream so that a following east_score_table_* overlaps them.
+ * east_index_copy / east_index_devptr / east_free wait for them (option "sync_build" = 1 makes the
+ * build itself wait). */
 int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m,
                     int32_t n_docs, int device, east_index **out);
 int east_build_dev(const uint32_t *text_dev, const int64_t *doc_off_host, const int32_t *doc_m_host,

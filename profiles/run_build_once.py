@@ -24,6 +24,6 @@ out = torch.empty(docs * 1000, dtype=torch.float64, device="cuda")
 for _ in range(iters):
     idx = _capi.DeviceIndex.build_dev(dev.data_ptr(), doc_off, doc_m)
     idx.score_table_dev(kp_dev.data_ptr(), off, out.data_ptr(), True)
-    print(idx.info(), [(n, round(m, 3)) for n, m in idx.build_timings + idx.score_timings])
-    idx.close()
+    info = idx.info(); idx.close()
+    print(info, [(n, round(m, 3)) for n, m in idx.build_timings + idx.score_timings])
 torch.cuda.synchronize()

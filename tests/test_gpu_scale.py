@@ -115,6 +115,7 @@ def test_config3_single_200mb_document():
     idx = _capi.DeviceIndex([packed], [m])
     info = idx.info()
     assert info["fast_path"] and info["n_total"] == packed.size
+    idx.wait()
     build_ms = sum(ms for _, ms in idx.build_timings)
     print("config3: n=%d m=%d text=%.1f MB build=%.1f ms -> %.1f MB/s, rounds=%d, stages=%s" % (
         packed.size, m, text_bytes / 1e6, build_ms, text_bytes / 1e6 / (build_ms * 1e-3), info["rounds"],
