@@ -308,6 +308,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.doc_off_host = idx->doc_off.data();
         in.sort_batch_elems = get_option("sort_batch_elems", 0);
         in.local_group_sort = get_option("doubling_radix", 0) ? 0 : 1;
+        in.segmented_sort = get_option("global_sort", 0) ? 0 : 1;
         SaOutput so;
         so.sa = idx->sa; so.rank = rank.p;
         build_suffix_array(in, so, tm, s);

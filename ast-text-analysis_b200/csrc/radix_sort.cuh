@@ -33,6 +33,17 @@ static inline size_t rs_scratch_bytes(int64_t n, int passes) {
     return ((size_t)rs_num_tiles(n) * 256 * passes + 64) * sizeof(uint32_t);
 }
 
+// Segmented mode: the sort runs inside independent segments (documents).  Every tile belongs to
+// exactly one segment; digit offsets are per segment and the look-back chain restarts at every
+// segment, so the segment id never has to be part of the sorted bits and no tile ever walks
+// more than (segment size / tile) predecessors.
+struct RsTileDesc {
+    int32_t start;      // first element of the tile (absolute index into the key/value arrays)
+    int32_t n;          // elements in the tile (<= TILE)
+    int32_t seg;        // segment index (row of the per-segment histogram)
+    int32_t seg_start;  // first element of the segment
+};
+
 #ifdef __CUDACC__
 
 // Accumulate the digits of one key into a CTA-private histogram s_hist[passes][256].
@@ -116,7 +127,8 @@ template <int THREADS, int ITEMS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
               const uint32_t *__restrict__ vin, uint32_t *__restrict__ vout, int32_t n, int shift,
-              const uint32_t *__restrict__ hist_excl, volatile uint32_t *status, uint32_t *ticket) {
+              const uint32_t *__restrict__ hist_excl, volatile uint32_t *status, uint32_t *ticket,
+              const RsTileDesc *__restrict__ descs, int hist_seg_stride) {
     using Cfg = RsCfg<THREADS, ITEMS>;
     constexpr int WARPS = Cfg::WARPS, TILE = Cfg::TILE;
     extern __shared__ __align__(16) uint32_t rs_smem[];
@@ -134,8 +146,20 @@ k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
     for (int i = 0; i < 8; ++i) s_cnt[w][lane + 32 * i] = 0;
     __syncthreads();
     const uint32_t tile = *s_tile;
-    const int64_t tile_base = (int64_t)tile * TILE;
-    const int tile_n = (int)min((int64_t)TILE, (int64_t)n - tile_base);
+    int64_t tile_base = (int64_t)tile * TILE;
+    int tile_n;
+    bool first = tile == 0;   // first tile of its segment: nothing to look back at
+    uint32_t out_base = 0;    // where the segment starts in the output
+    if (descs != nullptr) {
+        const RsTileDesc d = descs[tile];
+        tile_base = d.start;
+        tile_n = d.n;
+        first = d.start == d.seg_start;
+        out_base = (uint32_t)d.seg_start;
+        hist_excl += (size_t)d.seg * hist_seg_stride;
+    } else {
+        tile_n = (int)min((int64_t)TILE, (int64_t)n - tile_base);
+    }
 
     // ---- load (warp-striped: item j of lane l is element w*32*ITEMS + j*32 + l of the tile)
     uint64_t key[ITEMS];
@@ -184,7 +208,7 @@ k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
             total += c;
         }
         // publish the tile aggregate as early as possible
-        if (tile == 0) *my_status = RS_FLAG_PREFIX | total;
+        if (first) *my_status = RS_FLAG_PREFIX | total;
         else *my_status = RS_FLAG_AGG | total;
     }
     // ---- exclusive scan of totals over the 256 digits -> local start of each digit run
@@ -208,7 +232,7 @@ k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
         // words of RS_LOOKBACK predecessors are fetched together (independent loads, one L2 round
         // trip) and consumed in order; a word that is not published yet restarts the fetch there.
         uint32_t excl = 0;
-        if (tile > 0) {
+        if (!first) {
             int64_t prev = (int64_t)tile - 1;
             bool done = false;
             while (!done) {
@@ -230,7 +254,7 @@ k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
             }
             *my_status = RS_FLAG_PREFIX | (excl + total);
         }
-        s_gbase[t] = hist_excl[t] + excl - s_dstart[t];
+        s_gbase[t] = out_base + hist_excl[t] + excl - s_dstart[t];
     }
     __syncthreads();
 
@@ -273,5 +297,12 @@ k_rs_onesweep(const uint64_t *__restrict__ kin, uint64_t *__restrict__ kout,
 // Returns 0 if the result is in (ka, va), 1 if in (kb, vb).
 int radix_sort_pairs(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int32_t n, int nbits,
                      uint32_t *hist, bool hist_ready, void *scratch, cudaStream_t s, int variant = 0);
+
+// Segmented variant: descs[num_tiles] (device) describe tiles of RS_SEG_TILE elements that never
+// cross a segment; hist[n_seg][passes][256] holds the per-segment digit counts (already accumulated).
+constexpr int RS_SEG_TILE = 4096;
+int radix_sort_pairs_segmented(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int nbits,
+                               const RsTileDesc *descs, int num_tiles, int64_t n_total, uint32_t *hist, int n_seg,
+                               void *scratch, cudaStream_t s);
 
 }  // namespace east

@@ -40,7 +40,8 @@ static void launch_onesweep(const uint64_t *kin, uint64_t *kout, const uint32_t 
     const int tiles = rs_num_tiles(n, Cfg::TILE);
     EAST_BYTES(24.0 * n);  // read + write of an 8-byte key and a 4-byte value per element
     if (g_time_kernels) ktime_begin("k_rs_onesweep", s);
-    kern<<<tiles, THREADS, Cfg::SMEM, s>>>(kin, kout, vin, vout, n, shift, hist_excl, status, ticket);
+    kern<<<tiles, THREADS, Cfg::SMEM, s>>>(kin, kout, vin, vout, n, shift, hist_excl, status, ticket,
+                                           (const RsTileDesc *)nullptr, 0);
     if (g_time_kernels) ktime_end(s);
     ++g_launches;
     g_next_bytes = 0.0;
@@ -84,6 +85,47 @@ int radix_sort_pairs(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int
             default: launch_onesweep<256, 16, 3>(kin, kout, vin, vout, n, 8 * p, hist + 256 * p, st, tickets + p, s); break;
         }
 #undef RS_CASE
+        cur ^= 1;
+    }
+    return cur;
+}
+
+int radix_sort_pairs_segmented(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_t *vb, int nbits,
+                               const RsTileDesc *descs, int num_tiles, int64_t n_total, uint32_t *hist, int n_seg,
+                               void *scratch, cudaStream_t s) {
+    if (num_tiles <= 0) return 0;
+    int passes = rs_num_passes(nbits);
+    if (passes < 1) passes = 1;
+    if (passes > RS_MAX_PASSES) throw Error(-1, "radix_sort_pairs_segmented: too many key bits");
+    using Cfg = RsCfg<256, 16>;
+    static_assert(Cfg::TILE == RS_SEG_TILE, "tile descriptors are built for the 256 x 16 kernel");
+    auto kern = k_rs_onesweep<256, 16, 3>;
+    static bool configured = false;
+    if (!configured) {
+        EAST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        configured = true;
+    }
+    // exclusive scan of every (segment, pass) row of 256 bins
+    EAST_LAUNCH(k_rs_scan_hist, n_seg * passes, 256, 0, s, hist);
+    const size_t status_words = (size_t)num_tiles * 256;
+    EAST_CUDA(cudaMemsetAsync(scratch, 0, (status_words * passes + 64) * sizeof(uint32_t), s));
+    uint32_t *status = (uint32_t *)scratch;
+    uint32_t *tickets = status + status_words * passes;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        const uint64_t *kin = cur ? kb : ka;
+        uint64_t *kout = cur ? ka : kb;
+        const uint32_t *vin = cur ? vb : va;
+        uint32_t *vout = cur ? va : vb;
+        EAST_BYTES(24.0 * (double)n_total);  // read + write of an 8-byte key and a 4-byte value per element
+        if (g_time_kernels) ktime_begin("k_rs_onesweep", s);
+        kern<<<num_tiles, 256, Cfg::SMEM, s>>>(kin, kout, vin, vout, 0, 8 * p, hist + 256 * p, status + status_words * p,
+                                               tickets + p, descs, passes * 256);
+        if (g_time_kernels) ktime_end(s);
+        ++g_launches;
+        g_next_bytes = 0.0;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw Error(-2, std::string("k_rs_onesweep (segmented) launch: ") + cudaGetErrorString(e));
         cur ^= 1;
     }
     return cur;
@@ -389,6 +431,76 @@ k_keygen0_fast(const uint8_t *__restrict__ T8, int32_t n, int32_t begin, int32_t
     }
     __syncthreads();
     rs_hist_flush(s_hist, g_hist, kp.passes);
+}
+
+// Segmented variant of the fast-path key generator: works on the sort's tile descriptors (a tile
+// never crosses a document, so the document id is a per-tile constant) and accumulates the digit
+// histograms PER DOCUMENT (hist[seg][pass][256]).  A block owns a contiguous run of tiles and
+// flushes its shared-memory histogram only when the document changes.
+__global__ void __launch_bounds__(KG_THREADS)
+k_keygen0_fast_seg(const uint8_t *__restrict__ T8, int32_t n, const RsTileDesc *__restrict__ descs, int num_tiles,
+                   int tiles_per_block, KeyParams kp, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                   uint32_t *g_hist) {
+    __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
+    __shared__ __align__(16) uint8_t s_t[KG_TILE + KG_HALO + 32];
+    const int b = kp.b, kc = kp.kc;
+    const int groups = (kc + 7) >> 3, rem = kc - 8 * (groups - 1);
+    const uint64_t term8 = 0x0101010101010101ull * (uint64_t)kp.term;
+    const int t_lo = blockIdx.x * tiles_per_block, t_hi = min(num_tiles, t_lo + tiles_per_block);
+    int cur_seg = -1;
+    for (int i = threadIdx.x; i < kp.passes * 256; i += blockDim.x) s_hist[i] = 0;
+    for (int ti = t_lo; ti < t_hi; ++ti) {
+        const RsTileDesc d = descs[ti];
+        if (d.seg != cur_seg) {
+            __syncthreads();
+            if (cur_seg >= 0) {
+                rs_hist_flush(s_hist, g_hist + (size_t)cur_seg * kp.passes * 256, kp.passes);
+                __syncthreads();
+                for (int i = threadIdx.x; i < kp.passes * 256; i += blockDim.x) s_hist[i] = 0;
+            }
+            cur_seg = d.seg;
+        }
+        for (int half = 0; half < d.n; half += KG_TILE) {
+            const int32_t base = d.start + half;
+            const int32_t a0 = base & ~15;            // 16-byte aligned staging window
+            const int shift = base - a0;
+            const int cnt = min(KG_TILE, d.n - half);
+            __syncthreads();
+            for (int o = threadIdx.x * 16; o < KG_TILE + KG_HALO + 32; o += blockDim.x * 16) {
+                const int64_t g = (int64_t)a0 + o;
+                if (g + 16 <= n) *reinterpret_cast<uint4 *>(s_t + o) = *reinterpret_cast<const uint4 *>(T8 + g);
+                else for (int q = 0; q < 16; ++q) s_t[o + q] = (g + q < n) ? T8[g + q] : 0;
+            }
+            __syncthreads();
+#pragma unroll 2
+            for (int it = 0; it < KG_ITEMS; ++it) {
+                const int o = it * KG_THREADS + threadIdx.x;
+                const bool valid = o < cnt;
+                uint64_t key = 0;
+                if (valid) {
+                    int tpos = kc;
+                    for (int gq = 0; gq < groups; ++gq) {
+                        const uint64_t x = lds8(s_t, o + shift + 8 * gq);
+                        if (tpos == kc) {
+                            const uint64_t tt = x ^ term8;
+                            const uint64_t z = (tt - 0x0101010101010101ull) & ~tt & 0x8080808080808080ull;
+                            if (z) tpos = min(kc, 8 * gq + ((__ffsll((long long)z) - 1) >> 3));
+                        }
+                        const uint64_t f = pack8(x, b);
+                        if (gq + 1 < groups) key = (key << (8 * b)) | f;
+                        else key = (key << (rem * b)) | (f >> ((8 - rem) * b));
+                    }
+                    if (tpos < kc - 1) key &= ~((1ull << (b * (kc - 1 - tpos))) - 1ull);
+                    if (kc * b < 64) key |= (uint64_t)d.seg << (kc * b);
+                    keys[base + o] = key;
+                    vals[base + o] = (uint32_t)(base + o);
+                }
+                rs_hist_add(s_hist, key, kp.passes, valid, kp.passes);  // text symbols only: plain atomics
+            }
+        }
+    }
+    __syncthreads();
+    if (cur_seg >= 0) rs_hist_flush(s_hist, g_hist + (size_t)cur_seg * kp.passes * 256, kp.passes);
 }
 
 // general path: raw code points + 1, window cut at the end of the document (pad 0)
@@ -740,7 +852,12 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     if (kc > KG_HALO) kc = KG_HALO;
     // one symbol less when that saves a whole radix pass over all N suffixes and still leaves a
     // window of >= 8 symbols (measured on the Zipf workload: 55-bit keys / 7 passes beat 60 / 8)
-    if (kc > 8 && rs_num_passes(dbits + (kc - 1) * kp.b) < rs_num_passes(dbits + kc * kp.b)) --kc;
+    {
+        // bits that actually get sorted: without the document id when the per-document sort applies
+        const bool seg_like = fast && in.segmented_sort && (int64_t)n / D >= 2 * RS_SEG_TILE && in.sort_batch_elems == 0;
+        const int extra = seg_like ? 0 : dbits;
+        if (kc > 8 && rs_num_passes(extra + (kc - 1) * kp.b) < rs_num_passes(extra + kc * kp.b)) --kc;
+    }
     if (in.key_chars > 0 && in.key_chars < kc) kc = in.key_chars;
     kp.kc = kc;
     const int key_bits = dbits + kc * kp.b;
@@ -769,15 +886,44 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                     (uint8_t)kp.term, t8.p);
     }
 
-    // Round 0 is sorted in batches of 2^g whole documents (documents are independent and the
-    // document id tops every key): inside a batch only the low g bits of the id vary, so fewer
-    // key bits need sorting, and the ping-pong buffers of a batch (~24 B per suffix) stay resident
-    // in the 126 MB L2 across all passes instead of streaming through HBM eight times.
     tm.mark("keygen0+sort0");
+    int cur = 0;
+    const bool segmented = fast && in.segmented_sort && (int64_t)n / D >= 2 * RS_SEG_TILE && in.sort_batch_elems == 0;
+    out.segmented = segmented ? 1 : 0;
+    if (segmented) {
+        // ---- per-document (segmented) sort: every tile belongs to one document, digit offsets and
+        // look-back chains are per document, the document id is not part of the sorted bits
+        const int sort_bits = kc * kp.b;
+        kp.passes = rs_num_passes(sort_bits);
+        out.key_bits = sort_bits;
+        std::vector<RsTileDesc> descs;
+        descs.reserve((size_t)n / RS_SEG_TILE + D + 1);
+        for (int d = 0; d < D; ++d) {
+            const int32_t e0 = in.doc_off_host[d], e1 = in.doc_off_host[d + 1];
+            for (int32_t st = e0; st < e1; st += RS_SEG_TILE)
+                descs.push_back(RsTileDesc{st, std::min<int32_t>(RS_SEG_TILE, e1 - st), d, e0});
+        }
+        const int num_tiles = (int)descs.size();
+        DevBuf<RsTileDesc> d_descs(descs.size(), s);
+        EAST_CUDA(cudaMemcpyAsync(d_descs.p, descs.data(), sizeof(RsTileDesc) * descs.size(), cudaMemcpyHostToDevice, s));
+        DevBuf<uint32_t> hist_seg((size_t)D * kp.passes * 256, s);
+        EAST_CUDA(cudaMemsetAsync(hist_seg.p, 0, sizeof(uint32_t) * (size_t)D * kp.passes * 256, s));
+        const int blocks = std::min(num_tiles, EAST_NUM_SMS * 4);
+        const int per_block = (num_tiles + blocks - 1) / blocks;
+        EAST_BYTES(13.0 * n);
+        EAST_LAUNCH(k_keygen0_fast_seg, (num_tiles + per_block - 1) / per_block, KG_THREADS, 0, s, t8.p, n, d_descs.p,
+                    num_tiles, per_block, kp, keys_a.p, vals_a.p, hist_seg.p);
+        DevBuf<uint8_t> seg_scratch(((size_t)num_tiles * 256 * kp.passes + 64) * sizeof(uint32_t), s);
+        cur = radix_sort_pairs_segmented(keys_a.p, keys_b.p, vals_a.p, vals_b.p, sort_bits, d_descs.p, num_tiles, n,
+                                         hist_seg.p, D, seg_scratch.p, s);
+        EAST_CUDA(cudaStreamSynchronize(s));  // descs (host vector) must outlive its copy
+    } else {
+    // Global sort (document id on top of the key).  It may be cut into batches of 2^g whole
+    // documents (option sort_batch_elems): inside a batch only the low g bits of the id vary.
+    // Measured on B200: batching is a LOSS (every launch pays ~13 us of ramp-up/tail and the kernel
+    // is latency- not bandwidth-bound), so the default sorts the whole batch at once.
     int g = dbits;
     {
-        // measured on B200: batching is a LOSS (every launch pays ~13 us of ramp-up/tail and the
-        // kernel is latency- not bandwidth-bound), so the default sorts the whole batch at once
         const int64_t target = in.sort_batch_elems > 0 ? in.sort_batch_elems : (int64_t)n;
         const int64_t avg = std::max<int64_t>(1, (int64_t)n / D);
         int want = 0;
@@ -787,7 +933,6 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     const int sort_bits = kc * kp.b + g;
     kp.passes = rs_num_passes(sort_bits);
     out.key_bits = sort_bits;
-    int cur = 0;
     for (int d0 = 0; d0 < D; d0 += (1 << g)) {
         const int d1 = std::min(D, d0 + (1 << g));
         const int32_t e0 = in.doc_off_host[d0], e1 = in.doc_off_host[d1];
@@ -804,6 +949,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         }
         cur = radix_sort_pairs(keys_a.p + e0, keys_b.p + e0, vals_a.p + e0, vals_b.p + e0, nb, sort_bits, hist.p, true,
                                scratch.p, s, in.rs_variant);
+    }
     }
 
     // scorer acceleration (fast path): first ranks of all (document, 2-gram) buckets

@@ -15,6 +15,7 @@ struct SaInput {
     int force_general;        // testing: never take the terminator-class fast path
     int rs_variant = 0;       // tuning: radix-sort kernel shape (see radix_sort_pairs)
     const int32_t *doc_off_host = nullptr;  // host copy of doc_off
+    int segmented_sort = 1;                 // round 0: per-document tiles / histograms when documents are large
     int local_group_sort = 1;               // doubling rounds: rank inside small groups instead of radix passes
     int64_t sort_batch_elems = 0;           // round-0 sort batch in suffixes (0 = whole batch at once)
 };
@@ -33,6 +34,7 @@ struct SaOutput {
     int key_bits = 0;
     int rounds = 0;
     uint32_t active_after_round0 = 0;
+    int segmented = 0;               // round 0 used the per-document sort
     int radix_fallback_rounds = 0;   // doubling rounds that met a group > GS_MAX and used the radix sort
 };
 

@@ -418,3 +418,26 @@ def test_score_table_tiles_over_documents(oracle_mod):
     assert np.array_equal(full.view(np.uint64), tiled.view(np.uint64))
     exp = oracle_mod.OracleEASA(text=packed[8], m=ms[8]).score_many(codes, off, True)
     assert np.array_equal(tiled[8].view(np.uint64), exp.view(np.uint64))
+
+
+def test_segmented_and_global_round0_sort_agree(oracle_mod):
+    """Large documents take the per-document (segmented) radix sort; the global sort (document id in
+    the sorted bits) must give the same index.  Mixed sizes: tiny documents get tiny tiles."""
+    import synth
+    from east import utils
+    from east.asts import utils as au
+    capi = _capi()
+    sizes = [30000, 200, 12000, 60, 25000, 9000]
+    cols = [utils.text_to_strings_collection(synth.document(sz, 500 + i)) for i, sz in enumerate(sizes)]
+    packed = [au.pack_strings_collection(c) for c in cols]
+    ms = [len(c) for c in cols]
+    oracles = [oracle_mod.OracleEASA(text=p, m=m) for p, m in zip(packed, ms)]
+    try:
+        for global_sort in (0, 1):
+            capi.set_option("global_sort", global_sort)
+            idx = capi.DeviceIndex(packed, ms)
+            for d, o in enumerate(oracles):
+                _check_arrays(idx, d, o, (global_sort, d))
+            idx.close()
+    finally:
+        capi.set_option("global_sort", 0)
