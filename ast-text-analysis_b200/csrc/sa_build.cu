@@ -888,6 +888,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
 
     tm.mark("keygen0+sort0");
     int cur = 0;
+    std::vector<RsTileDesc> descs;  // lives until the function's next host sync: source of an async copy
     const bool segmented = fast && in.segmented_sort && (int64_t)n / D >= 2 * RS_SEG_TILE && in.sort_batch_elems == 0;
     out.segmented = segmented ? 1 : 0;
     if (segmented) {
@@ -896,7 +897,6 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         const int sort_bits = kc * kp.b;
         kp.passes = rs_num_passes(sort_bits);
         out.key_bits = sort_bits;
-        std::vector<RsTileDesc> descs;
         descs.reserve((size_t)n / RS_SEG_TILE + D + 1);
         for (int d = 0; d < D; ++d) {
             const int32_t e0 = in.doc_off_host[d], e1 = in.doc_off_host[d + 1];
@@ -916,7 +916,6 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         DevBuf<uint8_t> seg_scratch(((size_t)num_tiles * 256 * kp.passes + 64) * sizeof(uint32_t), s);
         cur = radix_sort_pairs_segmented(keys_a.p, keys_b.p, vals_a.p, vals_b.p, sort_bits, d_descs.p, num_tiles, n,
                                          hist_seg.p, D, seg_scratch.p, s);
-        EAST_CUDA(cudaStreamSynchronize(s));  // descs (host vector) must outlive its copy
     } else {
     // Global sort (document id on top of the key).  It may be cut into batches of 2^g whole
     // documents (option sort_batch_elems): inside a batch only the low g bits of the id vary.

@@ -34,8 +34,8 @@ for kc, bt in itertools.product([int(x) for x in a.key_chars.split(",")], [int(x
             t0 = time.perf_counter()
             idx = _capi.DeviceIndex.build_dev(dev.data_ptr(), doc_off, doc_m)
             wall = (time.perf_counter() - t0) * 1e3
-            ks = _capi.kernel_stats()
             info = idx.info(); idx.close(); st = dict(idx.build_timings)
+            ks = _capi.kernel_stats()
             one = ks["k_rs_onesweep"]
             row = (wall, one["ms"], one["launches"], one["bytes"] / (one["ms"] * 1e-3) / 1e9, st, info["rounds"])
             if best is None or row[0] < best[0]:
