@@ -148,7 +148,7 @@ struct east_index {
     uint32_t *bkt = nullptr;        // fast path: 2-gram bucket table
     std::vector<uint8_t> code_table;
     int sym_bits = 0, term_code = 0;
-    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0;
+    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0;
     uint32_t active_after_round0 = 0;
     // LCP / child / annotation tables are produced on an auxiliary stream after the suffix array is
     // final, so a score call (which needs only SA + text) overlaps them; readers wait on ev_tables
@@ -309,11 +309,16 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.sort_batch_elems = get_option("sort_batch_elems", 0);
         in.local_group_sort = get_option("doubling_radix", 0) ? 0 : 1;
         in.segmented_sort = get_option("global_sort", 0) ? 0 : 1;
+        // the per-document shared-memory sort is the default for small documents; any tuning option of
+        // the global prefix-doubling sort (and "no_doc_sort") selects the global sort instead
+        in.doc_sort = (get_option("no_doc_sort", 0) || in.key_chars || in.rs_variant || in.sort_batch_elems ||
+                       !in.segmented_sort || !in.local_group_sort) ? 0 : 1;
         SaOutput so;
         so.sa = idx->sa; so.rank = rank.p;
         build_suffix_array(in, so, tm, s);
         idx->rounds = so.rounds; idx->fast_path = so.fast_path; idx->key_chars = so.key_chars;
         idx->key_bits = so.key_bits; idx->active_after_round0 = so.active_after_round0;
+        idx->doc_sorted = so.doc_sorted; idx->doc_sort_overflow = so.doc_sort_overflow;
         idx->t8 = so.t8.p; so.t8.p = nullptr;      // ownership moves to the index
         idx->bkt = so.bkt.p; so.bkt.p = nullptr;
         idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
@@ -399,6 +404,19 @@ int east_index_doc(const east_index *idx, int32_t doc, int64_t *offset, int64_t 
     if (offset) *offset = idx->doc_off[doc];
     if (n) *n = idx->doc_off[doc + 1] - idx->doc_off[doc];
     if (m) *m = idx->doc_m[doc];
+    return EAST_OK;
+}
+
+int east_index_stat(const east_index *idx, const char *name, int64_t *value) {
+    if (!idx || !name || !value) return fail(EAST_ERR_INVALID, "NULL argument");
+    if (!strcmp(name, "doc_sorted")) *value = idx->doc_sorted;
+    else if (!strcmp(name, "doc_sort_overflow")) *value = idx->doc_sort_overflow;
+    else if (!strcmp(name, "key_chars")) *value = idx->key_chars;
+    else if (!strcmp(name, "key_bits")) *value = idx->key_bits;
+    else if (!strcmp(name, "rounds")) *value = idx->rounds;
+    else if (!strcmp(name, "active_after_round0")) *value = idx->active_after_round0;
+    else if (!strcmp(name, "fast_path")) *value = idx->fast_path;
+    else return fail(EAST_ERR_INVALID, "unknown stat name");
     return EAST_OK;
 }
 

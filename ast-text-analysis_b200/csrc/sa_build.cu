@@ -865,6 +865,52 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     out.key_chars = kc;
     out.key_bits = key_bits;
 
+    tm.mark("encode");
+    DevBuf<uint8_t> t8;
+    if (fast) {
+        DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
+        EAST_CUDA(cudaMemcpyAsync(d_table.p, table.data(), EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
+        t8 = DevBuf<uint8_t>((size_t)n + 128, s);
+        EAST_BYTES(5.0 * n);
+        EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_table.p,
+                    (uint8_t)kp.term, t8.p);
+    }
+    out.code_table = table;
+    out.term_code = fast ? (int)kp.term : 0;
+
+    // ---- small documents: one CTA per document, everything in shared memory (doc_sort.cu)
+    if (fast && in.doc_sort) {
+        int32_t max_doc_n = 0;
+        for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);
+        DocSortPlan plan;
+        if (doc_sort_plan(sigma, max_doc_n, plan)) {
+            tm.mark("doc_sort");
+            DevBuf<uint32_t> flag(1, s);
+            EAST_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), s));
+            if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
+                const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
+                out.bkt = DevBuf<uint32_t>(entries, s);
+                EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+                out.sym_bits = plan.b;
+            }
+            doc_sort_launch(plan, t8.p, in.doc_off, D, n, kp.term, out.sa, out.bkt.p, flag.p, s);
+            uint32_t overflow = 0;
+            EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            EAST_CUDA(cudaStreamSynchronize(s));
+            if (!overflow) {
+                out.doc_sorted = 1;
+                out.rounds = 1;
+                out.key_chars = plan.G + plan.WS;
+                out.key_bits = plan.b * (plan.G + plan.WS);
+                out.t8 = std::move(t8);
+                return;
+            }
+            out.doc_sort_overflow = 1;   // a bucket of > 8192 suffixes: the global sort below redoes the batch
+            out.bkt = DevBuf<uint32_t>();
+            out.sym_bits = 0;
+        }
+    }
+
     // buffers: ping-pong keys/values, active-list side arrays, histogram + look-back scratch
     DevBuf<uint64_t> keys_a(n, s), keys_b(n, s);
     DevBuf<uint32_t> vals_a(n, s), vals_b(n, s);
@@ -874,17 +920,6 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     DevBuf<uint64_t> rr_status((size_t)rr_tiles_max + 2, s);
     DevBuf<uint32_t> rr_misc(8, s);  // [0] ticket, [1] kept count
     uint32_t *rank = out.rank;
-
-    tm.mark("encode");
-    DevBuf<uint8_t> t8;
-    if (fast) {
-        DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
-        EAST_CUDA(cudaMemcpyAsync(d_table.p, table.data(), EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
-        t8 = DevBuf<uint8_t>((size_t)n + 64, s);
-        EAST_BYTES(5.0 * n);
-        EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_table.p,
-                    (uint8_t)kp.term, t8.p);
-    }
 
     tm.mark("keygen0+sort0");
     int cur = 0;
@@ -959,8 +994,6 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         out.sym_bits = kp.b;
     }
-    out.code_table = table;
-    out.term_code = fast ? (int)kp.term : 0;
     tm.mark("rerank0");
     DevBuf<uint32_t> act_vals(n, s), act_slots(n, s), act_prim(n, s);
     DevBuf<uint32_t> nxt_vals, nxt_slots, nxt_prim;

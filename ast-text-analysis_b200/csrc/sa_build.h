@@ -18,6 +18,7 @@ struct SaInput {
     int segmented_sort = 1;                 // round 0: per-document tiles / histograms when documents are large
     int local_group_sort = 1;               // doubling rounds: rank inside small groups instead of radix passes
     int64_t sort_batch_elems = 0;           // round-0 sort batch in suffixes (0 = whole batch at once)
+    int doc_sort = 1;                       // small documents: one CTA sorts a whole document in shared memory
 };
 
 struct SaOutput {
@@ -36,9 +37,21 @@ struct SaOutput {
     uint32_t active_after_round0 = 0;
     int segmented = 0;               // round 0 used the per-document sort
     int radix_fallback_rounds = 0;   // doubling rounds that met a group > GS_MAX and used the radix sort
+    int doc_sorted = 0;              // the per-document shared-memory sort produced the suffix array
+    int doc_sort_overflow = 0;       // it met a bucket it cannot sort and the global sort took over
 };
 
 void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s);
+
+// per-document shared-memory suffix sort (doc_sort.cu)
+struct DocSortPlan {
+    int b = 0, G = 0, WS = 0;   // bits per symbol, symbols per bucket id, symbols per key word
+    int text_cap = 0, bits_words = 0;
+    size_t smem = 0;
+};
+bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan);
+void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const int32_t *doc_off, int n_docs, int64_t n_total,
+                     uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s);
 
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch

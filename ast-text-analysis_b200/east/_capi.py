@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "east_free", "east_index_info", "east_index_doc", "east_index_copy", "east_index_devptr",
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
     "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
-    "east_score_probes_dev",
+    "east_score_probes_dev", "east_index_stat",
 ]
 
 _lib = None
@@ -58,6 +58,7 @@ def load():
     L.east_free.restype = None
     L.east_index_info.argtypes = [_vp, _i32p, _i64p, _i32p, _i32p, _i32p]
     L.east_index_doc.argtypes = [_vp, ctypes.c_int32, _i64p, _i64p, _i32p]
+    L.east_index_stat.argtypes = [_vp, ctypes.c_char_p, _i64p]
     L.east_index_copy.argtypes = [_vp, ctypes.c_int32, ctypes.c_int, _i32p]
     L.east_index_devptr.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp)]
     L.east_score_table_host.argtypes = [_vp, _u32p, _i64p, ctypes.c_int32, ctypes.c_int, _f64p]
@@ -233,7 +234,13 @@ class DeviceIndex(object):
         _check(load().east_index_info(self._h, ctypes.byref(n_docs), ctypes.byref(n_total), ctypes.byref(dev),
                                       ctypes.byref(rounds), ctypes.byref(fast)))
         return {"n_docs": n_docs.value, "n_total": n_total.value, "device": dev.value,
-                "rounds": rounds.value, "fast_path": bool(fast.value)}
+                "rounds": rounds.value, "fast_path": bool(fast.value),
+                "doc_sorted": bool(self.stat("doc_sorted")), "doc_sort_overflow": bool(self.stat("doc_sort_overflow"))}
+
+    def stat(self, name):
+        v = ctypes.c_int64(0)
+        _check(load().east_index_stat(self._h, name.encode(), ctypes.byref(v)))
+        return int(v.value)
 
     def array(self, doc, which):
         if not 0 <= doc < self.n_docs:

@@ -73,6 +73,10 @@ void east_free(east_index *idx);
 int east_index_info(const east_index *idx, int32_t *n_docs, int64_t *n_total, int32_t *device,
                     int32_t *rounds, int32_t *fast_path);
 int east_index_doc(const east_index *idx, int32_t doc, int64_t *offset, int64_t *n, int32_t *m);
+/* how the suffix array was built (tests assert which kernel path ran): name is one of
+ * "doc_sorted" (1 = the per-document shared-memory sort, doc_sort.cu), "doc_sort_overflow",
+ * "key_chars", "key_bits", "rounds", "active_after_round0", "fast_path" */
+int east_index_stat(const east_index *idx, const char *name, int64_t *value);
 /* copy one array of one document to a host int32 buffer of n entries */
 int east_index_copy(const east_index *idx, int32_t doc, int which, int32_t *dst_host);
 /* device pointer to the whole-batch array (global ranks/positions); for tests and benches */

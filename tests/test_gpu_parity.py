@@ -18,6 +18,16 @@ def _capi():
     return _capi
 
 
+@pytest.fixture(autouse=True, params=["doc_sort", "global_sort"])
+def sa_path(request):
+    """Every test runs twice: with the per-document shared-memory suffix sort (doc_sort.cu, the default
+    for documents of < 64 Ki code points) and with the global prefix-doubling sort (sa_build.cu)."""
+    capi = _capi()
+    capi.set_option("no_doc_sort", 1 if request.param == "global_sort" else 0)
+    yield request.param
+    capi.set_option("no_doc_sort", 0)
+
+
 def _build(strings_collections, device=0):
     from east.asts import utils
     packed = [utils.pack_strings_collection(c) for c in strings_collections]
@@ -114,13 +124,14 @@ def test_random_collections_vs_oracle(oracle_mod, force_general):
         capi.set_option("force_general", 0)
 
 
-def test_zipf_documents_vs_oracle(oracle_mod):
+def test_zipf_documents_vs_oracle(oracle_mod, sa_path):
     import synth
     capi = _capi()
     packed, ms, cols = synth.packed_collection(6, 10000)
     idx = capi.DeviceIndex(packed, ms)
     info = idx.info()
     assert info["fast_path"] and info["rounds"] <= 6
+    assert info["doc_sorted"] == (sa_path == "doc_sort")
     oracles = [oracle_mod.OracleEASA(text=p, m=m) for p, m in zip(packed, ms)]
     for d, o in enumerate(oracles):
         _check_arrays(idx, d, o, d)
@@ -152,7 +163,7 @@ def test_key_window_sizes_give_the_same_arrays(oracle_mod):
         capi.set_option("key_chars", 0)
 
 
-def test_deep_lcp_and_degenerate_inputs(oracle_mod):
+def test_deep_lcp_and_degenerate_inputs(oracle_mod, sa_path):
     rng = np.random.default_rng(3)
     s = "".join(rng.choice(list("AB"), size=700))
     cols = [[s] * 5,            # analysis/utils.py:5-9 worst case: identical strings
@@ -163,7 +174,10 @@ def test_deep_lcp_and_degenerate_inputs(oracle_mod):
     idx = _build(cols)
     for d, c in enumerate(cols):
         _check_arrays(idx, d, oracle_mod.OracleEASA(c), d)
-    assert idx.info()["rounds"] >= 5
+    if sa_path == "global_sort":
+        assert idx.info()["rounds"] >= 5
+    else:
+        assert idx.info()["doc_sorted"]
     # [" "].score("AB") == 0
     assert idx.score_one(3, np.array([65, 66], dtype=np.uint32)) == 0.0
 
@@ -441,3 +455,43 @@ def test_segmented_and_global_round0_sort_agree(oracle_mod):
             idx.close()
     finally:
         capi.set_option("global_sort", 0)
+
+
+def test_doc_sort_bucket_overflow_falls_back_to_the_global_sort(oracle_mod, sa_path):
+    # one bucket of > 8192 suffixes (a run of 9000 equal symbols) is more than a CTA sorts in shared
+    # memory: the build must notice, redo the batch with the global sort and still be exact
+    if sa_path != "doc_sort":
+        pytest.skip("per-document sort only")
+    cols = [["A" * 9000, "AB"], ["XABXAC", "HI"]]
+    idx = _build(cols)
+    info = idx.info()
+    assert info["doc_sort_overflow"] and not info["doc_sorted"]
+    for d, c in enumerate(cols):
+        _check_arrays(idx, d, oracle_mod.OracleEASA(c), d)
+    # buckets of 1025..8192 suffixes: sorted by the whole CTA
+    cols = [["A" * 5000, "BA" * 1200], ["C" * 1100]]
+    idx = _build(cols)
+    assert idx.info()["doc_sorted"]
+    for d, c in enumerate(cols):
+        _check_arrays(idx, d, oracle_mod.OracleEASA(c), d)
+
+
+def test_doc_sort_alphabet_sizes(oracle_mod, sa_path):
+    # bits per symbol 1..7 select different bucket / key geometries (G, WS) of the per-document sort
+    if sa_path != "doc_sort":
+        pytest.skip("per-document sort only")
+    rng = np.random.default_rng(5)
+    pool = [chr(c) for c in range(0x21, 0x7f)] + [chr(c) for c in range(0x410, 0x450)]
+    for sigma in (1, 2, 3, 6, 7, 8, 14, 15, 16, 30, 31, 32, 62, 63, 64, 120, 126):
+        alpha = pool[:sigma]
+        cols = []
+        for _ in range(3):
+            m = int(rng.integers(1, 30))
+            cols.append(["".join(rng.choice(alpha, size=int(rng.integers(1, 60)))) for _ in range(m)])
+        # repeated phrases: ties beyond the first key word
+        cols.append(["".join(rng.choice(alpha, size=50)) * 3] * 4)
+        idx = _build(cols)
+        assert idx.info()["doc_sorted"], sigma
+        for d, c in enumerate(cols):
+            _check_arrays(idx, d, oracle_mod.OracleEASA(c), (sigma, d))
+        idx.close()
