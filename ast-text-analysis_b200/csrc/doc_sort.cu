@@ -14,64 +14,89 @@
 //   1  stage the byte-coded text in shared memory (128-bit loads)
 //   2  histogram of the G-gram bucket ids (window cut after the first terminator): packed 16-bit
 //      shared-memory counters
-//   3  exclusive scan -> bucket starts; bitmap of the ranks where a bucket starts; list of the
+//   3  exclusive scan -> bucket starts; bitmap of the ranks where a bucket starts; work list of the
 //      buckets larger than a warp; the scorer's 2-gram table (first rank of every 2-gram)
 //   4  scatter every suffix into its bucket (shared-memory cursor atomics, 4-byte global stores
-//      that stay in L2)
-//   5a buckets of <= 32 suffixes: one warp per window of 32 ranks ranks every suffix inside its own
-//      bucket by counting the smaller ones; keys are the next WS symbols packed into 64 bits, ties go
-//      to a byte-wise SWAR comparison of the shared-memory text
-//   5b larger buckets: bitonic sort in shared memory by groups of 4 warps (<= 1024 suffixes) or by
-//      the whole CTA (<= 8192); anything larger raises the overflow flag and the host falls back to
-//      the global sort.
+//      that stay in L2); the bucket of the bare terminators is final at once (rank = string index)
+//   5  refine the buckets of more than 32 suffixes, level by level, by groups of 4 warps: skip the
+//      prefix all members share (SWAR compare against the first member), counting-sort the members
+//      on the next S2 symbols in shared memory, mark the new bucket starts, queue what is still
+//      larger than a warp; a bucket whose members are identical up to their terminator is ranked by
+//      position
+//   6  buckets of <= 32 suffixes: one warp per window of 32 ranks ranks every suffix inside its own
+//      bucket by counting the smaller ones; keys are the next 8 symbols (raw bytes, byte-reversed),
+//      ties go to a byte-wise SWAR comparison of the shared-memory text.
+// A bucket of more than 4096 suffixes raises the overflow flag: the host redoes the batch with the
+// global sort.
 #include "sa_build.h"
 
 namespace east {
 
 constexpr int DS_THREADS = 1024;
 constexpr int DS_WARPS = DS_THREADS / 32;
-constexpr int DS_GROUP = 128;                       // threads of a medium-bucket sorting group
+constexpr int DS_GROUP = 128;                       // threads of a bucket-refining group
+constexpr int DS_GWARPS = DS_GROUP / 32;
 constexpr int DS_NGROUPS = DS_THREADS / DS_GROUP;   // 8
-constexpr int DS_MED_MAX = 1024;                    // largest bucket a group sorts
-constexpr int DS_BIG_MAX = 8192;                    // largest bucket the CTA sorts
-constexpr int DS_SCR_BYTES = DS_BIG_MAX * 10;       // u64 key + u16 position per element: 80 KB
-constexpr int DS_BIG_CAP = 2048;                    // >= 65535 / 33 buckets can be larger than a warp
+constexpr int DS_REFINE_MAX = 4096;                 // largest bucket a group refines
+constexpr int DS_SUB_BINS = 1024;                   // bins of one refinement level (S2 * b <= 10 bits)
+constexpr int DS_GRP_BYTES = DS_REFINE_MAX * 2 + DS_SUB_BINS * 4;   // staged positions + bin counters: 12 KB
+constexpr int DS_SCR_BYTES = DS_NGROUPS * DS_GRP_BYTES;             // 96 KB (>= 64 KB of phase-2 counters)
+constexpr int DS_WARP_MAX = 1024;                   // largest bucket one warp refines (one symbol per level)
+constexpr int DS_WARP_BYTES = DS_WARP_MAX * 2 + 128 * 4;   // per-warp scratch: staged positions + <= 128 bin counters
+constexpr int DS_LIST_CAP = 2048;                   // >= 65535 / 33 buckets can be larger than a warp
 constexpr int DS_WIN_BYTES = 64 * 8 + 64 * 4;       // per-warp window scratch: 64 keys + 64 positions
+constexpr int DS_INF = 0x7fffffff;
+static_assert(DS_WARPS * DS_WARP_BYTES <= DS_SCR_BYTES && DS_WARPS * DS_WIN_BYTES <= DS_SCR_BYTES, "scratch");
 
 struct DocSortParams {
     const uint8_t *t8;        // byte-coded text of the batch (n + 128 bytes allocated)
+    const uint32_t *text;     // code points of the batch (only the terminators are read: string index)
     const int32_t *doc_off;
+    const int32_t *doc_m;     // strings (= terminators) per document
     int32_t *sa;              // out: global text positions in suffix order, doc-major
     uint32_t *bkt;            // out (optional): first global rank of every (document, 2-gram)
-    uint32_t *overflow;       // out: set when a bucket exceeds DS_BIG_MAX
-    int b, G, WS;             // bits per symbol, symbols per bucket id, symbols per 64-bit key word
+    uint32_t *overflow;       // out: set when a bucket exceeds DS_REFINE_MAX
+    int b, G, S2;             // bits per symbol, symbols per bucket id, symbols per refinement level
     uint32_t term;            // terminator class code
     int text_cap;             // bytes reserved for the staged text
     int bits_words;           // words of the bucket-start bitmap
+    unsigned long long *phase_clk;  // optional (profiling): SM cycles per phase, summed over the CTAs
 };
 
-// 8 bytes of shared memory at an arbitrary byte offset from a 16-byte aligned base
+// 8 bytes of shared memory at an arbitrary byte offset from a 16-byte aligned base: three aligned
+// 32-bit loads and two funnel shifts (64-bit variable shifts cost several instructions each)
 __device__ __forceinline__ uint64_t ds_lds8(const uint8_t *base, int o) {
-    const uint64_t *q = reinterpret_cast<const uint64_t *>(base + (o & ~7));
-    const int sh = (o & 7) * 8;
-    const uint64_t lo = q[0];
-    if (sh == 0) return lo;
-    return (lo >> sh) | (q[1] << (64 - sh));
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(base + (o & ~3));
+    const uint32_t sh = (uint32_t)(o & 3) * 8u;
+    const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+    return ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+}
+__device__ __forceinline__ uint32_t ds_lds4(const uint8_t *base, int o) {
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(base + (o & ~3));
+    return __funnelshift_r(q[0], q[1], (uint32_t)(o & 3) * 8u);
+}
+
+// 0x80 in every zero byte of v (exact for every byte, unlike the borrow trick below)
+__device__ __forceinline__ uint32_t ds_zero4(uint32_t v) {
+    return ~(((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v | 0x7f7f7f7fu);
 }
 
 __device__ __forceinline__ uint64_t ds_haszero(uint64_t v) {
     return (v - 0x0101010101010101ull) & ~v & 0x8080808080808080ull;
 }
 
-// 8 consecutive byte codes (first symbol in the lowest byte) -> 8*b bits, first symbol on top
-__device__ __forceinline__ uint64_t ds_pack8(uint64_t x, int b) {
-    x = ((x & 0x00ff00ff00ff00ffull) << b) | ((x >> 8) & 0x00ff00ff00ff00ffull);
-    x = ((x & 0x0000ffff0000ffffull) << (2 * b)) | ((x >> 16) & 0x0000ffff0000ffffull);
-    return ((x & 0x00000000ffffffffull) << (4 * b)) | (x >> 32);
+// bucket id from the first nsym <= 4 symbols held in the low bytes of w, cut after the first terminator
+__device__ __forceinline__ uint32_t ds_id_from_word(uint32_t w, uint32_t term4, int b, int nsym) {
+    const uint32_t z = ds_zero4(w ^ term4) & (0xffffffffu >> (8 * (4 - nsym)));
+    if (z) w &= 0xffffffffu >> (8 * (3 - ((__ffs(z) - 1) >> 3)));
+    uint32_t id = 0;
+    for (int g = 0; g < nsym; ++g) id = (id << b) | ((w >> (8 * g)) & 0xffu);
+    return id;
 }
 
-// bucket id of the suffix at byte offset o: its first G symbols, cut after the first terminator
-__device__ __forceinline__ uint32_t ds_bucket(const uint8_t *s_raw, int o, uint64_t term8, int b, int G) {
+// bucket id of the suffix at byte offset o: its first nsym symbols, cut after the first terminator
+__device__ __forceinline__ uint32_t ds_bucket(const uint8_t *s_raw, int o, uint64_t term8, int b, int nsym) {
+    if (nsym <= 4) return ds_id_from_word(ds_lds4(s_raw, o), (uint32_t)term8, b, nsym);
     uint64_t x = ds_lds8(s_raw, o);
     const uint64_t z = ds_haszero(x ^ term8);
     if (z) {
@@ -79,32 +104,48 @@ __device__ __forceinline__ uint32_t ds_bucket(const uint8_t *s_raw, int o, uint6
         if (k < 7) x &= (1ull << (8 * (k + 1))) - 1ull;
     }
     uint32_t id = 0;
-    for (int g = 0; g < G; ++g) id = (id << b) | (uint32_t)((x >> (8 * g)) & 0xffull);
+    for (int g = 0; g < nsym; ++g) id = (id << b) | (uint32_t)((x >> (8 * g)) & 0xffull);
     return id;
 }
 
-// sort key of the suffix at byte offset o: symbols [G, G+WS) of its cut window in the upper bits,
-// bit 0 = "the window [0, G+WS) contains the terminator" (then equal keys are ordered by position)
-__device__ __forceinline__ uint64_t ds_key(const uint8_t *s_raw, int o, uint64_t term8, int b, int G, int WS) {
-    uint64_t x0 = ds_lds8(s_raw, o), x1 = ds_lds8(s_raw, o + 8);
-    const uint64_t z0 = ds_haszero(x0 ^ term8);
-    int tl = 16;  // offset of the first terminator among the 16 symbols (16 = none)
-    if (z0) {
-        tl = (__ffsll((long long)z0) - 1) >> 3;
+// bucket ids of 8 consecutive suffixes starting at byte offset o (one 16-byte window, shared loads)
+struct Ids8 { uint32_t id[8]; };
+__device__ __forceinline__ Ids8 ds_bucket8(const uint8_t *s_raw, int o, uint64_t term8, int b, int nsym) {
+    Ids8 r;
+    if (nsym <= 4) {
+        const uint64_t x0 = ds_lds8(s_raw, o), x1 = ds_lds8(s_raw, o + 8);
+        const uint32_t W[4] = {(uint32_t)x0, (uint32_t)(x0 >> 32), (uint32_t)x1, (uint32_t)(x1 >> 32)};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            r.id[j] = ds_id_from_word(__funnelshift_r(W[j >> 2], W[(j >> 2) + 1], (uint32_t)(j & 3) * 8u), (uint32_t)term8, b, nsym);
     } else {
-        const uint64_t z1 = ds_haszero(x1 ^ term8);
-        if (z1) tl = 8 + ((__ffsll((long long)z1) - 1) >> 3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r.id[j] = ds_bucket(s_raw, o + j, term8, b, nsym);
     }
-    if (tl < 7) { x0 &= (1ull << (8 * (tl + 1))) - 1ull; x1 = 0; }
-    else if (tl == 7) x1 = 0;
-    else if (tl < 15) x1 &= (1ull << (8 * (tl - 7))) - 1ull;
-    // bytes G .. G+15 of the window
-    const uint64_t y0 = (x0 >> (8 * G)) | (x1 << (64 - 8 * G));   // 1 <= G <= 7
-    const uint64_t y1 = x1 >> (8 * G);
-    uint64_t w;
-    if (WS > 8) w = (ds_pack8(y0, b) << (b * (WS - 8))) | (ds_pack8(y1, b) >> (b * (16 - WS)));
-    else w = ds_pack8(y0, b) >> (b * (8 - WS));
-    return (w << 1) | (tl < G + WS ? 1ull : 0ull);
+    return r;
+}
+
+// does a bucket id of nsym symbols contain the terminator (then all its members are identical)
+__device__ __forceinline__ bool ds_id_has_term(uint32_t id, int nsym, int b, uint32_t term) {
+    const uint32_t mask = (1u << b) - 1u;
+    bool t = false;
+    for (int g = 0; g < nsym; ++g) t = t || (((id >> (g * b)) & mask) == term);
+    return t;
+}
+
+// window key of the suffix at byte offset o: symbols [G, G+8) of its cut window as raw bytes, first
+// symbol in the top byte.  0 when the terminator is among the first G symbols.
+__device__ __forceinline__ uint64_t ds_key8(const uint8_t *s_raw, int o, uint64_t term8, int G) {
+    const uint64_t x0 = ds_lds8(s_raw, o), x1 = ds_lds8(s_raw, o + 8);
+    if (ds_haszero(x0 ^ term8) & ((1ull << (8 * G)) - 1ull)) return 0ull;
+    uint64_t y = (x0 >> (8 * G)) | (x1 << (64 - 8 * G));   // 1 <= G <= 7
+    const uint64_t z = ds_haszero(y ^ term8);
+    if (z) {
+        const int k = (__ffsll((long long)z) - 1) >> 3;
+        if (k < 7) y &= (1ull << (8 * (k + 1))) - 1ull;
+    }
+    const uint32_t hi = __byte_perm((uint32_t)y, 0u, 0x0123), lo = __byte_perm((uint32_t)(y >> 32), 0u, 0x0123);
+    return ((uint64_t)hi << 32) | lo;
 }
 
 // suffixes at byte offsets oi, oj agree on [0, from) and have no terminator there: is i < j ?
@@ -123,65 +164,194 @@ __device__ __forceinline__ bool ds_deep_less(const uint8_t *s_raw, int oi, int o
     }
 }
 
-// (key, position) order; padding entries carry key ~0 and compare by position only
-__device__ __forceinline__ bool ds_less(const uint8_t *s_raw, int shift, uint64_t ka, uint32_t pa, uint64_t kb,
-                                        uint32_t pb, int from, uint64_t term8) {
-    if (ka != kb) return ka < kb;
-    if ((ka & 1ull) || ka == ~0ull) return pa < pb;
-    return ds_deep_less(s_raw, shift + (int)pa, shift + (int)pb, from, term8);
+__device__ __forceinline__ void ds_group_sync(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(DS_GROUP) : "memory");
 }
 
-__device__ __forceinline__ void ds_group_sync(int id, int nthr) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory");
+
+struct DocCtx {
+    const uint8_t *s_raw;
+    int shift;
+    uint64_t term8;
+    uint32_t term;
+    int b, S2;
+    int32_t base;
+    int32_t *sa_doc;
+    uint32_t *s_bits;
+    uint32_t *overflow;
+};
+
+// rank the members of a bucket whose suffixes are identical up to their terminator by position:
+// every member counts the members that start earlier (positions staged as 16-bit values)
+__device__ __forceinline__ void ds_rank_by_position(const DocCtx &c, const uint16_t *pos, int start, int size, int t, int nthr) {
+    const uint32_t *p2 = reinterpret_cast<const uint32_t *>(pos);
+    for (int e = t; e < size; e += nthr) {
+        const uint32_t pe = pos[e];
+        int below = 0;
+        for (int q = 0; q < (size >> 1); ++q) {
+            const uint32_t v = p2[q];
+            below += ((v & 0xffffu) < pe ? 1 : 0) + ((v >> 16) < pe ? 1 : 0);
+        }
+        if ((size & 1) && pos[size - 1] < pe) ++below;
+        c.sa_doc[start + below] = c.base + (int32_t)pe;
+    }
 }
 
-// bitonic sort of P (power of two) elements in shared memory by `nthr` threads (index tid).
-// sync_id: 0 = __syncthreads (whole CTA), else named barrier id for nthr threads
-__device__ void ds_bitonic(uint64_t *keys, uint16_t *pos, int P, int tid, int nthr, int sync_id,
-                           const uint8_t *s_raw, int shift, int from, uint64_t term8) {
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += nthr) {
-                // t-th compare-exchange of this stage: partner indices differ in bit j
-                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int hi = lo | j;
-                const bool up = (lo & k) == 0;
-                const uint64_t ka = keys[lo], kb = keys[hi];
-                const uint32_t pa = pos[lo], pb = pos[hi];
-                const bool b_lt_a = ds_less(s_raw, shift, kb, pb, ka, pa, from, term8);
-                if (b_lt_a == up) {
-                    keys[lo] = kb; keys[hi] = ka;
-                    pos[lo] = (uint16_t)pb; pos[hi] = (uint16_t)pa;
+// symbols the members share beyond `depth` (DS_INF: all members are the same string tail), as seen
+// by this thread's members e = t, t + nthr, ...: compare everybody with member 0
+__device__ __forceinline__ int ds_common_prefix(const DocCtx &c, const uint16_t *pos, int size, int depth, int t, int nthr) {
+    const int o0 = c.shift + (int)pos[0] + depth;
+    int cp = DS_INF;
+    for (int e = t; e < size; e += nthr) {
+        const int oi = c.shift + (int)pos[e] + depth;
+        int k = 0;
+        while (k < cp) {
+            const uint64_t x = ds_lds8(c.s_raw, oi + k), y = ds_lds8(c.s_raw, o0 + k);
+            const uint64_t stop = (x ^ y) | ds_haszero(y ^ c.term8);
+            if (stop) {
+                const int j = (__ffsll((long long)stop) - 1) >> 3;
+                if (((x >> (8 * j)) & 0xffull) != ((y >> (8 * j)) & 0xffull)) cp = min(cp, k + j);
+                break;  // else: identical up to and including the terminator
+            }
+            k += 8;
+        }
+    }
+    return cp;
+}
+
+// One refinement step of one bucket of <= DS_WARP_MAX suffixes by ONE warp: skip the shared prefix,
+// counting-sort on the first symbol that differs (2^b <= 128 bins), no block-level barrier.
+__device__ void ds_refine_warp(const DocCtx &c, uint2 entry, int lane, uint8_t *wscr, uint2 *next_list, uint32_t *next_n) {
+    const int start = (int)(entry.x & 0xffffu), size = (int)(entry.x >> 16);
+    const int depth = (int)(entry.y & 0xffffu);
+    bool terminal = (entry.y >> 16) != 0u;
+    uint16_t *wpos = reinterpret_cast<uint16_t *>(wscr);
+    uint32_t *whist = reinterpret_cast<uint32_t *>(wscr + DS_WARP_MAX * 2);
+    const int NB1 = 1 << c.b;
+
+    for (int e = lane; e < size; e += 32) wpos[e] = (uint16_t)(c.sa_doc[start + e] - c.base);
+    for (int i = lane; i < NB1; i += 32) whist[i] = 0;
+    __syncwarp();
+    int d2 = depth;
+    if (!terminal) {
+        const int cp = __reduce_min_sync(0xffffffffu, ds_common_prefix(c, wpos, size, depth, lane, 32));
+        if (cp == DS_INF) terminal = true;
+        else d2 = depth + cp;
+    }
+    if (terminal) {
+        ds_rank_by_position(c, wpos, start, size, lane, 32);
+        __syncwarp();
+        return;
+    }
+    for (int e = lane; e < size; e += 32) atomicAdd(&whist[c.s_raw[c.shift + (int)wpos[e] + d2]], 1u);
+    __syncwarp();
+    uint32_t run = 0;
+    for (int i0 = 0; i0 < NB1; i0 += 32) {
+        const int i = i0 + lane;
+        const uint32_t cnt = (i < NB1) ? whist[i] : 0u;
+        uint32_t x = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        const uint32_t excl = run + x - cnt;
+        if (i < NB1) whist[i] = excl;  // scatter cursor
+        if (cnt) {
+            const uint32_t r = (uint32_t)start + excl;
+            if (excl) atomicOr(&c.s_bits[r >> 5], 1u << (r & 31));
+            if (cnt > 32u) {
+                const uint32_t slot = atomicAdd(next_n, 1u);
+                if (slot < (uint32_t)DS_LIST_CAP)
+                    next_list[slot] = make_uint2(r | (cnt << 16), (uint32_t)(d2 + 1) | (((uint32_t)i == c.term ? 1u : 0u) << 16));
+            }
+        }
+        run += __shfl_sync(0xffffffffu, x, 31);
+    }
+    __syncwarp();
+    for (int e = lane; e < size; e += 32) {
+        const uint32_t pe = wpos[e];
+        const uint32_t r = atomicAdd(&whist[c.s_raw[c.shift + (int)pe + d2]], 1u);
+        c.sa_doc[start + (int)r] = c.base + (int32_t)pe;
+    }
+    __syncwarp();
+}
+
+// One refinement step of one bucket by one group of DS_GROUP threads (gt = thread index in the group,
+// g = group index).  entry: x = start | size << 16, y = depth | terminal << 16.
+__device__ void ds_refine(const DocCtx &c, uint2 entry, int g, int gt, uint8_t *gscr, int *s_gmin, uint32_t *s_gw,
+                          uint2 *next_list, uint32_t *next_n) {
+    const int start = (int)(entry.x & 0xffffu), size = (int)(entry.x >> 16);
+    const int depth = (int)(entry.y & 0xffffu);
+    bool terminal = (entry.y >> 16) != 0u;
+    uint16_t *gpos = reinterpret_cast<uint16_t *>(gscr);
+    uint32_t *ghist = reinterpret_cast<uint32_t *>(gscr + DS_REFINE_MAX * 2);
+    const int lane = gt & 31, gw = gt >> 5;
+    const int NB2 = 1 << (c.S2 * c.b);
+
+    for (int e = gt; e < size; e += DS_GROUP) gpos[e] = (uint16_t)(c.sa_doc[start + e] - c.base);
+    if (!terminal) for (int i = gt; i < NB2; i += DS_GROUP) ghist[i] = 0;
+    if (gt == 0) s_gmin[g] = DS_INF;
+    ds_group_sync(1 + g);
+
+    int d2 = depth;
+    if (!terminal) {
+        const int mycp = __reduce_min_sync(0xffffffffu, ds_common_prefix(c, gpos, size, depth, gt, DS_GROUP));
+        if (lane == 0 && mycp != DS_INF) atomicMin(&s_gmin[g], mycp);
+        ds_group_sync(1 + g);
+        const int cp = s_gmin[g];
+        if (cp == DS_INF) terminal = true;  // every member is the same string tail: order by position
+        else d2 = depth + cp;
+    }
+
+    if (terminal) {
+        ds_rank_by_position(c, gpos, start, size, gt, DS_GROUP);
+        ds_group_sync(1 + g);
+        return;
+    }
+
+    // counting sort on the S2 symbols at offset d2
+    for (int e = gt; e < size; e += DS_GROUP)
+        atomicAdd(&ghist[ds_bucket(c.s_raw, c.shift + (int)gpos[e] + d2, c.term8, c.b, c.S2)], 1u);
+    ds_group_sync(1 + g);
+    {
+        const int PB = (NB2 + DS_GROUP - 1) / DS_GROUP;
+        const int b0 = min(NB2, gt * PB), b1 = min(NB2, b0 + PB);
+        uint32_t sum = 0;
+        for (int i = b0; i < b1; ++i) sum += ghist[i];
+        uint32_t x = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_gw[g * DS_GWARPS + gw] = x;
+        ds_group_sync(1 + g);
+        uint32_t run = x - sum;
+        for (int i = 0; i < gw; ++i) run += s_gw[g * DS_GWARPS + i];
+        for (int i = b0; i < b1; ++i) {
+            const uint32_t cnt = ghist[i];
+            ghist[i] = run;  // scatter cursor
+            if (cnt) {
+                const uint32_t r = (uint32_t)start + run;
+                if (run) atomicOr(&c.s_bits[r >> 5], 1u << (r & 31));
+                if (cnt > 32u) {
+                    const uint32_t slot = atomicAdd(next_n, 1u);
+                    const uint32_t term_flag = ds_id_has_term((uint32_t)i, c.S2, c.b, c.term) ? 1u : 0u;
+                    if (slot < (uint32_t)DS_LIST_CAP)
+                        next_list[slot] = make_uint2(r | (cnt << 16), (uint32_t)(d2 + c.S2) | (term_flag << 16));
                 }
             }
-            if (sync_id == 0) __syncthreads();
-            else ds_group_sync(sync_id, nthr);
+            run += cnt;
         }
     }
-}
-
-// sort one bucket [start, start+size) of the document's suffix array with `nthr` threads
-__device__ void ds_sort_bucket(int32_t *sa_doc, int32_t base, int start, int size, uint64_t *keys, uint16_t *pos,
-                               int tid, int nthr, int sync_id, const uint8_t *s_raw, int shift,
-                               const DocSortParams &p, uint64_t term8) {
-    int P = 64;
-    while (P < size) P <<= 1;
-    for (int e = tid; e < P; e += nthr) {
-        if (e < size) {
-            const int li = sa_doc[start + e] - base;
-            keys[e] = ds_key(s_raw, shift + li, term8, p.b, p.G, p.WS);
-            pos[e] = (uint16_t)li;
-        } else {
-            keys[e] = ~0ull;
-            pos[e] = (uint16_t)(e & 0xffff);
-        }
+    ds_group_sync(1 + g);
+    for (int e = gt; e < size; e += DS_GROUP) {
+        const uint32_t pe = gpos[e];
+        const uint32_t r = atomicAdd(&ghist[ds_bucket(c.s_raw, c.shift + (int)pe + d2, c.term8, c.b, c.S2)], 1u);
+        c.sa_doc[start + (int)r] = c.base + (int32_t)pe;
     }
-    if (sync_id == 0) __syncthreads();
-    else ds_group_sync(sync_id, nthr);
-    ds_bitonic(keys, pos, P, tid, nthr, sync_id, s_raw, shift, p.G + p.WS, term8);
-    for (int e = tid; e < size; e += nthr) sa_doc[start + e] = base + (int32_t)pos[e];
-    if (sync_id == 0) __syncthreads();
-    else ds_group_sync(sync_id, nthr);
+    ds_group_sync(1 + g);
 }
 
 __global__ void __launch_bounds__(DS_THREADS, 1)
@@ -190,96 +360,190 @@ k_doc_suffix_sort(DocSortParams p) {
     uint8_t *s_raw = ds_smem;                                                    // staged text
     uint32_t *s_scr = reinterpret_cast<uint32_t *>(ds_smem + p.text_cap);        // counters, later sort scratch
     uint32_t *s_bits = reinterpret_cast<uint32_t *>(ds_smem + p.text_cap + DS_SCR_BYTES);
-    uint32_t *s_big = s_bits + p.bits_words;
+    uint2 *s_list0 = reinterpret_cast<uint2 *>(s_bits + p.bits_words);           // bits_words is even
+    uint2 *s_list1 = s_list0 + DS_LIST_CAP;
     __shared__ uint32_t s_warp_sum[DS_WARPS];
-    __shared__ uint32_t s_nbig;
+    __shared__ uint32_t s_nlist[2];
+    __shared__ uint32_t s_work;
+    __shared__ int s_gmin[DS_NGROUPS];
+    __shared__ uint32_t s_gw[DS_NGROUPS * DS_GWARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int doc = blockIdx.x;
     const int32_t base = p.doc_off[doc];
     const int n = p.doc_off[doc + 1] - base;
-    const int b = p.b, G = p.G, WS = p.WS;
+    const int b = p.b, G = p.G;
     const uint64_t term8 = 0x0101010101010101ull * (uint64_t)p.term;
     const int NB = 1 << (G * b);      // bucket ids
     const int NW = NB >> 1;           // counter words (two 16-bit counters each)
+    const uint32_t term_bucket = p.term << ((G - 1) * b);   // the suffixes that ARE a terminator
     int32_t *sa_doc = p.sa + base;    // plain pointer: written and re-read by this CTA
+
+    long long t_prev = clock64();
+#define DS_STAMP(k)                                                                     \
+    do {                                                                                \
+        if (p.phase_clk && tid == 0) {                                                  \
+            const long long t_now = clock64();                                          \
+            atomicAdd(&p.phase_clk[k], (unsigned long long)(t_now - t_prev));           \
+            t_prev = t_now;                                                             \
+        }                                                                               \
+    } while (0)
 
     // ---- phase 1: stage the text, clear counters / bitmap
     const int32_t a0 = base & ~15;
     const int shift = base - a0;
     {
         const int nbytes = (shift + n + 48 + 15) & ~15;
-        for (int o = tid * 16; o < nbytes; o += DS_THREADS * 16)
-            *reinterpret_cast<uint4 *>(s_raw + o) = *reinterpret_cast<const uint4 *>(p.t8 + a0 + o);
+        const int m = p.doc_m[doc];
+        const uint32_t term4 = (uint32_t)term8;
+        for (int o = tid * 16; o < nbytes; o += DS_THREADS * 16) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p.t8 + a0 + o);
+            *reinterpret_cast<uint4 *>(s_raw + o) = v;
+            // the suffixes that ARE a terminator form the last bucket (term is the top code) and are
+            // ordered by string index = terminator value - 0x0A00: final right here, while the
+            // loads of the code points overlap the staging
+            const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int wi = 0; wi < 4; ++wi) {
+                uint32_t z = ds_zero4(wv[wi] ^ term4);
+                while (z) {
+                    const int i = o + 4 * wi + ((__ffs(z) - 1) >> 3) - shift;
+                    z &= z - 1u;
+                    if (i >= 0 && i < n) sa_doc[n - m + (int)(p.text[base + i] - EAST_TERM_BASE)] = base + i;
+                }
+            }
+        }
         for (int i = tid; i < NW; i += DS_THREADS) s_scr[i] = 0;
         for (int i = tid; i < p.bits_words; i += DS_THREADS) s_bits[i] = 0;
-        if (tid == 0) s_nbig = 0;
+        if (tid < 2) s_nlist[tid] = 0;
     }
     __syncthreads();
+    DS_STAMP(0);
 
     // ---- phase 2: bucket histogram
-    for (int i = tid; i < n; i += DS_THREADS) {
-        const uint32_t id = ds_bucket(s_raw, shift + i, term8, b, G);
-        atomicAdd(&s_scr[id >> 1], (id & 1u) ? 0x10000u : 1u);
+    for (int c0 = tid * 8; c0 < n; c0 += DS_THREADS * 8) {
+        const Ids8 ids = ds_bucket8(s_raw, shift + c0, term8, b, G);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c0 + j < n) atomicAdd(&s_scr[ids.id[j] >> 1], (ids.id[j] & 1u) ? 0x10000u : 1u);
     }
     __syncthreads();
+    DS_STAMP(1);
 
-    // ---- phase 3: exclusive scan of the counters (each thread owns CW consecutive words)
+    // ---- phase 3: exclusive scan of the counters.  Warp w owns WPW consecutive counter words and
+    // walks them 32 at a time (lane-contiguous: no bank conflicts), carrying the running rank.
     {
-        const int CW = (NW + DS_THREADS - 1) / DS_THREADS;
-        const int w0 = tid * CW, w1 = min(NW, w0 + CW);
+        const int WPW = max(32, NW / DS_WARPS);
+        const int w0 = min(NW, warp * WPW), w1 = min(NW, w0 + WPW);
         uint32_t sum = 0;
-        for (int w = w0; w < w1; ++w) { const uint32_t v = s_scr[w]; sum += (v & 0xffffu) + (v >> 16); }
-        uint32_t x = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) s_warp_sum[warp] = x;
+        for (int w = w0 + lane; w < w1; w += 32) { const uint32_t v = s_scr[w]; sum += (v & 0xffffu) + (v >> 16); }
+        sum = __reduce_add_sync(0xffffffffu, sum);
+        if (lane == 0) s_warp_sum[warp] = sum;
         __syncthreads();
-        uint32_t run = x - sum;
+        uint32_t run = 0;
         for (int i = 0; i < warp; ++i) run += s_warp_sum[i];
         const int sub = (G - 2) * b;                 // a 2-gram owns 2^sub consecutive bucket ids
         const uint32_t sub_mask = (1u << sub) - 1u;
         uint32_t *bkt_row = p.bkt ? p.bkt + ((size_t)doc << (2 * b)) : nullptr;
-        for (int w = w0; w < w1; ++w) {
-            const uint32_t v = s_scr[w];
-            uint32_t packed = 0;
+        for (int wb = w0; wb < w1; wb += 32) {
+            const int w = wb + lane;
+            const uint32_t v = (w < w1) ? s_scr[w] : 0u;
+            const uint32_t c0 = v & 0xffffu, c1 = v >> 16;
+            uint32_t x = c0 + c1;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t id = 2u * (uint32_t)w + (uint32_t)h;
-                const uint32_t c = h ? (v >> 16) : (v & 0xffffu);
-                if (bkt_row && (id & sub_mask) == 0u) bkt_row[id >> sub] = (uint32_t)base + run;
-                if (c) {
-                    atomicOr(&s_bits[run >> 5], 1u << (run & 31));
-                    if (c > 32u) {
-                        if (c > (uint32_t)DS_BIG_MAX) atomicOr(p.overflow, 1u);
-                        else {
-                            const uint32_t slot = atomicAdd(&s_nbig, 1u);
-                            if (slot < (uint32_t)DS_BIG_CAP) s_big[slot] = (run << 16) | c;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            const uint32_t st0 = run + x - (c0 + c1), st1 = st0 + c0;   // first ranks of buckets 2w, 2w+1
+            run += __shfl_sync(0xffffffffu, x, 31);
+            if (w < w1) {
+                const uint32_t id0 = 2u * (uint32_t)w;
+                if (bkt_row) {
+                    if ((id0 & sub_mask) == 0u) bkt_row[id0 >> sub] = (uint32_t)base + st0;
+                    if (sub == 0) bkt_row[id0 + 1u] = (uint32_t)base + st1;
+                }
+                s_scr[w] = (st0 & 0xffffu) | (st1 << 16);  // bucket starts, used as the scatter cursors
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t id = id0 + (uint32_t)h, cnt = h ? c1 : c0, st = h ? st1 : st0;
+                    if (cnt) {
+                        atomicOr(&s_bits[st >> 5], 1u << (st & 31));
+                        if (cnt > 32u && id != term_bucket) {
+                            if (cnt > (uint32_t)DS_REFINE_MAX) atomicOr(p.overflow, 1u);
+                            else {
+                                const uint32_t slot = atomicAdd(&s_nlist[0], 1u);
+                                const uint32_t term_flag = ds_id_has_term(id, G, b, p.term) ? 1u : 0u;
+                                if (slot < (uint32_t)DS_LIST_CAP)
+                                    s_list0[slot] = make_uint2(st | (cnt << 16), (uint32_t)G | (term_flag << 16));
+                            }
                         }
                     }
                 }
-                packed |= (run & 0xffffu) << (16 * h);
-                run += c;
             }
-            s_scr[w] = packed;  // bucket start, used as the scatter cursor
         }
         if (tid == 0) atomicOr(&s_bits[n >> 5], 1u << (n & 31));  // sentinel: "a bucket starts at rank n"
     }
     __syncthreads();
+    DS_STAMP(2);
 
     // ---- phase 4: scatter the suffixes into their buckets (arbitrary order inside a bucket)
-    for (int i = tid; i < n; i += DS_THREADS) {
-        const uint32_t id = ds_bucket(s_raw, shift + i, term8, b, G);
-        const uint32_t old = atomicAdd(&s_scr[id >> 1], (id & 1u) ? 0x10000u : 1u);
-        const uint32_t r = (id & 1u) ? (old >> 16) : (old & 0xffffu);
-        sa_doc[r] = base + i;
+    for (int c0 = tid * 8; c0 < n; c0 += DS_THREADS * 8) {
+        const Ids8 ids = ds_bucket8(s_raw, shift + c0, term8, b, G);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t id = ids.id[j];
+            if (c0 + j < n && id != term_bucket) {   // bare terminators were placed in phase 1
+                const uint32_t old = atomicAdd(&s_scr[id >> 1], (id & 1u) ? 0x10000u : 1u);
+                sa_doc[(id & 1u) ? (old >> 16) : (old & 0xffffu)] = base + c0 + j;
+            }
+        }
     }
     __syncthreads();
+    DS_STAMP(3);
 
-    // ---- phase 5a: windows of 32 ranks; every bucket of <= 32 suffixes that STARTS in the window
+    // ---- phase 5: refine the buckets of more than 32 suffixes, level by level
+    {
+        DocCtx c;
+        c.s_raw = s_raw; c.shift = shift; c.term8 = term8; c.term = p.term; c.b = b; c.S2 = p.S2;
+        c.base = base; c.sa_doc = sa_doc; c.s_bits = s_bits; c.overflow = p.overflow;
+        const int g = tid / DS_GROUP, gt = tid % DS_GROUP;
+        uint8_t *gscr = reinterpret_cast<uint8_t *>(s_scr) + g * DS_GRP_BYTES;
+        uint8_t *wscr = reinterpret_cast<uint8_t *>(s_scr) + warp * DS_WARP_BYTES;
+        int cur = 0;
+        while (true) {
+            const int cnt = min((int)s_nlist[cur], DS_LIST_CAP);
+            __syncthreads();
+            if (cnt == 0) break;
+            if (tid == 0) { s_nlist[cur ^ 1] = 0; s_work = 0; }
+            __syncthreads();
+            uint2 *list = cur ? s_list1 : s_list0, *next = cur ? s_list0 : s_list1;
+            // buckets of <= DS_WARP_MAX suffixes: one warp each, taken from a shared work counter
+            bool any_big = false;
+            while (true) {
+                int e = 0;
+                if (lane == 0) e = (int)atomicAdd(&s_work, 1u);
+                e = __shfl_sync(0xffffffffu, e, 0);
+                if (e >= cnt) break;
+                const uint2 entry = list[e];
+                if ((entry.x >> 16) > (uint32_t)DS_WARP_MAX) { any_big = true; continue; }
+                ds_refine_warp(c, entry, lane, wscr, next, &s_nlist[cur ^ 1]);
+            }
+            // larger ones (rare): groups of 4 warps
+            if (__syncthreads_or(any_big ? 1 : 0)) {
+                for (int e = g; e < cnt; e += DS_NGROUPS) {
+                    const uint2 entry = list[e];
+                    if ((entry.x >> 16) <= (uint32_t)DS_WARP_MAX) continue;
+                    ds_refine(c, entry, g, gt, gscr, s_gmin, s_gw, next, &s_nlist[cur ^ 1]);
+                }
+                __syncthreads();
+            }
+            cur ^= 1;
+        }
+    }
+    DS_STAMP(4);
+
+    // ---- phase 6: windows of 32 ranks; every bucket of <= 32 suffixes that STARTS in the window
     {
         uint64_t *wkeys = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_scr) + warp * DS_WIN_BYTES);
         uint32_t *wpos = reinterpret_cast<uint32_t *>(wkeys + 64);
@@ -299,7 +563,7 @@ k_doc_suffix_sort(DocSortParams p) {
             }
             const int last_start = 32 * w + (31 - __clz(word));
             int nseg = __popc(word);
-            if (r1 - last_start > 32) { r1 = last_start; --nseg; }  // a large bucket: phase 5b
+            if (r1 - last_start > 32) { r1 = last_start; --nseg; }  // a bucket of > 32 identical tails: already in position order
             const int len = r1 - r0;   // <= 63
             if (len <= nseg) continue; // only singletons
             uint64_t key[2];
@@ -318,7 +582,7 @@ k_doc_suffix_sort(DocSortParams p) {
                     se[s] = gt ? (32 * w + (__ffs(gt) - 1) - r0) : len;
                     if (se[s] > len) se[s] = len;
                     if (se[s] - sb[s] > 1) {
-                        key[s] = ds_key(s_raw, shift + li[s], term8, b, G, WS);
+                        key[s] = ds_key8(s_raw, shift + li[s], term8, G);
                         wkeys[x] = key[s];
                     }
                     wpos[x] = (uint32_t)li[s];
@@ -332,16 +596,17 @@ k_doc_suffix_sort(DocSortParams p) {
                 out[s] = x;
                 if (x < len && se[s] - sb[s] > 1) {
                     int below = 0;
-                    for (int c = sb[s]; c < se[s]; ++c) {
-                        if (c == x) continue;
-                        const uint64_t kc = wkeys[c];
-                        if (kc < key[s]) ++below;
-                        else if (kc == key[s]) {
-                            const uint32_t pc = wpos[c];
-                            const bool less = (kc & 1ull) ? (pc < (uint32_t)li[s])
-                                                          : ds_deep_less(s_raw, shift + (int)pc, shift + li[s], G + WS, term8);
-                            if (less) ++below;
+                    const uint32_t last = (uint32_t)key[s] & 0xffu;
+                    const bool by_pos = last == 0u || last == p.term;   // the window reaches the terminator
+                    for (int q = sb[s]; q < se[s]; ++q) {
+                        const uint64_t kq = wkeys[q];
+                        bool less = kq < key[s];
+                        if (kq == key[s] && q != x) {
+                            const uint32_t pq = wpos[q];
+                            less = by_pos ? (pq < (uint32_t)li[s])
+                                          : ds_deep_less(s_raw, shift + (int)pq, shift + li[s], G + 8, term8);
                         }
+                        below += less ? 1 : 0;
                     }
                     out[s] = sb[s] + below;
                 }
@@ -355,36 +620,8 @@ k_doc_suffix_sort(DocSortParams p) {
             __syncwarp();
         }
     }
-    __syncthreads();
-
-    // ---- phase 5b: buckets of more than 32 suffixes
-    {
-        const int nbig = min((int)s_nbig, DS_BIG_CAP);
-        // medium: one group of 4 warps per bucket
-        const int g = tid / DS_GROUP, gt = tid % DS_GROUP;
-        uint64_t *gkeys = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_scr) + g * (DS_MED_MAX * 10));
-        uint16_t *gpos = reinterpret_cast<uint16_t *>(gkeys + DS_MED_MAX);
-        bool any_large = false;
-        for (int e = g; e < nbig; e += DS_NGROUPS) {
-            const uint32_t ent = s_big[e];
-            const int start = (int)(ent >> 16);
-            const int size = (int)(ent & 0xffffu);
-            if (size > DS_MED_MAX) { any_large = true; continue; }
-            ds_sort_bucket(sa_doc, base, start, size, gkeys, gpos, gt, DS_GROUP, 1 + g, s_raw, shift, p, term8);
-        }
-        // large: the whole CTA, one bucket after the other (rare)
-        if (__syncthreads_or(any_large ? 1 : 0)) {
-            uint64_t *bkeys = reinterpret_cast<uint64_t *>(s_scr);
-            uint16_t *bpos = reinterpret_cast<uint16_t *>(bkeys + DS_BIG_MAX);
-            for (int e = 0; e < nbig; ++e) {
-                const uint32_t ent = s_big[e];
-                const int start = (int)(ent >> 16);
-                const int size = (int)(ent & 0xffffu);
-                if (size <= DS_MED_MAX) continue;
-                ds_sort_bucket(sa_doc, base, start, size, bkeys, bpos, tid, DS_THREADS, 0, s_raw, shift, p, term8);
-            }
-        }
-    }
+    DS_STAMP(5);
+#undef DS_STAMP
 }
 
 // Host side: can the batch take the per-document path, and with which parameters
@@ -395,26 +632,31 @@ bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan) {
     int G = 15 / b;
     if (G > 7) G = 7;
     if (G < 2) return false;
-    int WS = 63 / b;
-    if (WS > 16 - G) WS = 16 - G;
-    plan.b = b; plan.G = G; plan.WS = WS;
+    int S2 = 10 / b;
+    if (S2 < 1) S2 = 1;
+    if (S2 > 7) S2 = 7;
+    plan.b = b; plan.G = G; plan.S2 = S2;
     plan.text_cap = (max_doc_n + 15 + 48 + 16 + 15) & ~15;
-    plan.bits_words = (max_doc_n >> 5) + 3;
-    plan.smem = (size_t)plan.text_cap + DS_SCR_BYTES + sizeof(uint32_t) * ((size_t)plan.bits_words + DS_BIG_CAP);
+    plan.bits_words = ((max_doc_n >> 5) + 3 + 1) & ~1;
+    plan.smem = (size_t)plan.text_cap + DS_SCR_BYTES + sizeof(uint32_t) * (size_t)plan.bits_words +
+                2 * sizeof(uint2) * (size_t)DS_LIST_CAP;
     return plan.smem <= (size_t)220 * 1024;
 }
 
-void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const int32_t *doc_off, int n_docs, int64_t n_total,
-                     uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s) {
+void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
+                     const int32_t *doc_m, int n_docs,
+                     int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
+                     unsigned long long *phase_clk) {
     static bool configured = false;
     if (!configured) {
         EAST_CUDA(cudaFuncSetAttribute(k_doc_suffix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         configured = true;
     }
     DocSortParams p;
-    p.t8 = t8; p.doc_off = doc_off; p.sa = sa; p.bkt = bkt; p.overflow = overflow;
-    p.b = plan.b; p.G = plan.G; p.WS = plan.WS; p.term = term;
+    p.t8 = t8; p.text = text; p.doc_off = doc_off; p.doc_m = doc_m; p.sa = sa; p.bkt = bkt; p.overflow = overflow;
+    p.b = plan.b; p.G = plan.G; p.S2 = plan.S2; p.term = term;
     p.text_cap = plan.text_cap; p.bits_words = plan.bits_words;
+    p.phase_clk = phase_clk;
     EAST_BYTES(9.0 * (double)n_total);  // byte text in, suffix array out + one re-read (L2-resident scatter)
     EAST_LAUNCH(k_doc_suffix_sort, n_docs, DS_THREADS, plan.smem, s, p);
 }

@@ -18,6 +18,9 @@
 //          range, a reference quirk) symbols are raw code points and nothing is special-cased.
 // Round r  (h = kc, 2kc, ...) re-sorts only the suffixes that still share their rank with
 //          another one, by (own rank, rank[i+h]), and re-ranks; the active set shrinks fast.
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 #include "radix_sort.cuh"
 #include "sa_build.h"
 
@@ -893,15 +896,29 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
                 out.sym_bits = plan.b;
             }
-            doc_sort_launch(plan, t8.p, in.doc_off, D, n, kp.term, out.sa, out.bkt.p, flag.p, s);
+            static const bool profile = getenv("EAST_DOC_SORT_PROFILE") != nullptr;
+            DevBuf<unsigned long long> clk;
+            if (profile) {
+                clk = DevBuf<unsigned long long>(8, s);
+                EAST_CUDA(cudaMemsetAsync(clk.p, 0, 8 * sizeof(unsigned long long), s));
+            }
+            doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, D, n, kp.term, out.sa, out.bkt.p, flag.p, s, clk.p);
             uint32_t overflow = 0;
             EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             EAST_CUDA(cudaStreamSynchronize(s));
+            if (profile) {
+                unsigned long long h[8];
+                EAST_CUDA(cudaMemcpy(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost));
+                static const char *names[6] = {"load", "hist", "scan", "scatter", "refine", "windows"};
+                fprintf(stderr, "[east] doc_sort phases, kilo-cycles per document:");
+                for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.1f", names[k], (double)h[k] / D / 1e3);
+                fprintf(stderr, "\n");
+            }
             if (!overflow) {
                 out.doc_sorted = 1;
                 out.rounds = 1;
-                out.key_chars = plan.G + plan.WS;
-                out.key_bits = plan.b * (plan.G + plan.WS);
+                out.key_chars = plan.G + 8;
+                out.key_bits = plan.b * plan.G + 64;
                 out.t8 = std::move(t8);
                 return;
             }

@@ -45,13 +45,15 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
 
 // per-document shared-memory suffix sort (doc_sort.cu)
 struct DocSortPlan {
-    int b = 0, G = 0, WS = 0;   // bits per symbol, symbols per bucket id, symbols per key word
+    int b = 0, G = 0, S2 = 0;   // bits per symbol, symbols per bucket id, symbols per refinement level
     int text_cap = 0, bits_words = 0;
     size_t smem = 0;
 };
 bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan);
-void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const int32_t *doc_off, int n_docs, int64_t n_total,
-                     uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s);
+void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
+                     const int32_t *doc_m, int n_docs,
+                     int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
+                     unsigned long long *phase_clk = nullptr /* profiling: 8 cycle counters */);
 
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch

@@ -458,7 +458,7 @@ def test_segmented_and_global_round0_sort_agree(oracle_mod):
 
 
 def test_doc_sort_bucket_overflow_falls_back_to_the_global_sort(oracle_mod, sa_path):
-    # one bucket of > 8192 suffixes (a run of 9000 equal symbols) is more than a CTA sorts in shared
+    # one bucket of > 4096 suffixes (a run of 9000 equal symbols) is more than a group refines in shared
     # memory: the build must notice, redo the batch with the global sort and still be exact
     if sa_path != "doc_sort":
         pytest.skip("per-document sort only")
@@ -468,8 +468,8 @@ def test_doc_sort_bucket_overflow_falls_back_to_the_global_sort(oracle_mod, sa_p
     assert info["doc_sort_overflow"] and not info["doc_sorted"]
     for d, c in enumerate(cols):
         _check_arrays(idx, d, oracle_mod.OracleEASA(c), d)
-    # buckets of 1025..8192 suffixes: sorted by the whole CTA
-    cols = [["A" * 5000, "BA" * 1200], ["C" * 1100]]
+    # buckets of thousands of suffixes that stay below the limit: many refinement levels
+    cols = [["A" * 3000, "BA" * 1200], ["C" * 1100], ["AB" * 40] * 60]
     idx = _build(cols)
     assert idx.info()["doc_sorted"]
     for d, c in enumerate(cols):
