@@ -148,7 +148,7 @@ struct east_index {
     uint32_t *bkt = nullptr;        // fast path: 2-gram bucket table
     std::vector<uint8_t> code_table;
     int sym_bits = 0, term_code = 0;
-    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0;
+    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0, tables_fused = 0;
     uint32_t active_after_round0 = 0;
     // LCP / child / annotation tables are produced on an auxiliary stream after the suffix array is
     // final, so a score call (which needs only SA + text) overlaps them; readers wait on ev_tables
@@ -313,6 +313,9 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         // the global prefix-doubling sort (and "no_doc_sort") selects the global sort instead
         in.doc_sort = (get_option("no_doc_sort", 0) || in.key_chars || in.rs_variant || in.sort_batch_elems ||
                        !in.segmented_sort || !in.local_group_sort) ? 0 : 1;
+        if (!get_option("no_fused_tables", 0)) {
+            in.lcp = idx->lcp; in.up = idx->up; in.down = idx->down; in.next = idx->next; in.ann = idx->ann;
+        }
         SaOutput so;
         so.sa = idx->sa; so.rank = rank.p;
         build_suffix_array(in, so, tm, s);
@@ -322,24 +325,29 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         idx->t8 = so.t8.p; so.t8.p = nullptr;      // ownership moves to the index
         idx->bkt = so.bkt.p; so.bkt.p = nullptr;
         idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
-        // the suffix array is final here (the doubling loop ended on a host sync)
-        cudaStream_t ts = s;
-        if (overlap) {
-            ts = aux_stream(device);
-            cudaEvent_t fork;
-            EAST_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-            EAST_CUDA(cudaEventRecord(fork, s));
-            EAST_CUDA(cudaStreamWaitEvent(ts, fork, 0));
-            EAST_CUDA(cudaEventDestroy(fork));
-            tm.s = ts;
-        }
-        build_lcp_tables(idx->text, idx->t8, idx->term_code, idx->sa, idx->d_doc_off, idx->d_doc_m, n_docs, n, idx->lcp, idx->up,
-                         idx->down, idx->next, idx->ann, tm, ts, (int)get_option("child_variant", 0));
-        tm.finish();
-        if (overlap) {
-            EAST_CUDA(cudaEventCreateWithFlags(&idx->ev_tables, cudaEventDisableTiming));
-            EAST_CUDA(cudaEventRecord(idx->ev_tables, ts));
-            idx->tables_pending = true;
+        idx->tables_fused = so.tables_done;
+        if (so.tables_done) {
+            tm.finish();   // the per-document kernel produced every table: nothing is pending
+        } else {
+            // the suffix array is final here (the doubling loop ended on a host sync)
+            cudaStream_t ts = s;
+            if (overlap) {
+                ts = aux_stream(device);
+                cudaEvent_t fork;
+                EAST_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+                EAST_CUDA(cudaEventRecord(fork, s));
+                EAST_CUDA(cudaStreamWaitEvent(ts, fork, 0));
+                EAST_CUDA(cudaEventDestroy(fork));
+                tm.s = ts;
+            }
+            build_lcp_tables(idx->text, idx->t8, idx->term_code, idx->sa, idx->d_doc_off, idx->d_doc_m, n_docs, n, idx->lcp, idx->up,
+                             idx->down, idx->next, idx->ann, tm, ts, (int)get_option("child_variant", 0));
+            tm.finish();
+            if (overlap) {
+                EAST_CUDA(cudaEventCreateWithFlags(&idx->ev_tables, cudaEventDisableTiming));
+                EAST_CUDA(cudaEventRecord(idx->ev_tables, ts));
+                idx->tables_pending = true;
+            }
         }
     }
     if (!overlap) {
@@ -411,6 +419,7 @@ int east_index_stat(const east_index *idx, const char *name, int64_t *value) {
     if (!idx || !name || !value) return fail(EAST_ERR_INVALID, "NULL argument");
     if (!strcmp(name, "doc_sorted")) *value = idx->doc_sorted;
     else if (!strcmp(name, "doc_sort_overflow")) *value = idx->doc_sort_overflow;
+    else if (!strcmp(name, "tables_fused")) *value = idx->tables_fused;
     else if (!strcmp(name, "key_chars")) *value = idx->key_chars;
     else if (!strcmp(name, "key_bits")) *value = idx->key_bits;
     else if (!strcmp(name, "rounds")) *value = idx->rounds;

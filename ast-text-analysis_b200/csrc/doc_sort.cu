@@ -61,6 +61,9 @@ struct DocSortParams {
     int text_cap;             // bytes reserved for the staged text
     int bits_words;           // words of the bucket-start bitmap
     unsigned long long *phase_clk;  // optional (profiling): SM cycles per phase, summed over the CTAs
+    // optional fused tables (all or none): LCP (easa.py:247-266), child table (:268-304), annotation (:306-331);
+    // up/down/next/ann must be zero-filled by the caller, lcp is written for every rank
+    int32_t *lcp, *up, *down, *next, *ann;
 };
 
 // 8 bytes of shared memory at an arbitrary byte offset from a 16-byte aligned base: three aligned
@@ -89,9 +92,13 @@ __device__ __forceinline__ uint64_t ds_haszero(uint64_t v) {
 __device__ __forceinline__ uint32_t ds_id_from_word(uint32_t w, uint32_t term4, int b, int nsym) {
     const uint32_t z = ds_zero4(w ^ term4) & (0xffffffffu >> (8 * (4 - nsym)));
     if (z) w &= 0xffffffffu >> (8 * (3 - ((__ffs(z) - 1) >> 3)));
-    uint32_t id = 0;
-    for (int g = 0; g < nsym; ++g) id = (id << b) | ((w >> (8 * g)) & 0xffu);
-    return id;
+    const uint32_t s0 = w & 0xffu, s1 = (w >> 8) & 0xffu, s2 = (w >> 16) & 0xffu, s3 = w >> 24;
+    switch (nsym) {   // uniform: no variable-shift loop
+        case 1: return s0;
+        case 2: return (s0 << b) | s1;
+        case 3: return (((s0 << b) | s1) << b) | s2;
+        default: return (((((s0 << b) | s1) << b) | s2) << b) | s3;
+    }
 }
 
 // bucket id of the suffix at byte offset o: its first nsym symbols, cut after the first terminator
@@ -352,6 +359,63 @@ __device__ void ds_refine(const DocCtx &c, uint2 entry, int g, int gt, uint8_t *
         c.sa_doc[start + (int)r] = c.base + (int32_t)pe;
     }
     ds_group_sync(1 + g);
+}
+
+// min-pyramid over the document's LCP values in shared memory (16-bit: lcp < n <= 65535):
+// lv[0] = lcp, lv[k+1][i] = min(lv[k][32 i .. 32 i + 31])
+struct SPyr {
+    const uint16_t *lcp;    // level 0
+    const int *off;         // shared memory: element offset of level k from lcp
+    const int *size_;       // shared memory: entries of level k
+    int levels;
+    __device__ __forceinline__ const uint16_t *lv(int k) const { return lcp + off[k]; }
+    __device__ __forceinline__ int size(int k) const { return size_[k]; }
+};
+
+// largest q < p with lcp[q] <= l (exists: lcp[0] = 0)
+__device__ __forceinline__ int ds_prev_le(const SPyr &M, int p, uint32_t l) {
+    int idx = p, level = 0, j;
+    while (true) {
+        const int gs = idx & ~31;
+        const uint16_t *a = M.lv(level);
+        for (j = idx - 1; j >= gs; --j)
+            if (a[j] <= l) goto found;
+        idx >>= 5;
+        ++level;
+        if (level >= M.levels) return 0;
+    }
+found:
+    while (level > 0) {
+        --level;
+        const uint16_t *a = M.lv(level);
+        int c = min(j * 32 + 31, M.size(level) - 1);
+        while (a[c] > l) --c;
+        j = c;
+    }
+    return j;
+}
+
+// smallest e > p with lcp[e] < l, or n
+__device__ __forceinline__ int ds_next_lt(const SPyr &M, int p, uint32_t l, int n) {
+    int idx = p, level = 0, j;
+    while (true) {
+        const int ge = min((idx | 31) + 1, M.size(level));
+        const uint16_t *a = M.lv(level);
+        for (j = idx + 1; j < ge; ++j)
+            if (a[j] < l) goto found;
+        idx >>= 5;
+        ++level;
+        if (level >= M.levels) return n;
+    }
+found:
+    while (level > 0) {
+        --level;
+        const uint16_t *a = M.lv(level);
+        int c = j * 32;
+        while (a[c] >= l) ++c;
+        j = c;
+    }
+    return j;
 }
 
 __global__ void __launch_bounds__(DS_THREADS, 1)
@@ -621,6 +685,130 @@ k_doc_suffix_sort(DocSortParams p) {
         }
     }
     DS_STAMP(5);
+    if (p.lcp == nullptr) return;
+
+    // ---- phase 7: LCP of neighbouring suffixes from the staged text; 16-bit copy + min-pyramid in the
+    // (now free) scratch, which continues into the bitmap and the work lists
+    __syncthreads();
+    uint16_t *s_lcp = reinterpret_cast<uint16_t *>(s_scr);
+    __shared__ int s_pyr_off[4], s_pyr_size[4], s_pyr_levels;
+    if (tid == 0) {
+        int off = 0, sz = n, levels = 1;
+        s_pyr_off[0] = 0; s_pyr_size[0] = n;
+        for (int k = 1; k < 4; ++k) {
+            off += (sz + 1) & ~1;
+            sz = (sz + 31) >> 5;
+            s_pyr_off[k] = off; s_pyr_size[k] = sz;
+            levels = k + 1;
+            if (sz <= 1) break;
+        }
+        s_pyr_levels = levels;
+    }
+    __syncthreads();
+    SPyr M;
+    M.lcp = s_lcp; M.off = s_pyr_off; M.size_ = s_pyr_size; M.levels = s_pyr_levels;
+    uint16_t *s_lv1 = s_lcp + s_pyr_off[1];
+    constexpr int LU = 4;   // ranks per thread and round: their suffix-array loads (L2 latency) are issued together
+    for (int r0 = 0; r0 < n; r0 += LU * DS_THREADS) {
+        int pi[LU], pj[LU];
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int r = r0 + u * DS_THREADS + tid;
+            pi[u] = (r > 0 && r < n) ? sa_doc[r - 1] : 0;
+            pj[u] = (r > 0 && r < n) ? sa_doc[r] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < LU; ++u) {
+            const int r = r0 + u * DS_THREADS + tid;
+            uint32_t h = 0xffffu;
+            if (r < n) {
+                h = 0;
+                if (r > 0) {
+                    const int oi = shift + (pi[u] - base), oj = shift + (pj[u] - base);
+                    while (true) {
+                        const uint64_t x = ds_lds8(s_raw, oi + (int)h), y = ds_lds8(s_raw, oj + (int)h);
+                        const uint64_t stop = (x ^ y) | ds_haszero(x ^ term8);   // distinct terminators differ
+                        if (stop) { h += (uint32_t)((__ffsll((long long)stop) - 1) >> 3); break; }
+                        h += 8;
+                    }
+                }
+                p.lcp[base + r] = (int32_t)h;
+                s_lcp[r] = (uint16_t)h;
+            }
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, h);
+            if (lane == 0 && (r - lane) < n) s_lv1[r >> 5] = (uint16_t)wmin;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k < M.levels; ++k) {
+        for (int c = warp; c < M.size(k); c += DS_WARPS) {
+            const int i = c * 32 + lane;
+            const uint32_t v = (i < M.size(k - 1)) ? M.lv(k - 1)[i] : 0xffffu;
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, v);
+            if (lane == 0) s_lcp[s_pyr_off[k] + c] = (uint16_t)wmin;
+        }
+        __syncthreads();
+    }
+    DS_STAMP(6);
+
+    // ---- phase 8: child table and annotation.  Thread t walks C consecutive ranks with the reference's
+    // own stack discipline (easa.py:268-331): the stack holds the ranks whose next smaller LCP value
+    // has not been met yet, LCP values non-decreasing from bottom to top.  Pushing rank r: the top is
+    // q = PSE(r) (largest q < r with lcp[q] <= lcp[r]); popping t because of r: r = NSV(t) (smallest
+    // e > t with lcp[e] < lcp[t]).  What lies outside the chunk -- q of a rank pushed on an empty
+    // stack, e of the ranks still stacked at the end -- comes from the min-pyramid.  Closed forms as
+    // in tables.cu: lcp[q] == l -> next[q] = r; else r is the first l-index of [q .. e-1]:
+    // ann[r] = e - q, up[e] = r if lcp[q] <= lcp[e], down[q] = r if lcp[e] <= lcp[q] (e inside the
+    // document).  Values are ranks local to the document, 0 = none (arrays zero-filled by the host).
+    // The stacks (one byte per entry: offset in the chunk | 0x80 = first l-index) reuse the text area.
+    {
+        const int m = p.doc_m[doc];
+        const int C = max(8, (n + DS_THREADS - 1) / DS_THREADS);   // <= 64
+        const int c0 = tid * C, c1 = min(n, c0 + C);
+        uint8_t *stk = s_raw + tid * C;
+        int depth = 0;
+        int q_bot = 0;   // PSE of the bottom entry (outside the chunk)
+        auto close_interval = [&](int t, int q, int e, uint32_t le) {   // t: first l-index of [q .. e-1]
+            p.ann[base + t] = e - q;
+            if (e < n) {
+                const uint32_t lq = s_lcp[q];
+                if (lq <= le) p.up[base + e] = t;
+                if (le <= lq) p.down[base + q] = t;
+            }
+        };
+        for (int r = c0; r < c1; ++r) {
+            const uint32_t l = s_lcp[r];
+            // pop every stacked rank with a larger LCP value: r is its NSV
+            while (depth > 0) {
+                const uint32_t top = stk[depth - 1];
+                const int t = c0 + (int)(top & 0x7fu);
+                if (s_lcp[t] <= l) break;
+                --depth;
+                if (top & 0x80u) close_interval(t, depth > 0 ? c0 + (int)(stk[depth - 1] & 0x7fu) : q_bot, r, l);
+            }
+            uint32_t first = 0;
+            if (r == 0) {
+                p.ann[base] = n - m;   // easa.py:329; rank 0 is nobody's first l-index and is never popped
+            } else {
+                int q;
+                if (depth > 0) q = c0 + (int)(stk[depth - 1] & 0x7fu);
+                else { q = ds_prev_le(M, r, l); q_bot = q; }
+                if (s_lcp[q] == l) p.next[base + q] = r;
+                else first = 0x80u;
+            }
+            stk[depth++] = (uint8_t)((uint32_t)(r - c0) | first);
+        }
+        // ranks still stacked: their NSV lies beyond the chunk
+        while (depth > 0) {
+            const uint32_t top = stk[--depth];
+            if (top & 0x80u) {
+                const int t = c0 + (int)(top & 0x7fu);
+                const int e = ds_next_lt(M, t, s_lcp[t], n);
+                close_interval(t, depth > 0 ? c0 + (int)(stk[depth - 1] & 0x7fu) : q_bot, e, e < n ? s_lcp[e] : 0u);
+            }
+        }
+    }
+    DS_STAMP(7);
 #undef DS_STAMP
 }
 
@@ -638,15 +826,19 @@ bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan) {
     plan.b = b; plan.G = G; plan.S2 = S2;
     plan.text_cap = (max_doc_n + 15 + 48 + 16 + 15) & ~15;
     plan.bits_words = ((max_doc_n >> 5) + 3 + 1) & ~1;
-    plan.smem = (size_t)plan.text_cap + DS_SCR_BYTES + sizeof(uint32_t) * (size_t)plan.bits_words +
-                2 * sizeof(uint2) * (size_t)DS_LIST_CAP;
+    const size_t after_text = DS_SCR_BYTES + sizeof(uint32_t) * (size_t)plan.bits_words + 2 * sizeof(uint2) * (size_t)DS_LIST_CAP;
+    plan.smem = (size_t)plan.text_cap + after_text;
+    // fused LCP / child / annotation phases: 16-bit LCP copy + pyramid levels overlay everything after the text
+    size_t need = 0;
+    for (int sz = max_doc_n, k = 0; k < 4; ++k) { need += 2 * (((size_t)sz + 1) & ~(size_t)1); if (sz <= 1) break; sz = (sz + 31) >> 5; }
+    plan.tables_fit = need <= after_text ? 1 : 0;
     return plan.smem <= (size_t)220 * 1024;
 }
 
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
                      const int32_t *doc_m, int n_docs,
                      int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
-                     unsigned long long *phase_clk) {
+                     unsigned long long *phase_clk, const DocSortTables *tables) {
     static bool configured = false;
     if (!configured) {
         EAST_CUDA(cudaFuncSetAttribute(k_doc_suffix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -657,7 +849,10 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     p.b = plan.b; p.G = plan.G; p.S2 = plan.S2; p.term = term;
     p.text_cap = plan.text_cap; p.bits_words = plan.bits_words;
     p.phase_clk = phase_clk;
-    EAST_BYTES(9.0 * (double)n_total);  // byte text in, suffix array out + one re-read (L2-resident scatter)
+    p.lcp = p.up = p.down = p.next = p.ann = nullptr;
+    if (tables && plan.tables_fit) { p.lcp = tables->lcp; p.up = tables->up; p.down = tables->down; p.next = tables->next; p.ann = tables->ann; }
+    // byte text in, suffix array out + one re-read (L2-resident scatter); with tables: LCP + annotation out
+    EAST_BYTES((p.lcp ? 17.0 : 9.0) * (double)n_total);
     EAST_LAUNCH(k_doc_suffix_sort, n_docs, DS_THREADS, plan.smem, s, p);
 }
 

@@ -902,20 +902,30 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 clk = DevBuf<unsigned long long>(8, s);
                 EAST_CUDA(cudaMemsetAsync(clk.p, 0, 8 * sizeof(unsigned long long), s));
             }
-            doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, D, n, kp.term, out.sa, out.bkt.p, flag.p, s, clk.p);
+            DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
+            const bool fuse = in.lcp != nullptr && plan.tables_fit;
+            if (fuse) {
+                EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, s));
+                EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, s));
+                EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
+                EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
+            }
+            doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, D, n, kp.term, out.sa, out.bkt.p, flag.p, s, clk.p,
+                            fuse ? &tables : nullptr);
             uint32_t overflow = 0;
             EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             EAST_CUDA(cudaStreamSynchronize(s));
             if (profile) {
                 unsigned long long h[8];
                 EAST_CUDA(cudaMemcpy(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost));
-                static const char *names[6] = {"load", "hist", "scan", "scatter", "refine", "windows"};
+                static const char *names[8] = {"load", "hist", "scan", "scatter", "refine", "windows", "lcp", "child_ann"};
                 fprintf(stderr, "[east] doc_sort phases, kilo-cycles per document:");
-                for (int k = 0; k < 6; ++k) fprintf(stderr, " %s %.1f", names[k], (double)h[k] / D / 1e3);
+                for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.1f", names[k], (double)h[k] / D / 1e3);
                 fprintf(stderr, "\n");
             }
             if (!overflow) {
                 out.doc_sorted = 1;
+                out.tables_done = fuse ? 1 : 0;
                 out.rounds = 1;
                 out.key_chars = plan.G + 8;
                 out.key_bits = plan.b * plan.G + 64;

@@ -19,6 +19,8 @@ struct SaInput {
     int local_group_sort = 1;               // doubling rounds: rank inside small groups instead of radix passes
     int64_t sort_batch_elems = 0;           // round-0 sort batch in suffixes (0 = whole batch at once)
     int doc_sort = 1;                       // small documents: one CTA sorts a whole document in shared memory
+    // destination of the LCP / child / annotation tables: the per-document kernel fills them itself
+    int32_t *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
 };
 
 struct SaOutput {
@@ -39,6 +41,7 @@ struct SaOutput {
     int radix_fallback_rounds = 0;   // doubling rounds that met a group > GS_MAX and used the radix sort
     int doc_sorted = 0;              // the per-document shared-memory sort produced the suffix array
     int doc_sort_overflow = 0;       // it met a bucket it cannot sort and the global sort took over
+    int tables_done = 0;             // LCP / child / annotation tables were produced by the per-document kernel
 };
 
 void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s);
@@ -48,12 +51,15 @@ struct DocSortPlan {
     int b = 0, G = 0, S2 = 0;   // bits per symbol, symbols per bucket id, symbols per refinement level
     int text_cap = 0, bits_words = 0;
     size_t smem = 0;
+    int tables_fit = 0;         // the fused LCP / child / annotation phases fit the shared memory too
 };
+struct DocSortTables { int32_t *lcp, *up, *down, *next, *ann; };   // up/down/next zero-filled by the caller
 bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan);
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
                      const int32_t *doc_m, int n_docs,
                      int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
-                     unsigned long long *phase_clk = nullptr /* profiling: 8 cycle counters */);
+                     unsigned long long *phase_clk = nullptr /* profiling: 8 cycle counters */,
+                     const DocSortTables *tables = nullptr /* also produce LCP, child table, annotation */);
 
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch

@@ -245,6 +245,10 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     debug = bool(os.environ.get("EAST_BENCH_DEBUG"))
+    for kv in os.environ.get("EAST_BENCH_OPTS", "").split(","):   # tuning experiments: "name=value,..."
+        if "=" in kv:
+            name, value = kv.split("=")
+            _capi.set_option(name, int(value))
 
     def step_device():
         ta = time.perf_counter()

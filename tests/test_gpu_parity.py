@@ -18,14 +18,18 @@ def _capi():
     return _capi
 
 
-@pytest.fixture(autouse=True, params=["doc_sort", "global_sort"])
+@pytest.fixture(autouse=True, params=["doc_sort", "doc_sort_split_tables", "global_sort"])
 def sa_path(request):
-    """Every test runs twice: with the per-document shared-memory suffix sort (doc_sort.cu, the default
-    for documents of < 64 Ki code points) and with the global prefix-doubling sort (sa_build.cu)."""
+    """Every test runs three times: with the per-document shared-memory kernel (doc_sort.cu, the default
+    for documents of < 64 Ki code points) producing suffix array AND tables; with that kernel producing the
+    suffix array only and the batch-wide LCP / child / annotation kernels (tables.cu) after it; and with
+    the global prefix-doubling sort (sa_build.cu)."""
     capi = _capi()
     capi.set_option("no_doc_sort", 1 if request.param == "global_sort" else 0)
+    capi.set_option("no_fused_tables", 1 if request.param == "doc_sort_split_tables" else 0)
     yield request.param
     capi.set_option("no_doc_sort", 0)
+    capi.set_option("no_fused_tables", 0)
 
 
 def _build(strings_collections, device=0):
@@ -131,7 +135,8 @@ def test_zipf_documents_vs_oracle(oracle_mod, sa_path):
     idx = capi.DeviceIndex(packed, ms)
     info = idx.info()
     assert info["fast_path"] and info["rounds"] <= 6
-    assert info["doc_sorted"] == (sa_path == "doc_sort")
+    assert info["doc_sorted"] == sa_path.startswith("doc_sort")
+    assert bool(idx.stat("tables_fused")) == (sa_path == "doc_sort")
     oracles = [oracle_mod.OracleEASA(text=p, m=m) for p, m in zip(packed, ms)]
     for d, o in enumerate(oracles):
         _check_arrays(idx, d, o, d)
@@ -460,7 +465,7 @@ def test_segmented_and_global_round0_sort_agree(oracle_mod):
 def test_doc_sort_bucket_overflow_falls_back_to_the_global_sort(oracle_mod, sa_path):
     # one bucket of > 4096 suffixes (a run of 9000 equal symbols) is more than a group refines in shared
     # memory: the build must notice, redo the batch with the global sort and still be exact
-    if sa_path != "doc_sort":
+    if not sa_path.startswith("doc_sort"):
         pytest.skip("per-document sort only")
     cols = [["A" * 9000, "AB"], ["XABXAC", "HI"]]
     idx = _build(cols)
@@ -478,7 +483,7 @@ def test_doc_sort_bucket_overflow_falls_back_to_the_global_sort(oracle_mod, sa_p
 
 def test_doc_sort_alphabet_sizes(oracle_mod, sa_path):
     # bits per symbol 1..7 select different bucket / key geometries (G, WS) of the per-document sort
-    if sa_path != "doc_sort":
+    if not sa_path.startswith("doc_sort"):
         pytest.skip("per-document sort only")
     rng = np.random.default_rng(5)
     pool = [chr(c) for c in range(0x21, 0x7f)] + [chr(c) for c in range(0x410, 0x450)]
