@@ -148,7 +148,7 @@ struct east_index {
     uint32_t *bkt = nullptr;        // fast path: 2-gram bucket table
     std::vector<uint8_t> code_table;
     int sym_bits = 0, term_code = 0;
-    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0, tables_fused = 0;
+    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0, tables_fused = 0, pipelined = 0, pipeline_miss = 0;
     uint32_t active_after_round0 = 0;
     // LCP / child / annotation tables are produced on an auxiliary stream after the suffix array is
     // final, so a score call (which needs only SA + text) overlaps them; readers wait on ev_tables
@@ -159,6 +159,19 @@ struct east_index {
 
 // per-device auxiliary (non-blocking) stream for the table kernels
 static cudaStream_t aux_stream(int device) {
+    static std::mutex m;
+    static std::map<int, cudaStream_t> streams;
+    std::lock_guard<std::mutex> g(m);
+    auto it = streams.find(device);
+    if (it != streams.end()) return it->second;
+    cudaStream_t st;
+    EAST_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    streams[device] = st;
+    return st;
+}
+
+// per-device copy stream of the pipelined host build
+static cudaStream_t copy_stream(int device) {
     static std::mutex m;
     static std::map<int, cudaStream_t> streams;
     std::lock_guard<std::mutex> g(m);
@@ -267,9 +280,21 @@ static void free_index(east_index *idx) {
     delete idx;
 }
 
+struct ChunkPlan {   // pipelined host build: runs of whole documents and the events of their copies
+    std::vector<int32_t> doc;          // n_chunks + 1 document boundaries
+    std::vector<cudaEvent_t> ready;
+    ~ChunkPlan() { for (auto e : ready) cudaEventDestroy(e); }
+};
+
 static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t *doc_off, const int32_t *doc_m,
-                        int32_t n_docs, int device, cudaStream_t s, east_index **out) {
+                        int32_t n_docs, int device, cudaStream_t s, east_index **out, const ChunkPlan *chunks = nullptr) {
     std::unique_ptr<east_index, void (*)(east_index *)> idx(new east_index(), free_index);
+    // pipelined build: whatever happens, the copy stream must be done with the text before the index
+    // (declared above, destroyed after this guard) can free it
+    struct CopyGuard {
+        cudaStream_t cs; bool armed;
+        ~CopyGuard() { if (armed) cudaStreamSynchronize(cs); }
+    } copy_guard{chunks ? copy_stream(device) : (cudaStream_t)0, chunks != nullptr};
     idx->device = device;
     idx->n_docs = n_docs;
     idx->text = const_cast<uint32_t *>(text_dev);
@@ -316,9 +341,17 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         if (!get_option("no_fused_tables", 0)) {
             in.lcp = idx->lcp; in.up = idx->up; in.down = idx->down; in.next = idx->next; in.ann = idx->ann;
         }
+        if (chunks && in.doc_sort) {
+            in.n_chunks = (int)chunks->ready.size();
+            in.chunk_doc = chunks->doc.data();
+            in.chunk_ready = chunks->ready.data();
+        } else if (chunks) {   // the global sort needs the whole text: wait for every copy
+            for (auto e : chunks->ready) EAST_CUDA(cudaStreamWaitEvent(s, e, 0));
+        }
         SaOutput so;
         so.sa = idx->sa; so.rank = rank.p;
         build_suffix_array(in, so, tm, s);
+        idx->pipelined = so.pipelined; idx->pipeline_miss = so.pipeline_miss;
         idx->rounds = so.rounds; idx->fast_path = so.fast_path; idx->key_chars = so.key_chars;
         idx->key_bits = so.key_bits; idx->active_after_round0 = so.active_after_round0;
         idx->doc_sorted = so.doc_sorted; idx->doc_sort_overflow = so.doc_sort_overflow;
@@ -376,12 +409,54 @@ int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t 
     EAST_API_BEGIN
     check_build_args(text, doc_off, doc_m, n_docs, out);
     use_device(device);
-    const size_t bytes = sizeof(uint32_t) * (size_t)doc_off[n_docs];
+    const int64_t n = doc_off[n_docs];
+    const size_t bytes = sizeof(uint32_t) * (size_t)n;
     // stream-ordered pool allocation (cudaMalloc/cudaFree take device-wide locks and synchronise)
     uint32_t *d_text = (uint32_t *)dev_alloc(bytes, 0);
-    cudaError_t e = cudaMemcpyAsync(d_text, text, bytes, cudaMemcpyHostToDevice, 0);
-    if (e != cudaSuccess) { dev_free(d_text, 0); throw Error(EAST_ERR_CUDA, cudaGetErrorString(e)); }
-    build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out);  // owns d_text from here on
+    // Large batches of small documents: copy in runs of whole documents on a copy stream so that the
+    // per-document kernels of run c overlap the copy of run c+1 (worth it with pinned host memory)
+    int64_t max_doc = 0;
+    for (int32_t d = 0; d < n_docs; ++d) max_doc = std::max(max_doc, doc_off[d + 1] - doc_off[d]);
+    const int64_t chunk_target = get_option("pipeline_chunk", (int64_t)1 << 22);
+    int want = (int)std::min<int64_t>(16, n / chunk_target);
+    const bool pipelined = want >= 2 && n_docs >= 2 * EAST_NUM_SMS && max_doc <= 65535 && !get_option("no_pipeline", 0) &&
+                           !get_option("no_doc_sort", 0);
+    cudaError_t e = cudaSuccess;
+    if (!pipelined) {
+        e = cudaMemcpyAsync(d_text, text, bytes, cudaMemcpyHostToDevice, 0);
+        if (e != cudaSuccess) { dev_free(d_text, 0); throw Error(EAST_ERR_CUDA, cudaGetErrorString(e)); }
+        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out);  // owns d_text from here on
+    } else {
+        ChunkPlan plan;
+        cudaStream_t cs = copy_stream(device);
+        try {
+            // the allocation was made on stream 0: the copy stream must not run ahead of it
+            cudaEvent_t alloc_done;
+            EAST_CUDA(cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming));
+            EAST_CUDA(cudaEventRecord(alloc_done, 0));
+            EAST_CUDA(cudaStreamWaitEvent(cs, alloc_done, 0));
+            EAST_CUDA(cudaEventDestroy(alloc_done));
+            // runs of whole documents, a multiple of the SM count each: one per-document CTA per SM and wave,
+            // so a run costs exactly its waves (10 runs of 100 documents on 148 SMs would cost 10 waves, not 7)
+            const int32_t per_run = (int32_t)(((int64_t)(n_docs + want - 1) / want + EAST_NUM_SMS - 1) / EAST_NUM_SMS) * EAST_NUM_SMS;
+            plan.doc.push_back(0);
+            for (int32_t d = 0; d < n_docs; d += per_run) {
+                const int32_t d1 = std::min(n_docs, d + per_run);
+                const int64_t e0 = doc_off[d], e1 = doc_off[d1];
+                EAST_CUDA(cudaMemcpyAsync(d_text + e0, text + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, cs));
+                cudaEvent_t ev;
+                EAST_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                plan.ready.push_back(ev);
+                EAST_CUDA(cudaEventRecord(ev, cs));
+                plan.doc.push_back(d1);
+            }
+        } catch (...) {
+            cudaStreamSynchronize(cs);
+            dev_free(d_text, 0);
+            throw;
+        }
+        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, &plan);
+    }
     EAST_API_END
 }
 
@@ -420,6 +495,8 @@ int east_index_stat(const east_index *idx, const char *name, int64_t *value) {
     if (!strcmp(name, "doc_sorted")) *value = idx->doc_sorted;
     else if (!strcmp(name, "doc_sort_overflow")) *value = idx->doc_sort_overflow;
     else if (!strcmp(name, "tables_fused")) *value = idx->tables_fused;
+    else if (!strcmp(name, "pipelined")) *value = idx->pipelined;
+    else if (!strcmp(name, "pipeline_miss")) *value = idx->pipeline_miss;
     else if (!strcmp(name, "key_chars")) *value = idx->key_chars;
     else if (!strcmp(name, "key_bits")) *value = idx->key_bits;
     else if (!strcmp(name, "rounds")) *value = idx->rounds;

@@ -60,6 +60,7 @@ struct DocSortParams {
     uint32_t term;            // terminator class code
     int text_cap;             // bytes reserved for the staged text
     int bits_words;           // words of the bucket-start bitmap
+    int doc_begin;            // first document of this launch (CTA x sorts document doc_begin + x)
     unsigned long long *phase_clk;  // optional (profiling): SM cycles per phase, summed over the CTAs
     // optional fused tables (all or none): LCP (easa.py:247-266), child table (:268-304), annotation (:306-331);
     // up/down/next/ann must be zero-filled by the caller, lcp is written for every rank
@@ -433,7 +434,7 @@ k_doc_suffix_sort(DocSortParams p) {
     __shared__ uint32_t s_gw[DS_NGROUPS * DS_GWARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int doc = blockIdx.x;
+    const int doc = p.doc_begin + (int)blockIdx.x;
     const int32_t base = p.doc_off[doc];
     const int n = p.doc_off[doc + 1] - base;
     const int b = p.b, G = p.G;
@@ -453,13 +454,20 @@ k_doc_suffix_sort(DocSortParams p) {
         }                                                                               \
     } while (0)
 
-    // ---- phase 1: stage the text, clear counters / bitmap
+    // ---- phase 1: stage the text, clear counters / bitmap; place and VALIDATE the terminators
     const int32_t a0 = base & ~15;
     const int shift = base - a0;
     {
         const int nbytes = (shift + n + 48 + 15) & ~15;
         const int m = p.doc_m[doc];
         const uint32_t term4 = (uint32_t)term8;
+        for (int k = tid; k < m; k += DS_THREADS) sa_doc[n - m + k] = -1;
+        for (int i = tid; i < NW; i += DS_THREADS) s_scr[i] = 0;
+        for (int i = tid; i < p.bits_words; i += DS_THREADS) s_bits[i] = 0;
+        if (tid < 2) s_nlist[tid] = 0;
+        if (tid == 0) s_work = 0;   // here: number of terminator codes seen
+        __syncthreads();
+        int bad = 0;
         for (int o = tid * 16; o < nbytes; o += DS_THREADS * 16) {
             const uint4 v = *reinterpret_cast<const uint4 *>(p.t8 + a0 + o);
             *reinterpret_cast<uint4 *>(s_raw + o) = v;
@@ -473,13 +481,27 @@ k_doc_suffix_sort(DocSortParams p) {
                 while (z) {
                     const int i = o + 4 * wi + ((__ffs(z) - 1) >> 3) - shift;
                     z &= z - 1u;
-                    if (i >= 0 && i < n) sa_doc[n - m + (int)(p.text[base + i] - EAST_TERM_BASE)] = base + i;
+                    if (i >= 0 && i < n) {
+                        const uint32_t k = p.text[base + i] - EAST_TERM_BASE;
+                        if (k < (uint32_t)m) sa_doc[n - m + (int)k] = base + i; else bad = 1;
+                        atomicAdd(&s_work, 1u);
+                    }
                 }
             }
         }
-        for (int i = tid; i < NW; i += DS_THREADS) s_scr[i] = 0;
-        for (int i = tid; i < p.bits_words; i += DS_THREADS) s_bits[i] = 0;
-        if (tid < 2) s_nlist[tid] = 0;
+        __syncthreads();
+        // The layout every later phase relies on (east/asts/utils.py:25-40): exactly m terminator codes,
+        // string k ends with 0x0A00 + k, the document ends with its last terminator.  A build that
+        // runs ahead of the validating text scan (pipelined host build) finds out here.
+        if (s_work != (uint32_t)m) bad = 1;
+        for (int k = tid; k < m; k += DS_THREADS) {
+            const int32_t v = sa_doc[n - m + k];
+            if (v < 0 || (k > 0 && sa_doc[n - m + k - 1] >= v) || (k == m - 1 && v != base + n - 1)) bad = 1;
+        }
+        if (__syncthreads_or(bad)) {
+            if (tid == 0) atomicOr(p.overflow, 2u);
+            return;
+        }
     }
     __syncthreads();
     DS_STAMP(0);
@@ -836,7 +858,7 @@ bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan) {
 }
 
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
-                     const int32_t *doc_m, int n_docs,
+                     const int32_t *doc_m, int doc_begin, int n_docs,
                      int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
                      unsigned long long *phase_clk, const DocSortTables *tables) {
     static bool configured = false;
@@ -849,6 +871,7 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     p.b = plan.b; p.G = plan.G; p.S2 = plan.S2; p.term = term;
     p.text_cap = plan.text_cap; p.bits_words = plan.bits_words;
     p.phase_clk = phase_clk;
+    p.doc_begin = doc_begin;
     p.lcp = p.up = p.down = p.next = p.ann = nullptr;
     if (tables && plan.tables_fit) { p.lcp = tables->lcp; p.up = tables->up; p.down = tables->down; p.next = tables->next; p.ann = tables->ann; }
     // byte text in, suffix array out + one re-read (L2-resident scatter); with tables: LCP + annotation out

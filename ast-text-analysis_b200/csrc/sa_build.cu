@@ -309,31 +309,63 @@ k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict
     }
 }
 
-// dense byte codes: 1..sigma for present code points < 0x0A00, sigma+1 for every terminator
+// dense byte codes: 1..sigma for present code points < 0x0A00, sigma+1 for every terminator.
+// Encodes [begin, end) (begin a multiple of 4 or a document start handled by the scalar edges);
+// *miss is set when a code point below 0x0A00 has no code (speculative alphabet, see below).
 __global__ void __launch_bounds__(256)
-k_encode_text(const uint32_t *__restrict__ T, int32_t n, const uint8_t *__restrict__ code_table,
-              uint8_t term_code, uint8_t *__restrict__ T8) {
+k_encode_text(const uint32_t *__restrict__ T, int32_t begin, int32_t end, const uint8_t *__restrict__ code_table,
+              uint8_t term_code, uint8_t *__restrict__ T8, uint32_t *miss) {
     __shared__ uint8_t s_code[EAST_TERM_BASE];
     for (int i = threadIdx.x; i < (int)EAST_TERM_BASE; i += blockDim.x) s_code[i] = code_table[i];
     __syncthreads();
+    const int32_t a0 = begin & ~3;   // groups of 4 aligned code points; the edges are masked
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    bool missed = false;
+    for (int64_t i = a0 + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < end; i += stride) {
+        const bool full = i >= begin && i + 3 < end;
         uint32_t c[4];
-        if (i + 3 < n) {
+        if (full) {
             uint4 v = *reinterpret_cast<const uint4 *>(T + i);  // 128-bit load
             c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
         } else {
-            for (int q = 0; q < 4; ++q) c[q] = (i + q < n) ? T[i + q] : 0u;
+            for (int q = 0; q < 4; ++q) c[q] = (i + q >= begin && i + q < end) ? T[i + q] : EAST_TERM_BASE;
         }
         uint32_t packed = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint32_t e = (c[q] < EAST_TERM_BASE) ? s_code[c[q]] : term_code;
+            missed = missed || e == 0u;
             packed |= e << (8 * q);
         }
-        if (i + 3 < n) *reinterpret_cast<uint32_t *>(T8 + i) = packed;
-        else for (int q = 0; q < 4 && i + q < n; ++q) T8[i + q] = (uint8_t)(packed >> (8 * q));
+        if (full) *reinterpret_cast<uint32_t *>(T8 + i) = packed;
+        else for (int q = 0; q < 4; ++q) if (i + q >= begin && i + q < end) T8[i + q] = (uint8_t)(packed >> (8 * q));
     }
+    if (missed && miss) atomicOr(miss, 1u);
+}
+
+// bitmap of the code points below 0x0A00 that occur in T[0, n): the speculative alphabet of a pipelined build
+__global__ void __launch_bounds__(256)
+k_alphabet(const uint32_t *__restrict__ T, int32_t n, uint32_t *present) {
+    __shared__ uint32_t s_present[EAST_TERM_BASE / 32];
+    for (int i = threadIdx.x; i < (int)(EAST_TERM_BASE / 32); i += blockDim.x) s_present[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        uint32_t c[4];
+        if (i + 3 < n) {
+            uint4 v = *reinterpret_cast<const uint4 *>(T + i);
+            c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+        } else {
+            for (int q = 0; q < 4; ++q) c[q] = (i + q < n) ? T[i + q] : EAST_TERM_BASE;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (c[q] < EAST_TERM_BASE && !(((volatile uint32_t *)s_present)[c[q] >> 5] & (1u << (c[q] & 31))))
+                atomicOr(&s_present[c[q] >> 5], 1u << (c[q] & 31));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)(EAST_TERM_BASE / 32); i += blockDim.x)
+        if (s_present[i]) atomicOr(&present[i], s_present[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -818,17 +850,122 @@ k_bucket_fill(uint32_t *__restrict__ bkt, int entries, const int32_t *__restrict
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
-void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s) {
+// Pipelined host build (east_build_host on a large batch of small documents): the text arrives chunk
+// by chunk on a copy stream.  The alphabet is taken from chunk 0 (speculation: later chunks use no
+// other code point below 0x0A00), every chunk is encoded and sorted by the per-document kernel as soon
+// as it is resident, and ONE validating scan of the whole text at the end confirms the alphabet and the
+// terminator layout.  If it does not, nothing is kept and the ordinary build runs on the resident text.
+static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s, ScanResult &scan,
+                            DevBuf<ScanResult> &d_scan) {
     const int32_t n = in.n;
     const int D = in.n_docs;
+    int32_t max_doc_n = 0;
+    for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);
+    tm.mark("alphabet");
+    DevBuf<uint32_t> d_present(EAST_TERM_BASE / 32, s);
+    EAST_CUDA(cudaMemsetAsync(d_present.p, 0, sizeof(uint32_t) * (EAST_TERM_BASE / 32), s));
+    EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
+    const int32_t n0 = in.doc_off_host[in.chunk_doc[1]];
+    EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_present.p);
+    uint32_t present[EAST_TERM_BASE / 32];
+    EAST_CUDA(cudaMemcpyAsync(present, d_present.p, sizeof(present), cudaMemcpyDeviceToHost, s));
+    EAST_CUDA(cudaStreamSynchronize(s));
+    int sigma = 0;
+    std::vector<uint8_t> table(EAST_TERM_BASE, 0);
+    for (uint32_t c = 0; c < EAST_TERM_BASE; ++c)
+        if (present[c >> 5] & (1u << (c & 31))) { ++sigma; table[c] = (uint8_t)(sigma & 0xff); }
+    DocSortPlan plan;
+    const bool eligible = sigma <= 253 && doc_sort_plan(sigma, max_doc_n, plan);
+    const uint32_t term = (uint32_t)sigma + 1;
+
+    DevBuf<uint8_t> t8;
+    DevBuf<uint32_t> flags(2, s);   // [0] doc_sort overflow, [1] encode miss
+    if (eligible) {
+        tm.mark("doc_sort");
+        DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
+        EAST_CUDA(cudaMemcpyAsync(d_table.p, table.data(), EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
+        t8 = DevBuf<uint8_t>((size_t)n + 128, s);
+        EAST_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(uint32_t), s));
+        if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
+            const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
+            out.bkt = DevBuf<uint32_t>(entries, s);
+            EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            out.sym_bits = plan.b;
+        }
+        DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
+        const bool fuse = in.lcp != nullptr && plan.tables_fit;
+        if (fuse) {
+            EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, s));
+            EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, s));
+            EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
+            EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
+        }
+        for (int c = 0; c < in.n_chunks; ++c) {
+            const int d0 = in.chunk_doc[c], d1 = in.chunk_doc[c + 1];
+            const int32_t e0 = in.doc_off_host[d0], e1 = in.doc_off_host[d1];
+            if (c > 0) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
+            EAST_BYTES(5.0 * (e1 - e0));
+            EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, s, in.text, e0, e1, d_table.p,
+                        (uint8_t)term, t8.p, flags.p + 1);
+            doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
+                            flags.p, s, nullptr, fuse ? &tables : nullptr);
+        }
+        out.tables_done = fuse ? 1 : 0;
+    } else {
+        for (int c = 1; c < in.n_chunks; ++c) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
+    }
+    // the validating scan (also what the ordinary build starts with)
     tm.mark("scan_text");
-    DevBuf<ScanResult> d_scan(1, s);
     EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
     EAST_BYTES(4.0 * n);
     EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p);
-    ScanResult scan;
+    uint32_t h_flags[2] = {0u, 0u};
     EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
+    if (eligible) EAST_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
     EAST_CUDA(cudaStreamSynchronize(s));
+    bool ok = eligible && !scan.bad && scan.n_term == (uint32_t)in.m_total && !h_flags[0] && !h_flags[1];
+    for (int w = 0; ok && w < (int)(EAST_TERM_BASE / 32); ++w) ok = scan.present[w] == present[w];
+    if (!ok) {
+        out.pipeline_miss = eligible ? 1 : 0;
+        out.doc_sort_overflow = (h_flags[0] & 1u) ? 1 : 0;
+        out.tables_done = 0;
+        out.bkt = DevBuf<uint32_t>();
+        out.sym_bits = 0;
+        return false;
+    }
+    out.pipelined = 1;
+    out.fast_path = 1;
+    out.sigma = sigma;
+    out.doc_sorted = 1;
+    out.rounds = 1;
+    out.key_chars = plan.G + 8;
+    out.key_bits = plan.b * plan.G + 64;
+    out.code_table = table;
+    out.term_code = (int)term;
+    out.t8 = std::move(t8);
+    return true;
+}
+
+void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s) {
+    const int32_t n = in.n;
+    const int D = in.n_docs;
+    DevBuf<ScanResult> d_scan(1, s);
+    ScanResult scan;
+    bool scanned = false;
+    bool allow_doc_sort = in.doc_sort != 0;
+    if (in.n_chunks > 0) {
+        if (build_pipelined(in, out, tm, s, scan, d_scan)) return;
+        scanned = true;                       // the validating scan is the ordinary build's first step
+        if (out.doc_sort_overflow) allow_doc_sort = false;
+    }
+    if (!scanned) {
+        tm.mark("scan_text");
+        EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
+        EAST_BYTES(4.0 * n);
+        EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p);
+        EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
+        EAST_CUDA(cudaStreamSynchronize(s));
+    }
 
     int sigma = 0;
     std::vector<uint8_t> table(EAST_TERM_BASE, 0);
@@ -875,14 +1012,14 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         EAST_CUDA(cudaMemcpyAsync(d_table.p, table.data(), EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
         t8 = DevBuf<uint8_t>((size_t)n + 128, s);
         EAST_BYTES(5.0 * n);
-        EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_table.p,
-                    (uint8_t)kp.term, t8.p);
+        EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, 0, n, d_table.p,
+                    (uint8_t)kp.term, t8.p, (uint32_t *)nullptr);
     }
     out.code_table = table;
     out.term_code = fast ? (int)kp.term : 0;
 
     // ---- small documents: one CTA per document, everything in shared memory (doc_sort.cu)
-    if (fast && in.doc_sort) {
+    if (fast && allow_doc_sort) {
         int32_t max_doc_n = 0;
         for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);
         DocSortPlan plan;
@@ -910,7 +1047,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
                 EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
             }
-            doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, D, n, kp.term, out.sa, out.bkt.p, flag.p, s, clk.p,
+            doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, 0, D, n, kp.term, out.sa, out.bkt.p, flag.p, s, clk.p,
                             fuse ? &tables : nullptr);
             uint32_t overflow = 0;
             EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -21,6 +21,11 @@ struct SaInput {
     int doc_sort = 1;                       // small documents: one CTA sorts a whole document in shared memory
     // destination of the LCP / child / annotation tables: the per-document kernel fills them itself
     int32_t *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
+    // pipelined host build: the text arrives in n_chunks runs of whole documents; chunk c = documents
+    // [chunk_doc[c], chunk_doc[c+1]) is resident once chunk_ready[c] has fired (recorded on the copy stream)
+    int n_chunks = 0;
+    const int32_t *chunk_doc = nullptr;
+    const cudaEvent_t *chunk_ready = nullptr;
 };
 
 struct SaOutput {
@@ -42,6 +47,8 @@ struct SaOutput {
     int doc_sorted = 0;              // the per-document shared-memory sort produced the suffix array
     int doc_sort_overflow = 0;       // it met a bucket it cannot sort and the global sort took over
     int tables_done = 0;             // LCP / child / annotation tables were produced by the per-document kernel
+    int pipelined = 0;               // the build overlapped the host-to-device copy (speculative alphabet held)
+    int pipeline_miss = 0;           // it did not hold (later chunks brought new symbols / bad layout): redone
 };
 
 void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s);
@@ -56,8 +63,8 @@ struct DocSortPlan {
 struct DocSortTables { int32_t *lcp, *up, *down, *next, *ann; };   // up/down/next zero-filled by the caller
 bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan);
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
-                     const int32_t *doc_m, int n_docs,
-                     int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
+                     const int32_t *doc_m, int doc_begin, int n_docs,
+                     int64_t n_total /* code points of these documents */, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
                      unsigned long long *phase_clk = nullptr /* profiling: 8 cycle counters */,
                      const DocSortTables *tables = nullptr /* also produce LCP, child table, annotation */);
 

@@ -277,14 +277,16 @@ def run_b200(args):
         tb = time.perf_counter()
         idx.score_table_into(kp_codes, kp_off, host_out_np, True)
         tc = time.perf_counter()
+        pipelined = idx.stat("pipelined")
         if world > 1:
             out_dev.copy_(host_out.view(-1), non_blocking=True)   # gather the table this step produced
             dist.all_gather_into_tensor(gathered, out_dev)
             torch.cuda.synchronize()
         idx.close()
         if debug:
-            sys.stderr.write("e2e: build_host %.2f ms, score_host %.2f ms, close %.2f ms\n" % (
-                (tb - ta) * 1e3, (tc - tb) * 1e3, (time.perf_counter() - tc) * 1e3))
+            sys.stderr.write("e2e: build_host %.2f ms, score_host %.2f ms, close %.2f ms %s pipelined=%d\n" % (
+                (tb - ta) * 1e3, (tc - tb) * 1e3, (time.perf_counter() - tc) * 1e3,
+                [(n, round(m, 3)) for n, m in idx.build_timings], pipelined))
 
     # ---- algorithmic bytes of the scorer for this workload: counted once by the instrumented scorer
     idx0 = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream)

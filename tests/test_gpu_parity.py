@@ -500,3 +500,45 @@ def test_doc_sort_alphabet_sizes(oracle_mod, sa_path):
         for d, c in enumerate(cols):
             _check_arrays(idx, d, oracle_mod.OracleEASA(c), (sigma, d))
         idx.close()
+
+
+def test_pipelined_host_build_matches_and_recovers(oracle_mod, sa_path):
+    # east_build_host copies large batches chunk by chunk and sorts chunk c while chunk c+1 is in flight,
+    # trusting the alphabet of chunk 0; a validating scan at the end confirms it or the build is redone
+    if sa_path == "global_sort":
+        pytest.skip("the pipelined build drives the per-document kernel")
+    import synth
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(400, 1200, first_seed=70)
+    try:
+        capi.set_option("pipeline_chunk", 40000)   # 3 runs of 148, 148, 104 documents
+        idx = capi.DeviceIndex(packed, ms)
+        assert idx.stat("pipelined") == 1 and idx.stat("pipeline_miss") == 0 and idx.info()["doc_sorted"]
+        for d in (0, 147, 148, 399):
+            _check_arrays(idx, d, oracle_mod.OracleEASA(text=packed[d], m=ms[d]), ("pipelined", d))
+        from east import utils
+        kps = [utils.prepare_text(k) for k in synth.keyphrases(20)]
+        codes, off = capi.pack_keyphrases(kps)
+        table = idx.score_table(codes, off, True)
+        capi.set_option("no_pipeline", 1)
+        ref = capi.DeviceIndex(packed, ms)
+        assert ref.stat("pipelined") == 0
+        assert np.array_equal(table.view(np.uint64), ref.score_table(codes, off, True).view(np.uint64))
+        capi.set_option("no_pipeline", 0)
+        # a symbol that first appears in a late chunk: the speculation fails, the result must not change
+        from east.asts import utils as au
+        late = au.pack_strings_collection(["0123456789 QUIZ", "ZEBRA9"])
+        packed2, ms2 = list(packed) + [late], list(ms) + [2]
+        idx2 = capi.DeviceIndex(packed2, ms2)
+        assert idx2.stat("pipeline_miss") == 1 and idx2.stat("pipelined") == 0
+        for d in (0, 400):
+            _check_arrays(idx2, d, oracle_mod.OracleEASA(text=packed2[d], m=ms2[d]), ("miss", d))
+        # a broken terminator layout in a late chunk: general path, still exact
+        weird = au.pack_strings_collection(["中文", "AB"])
+        idx3 = capi.DeviceIndex(list(packed) + [weird], list(ms) + [2])
+        assert idx3.stat("pipelined") == 0 and not idx3.info()["fast_path"]
+        o = oracle_mod.OracleEASA(text=weird, m=2)
+        assert np.array_equal(idx3.array(400, capi.SUFTAB), o.suftab)
+    finally:
+        capi.set_option("pipeline_chunk", 0)
+        capi.set_option("no_pipeline", 0)
