@@ -323,7 +323,6 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
     StageTimer &tm = *idx->build_timer;
     const bool overlap = get_option("sync_build", 0) == 0;
     {
-        DevBuf<uint32_t> rank(n, s);
         SaInput in;
         in.text = idx->text; in.doc_off = idx->d_doc_off; in.doc_m = idx->d_doc_m;
         in.n = n; in.n_docs = n_docs; in.m_total = idx->m_total;
@@ -349,7 +348,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
             for (auto e : chunks->ready) EAST_CUDA(cudaStreamWaitEvent(s, e, 0));
         }
         SaOutput so;
-        so.sa = idx->sa; so.rank = rank.p;
+        so.sa = idx->sa;
         build_suffix_array(in, so, tm, s);
         idx->pipelined = so.pipelined; idx->pipeline_miss = so.pipeline_miss;
         idx->rounds = so.rounds; idx->fast_path = so.fast_path; idx->key_chars = so.key_chars;
@@ -407,6 +406,8 @@ static void check_build_args(const void *text, const int64_t *doc_off, const int
 int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
                     int device, east_index **out) {
     EAST_API_BEGIN
+    static const bool debug = getenv("EAST_DEBUG_TIMING") != nullptr;
+    if (debug) fprintf(stderr, "[east] host %.3f ms  east_build_host enter\n", host_now_ms());
     check_build_args(text, doc_off, doc_m, n_docs, out);
     use_device(device);
     const int64_t n = doc_off[n_docs];
@@ -455,7 +456,9 @@ int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t 
             dev_free(d_text, 0);
             throw;
         }
+        if (debug) fprintf(stderr, "[east] host %.3f ms  copies queued\n", host_now_ms());
         build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, &plan);
+        if (debug) fprintf(stderr, "[east] host %.3f ms  build_common done\n", host_now_ms());
     }
     EAST_API_END
 }
@@ -615,7 +618,9 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
             EAST_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
             in.order = d_order.p;
         }
-        d_q8 = DevBuf<uint8_t>((size_t)total, s); d_generic = DevBuf<uint8_t>((size_t)total, s);
+        d_q8 = DevBuf<uint8_t>((size_t)total + 16, s);   // the scorer reads the queries 8 bytes at a time
+        d_generic = DevBuf<uint8_t>((size_t)total, s);
+        EAST_CUDA(cudaMemsetAsync(d_q8.p + total, 0, 16, s));
         EAST_CUDA(cudaMemcpyAsync(d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));
         EAST_CUDA(cudaMemcpyAsync(d_generic.p, generic.data(), (size_t)total, cudaMemcpyHostToDevice, s));
         in.t8 = idx->t8; in.q8 = d_q8.p; in.suf_generic = d_generic.p; in.sym_bits = idx->sym_bits;

@@ -1083,7 +1083,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     const int rr_tiles_max = (n + RR_TILE - 1) / RR_TILE;
     DevBuf<uint64_t> rr_status((size_t)rr_tiles_max + 2, s);
     DevBuf<uint32_t> rr_misc(8, s);  // [0] ticket, [1] kept count
-    uint32_t *rank = out.rank;
+    DevBuf<uint32_t> rank_buf(n, s);   // inverse permutation while the doubling rounds run
+    uint32_t *rank = rank_buf.p;
 
     tm.mark("keygen0+sort0");
     int cur = 0;

@@ -30,7 +30,6 @@ struct SaInput {
 
 struct SaOutput {
     int32_t *sa;              // device, n  (global text positions, doc-major rank order)
-    uint32_t *rank;           // device, n  (inverse permutation when done)
     DevBuf<uint8_t> t8;       // fast path: dense byte codes of the text (kept for later stages)
     DevBuf<uint32_t> bkt;     // fast path: 2-gram bucket table [n_docs << 2*sym_bits] + sentinel
     std::vector<uint8_t> code_table;  // code point (< 0x0A00) -> dense code (0 = absent)

@@ -20,6 +20,7 @@ namespace east {
 
 constexpr int SC_THREADS = 128;
 
+
 // character of suffix rank r at depth d as a comparable value: 0 = "no character" (sorts first)
 __device__ __forceinline__ uint64_t sym_at_(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa,
                                            int32_t r, int32_t d, int32_t end) {

@@ -302,7 +302,8 @@ def run_b200(args):
 
     # ---- device-timed arm (nvidia-smi needs ~100 ms to deliver its first sample: start it before the warm-up)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not os.environ.get("EAST_BENCH_NO_SAMPLER"):
+        sampler.start()
     for _ in range(args.warmup):
         step_device()
     barrier()
