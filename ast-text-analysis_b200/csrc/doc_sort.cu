@@ -600,7 +600,7 @@ k_doc_suffix_sort(DocSortParams p) {
         while (true) {
             const int cnt = min((int)s_nlist[cur], DS_LIST_CAP);
             __syncthreads();
-            if (cnt == 0) break;
+            if (cnt == 0) { if (tid == 0) s_work = 0; __syncthreads(); break; }   // s_work: the window counter of phase 6
             if (tid == 0) { s_nlist[cur ^ 1] = 0; s_work = 0; }
             __syncthreads();
             uint2 *list = cur ? s_list1 : s_list0, *next = cur ? s_list0 : s_list1;
@@ -634,7 +634,13 @@ k_doc_suffix_sort(DocSortParams p) {
         uint64_t *wkeys = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_scr) + warp * DS_WIN_BYTES);
         uint32_t *wpos = reinterpret_cast<uint32_t *>(wkeys + 64);
         const int nwin = (n + 31) >> 5;
-        for (int w = warp; w < nwin; w += DS_WARPS) {
+        while (true) {
+            // windows are handed out from a shared counter (static striding left warps idle for ~15 % of
+            // this phase: window cost varies with the bucket sizes)
+            int w = 0;
+            if (lane == 0) w = (int)atomicAdd(&s_work, 1u);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= nwin) break;
             uint32_t word = s_bits[w];
             const bool last_win = w == (n >> 5);              // the window that holds the sentinel bit of rank n
             if (last_win) word &= (1u << (n & 31)) - 1u;
@@ -654,11 +660,12 @@ k_doc_suffix_sort(DocSortParams p) {
             if (len <= nseg) continue; // only singletons
             uint64_t key[2];
             int li[2], sb[2], se[2];
+            const int nslots = len > 32 ? 2 : 1;   // warp-uniform: the second slot only exists for ranges of 33..63
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int x = lane + 32 * s;
                 key[s] = 0; li[s] = 0; sb[s] = 0; se[s] = 0;
-                if (x < len) {
+                if (s < nslots && x < len) {
                     const int r = r0 + x;
                     li[s] = sa_doc[r] - base;
                     const int wp = r - 32 * w;  // 0..63
@@ -680,7 +687,7 @@ k_doc_suffix_sort(DocSortParams p) {
             for (int s = 0; s < 2; ++s) {
                 const int x = lane + 32 * s;
                 out[s] = x;
-                if (x < len && se[s] - sb[s] > 1) {
+                if (s < nslots && x < len && se[s] - sb[s] > 1) {
                     int below = 0;
                     const uint32_t last = (uint32_t)key[s] & 0xffu;
                     const bool by_pos = last == 0u || last == p.term;   // the window reaches the terminator
@@ -701,7 +708,7 @@ k_doc_suffix_sort(DocSortParams p) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int x = lane + 32 * s;
-                if (x < len && se[s] - sb[s] > 1) sa_doc[r0 + out[s]] = base + li[s];
+                if (s < nslots && x < len && se[s] - sb[s] > 1) sa_doc[r0 + out[s]] = base + li[s];
             }
             __syncwarp();
         }
@@ -788,8 +795,14 @@ k_doc_suffix_sort(DocSortParams p) {
         const int C = max(8, (n + DS_THREADS - 1) / DS_THREADS);   // <= 64
         const int c0 = tid * C, c1 = min(n, c0 + C);
         uint8_t *stk = s_raw + tid * C;
+        // (rank, popping rank) records of the ranks pushed on an empty stack: 2 bytes each, in what is
+        // left of the scratch after the LCP copy and its pyramid
+        const int used = 2 * (s_pyr_off[M.levels - 1] + ((s_pyr_size[M.levels - 1] + 1) & ~1));
+        const int avail = DS_SCR_BYTES + 4 * p.bits_words + 2 * (int)sizeof(uint2) * DS_LIST_CAP - used;
+        const int R = max(0, min(24, avail / (2 * DS_THREADS)));
+        uint8_t *rec = reinterpret_cast<uint8_t *>(s_scr) + used + tid * 2 * R;
+        int nrec = 0;
         int depth = 0;
-        int q_bot = 0;   // PSE of the bottom entry (outside the chunk)
         auto close_interval = [&](int t, int q, int e, uint32_t le) {   // t: first l-index of [q .. e-1]
             p.ann[base + t] = e - q;
             if (e < n) {
@@ -798,39 +811,72 @@ k_doc_suffix_sort(DocSortParams p) {
                 if (le <= lq) p.down[base + q] = t;
             }
         };
-        for (int r = c0; r < c1; ++r) {
-            const uint32_t l = s_lcp[r];
-            // pop every stacked rank with a larger LCP value: r is its NSV
-            while (depth > 0) {
-                const uint32_t top = stk[depth - 1];
-                const int t = c0 + (int)(top & 0x7fu);
-                if (s_lcp[t] <= l) break;
+        // a rank that was pushed on an empty stack: its PSE lies before the chunk (every rank of
+        // [c0, t) is larger); e = its NSV if it was met inside the chunk, else -1
+        auto resolve_outside = [&](int t, int e) {
+            const uint32_t l = s_lcp[t];
+            const int q = ds_prev_le(M, c0, l);
+            if (s_lcp[q] == l) { p.next[base + q] = t; return; }
+            if (e < 0) e = ds_next_lt(M, c1 - 1, l, n);
+            close_interval(t, q, e, e < n ? s_lcp[e] : 0u);
+        };
+        // ---- the walk never leaves the chunk.  One action per iteration and lane -- pop the top (it is
+        // larger than lcp[r]: r is its NSV) or push r and advance -- so the lanes of a warp stay together:
+        // at most 2 C iterations ("pop everything, then push" waited for the longest pop run of the 32
+        // lanes at every rank).  Stack byte: offset in the chunk | 0x80 first l-index | 0x40 pushed on an
+        // empty stack (PSE unknown).
+        int r = c0;
+        uint32_t l = (r < c1) ? s_lcp[r] : 0u;
+        while (r < c1) {
+            uint32_t top = 0;
+            int t = 0;
+            bool pop = false;
+            if (depth > 0) {
+                top = stk[depth - 1];
+                t = c0 + (int)(top & 0x3fu);
+                pop = s_lcp[t] > l;
+            }
+            if (pop) {
                 --depth;
-                if (top & 0x80u) close_interval(t, depth > 0 ? c0 + (int)(stk[depth - 1] & 0x7fu) : q_bot, r, l);
-            }
-            uint32_t first = 0;
-            if (r == 0) {
-                p.ann[base] = n - m;   // easa.py:329; rank 0 is nobody's first l-index and is never popped
+                if (top & 0x40u) {
+                    if (nrec < R) { rec[2 * nrec] = (uint8_t)(top & 0x3fu); rec[2 * nrec + 1] = (uint8_t)(r - c0); ++nrec; }
+                    else resolve_outside(t, r);
+                } else if (top & 0x80u) {
+                    close_interval(t, c0 + (int)(stk[depth - 1] & 0x3fu), r, l);   // not the bottom: something is below
+                }
             } else {
-                int q;
-                if (depth > 0) q = c0 + (int)(stk[depth - 1] & 0x7fu);
-                else { q = ds_prev_le(M, r, l); q_bot = q; }
-                if (s_lcp[q] == l) p.next[base + q] = r;
-                else first = 0x80u;
-            }
-            stk[depth++] = (uint8_t)((uint32_t)(r - c0) | first);
-        }
-        // ranks still stacked: their NSV lies beyond the chunk
-        while (depth > 0) {
-            const uint32_t top = stk[--depth];
-            if (top & 0x80u) {
-                const int t = c0 + (int)(top & 0x7fu);
-                const int e = ds_next_lt(M, t, s_lcp[t], n);
-                close_interval(t, depth > 0 ? c0 + (int)(stk[depth - 1] & 0x7fu) : q_bot, e, e < n ? s_lcp[e] : 0u);
+                uint32_t flag = 0;
+                if (r == 0) {
+                    p.ann[base] = n - m;   // easa.py:329; rank 0 is nobody's first l-index and is never popped
+                } else if (depth > 0) {
+                    if (s_lcp[t] == l) p.next[base + t] = r;
+                    else flag = 0x80u;
+                } else {
+                    flag = 0x40u;
+                }
+                stk[depth++] = (uint8_t)((uint32_t)(r - c0) | flag);
+                ++r;
+                if (r < c1) l = s_lcp[r];
             }
         }
+        if (p.phase_clk) { __syncthreads(); DS_STAMP(7); }   // profiling only: split the phase
+        // ---- what lies outside the chunk, from the min-pyramid.  Farthest first in every lane: the
+        // bottom of the stack and the LAST record have the smallest LCP values, whose neighbours are
+        // thousands of ranks away (the ends of a first-letter block); met in the same iterations by all
+        // lanes they cost one long search per warp instead of one per iteration.
+        for (int i = 0; i < depth; ++i) {
+            const uint32_t ent = stk[i];
+            const int t = c0 + (int)(ent & 0x3fu);
+            if (ent & 0x40u) resolve_outside(t, -1);
+            else if (ent & 0x80u) {
+                const int e = ds_next_lt(M, c1 - 1, s_lcp[t], n);   // everything in (t, c1) is >= lcp[t]
+                close_interval(t, c0 + (int)(stk[i - 1] & 0x3fu), e, e < n ? s_lcp[e] : 0u);
+            }
+        }
+        for (int i = nrec - 1; i >= 0; --i) resolve_outside(c0 + (int)rec[2 * i], c0 + (int)rec[2 * i + 1]);
     }
-    DS_STAMP(7);
+    if (p.phase_clk) __syncthreads();
+    DS_STAMP(8);
 #undef DS_STAMP
 }
 

@@ -1036,8 +1036,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             static const bool profile = getenv("EAST_DOC_SORT_PROFILE") != nullptr;
             DevBuf<unsigned long long> clk;
             if (profile) {
-                clk = DevBuf<unsigned long long>(8, s);
-                EAST_CUDA(cudaMemsetAsync(clk.p, 0, 8 * sizeof(unsigned long long), s));
+                clk = DevBuf<unsigned long long>(16, s);
+                EAST_CUDA(cudaMemsetAsync(clk.p, 0, 16 * sizeof(unsigned long long), s));
             }
             DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
             const bool fuse = in.lcp != nullptr && plan.tables_fit;
@@ -1053,11 +1053,11 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             EAST_CUDA(cudaStreamSynchronize(s));
             if (profile) {
-                unsigned long long h[8];
+                unsigned long long h[16];
                 EAST_CUDA(cudaMemcpy(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost));
-                static const char *names[8] = {"load", "hist", "scan", "scatter", "refine", "windows", "lcp", "child_ann"};
+                static const char *names[9] = {"load", "hist", "scan", "scatter", "refine", "windows", "lcp", "stack_walk", "beyond_chunk"};
                 fprintf(stderr, "[east] doc_sort phases, kilo-cycles per document:");
-                for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %.1f", names[k], (double)h[k] / D / 1e3);
+                for (int k = 0; k < 9; ++k) fprintf(stderr, " %s %.1f", names[k], (double)h[k] / D / 1e3);
                 fprintf(stderr, "\n");
             }
             if (!overflow) {
