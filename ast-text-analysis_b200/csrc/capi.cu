@@ -546,84 +546,175 @@ int east_index_devptr(const east_index *idx, int which, const void **ptr) {
 }
 
 // ---- scoring ----------------------------------------------------------------------------
+// Everything the scorer derives from the keyphrases alone (and the index's alphabet): built once and
+// kept for the next call -- keyphrases_table scores the same keyphrases against one index after the
+// other (document tiles, ranks, benchmark steps).  A hit is confirmed by comparing the code points.
+struct KpPrepared {
+    int device = -1;
+    bool dedup = false, fast = false;
+    int sym_bits = 0;
+    std::vector<uint32_t> kp;          // host copy of the code points (cache key)
+    std::vector<int64_t> off;          // K + 1 offsets (cache key)
+    std::vector<uint8_t> code_table;   // alphabet of the index the dense codes were made for (cache key)
+    int64_t n_uniq = 0;
+    DevBuf<int32_t> d_off, d_suf, d_uniq_of, d_uniq_rep, d_order;
+    DevBuf<uint8_t> d_q8, d_generic;
+};
+static thread_local std::unique_ptr<KpPrepared> g_kp_cache;
+
+static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
+                                      bool dedup, cudaStream_t s) {
+    const int64_t total = kp_off[K];
+    if (total >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "keyphrase buffer too large");
+    for (int32_t k = 0; k < K; ++k)
+        if (kp_off[k + 1] <= kp_off[k]) throw Error(EAST_ERR_ZERODIV, "empty query: float division by zero");
+    std::vector<uint32_t> kp_host((size_t)total);
+    EAST_CUDA(cudaMemcpyAsync(kp_host.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    EAST_CUDA(cudaStreamSynchronize(s));
+    const bool fast = idx->bkt && idx->t8 && !get_option("score_generic", 0);
+    KpPrepared *c = g_kp_cache.get();
+    if (c && c->device == idx->device && c->dedup == dedup && c->fast == fast && (int64_t)c->off.size() == (int64_t)K + 1 &&
+        c->kp == kp_host && std::equal(c->off.begin(), c->off.end(), kp_off) &&
+        (!fast || (c->sym_bits == idx->sym_bits && c->code_table == idx->code_table)))
+        return c;
+    g_kp_cache.reset(new KpPrepared());
+    c = g_kp_cache.get();
+    c->device = idx->device; c->dedup = dedup; c->fast = fast; c->sym_bits = idx->sym_bits;
+    c->off.assign(kp_off, kp_off + K + 1);
+    if (fast) c->code_table = idx->code_table;
+
+    std::vector<int32_t> off32(K + 1), suf_kp((size_t)total);
+    for (int32_t k = 0; k <= K; ++k) off32[k] = (int32_t)kp_off[k];
+    for (int32_t k = 0; k < K; ++k)
+        for (int64_t p = kp_off[k]; p < kp_off[k + 1]; ++p) suf_kp[(size_t)p] = k;
+
+    // ---- identical query suffixes are walked once.  A suffix result depends only on the code points
+    // from its start to the end of its keyphrase (easa.py:98-131), and keyphrases built from a
+    // vocabulary share most word tails: 47 % distinct at 10^5 Zipf keyphrases, 72 % at 10^3.
+    // Suffix hashes are built backwards (h(s[i:]) from code[i] and h(s[i+1:])), equal hashes are
+    // confirmed by comparing the code points.
+    std::vector<int32_t> uniq_of((size_t)total), uniq_rep;
+    if (!dedup) {
+        uniq_rep.resize((size_t)total);
+        for (int64_t p = 0; p < total; ++p) { uniq_of[(size_t)p] = (int32_t)p; uniq_rep[(size_t)p] = (int32_t)p; }
+    } else {
+        std::vector<uint64_t> hash((size_t)total);
+        for (int32_t k = 0; k < K; ++k) {
+            uint64_t h = 0x9e3779b97f4a7c15ull;
+            for (int64_t p = kp_off[k + 1] - 1; p >= kp_off[k]; --p) {
+                h = h * 0x100000001b3ull + (uint64_t)kp_host[(size_t)p] + 0x632be59bd9b4e019ull;
+                h ^= h >> 29;
+                hash[(size_t)p] = h;
+            }
+        }
+        std::vector<int32_t> by_hash((size_t)total);
+        for (int64_t p = 0; p < total; ++p) by_hash[(size_t)p] = (int32_t)p;
+        auto suffix_len = [&](int32_t p) { return (int32_t)(kp_off[suf_kp[(size_t)p] + 1] - p); };
+        auto same = [&](int32_t a, int32_t b) {
+            const int32_t la = suffix_len(a);
+            return la == suffix_len(b) && std::equal(kp_host.begin() + a, kp_host.begin() + a + la, kp_host.begin() + b);
+        };
+        std::sort(by_hash.begin(), by_hash.end(), [&](int32_t a, int32_t b) {
+            return hash[(size_t)a] != hash[(size_t)b] ? hash[(size_t)a] < hash[(size_t)b] : a < b;
+        });
+        for (size_t i = 0; i < by_hash.size();) {
+            size_t j = i;
+            while (j < by_hash.size() && hash[(size_t)by_hash[j]] == hash[(size_t)by_hash[i]]) ++j;
+            // one hash value: almost always one distinct suffix; a collision splits the run
+            const size_t first_id = uniq_rep.size();
+            for (size_t a = i; a < j; ++a) {
+                const int32_t pa = by_hash[a];
+                int32_t id = -1;
+                for (size_t q = first_id; q < uniq_rep.size() && id < 0; ++q)
+                    if (same(uniq_rep[q], pa)) id = (int32_t)q;
+                if (id < 0) { id = (int32_t)uniq_rep.size(); uniq_rep.push_back(pa); }
+                uniq_of[(size_t)pa] = id;
+            }
+            i = j;
+        }
+    }
+    const int64_t n_uniq = (int64_t)uniq_rep.size();
+    c->n_uniq = n_uniq;
+    c->d_off = DevBuf<int32_t>(K + 1, s); c->d_suf = DevBuf<int32_t>((size_t)total, s);
+    c->d_uniq_of = DevBuf<int32_t>((size_t)total, s); c->d_uniq_rep = DevBuf<int32_t>((size_t)n_uniq, s);
+    EAST_CUDA(cudaMemcpyAsync(c->d_off.p, off32.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(c->d_suf.p, suf_kp.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(c->d_uniq_of.p, uniq_of.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(c->d_uniq_rep.p, uniq_rep.data(), sizeof(int32_t) * (size_t)n_uniq, cudaMemcpyHostToDevice, s));
+    std::vector<uint8_t> q8, generic;
+    std::vector<int32_t> order;
+    if (fast) {
+        // dense byte codes of the queries + per-suffix "contains a code point >= 0x0A00" flag
+        q8.resize((size_t)total); generic.resize((size_t)total);
+        for (int32_t k = 0; k < K; ++k) {
+            uint8_t weird = 0;
+            for (int64_t p = kp_off[k + 1] - 1; p >= kp_off[k]; --p) {
+                const uint32_t cp = kp_host[(size_t)p];
+                if (cp >= EAST_TERM_BASE) { weird = 1; q8[(size_t)p] = 0; }
+                else q8[(size_t)p] = idx->code_table[cp];
+                generic[(size_t)p] = weird;
+            }
+        }
+        // visit order of the distinct suffixes: counting sort by their first three dense symbols, so the
+        // threads of a warp walk neighbouring SA intervals (cache locality, less divergence)
+        const int b = idx->sym_bits;
+        const int nsym = (3 * b <= 18) ? 3 : ((2 * b <= 18) ? 2 : 1);
+        std::vector<uint32_t> bin((size_t)n_uniq);
+        std::vector<uint32_t> count(((size_t)1 << (nsym * b)) + 1, 0u);
+        for (int64_t u = 0; u < n_uniq; ++u) {
+            const int64_t p = uniq_rep[(size_t)u], pe = kp_off[suf_kp[(size_t)p] + 1];
+            uint32_t key = 0;
+            for (int q = 0; q < nsym; ++q) key = (key << b) | ((p + q < pe) ? q8[(size_t)(p + q)] : 0u);
+            bin[(size_t)u] = key;
+            ++count[key + 1];
+        }
+        for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
+        order.resize((size_t)n_uniq);
+        for (int64_t u = 0; u < n_uniq; ++u) order[count[bin[(size_t)u]]++] = (int32_t)u;
+        c->d_order = DevBuf<int32_t>((size_t)n_uniq, s);
+        c->d_q8 = DevBuf<uint8_t>((size_t)total, s);
+        c->d_generic = DevBuf<uint8_t>((size_t)total, s);
+        EAST_CUDA(cudaMemcpyAsync(c->d_order.p, order.data(), sizeof(int32_t) * (size_t)n_uniq, cudaMemcpyHostToDevice, s));
+        EAST_CUDA(cudaMemcpyAsync(c->d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));
+        EAST_CUDA(cudaMemcpyAsync(c->d_generic.p, generic.data(), (size_t)total, cudaMemcpyHostToDevice, s));
+    }
+    EAST_CUDA(cudaStreamSynchronize(s));   // the host staging vectors end here
+    // the entry outlives this call: whoever drops it frees on the legacy stream (every call that used it has synchronised)
+    c->d_off.s = c->d_suf.s = c->d_uniq_of.s = c->d_uniq_rep.s = c->d_order.s = 0;
+    c->d_q8.s = c->d_generic.s = 0;
+    c->kp = std::move(kp_host);
+    return c;
+}
+
 static void score_common(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
                          int normalized, double *out_dev, int32_t doc_begin, int32_t doc_count, cudaStream_t s,
                          double *suffix_out_dev /* optional: per-suffix results of the doc range */,
                          int64_t *probes_out = nullptr /* optional: run the probe-counting scorer */) {
-    const int64_t total = kp_off[K];
-    if (total >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "keyphrase buffer too large");
-    std::vector<int32_t> off32(K + 1), suf_kp((size_t)total);
-    for (int32_t k = 0; k <= K; ++k) off32[k] = (int32_t)kp_off[k];
-    for (int32_t k = 0; k < K; ++k) {
-        if (kp_off[k + 1] <= kp_off[k]) throw Error(EAST_ERR_ZERODIV, "empty query: float division by zero");
-        for (int64_t p = kp_off[k]; p < kp_off[k + 1]; ++p) suf_kp[(size_t)p] = k;
-    }
-    DevBuf<int32_t> d_off(K + 1, s), d_suf((size_t)total, s);
-    EAST_CUDA(cudaMemcpyAsync(d_off.p, off32.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, s));
-    EAST_CUDA(cudaMemcpyAsync(d_suf.p, suf_kp.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
-    // per-suffix results tmp[doc][suffix] are produced and consumed tile by tile over the documents,
-    // so the scratch stays <= ~1 GB however large K x D is (config 4: 1.3 M suffixes x 12 500 docs)
+    // per-suffix results wanted (return_suffix_scores): every suffix is its own "distinct" suffix
+    const bool dedup = !suffix_out_dev && !get_option("score_no_dedup", 0);
+    KpPrepared *kp = prepare_keyphrases(idx, kp_dev, kp_off, K, dedup, s);
+    const int64_t total = kp_off[K], n_uniq = kp->n_uniq;
+
+    // per-suffix results tmp[doc][distinct suffix] are produced and consumed tile by tile over the documents,
+    // so the scratch stays <= ~1 GB however large K x D is (config 4: 0.63 M distinct suffixes x 12 500 docs)
     DevBuf<double> tmp_own;
     double *tmp = suffix_out_dev;
     int32_t tile_docs = doc_count;
     if (!tmp) {
         const int64_t budget = get_option("score_tmp_doubles", (int64_t)1 << 27);
-        tile_docs = (int32_t)std::max<int64_t>(1, std::min<int64_t>(doc_count, budget / std::max<int64_t>(1, total)));
-        tmp_own = DevBuf<double>((size_t)tile_docs * (size_t)total, s);
+        tile_docs = (int32_t)std::max<int64_t>(1, std::min<int64_t>(doc_count, budget / std::max<int64_t>(1, n_uniq)));
+        tmp_own = DevBuf<double>((size_t)tile_docs * (size_t)n_uniq, s);
         tmp = tmp_own.p;
     }
     ScoreInput in;
     in.text = idx->text; in.sa = idx->sa;
     in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
-    in.kp = kp_dev; in.kp_off = d_off.p; in.suf_kp = d_suf.p; in.K = K; in.total_suffixes = (int32_t)total;
+    in.kp = kp_dev; in.kp_off = kp->d_off.p; in.suf_kp = kp->d_suf.p; in.K = K; in.total_suffixes = (int32_t)total;
+    in.uniq_of = kp->d_uniq_of.p; in.uniq_rep = kp->d_uniq_rep.p; in.n_uniq = (int32_t)n_uniq;
     in.normalized = normalized ? 1 : 0;
-    // fast path: dense byte codes of the queries + per-suffix "contains a code point >= 0x0A00" flag
-    DevBuf<uint8_t> d_q8, d_generic;
-    DevBuf<int32_t> d_order;
-    std::vector<uint8_t> q8, generic;
-    std::vector<int32_t> order;
-    if (idx->bkt && idx->t8 && !get_option("score_generic", 0)) {
-        std::vector<uint32_t> kp_host((size_t)total);
-        EAST_CUDA(cudaMemcpyAsync(kp_host.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
-        EAST_CUDA(cudaStreamSynchronize(s));
-        q8.resize((size_t)total); generic.resize((size_t)total);
-        for (int32_t k = 0; k < K; ++k) {
-            uint8_t weird = 0;
-            for (int64_t p = kp_off[k + 1] - 1; p >= kp_off[k]; --p) {
-                const uint32_t c = kp_host[(size_t)p];
-                if (c >= EAST_TERM_BASE) { weird = 1; q8[(size_t)p] = 0; }
-                else q8[(size_t)p] = idx->code_table[c];
-                generic[(size_t)p] = weird;
-            }
-        }
-        // visit order of the suffixes: counting sort by their first three dense symbols, so the
-        // threads of a warp walk neighbouring SA intervals (cache locality, less divergence)
-        {
-            const int b = idx->sym_bits;
-            const int nsym = (3 * b <= 18) ? 3 : ((2 * b <= 18) ? 2 : 1);
-            std::vector<uint32_t> bin((size_t)total);
-            std::vector<uint32_t> count(((size_t)1 << (nsym * b)) + 1, 0u);
-            for (int32_t k = 0; k < K; ++k)
-                for (int64_t p = kp_off[k]; p < kp_off[k + 1]; ++p) {
-                    uint32_t key = 0;
-                    for (int c = 0; c < nsym; ++c)
-                        key = (key << b) | ((p + c < kp_off[k + 1]) ? q8[(size_t)(p + c)] : 0u);
-                    bin[(size_t)p] = key;
-                    ++count[key + 1];
-                }
-            for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
-            order.resize((size_t)total);
-            for (int64_t p = 0; p < total; ++p) order[count[bin[(size_t)p]]++] = (int32_t)p;
-            d_order = DevBuf<int32_t>((size_t)total, s);
-            EAST_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
-            in.order = d_order.p;
-        }
-        d_q8 = DevBuf<uint8_t>((size_t)total + 16, s);   // the scorer reads the queries 8 bytes at a time
-        d_generic = DevBuf<uint8_t>((size_t)total, s);
-        EAST_CUDA(cudaMemsetAsync(d_q8.p + total, 0, 16, s));
-        EAST_CUDA(cudaMemcpyAsync(d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));
-        EAST_CUDA(cudaMemcpyAsync(d_generic.p, generic.data(), (size_t)total, cudaMemcpyHostToDevice, s));
-        in.t8 = idx->t8; in.q8 = d_q8.p; in.suf_generic = d_generic.p; in.sym_bits = idx->sym_bits;
+    if (kp->fast) {
+        in.order = kp->d_order.p;
+        in.t8 = idx->t8; in.q8 = kp->d_q8.p; in.suf_generic = kp->d_generic.p; in.sym_bits = idx->sym_bits;
         in.bkt = idx->bkt + ((size_t)doc_begin << (2 * idx->sym_bits));
     }
     in.algorithmic_bytes = (double)get_option("score_bytes", 0);
@@ -651,7 +742,7 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
         EAST_CUDA(cudaStreamSynchronize(s));
         *probes_out = (int64_t)h;
     }
-    EAST_CUDA(cudaStreamSynchronize(s));  // host staging vectors above must outlive the copies
+    EAST_CUDA(cudaStreamSynchronize(s));
     tm.collect();
 }
 

@@ -91,12 +91,16 @@ struct ScoreInput {
     const uint32_t *bkt = nullptr;      // [n_docs << 2*sym_bits] + 1, rows of the docs being scored
     const uint8_t *q8 = nullptr;        // dense codes of kp (0 = symbol absent from the batch)
     const uint8_t *suf_generic = nullptr;  // 1 = this suffix contains a code point >= 0x0A00: generic walk
-    const int32_t *order = nullptr;     // optional visit order of the suffixes (a permutation)
+    const int32_t *order = nullptr;     // optional visit order of the distinct suffixes (a permutation of 0..n_uniq-1)
+    // identical query suffixes (same code points to the end of their keyphrase) are walked once:
+    const int32_t *uniq_of = nullptr;   // device, total_suffixes: distinct-suffix id of every suffix
+    const int32_t *uniq_rep = nullptr;  // device, n_uniq: one suffix (index into kp) per distinct id
+    int32_t n_uniq = 0;
     int sym_bits = 0;
     unsigned long long *probe_count = nullptr;  // device counter: run the probe-counting variant
     double algorithmic_bytes = 0.0;             // 8 B x probes of this workload, if known (roofline numerator)
 };
-void score_table(const ScoreInput &in, double *suffix_tmp /*n_docs x total_suffixes*/, double *out_DxK,
+void score_table(const ScoreInput &in, double *suffix_tmp /*n_docs x n_uniq*/, double *out_DxK,
                  cudaStream_t s);
 
 void cooc_counts(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s);     // AND + POPC

@@ -174,23 +174,25 @@ template <bool PROBES>
 __global__ void __launch_bounds__(SC_THREADS)
 k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *probe_count) {
     unsigned long long probes = 0;
-    const int64_t total = (int64_t)in.n_docs * in.total_suffixes;
+    const int64_t total = (int64_t)in.n_docs * in.n_uniq;
     const int64_t stride = (int64_t)gridDim.x * SC_THREADS;
     for (int64_t idx = (int64_t)blockIdx.x * SC_THREADS + threadIdx.x; idx < total; idx += stride) {
-        const int32_t doc = (int32_t)(idx / in.total_suffixes);
-        int32_t sidx = (int32_t)(idx - (int64_t)doc * in.total_suffixes);
-        if (in.order) sidx = __ldg(in.order + sidx);
+        const int32_t doc = (int32_t)(idx / in.n_uniq);
+        int32_t u = (int32_t)(idx - (int64_t)doc * in.n_uniq);
+        if (in.order) u = __ldg(in.order + u);
+        const int32_t sidx = __ldg(in.uniq_rep + u);   // one of the identical suffixes
         const int32_t k = __ldg(in.suf_kp + sidx);
         const int32_t qend = __ldg(in.kp_off + k + 1);
         const int32_t start = __ldg(in.doc_off + doc), end = __ldg(in.doc_off + doc + 1);
+        double r;
         if (in.bkt != nullptr && !__ldg(in.suf_generic + sidx)) {
-            tmp[(int64_t)doc * in.total_suffixes + sidx] = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.bkt + ((size_t)doc << (2 * in.sym_bits)),
-                                                     in.sym_bits, start, end, __ldg(in.doc_m + doc), in.q8 + sidx,
-                                                     qend - sidx, in.normalized, probes);
+            r = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.bkt + ((size_t)doc << (2 * in.sym_bits)), in.sym_bits, start, end,
+                                              __ldg(in.doc_m + doc), in.q8 + sidx, qend - sidx, in.normalized, probes);
         } else {
-            tmp[(int64_t)doc * in.total_suffixes + sidx] = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx,
-                                                qend - sidx, in.normalized, probes);
+            r = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx, qend - sidx,
+                                         in.normalized, probes);
         }
+        tmp[(int64_t)doc * in.n_uniq + u] = r;
     }
     if (PROBES) {
         for (int o = 16; o > 0; o >>= 1) probes += __shfl_down_sync(0xffffffffu, probes, o);
@@ -198,40 +200,27 @@ k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *pr
     }
 }
 
-// One CTA per (document, run of CB_KP consecutive keyphrases): the per-suffix results of the run are
-// contiguous in tmp[doc][...]; they are staged through shared memory with coalesced loads, then every
-// thread adds up its own keyphrase's suffixes IN SUFFIX ORDER (the reference's fp64 order, easa.py:127-134).
-constexpr int CB_KP = 128;
-constexpr int CB_CHUNK = 2048;   // doubles staged per round
-__global__ void __launch_bounds__(CB_KP)
+// One thread per (document, keyphrase): adds up the results of the keyphrase's suffixes IN SUFFIX ORDER
+// (the reference's fp64 order, easa.py:127-134), each fetched through its distinct-suffix id from the
+// document's row of tmp (L2-resident: the row was just written).  Adjacent threads own adjacent
+// keyphrases, so the id loads are contiguous across the warp.
+__global__ void __launch_bounds__(SC_THREADS)
 k_score_combine(ScoreInput in, const double *__restrict__ tmp, double *__restrict__ out) {
-    __shared__ double s_val[CB_CHUNK];
-    const int blocks_per_doc = (in.K + CB_KP - 1) / CB_KP;
-    const int64_t total_blocks = (int64_t)in.n_docs * blocks_per_doc;
-    for (int64_t blk = blockIdx.x; blk < total_blocks; blk += gridDim.x) {
-        const int32_t doc = (int32_t)(blk / blocks_per_doc);
-        const int32_t k0 = (int32_t)(blk - (int64_t)doc * blocks_per_doc) * CB_KP;
-        const int32_t k1 = min(in.K, k0 + CB_KP);
-        const int32_t k = k0 + (int32_t)threadIdx.x;
-        const int32_t span_b = __ldg(in.kp_off + k0), span_e = __ldg(in.kp_off + k1);
-        int32_t b = 0, e = 0;
-        if (k < k1) { b = __ldg(in.kp_off + k); e = __ldg(in.kp_off + k + 1); }
-        const double *row = tmp + (int64_t)doc * in.total_suffixes;
+    const int64_t total = (int64_t)in.n_docs * in.K;
+    const int64_t stride = (int64_t)gridDim.x * SC_THREADS;
+    for (int64_t idx = (int64_t)blockIdx.x * SC_THREADS + threadIdx.x; idx < total; idx += stride) {
+        const int32_t doc = (int32_t)(idx / in.K);
+        const int32_t k = (int32_t)(idx - (int64_t)doc * in.K);
+        const int32_t b = __ldg(in.kp_off + k), e = __ldg(in.kp_off + k + 1);
+        const double *row = tmp + (int64_t)doc * in.n_uniq;
         double result = 0.0;
-        for (int32_t c0 = span_b; c0 < span_e; c0 += CB_CHUNK) {
-            const int32_t c1 = min(span_e, c0 + CB_CHUNK);
-            __syncthreads();
-            for (int32_t i = c0 + (int32_t)threadIdx.x; i < c1; i += CB_KP) s_val[i - c0] = row[i];
-            __syncthreads();
-            const int32_t lo = max(b, c0), hi = min(e, c1);
-            for (int32_t s = lo; s < hi; ++s) result = result + s_val[s - c0];
-        }
-        if (k < k1) out[(int64_t)doc * in.K + k] = result / (double)(e - b);
+        for (int32_t s = b; s < e; ++s) result = result + row[__ldg(in.uniq_of + s)];
+        out[idx] = result / (double)(e - b);
     }
 }
 
 void score_table(const ScoreInput &in, double *suffix_tmp, double *out_DxK, cudaStream_t s) {
-    const int64_t work = (int64_t)in.n_docs * in.total_suffixes;
+    const int64_t work = (int64_t)in.n_docs * in.n_uniq;
     if (work > 0) {
         if (in.probe_count) {
             EAST_LAUNCH(k_score_suffixes<true>, grid_for(work, SC_THREADS, 64), SC_THREADS, 0, s, in, suffix_tmp,
@@ -242,9 +231,9 @@ void score_table(const ScoreInput &in, double *suffix_tmp, double *out_DxK, cuda
                         (unsigned long long *)nullptr);
         }
     }
-    const int64_t cblocks = (int64_t)in.n_docs * ((in.K + CB_KP - 1) / CB_KP);
-    if (cblocks > 0)
-        EAST_LAUNCH(k_score_combine, grid_for(cblocks, 1, 32), CB_KP, 0, s, in, suffix_tmp, out_DxK);
+    const int64_t cells = (int64_t)in.n_docs * in.K;
+    if (cells > 0)
+        EAST_LAUNCH(k_score_combine, grid_for(cells, SC_THREADS, 64), SC_THREADS, 0, s, in, suffix_tmp, out_DxK);
 }
 
 // ------------------------------------------------------------------------------------------
