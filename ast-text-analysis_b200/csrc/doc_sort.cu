@@ -920,8 +920,9 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     p.doc_begin = doc_begin;
     p.lcp = p.up = p.down = p.next = p.ann = nullptr;
     if (tables && plan.tables_fit) { p.lcp = tables->lcp; p.up = tables->up; p.down = tables->down; p.next = tables->next; p.ann = tables->ann; }
-    // byte text in, suffix array out + one re-read (L2-resident scatter); with tables: LCP + annotation out
-    EAST_BYTES((p.lcp ? 17.0 : 9.0) * (double)n_total);
+    // algorithmic bytes per code point: 1 (byte text in) + 4 (suffix array out), with the fused tables + 5 x 4
+    // (LCP, up, down, next, annotation out)
+    EAST_BYTES((p.lcp ? 25.0 : 5.0) * (double)n_total);
     EAST_LAUNCH(k_doc_suffix_sort, n_docs, DS_THREADS, plan.smem, s, p);
 }
 

@@ -214,6 +214,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own log lines (NCCL_DEBUG=VERSION/INFO on some boxes) go to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join("/tmp", "nccl_%h_%p.log"))
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -388,6 +390,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": tinfo.get("source"),
+                     "note": tinfo.get("note"),
                      "peak_source": peak_kind,
                      "launches_per_step": dom["launches"] / args.steps, "ms_per_launch": per_launch_ms,
                      "algorithmic_bytes_per_launch": per_launch_bytes,
