@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--doc-bytes", type=int, default=50000)
     ap.add_argument("--keyphrases", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="table", choices=["table", "single_doc"],
+    ap.add_argument("--docs-total", type=int, default=100000, help="config4: documents of the whole job (sharded over the GPUs)")
+    ap.add_argument("--workload", default="table", choices=["table", "single_doc", "config4"],
                     help="table = BASELINE configs[1] (headline); single_doc = configs[2]: SA+LCP+annotation build "
                          "throughput of ONE document of --doc-bytes (use 200000000), replicas only for N>1")
     ap.add_argument("--cpu-sample-docs", type=int, default=0, help="0 = 2 documents per host core (max 64)")
@@ -477,8 +478,89 @@ def run_single_doc(args):
                                   for k, v in sorted(kstats.items(), key=lambda kv: -kv[1]["ms"])}}}))
 
 
+def run_config4(args):
+    """BASELINE configs[3]: 10^5 keyphrases x 10^5 documents (~10 KB each; BASELINE.json gives no size), documents
+    sharded over the GPUs (strong scaling: the job is fixed), per-rank [D_r, K] fp64 slices joined by ONE NCCL
+    all-gather.  A step = build the rank's documents + score + all-gather; device-timed, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import synth
+    from east import _capi, utils
+    from east.asts import utils as asts_utils
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join("/tmp", "nccl_%h_%p.log"))
+        dist.init_process_group("nccl", device_id=dev)
+    K = args.keyphrases if args.keyphrases != 1000 else 100000
+    doc_bytes = args.doc_bytes if args.doc_bytes != 50000 else 10000
+    D = args.docs_total // world   # contiguous document range of this rank
+    t0 = time.perf_counter()
+    packed, ms, _ = synth.packed_collection(D, doc_bytes, first_seed=1 + rank * D)
+    doc_m = np.array(ms, dtype=np.int32)
+    doc_off = np.zeros(D + 1, dtype=np.int64)
+    np.cumsum([len(p) for p in packed], out=doc_off[1:])
+    text_dev = torch.from_numpy(np.concatenate(packed).view(np.int32)).to(dev)
+    kps = [utils.prepare_text(k) for k in synth.keyphrases(K)]
+    kp_codes, kp_off = _capi.pack_keyphrases(kps)
+    kp_dev = torch.from_numpy(kp_codes.view(np.int32).copy()).to(dev)
+    prep_s = time.perf_counter() - t0
+    out_dev = torch.empty(D * K, dtype=torch.float64, device=dev)
+    gathered = torch.empty(world * D * K, dtype=torch.float64, device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step():
+        idx = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream)
+        idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_dev)
+            torch.cuda.synchronize()
+        t = idx.build_timings + idx.score_timings
+        idx.close()
+        return dict(idx.build_timings), dict(t).get("score", 0.0)
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        build_t, score_ms = step()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    checksum = float((gathered if world > 1 else out_dev)[:: max(1, D * K // 4096)].sum().item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * D * K / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "keyphrases_table (BASELINE configs[3]): %d keyphrases x %d synthetic Zipf docs x ~%d KB, "
+                                   "documents sharded over %d GPU(s), one NCCL all-gather of the [D_r, K] fp64 slices" % (
+                                       K, world * D, doc_bytes // 1000, world),
+                       "keyphrases": K, "docs_total": world * D, "docs_per_gpu": D, "doc_bytes": doc_bytes,
+                       "table_bytes": world * D * K * 8},
+            "breakdown": {"build_stages_ms": build_t, "score_ms": score_ms, "host_prep_s": prep_s, "checksum_sample": checksum}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    if args.workload == "config4" and args.impl == "b200":
+        return run_config4(args)
     if args.workload == "single_doc" and args.impl == "b200":
         return run_single_doc(args)
     if args.impl == "reference":

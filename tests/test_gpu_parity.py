@@ -542,3 +542,29 @@ def test_pipelined_host_build_matches_and_recovers(oracle_mod, sa_path):
     finally:
         capi.set_option("pipeline_chunk", 0)
         capi.set_option("no_pipeline", 0)
+
+
+def test_duplicate_query_suffixes_are_scored_once_and_identically(oracle_mod):
+    # identical query suffixes (same tail of the same word, repeated keyphrases) are walked once; the table
+    # must not depend on that (option score_no_dedup walks every suffix)
+    import synth
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(3, 4000, first_seed=90)
+    idx = capi.DeviceIndex(packed, ms)
+    words = ["ALPHA", "BETA", "ALPHABETA", "TA", "A", "GAMMA"]
+    rng = np.random.default_rng(2)
+    queries = [" ".join(rng.choice(words, size=int(rng.integers(1, 4)))) for _ in range(60)] + ["ALPHA", "ALPHA", "A"]
+    from east import utils
+    queries += [utils.prepare_text(k) for k in synth.keyphrases(30)] * 2
+    codes, off = capi.pack_keyphrases(queries)
+    for normalized in (True, False):
+        table = idx.score_table(codes, off, normalized)
+        try:
+            capi.set_option("score_no_dedup", 1)
+            plain = idx.score_table(codes, off, normalized)
+        finally:
+            capi.set_option("score_no_dedup", 0)
+        assert np.array_equal(table.view(np.uint64), plain.view(np.uint64))
+        for d in range(3):
+            exp = oracle_mod.OracleEASA(text=packed[d], m=ms[d]).score_many(codes, off, normalized)
+            assert np.array_equal(table[d].view(np.uint64), exp.view(np.uint64))
