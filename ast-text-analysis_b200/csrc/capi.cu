@@ -146,6 +146,7 @@ struct east_index {
     int32_t *sa = nullptr, *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
     uint8_t *t8 = nullptr;          // fast path: dense byte codes of the text
     uint32_t *bkt = nullptr;        // fast path: 2-gram bucket table
+    uint32_t *sk = nullptr;         // fast path: text bytes at offsets 2..5 of every suffix, in rank order
     std::vector<uint8_t> code_table;
     int sym_bits = 0, term_code = 0;
     int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0, tables_fused = 0, pipelined = 0, pipeline_miss = 0;
@@ -275,7 +276,7 @@ static void free_index(east_index *idx) {
     if (idx->owns_text && idx->text) cudaFreeAsync(idx->text, 0);
     for (void *p : {(void *)idx->d_doc_off, (void *)idx->d_doc_m, (void *)idx->sa, (void *)idx->lcp,
                     (void *)idx->up, (void *)idx->down, (void *)idx->next, (void *)idx->ann, (void *)idx->t8,
-                    (void *)idx->bkt})
+                    (void *)idx->bkt, (void *)idx->sk})
         if (p) cudaFreeAsync(p, 0);
     delete idx;
 }
@@ -337,6 +338,10 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         // the global prefix-doubling sort (and "no_doc_sort") selects the global sort instead
         in.doc_sort = (get_option("no_doc_sort", 0) || in.key_chars || in.rs_variant || in.sort_batch_elems ||
                        !in.segmented_sort || !in.local_group_sort) ? 0 : 1;
+        if (!get_option("no_suffix_keys", 0)) {
+            idx->sk = (uint32_t *)dev_alloc(sizeof(uint32_t) * (size_t)n, s);
+            in.sk = idx->sk;
+        }
         if (!get_option("no_fused_tables", 0)) {
             in.lcp = idx->lcp; in.up = idx->up; in.down = idx->down; in.next = idx->next; in.ann = idx->ann;
         }
@@ -358,6 +363,10 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         idx->bkt = so.bkt.p; so.bkt.p = nullptr;
         idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
         idx->tables_fused = so.tables_done;
+        if (idx->sk && !so.sk_done) {
+            if (idx->t8) fill_suffix_keys(idx->t8, idx->sa, n, idx->sk, s);    // global sort, fast path
+            else { dev_free(idx->sk, s); idx->sk = nullptr; }                  // general path: no byte text
+        }
         if (so.tables_done) {
             tm.finish();   // the per-document kernel produced every table: nothing is pending
         } else {
@@ -714,7 +723,7 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
     in.normalized = normalized ? 1 : 0;
     if (kp->fast) {
         in.order = kp->d_order.p;
-        in.t8 = idx->t8; in.q8 = kp->d_q8.p; in.suf_generic = kp->d_generic.p; in.sym_bits = idx->sym_bits;
+        in.t8 = idx->t8; in.sk = idx->sk; in.q8 = kp->d_q8.p; in.suf_generic = kp->d_generic.p; in.sym_bits = idx->sym_bits;
         in.bkt = idx->bkt + ((size_t)doc_begin << (2 * idx->sym_bits));
     }
     in.algorithmic_bytes = (double)get_option("score_bytes", 0);

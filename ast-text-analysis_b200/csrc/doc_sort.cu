@@ -65,6 +65,7 @@ struct DocSortParams {
     // optional fused tables (all or none): LCP (easa.py:247-266), child table (:268-304), annotation (:306-331);
     // up/down/next/ann must be zero-filled by the caller, lcp is written for every rank
     int32_t *lcp, *up, *down, *next, *ann;
+    uint32_t *sk;             // optional: the 4 text bytes at offsets 2..5 of every suffix, in rank order (scorer)
 };
 
 // 8 bytes of shared memory at an arbitrary byte offset from a 16-byte aligned base: three aligned
@@ -714,7 +715,13 @@ k_doc_suffix_sort(DocSortParams p) {
         }
     }
     DS_STAMP(5);
-    if (p.lcp == nullptr) return;
+    if (p.lcp == nullptr) {
+        if (p.sk) {   // suffix array only: the scorer's per-rank key bytes still come from the staged text
+            __syncthreads();
+            for (int r = tid; r < n; r += DS_THREADS) p.sk[base + r] = ds_lds4(s_raw, shift + (sa_doc[r] - base) + 2);
+        }
+        return;
+    }
 
     // ---- phase 7: LCP of neighbouring suffixes from the staged text; 16-bit copy + min-pyramid in the
     // (now free) scratch, which continues into the bitmap and the work lists
@@ -763,6 +770,7 @@ k_doc_suffix_sort(DocSortParams p) {
                 }
                 p.lcp[base + r] = (int32_t)h;
                 s_lcp[r] = (uint16_t)h;
+                if (p.sk) p.sk[base + r] = ds_lds4(s_raw, shift + ((r > 0 ? pj[u] : sa_doc[0]) - base) + 2);
             }
             const uint32_t wmin = __reduce_min_sync(0xffffffffu, h);
             if (lane == 0 && (r - lane) < n) s_lv1[r >> 5] = (uint16_t)wmin;
@@ -906,7 +914,7 @@ bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan) {
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
                      const int32_t *doc_m, int doc_begin, int n_docs,
                      int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
-                     unsigned long long *phase_clk, const DocSortTables *tables) {
+                     unsigned long long *phase_clk, const DocSortTables *tables, uint32_t *sk) {
     static bool configured = false;
     if (!configured) {
         EAST_CUDA(cudaFuncSetAttribute(k_doc_suffix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -918,6 +926,7 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     p.text_cap = plan.text_cap; p.bits_words = plan.bits_words;
     p.phase_clk = phase_clk;
     p.doc_begin = doc_begin;
+    p.sk = sk;
     p.lcp = p.up = p.down = p.next = p.ann = nullptr;
     if (tables && plan.tables_fit) { p.lcp = tables->lcp; p.up = tables->up; p.down = tables->down; p.next = tables->next; p.ann = tables->ann; }
     // algorithmic bytes per code point: 1 (byte text in) + 4 (suffix array out), with the fused tables + 5 x 4

@@ -908,7 +908,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, s, in.text, e0, e1, d_table.p,
                         (uint8_t)term, t8.p, flags.p + 1);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
-                            flags.p, s, nullptr, fuse ? &tables : nullptr);
+                            flags.p, s, nullptr, fuse ? &tables : nullptr, in.sk);
         }
         out.tables_done = fuse ? 1 : 0;
     } else {
@@ -934,6 +934,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
         return false;
     }
     out.pipelined = 1;
+    out.sk_done = in.sk ? 1 : 0;
     out.fast_path = 1;
     out.sigma = sigma;
     out.doc_sorted = 1;
@@ -1048,7 +1049,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
             }
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, 0, D, n, kp.term, out.sa, out.bkt.p, flag.p, s, clk.p,
-                            fuse ? &tables : nullptr);
+                            fuse ? &tables : nullptr, in.sk);
             uint32_t overflow = 0;
             EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             EAST_CUDA(cudaStreamSynchronize(s));
@@ -1063,6 +1064,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             if (!overflow) {
                 out.doc_sorted = 1;
                 out.tables_done = fuse ? 1 : 0;
+                out.sk_done = in.sk ? 1 : 0;
                 out.rounds = 1;
                 out.key_chars = plan.G + 8;
                 out.key_bits = plan.b * plan.G + 64;

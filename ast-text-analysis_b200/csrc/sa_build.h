@@ -21,6 +21,7 @@ struct SaInput {
     int doc_sort = 1;                       // small documents: one CTA sorts a whole document in shared memory
     // destination of the LCP / child / annotation tables: the per-document kernel fills them itself
     int32_t *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
+    uint32_t *sk = nullptr;                 // destination of the scorer's per-rank key bytes (fast path only)
     // pipelined host build: the text arrives in n_chunks runs of whole documents; chunk c = documents
     // [chunk_doc[c], chunk_doc[c+1]) is resident once chunk_ready[c] has fired (recorded on the copy stream)
     int n_chunks = 0;
@@ -46,6 +47,7 @@ struct SaOutput {
     int doc_sorted = 0;              // the per-document shared-memory sort produced the suffix array
     int doc_sort_overflow = 0;       // it met a bucket it cannot sort and the global sort took over
     int tables_done = 0;             // LCP / child / annotation tables were produced by the per-document kernel
+    int sk_done = 0;                 // the scorer's per-rank key bytes were produced
     int pipelined = 0;               // the build overlapped the host-to-device copy (speculative alphabet held)
     int pipeline_miss = 0;           // it did not hold (later chunks brought new symbols / bad layout): redone
 };
@@ -65,7 +67,8 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
                      const int32_t *doc_m, int doc_begin, int n_docs,
                      int64_t n_total /* code points of these documents */, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
                      unsigned long long *phase_clk = nullptr /* profiling: 8 cycle counters */,
-                     const DocSortTables *tables = nullptr /* also produce LCP, child table, annotation */);
+                     const DocSortTables *tables = nullptr /* also produce LCP, child table, annotation */,
+                     uint32_t *sk = nullptr /* also produce the scorer's per-rank key bytes */);
 
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch
@@ -89,6 +92,7 @@ struct ScoreInput {
     // fast path (terminator-class alphabet): dense byte text, byte-coded queries, 2-gram buckets
     const uint8_t *t8 = nullptr;
     const uint32_t *bkt = nullptr;      // [n_docs << 2*sym_bits] + 1, rows of the docs being scored
+    const uint32_t *sk = nullptr;       // per rank: text bytes at offsets 2..5 of the suffix (saves the SA -> text hop)
     const uint8_t *q8 = nullptr;        // dense codes of kp (0 = symbol absent from the batch)
     const uint8_t *suf_generic = nullptr;  // 1 = this suffix contains a code point >= 0x0A00: generic walk
     const int32_t *order = nullptr;     // optional visit order of the distinct suffixes (a permutation of 0..n_uniq-1)
@@ -102,6 +106,9 @@ struct ScoreInput {
 };
 void score_table(const ScoreInput &in, double *suffix_tmp /*n_docs x n_uniq*/, double *out_DxK,
                  cudaStream_t s);
+
+// sk[r] = the 4 byte codes at offsets 2..5 of suffix sa[r] (for indexes built by the global sort)
+void fill_suffix_keys(const uint8_t *t8, const int32_t *sa, int32_t n, uint32_t *sk, cudaStream_t s);
 
 void cooc_counts(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s);     // AND + POPC
 void cooc_counts_tc(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s);  // tcgen05

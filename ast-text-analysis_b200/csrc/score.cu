@@ -95,11 +95,14 @@ __device__ __forceinline__ double score_one_suffix(const uint32_t *__restrict__ 
 // codes (0 = absent from the batch: cannot match).  Same arithmetic, same order as the generic walk.
 template <bool PROBES>
 __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restrict__ T8, const int32_t *__restrict__ sa,
-                                                        const uint32_t *__restrict__ row, int b,
+                                                        const uint32_t *__restrict__ sk, const uint32_t *__restrict__ row, int b,
                                                         int32_t start, int32_t end, int32_t m,
                                                         const uint8_t *__restrict__ q, int32_t len, int normalized,
                                                         unsigned long long &probes) {
-#define SYM8(r, d) (PROBES ? (probes += 5, (uint32_t)T8[sa[r] + (d)]) : (uint32_t)T8[sa[r] + (d)])
+    // symbol of suffix rank r at depth d >= 2: depths 2..5 come from the per-rank key word (one load instead of
+    // the dependent SA -> text pair), deeper ones from the text
+#define SYM8(r, d) (PROBES ? (probes += 5, (uint32_t)T8[sa[r] + (d)]) \
+                           : ((sk != nullptr && (d) < 6) ? ((__ldg(sk + (r)) >> (8 * ((d) - 2))) & 0xffu) : (uint32_t)T8[sa[r] + (d)]))
     int32_t parent_f = (end - start) - m;
     const uint32_t c0 = q[0];
     if (c0 == 0) return 0.0;
@@ -186,7 +189,7 @@ k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *pr
         const int32_t start = __ldg(in.doc_off + doc), end = __ldg(in.doc_off + doc + 1);
         double r;
         if (in.bkt != nullptr && !__ldg(in.suf_generic + sidx)) {
-            r = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.bkt + ((size_t)doc << (2 * in.sym_bits)), in.sym_bits, start, end,
+            r = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.sk, in.bkt + ((size_t)doc << (2 * in.sym_bits)), in.sym_bits, start, end,
                                               __ldg(in.doc_m + doc), in.q8 + sidx, qend - sidx, in.normalized, probes);
         } else {
             r = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx, qend - sidx,
@@ -217,6 +220,20 @@ k_score_combine(ScoreInput in, const double *__restrict__ tmp, double *__restric
         for (int32_t s = b; s < e; ++s) result = result + row[__ldg(in.uniq_of + s)];
         out[idx] = result / (double)(e - b);
     }
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_suffix_keys(const uint8_t *__restrict__ t8, const int32_t *__restrict__ sa, int32_t n, uint32_t *__restrict__ sk) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+        const uint8_t *p = t8 + sa[r] + 2;   // the byte text carries 128 bytes of slack
+        sk[r] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    }
+}
+
+void fill_suffix_keys(const uint8_t *t8, const int32_t *sa, int32_t n, uint32_t *sk, cudaStream_t s) {
+    EAST_BYTES(12.0 * n);
+    EAST_LAUNCH(k_fill_suffix_keys, grid_for(n, 256, 16), 256, 0, s, t8, sa, n, sk);
 }
 
 void score_table(const ScoreInput &in, double *suffix_tmp, double *out_DxK, cudaStream_t s) {
