@@ -146,6 +146,7 @@ struct east_index {
     int32_t *sa = nullptr, *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
     uint8_t *t8 = nullptr;          // fast path: dense byte codes of the text
     uint32_t *bkt = nullptr;        // fast path: 2-gram bucket table
+    uint32_t *bkt3 = nullptr;       // per-document kernel, 5-bit symbols: 3-gram bucket table
     uint32_t *sk = nullptr;         // fast path: text bytes at offsets 2..5 of every suffix, in rank order
     std::vector<uint8_t> code_table;
     int sym_bits = 0, term_code = 0;
@@ -276,7 +277,7 @@ static void free_index(east_index *idx) {
     if (idx->owns_text && idx->text) cudaFreeAsync(idx->text, 0);
     for (void *p : {(void *)idx->d_doc_off, (void *)idx->d_doc_m, (void *)idx->sa, (void *)idx->lcp,
                     (void *)idx->up, (void *)idx->down, (void *)idx->next, (void *)idx->ann, (void *)idx->t8,
-                    (void *)idx->bkt, (void *)idx->sk})
+                    (void *)idx->bkt, (void *)idx->bkt3, (void *)idx->sk})
         if (p) cudaFreeAsync(p, 0);
     delete idx;
 }
@@ -338,6 +339,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         // the global prefix-doubling sort (and "no_doc_sort") selects the global sort instead
         in.doc_sort = (get_option("no_doc_sort", 0) || in.key_chars || in.rs_variant || in.sort_batch_elems ||
                        !in.segmented_sort || !in.local_group_sort) ? 0 : 1;
+        in.want_bkt3 = get_option("no_bkt3", 0) ? 0 : 1;
         if (!get_option("no_suffix_keys", 0)) {
             idx->sk = (uint32_t *)dev_alloc(sizeof(uint32_t) * (size_t)n, s);
             in.sk = idx->sk;
@@ -361,6 +363,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         idx->doc_sorted = so.doc_sorted; idx->doc_sort_overflow = so.doc_sort_overflow;
         idx->t8 = so.t8.p; so.t8.p = nullptr;      // ownership moves to the index
         idx->bkt = so.bkt.p; so.bkt.p = nullptr;
+        idx->bkt3 = so.bkt3.p; so.bkt3.p = nullptr;
         idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
         idx->tables_fused = so.tables_done;
         if (idx->sk && !so.sk_done) {
@@ -507,6 +510,7 @@ int east_index_stat(const east_index *idx, const char *name, int64_t *value) {
     if (!strcmp(name, "doc_sorted")) *value = idx->doc_sorted;
     else if (!strcmp(name, "doc_sort_overflow")) *value = idx->doc_sort_overflow;
     else if (!strcmp(name, "tables_fused")) *value = idx->tables_fused;
+    else if (!strcmp(name, "bkt3")) *value = idx->bkt3 != nullptr;
     else if (!strcmp(name, "pipelined")) *value = idx->pipelined;
     else if (!strcmp(name, "pipeline_miss")) *value = idx->pipeline_miss;
     else if (!strcmp(name, "key_chars")) *value = idx->key_chars;
@@ -725,6 +729,7 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
         in.order = kp->d_order.p;
         in.t8 = idx->t8; in.sk = idx->sk; in.q8 = kp->d_q8.p; in.suf_generic = kp->d_generic.p; in.sym_bits = idx->sym_bits;
         in.bkt = idx->bkt + ((size_t)doc_begin << (2 * idx->sym_bits));
+        if (idx->bkt3 && !get_option("score_no_bkt3", 0)) in.bkt3 = idx->bkt3 + ((size_t)doc_begin << (3 * idx->sym_bits));
     }
     in.algorithmic_bytes = (double)get_option("score_bytes", 0);
     DevBuf<unsigned long long> d_probes;
@@ -741,6 +746,7 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
         part.doc_off = in.doc_off + d0;
         part.doc_m = in.doc_m + d0;
         if (in.bkt) part.bkt = in.bkt + ((size_t)d0 << (2 * in.sym_bits));
+        if (in.bkt3) part.bkt3 = in.bkt3 + ((size_t)d0 << (3 * in.sym_bits));
         part.algorithmic_bytes = in.algorithmic_bytes * ((double)part.n_docs / (double)doc_count);
         score_table(part, tmp, out_dev + (size_t)d0 * K, s);
     }

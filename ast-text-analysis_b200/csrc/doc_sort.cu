@@ -55,6 +55,7 @@ struct DocSortParams {
     const int32_t *doc_m;     // strings (= terminators) per document
     int32_t *sa;              // out: global text positions in suffix order, doc-major
     uint32_t *bkt;            // out (optional): first global rank of every (document, 2-gram)
+    uint32_t *bkt3;           // out (optional, G == 3): first global rank of every (document, 3-gram) = bucket
     uint32_t *overflow;       // out: set when a bucket exceeds DS_REFINE_MAX
     int b, G, S2;             // bits per symbol, symbols per bucket id, symbols per refinement level
     uint32_t term;            // terminator class code
@@ -532,6 +533,7 @@ k_doc_suffix_sort(DocSortParams p) {
         const int sub = (G - 2) * b;                 // a 2-gram owns 2^sub consecutive bucket ids
         const uint32_t sub_mask = (1u << sub) - 1u;
         uint32_t *bkt_row = p.bkt ? p.bkt + ((size_t)doc << (2 * b)) : nullptr;
+        uint32_t *bkt3_row = p.bkt3 ? p.bkt3 + ((size_t)doc << (3 * b)) : nullptr;
         for (int wb = w0; wb < w1; wb += 32) {
             const int w = wb + lane;
             const uint32_t v = (w < w1) ? s_scr[w] : 0u;
@@ -550,6 +552,7 @@ k_doc_suffix_sort(DocSortParams p) {
                     if ((id0 & sub_mask) == 0u) bkt_row[id0 >> sub] = (uint32_t)base + st0;
                     if (sub == 0) bkt_row[id0 + 1u] = (uint32_t)base + st1;
                 }
+                if (bkt3_row) *reinterpret_cast<uint2 *>(bkt3_row + id0) = make_uint2((uint32_t)base + st0, (uint32_t)base + st1);
                 s_scr[w] = (st0 & 0xffffu) | (st1 << 16);  // bucket starts, used as the scatter cursors
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -913,7 +916,7 @@ bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan) {
 
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
                      const int32_t *doc_m, int doc_begin, int n_docs,
-                     int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
+                     int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *bkt3, uint32_t *overflow, cudaStream_t s,
                      unsigned long long *phase_clk, const DocSortTables *tables, uint32_t *sk) {
     static bool configured = false;
     if (!configured) {
@@ -921,7 +924,7 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
         configured = true;
     }
     DocSortParams p;
-    p.t8 = t8; p.text = text; p.doc_off = doc_off; p.doc_m = doc_m; p.sa = sa; p.bkt = bkt; p.overflow = overflow;
+    p.t8 = t8; p.text = text; p.doc_off = doc_off; p.doc_m = doc_m; p.sa = sa; p.bkt = bkt; p.bkt3 = (plan.G == 3) ? bkt3 : nullptr; p.overflow = overflow;
     p.b = plan.b; p.G = plan.G; p.S2 = plan.S2; p.term = term;
     p.text_cap = plan.text_cap; p.bits_words = plan.bits_words;
     p.phase_clk = phase_clk;

@@ -891,6 +891,13 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             out.bkt = DevBuf<uint32_t>(entries, s);
             EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             out.sym_bits = plan.b;
+            if (in.want_bkt3 && plan.G == 3 && ((size_t)D << (3 * plan.b)) * sizeof(uint32_t) <= ((size_t)8 << 30)) {
+                // the kernel's buckets ARE the 3-grams: their first ranks cost one more coalesced store and turn
+                // the scorer's depth-2 narrowing (a binary search over the largest intervals) into a lookup
+                const size_t e3 = ((size_t)D << (3 * plan.b)) + 1;
+                out.bkt3 = DevBuf<uint32_t>(e3, s);
+                EAST_CUDA(cudaMemcpyAsync(out.bkt3.p + e3 - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            }
         }
         DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
         const bool fuse = in.lcp != nullptr && plan.tables_fit;
@@ -908,7 +915,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, s, in.text, e0, e1, d_table.p,
                         (uint8_t)term, t8.p, flags.p + 1);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
-                            flags.p, s, nullptr, fuse ? &tables : nullptr, in.sk);
+                            out.bkt3.p, flags.p, s, nullptr, fuse ? &tables : nullptr, in.sk);
         }
         out.tables_done = fuse ? 1 : 0;
     } else {
@@ -930,6 +937,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
         out.doc_sort_overflow = (h_flags[0] & 1u) ? 1 : 0;
         out.tables_done = 0;
         out.bkt = DevBuf<uint32_t>();
+        out.bkt3 = DevBuf<uint32_t>();
         out.sym_bits = 0;
         return false;
     }
@@ -1033,6 +1041,13 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 out.bkt = DevBuf<uint32_t>(entries, s);
                 EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
                 out.sym_bits = plan.b;
+                if (in.want_bkt3 && plan.G == 3 && ((size_t)D << (3 * plan.b)) * sizeof(uint32_t) <= ((size_t)8 << 30)) {
+                    // the kernel's buckets ARE the 3-grams: their first ranks cost one more coalesced store and turn
+                    // the scorer's depth-2 narrowing (a binary search over the largest intervals) into a lookup
+                    const size_t e3 = ((size_t)D << (3 * plan.b)) + 1;
+                    out.bkt3 = DevBuf<uint32_t>(e3, s);
+                    EAST_CUDA(cudaMemcpyAsync(out.bkt3.p + e3 - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+                }
             }
             static const bool profile = getenv("EAST_DOC_SORT_PROFILE") != nullptr;
             DevBuf<unsigned long long> clk;
@@ -1048,7 +1063,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
                 EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
             }
-            doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, 0, D, n, kp.term, out.sa, out.bkt.p, flag.p, s, clk.p,
+            doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, 0, D, n, kp.term, out.sa, out.bkt.p, out.bkt3.p, flag.p, s, clk.p,
                             fuse ? &tables : nullptr, in.sk);
             uint32_t overflow = 0;
             EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -1073,6 +1088,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             }
             out.doc_sort_overflow = 1;   // a bucket of > 8192 suffixes: the global sort below redoes the batch
             out.bkt = DevBuf<uint32_t>();
+            out.bkt3 = DevBuf<uint32_t>();
             out.sym_bits = 0;
         }
     }

@@ -22,6 +22,7 @@ struct SaInput {
     // destination of the LCP / child / annotation tables: the per-document kernel fills them itself
     int32_t *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
     uint32_t *sk = nullptr;                 // destination of the scorer's per-rank key bytes (fast path only)
+    int want_bkt3 = 1;                      // per-document kernel: also keep its 3-gram bucket starts for the scorer
     // pipelined host build: the text arrives in n_chunks runs of whole documents; chunk c = documents
     // [chunk_doc[c], chunk_doc[c+1]) is resident once chunk_ready[c] has fired (recorded on the copy stream)
     int n_chunks = 0;
@@ -33,6 +34,7 @@ struct SaOutput {
     int32_t *sa;              // device, n  (global text positions, doc-major rank order)
     DevBuf<uint8_t> t8;       // fast path: dense byte codes of the text (kept for later stages)
     DevBuf<uint32_t> bkt;     // fast path: 2-gram bucket table [n_docs << 2*sym_bits] + sentinel
+    DevBuf<uint32_t> bkt3;    // per-document kernel with 5-bit symbols: 3-gram table [n_docs << 3*sym_bits] + sentinel
     std::vector<uint8_t> code_table;  // code point (< 0x0A00) -> dense code (0 = absent)
     int sym_bits = 0;
     int term_code = 0;
@@ -65,7 +67,7 @@ struct DocSortTables { int32_t *lcp, *up, *down, *next, *ann; };   // up/down/ne
 bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan);
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
                      const int32_t *doc_m, int doc_begin, int n_docs,
-                     int64_t n_total /* code points of these documents */, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *overflow, cudaStream_t s,
+                     int64_t n_total /* code points of these documents */, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *bkt3, uint32_t *overflow, cudaStream_t s,
                      unsigned long long *phase_clk = nullptr /* profiling: 8 cycle counters */,
                      const DocSortTables *tables = nullptr /* also produce LCP, child table, annotation */,
                      uint32_t *sk = nullptr /* also produce the scorer's per-rank key bytes */);
@@ -92,6 +94,7 @@ struct ScoreInput {
     // fast path (terminator-class alphabet): dense byte text, byte-coded queries, 2-gram buckets
     const uint8_t *t8 = nullptr;
     const uint32_t *bkt = nullptr;      // [n_docs << 2*sym_bits] + 1, rows of the docs being scored
+    const uint32_t *bkt3 = nullptr;     // optional [n_docs << 3*sym_bits] + 1: depth 2 is a table lookup too
     const uint32_t *sk = nullptr;       // per rank: text bytes at offsets 2..5 of the suffix (saves the SA -> text hop)
     const uint8_t *q8 = nullptr;        // dense codes of kp (0 = symbol absent from the batch)
     const uint8_t *suf_generic = nullptr;  // 1 = this suffix contains a code point >= 0x0A00: generic walk

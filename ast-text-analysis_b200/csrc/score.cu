@@ -95,7 +95,7 @@ __device__ __forceinline__ double score_one_suffix(const uint32_t *__restrict__ 
 // codes (0 = absent from the batch: cannot match).  Same arithmetic, same order as the generic walk.
 template <bool PROBES>
 __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restrict__ T8, const int32_t *__restrict__ sa,
-                                                        const uint32_t *__restrict__ sk, const uint32_t *__restrict__ row, int b,
+                                                        const uint32_t *__restrict__ sk, const uint32_t *__restrict__ row, const uint32_t *__restrict__ row3, int b,
                                                         int32_t start, int32_t end, int32_t m,
                                                         const uint8_t *__restrict__ q, int32_t len, int normalized,
                                                         unsigned long long &probes) {
@@ -125,6 +125,22 @@ __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restric
                 frac = frac + (double)size / (double)parent_f;
             }
             lo = nlo; hi = nhi; parent_f = size; d = 2;
+            if (row3 != nullptr && d < len && q[2] != 0) {
+                // depth 2 from the 3-gram table of the per-document build (its buckets): one lookup instead of
+                // the binary search over the largest intervals of the walk
+                const uint32_t x3 = (x << b) | q[2];
+                const int32_t l3 = (int32_t)__ldg(row3 + x3), h3 = (int32_t)__ldg(row3 + x3 + 1) - 1;
+                if (PROBES) probes += 8;
+                if (h3 < l3) len = 2;   // no such 3-gram: the walk ends here
+                else {
+                    size = h3 - l3 + 1;
+                    if (size != hi - lo + 1) {
+                        ++nodes;
+                        frac = frac + (double)size / (double)parent_f;
+                    }
+                    lo = l3; hi = h3; parent_f = size; d = 3;
+                }
+            }
             while (d < len) {
                 const uint32_t c = q[d];
                 if (c == 0) break;
@@ -189,7 +205,8 @@ k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *pr
         const int32_t start = __ldg(in.doc_off + doc), end = __ldg(in.doc_off + doc + 1);
         double r;
         if (in.bkt != nullptr && !__ldg(in.suf_generic + sidx)) {
-            r = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.sk, in.bkt + ((size_t)doc << (2 * in.sym_bits)), in.sym_bits, start, end,
+            r = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.sk, in.bkt + ((size_t)doc << (2 * in.sym_bits)),
+                                              in.bkt3 ? in.bkt3 + ((size_t)doc << (3 * in.sym_bits)) : nullptr, in.sym_bits, start, end,
                                               __ldg(in.doc_m + doc), in.q8 + sidx, qend - sidx, in.normalized, probes);
         } else {
             r = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx, qend - sidx,
