@@ -570,8 +570,9 @@ struct KpPrepared {
     std::vector<int64_t> off;          // K + 1 offsets (cache key)
     std::vector<uint8_t> code_table;   // alphabet of the index the dense codes were made for (cache key)
     int64_t n_uniq = 0;
-    DevBuf<int32_t> d_off, d_suf, d_uniq_of, d_uniq_rep, d_order;
-    DevBuf<uint8_t> d_q8, d_generic;
+    DevBuf<int32_t> d_off, d_uniq_of;
+    DevBuf<SufRec> d_recs;
+    DevBuf<uint8_t> d_q8;
 };
 static thread_local std::unique_ptr<KpPrepared> g_kp_cache;
 
@@ -648,17 +649,10 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
     }
     const int64_t n_uniq = (int64_t)uniq_rep.size();
     c->n_uniq = n_uniq;
-    c->d_off = DevBuf<int32_t>(K + 1, s); c->d_suf = DevBuf<int32_t>((size_t)total, s);
-    c->d_uniq_of = DevBuf<int32_t>((size_t)total, s); c->d_uniq_rep = DevBuf<int32_t>((size_t)n_uniq, s);
-    EAST_CUDA(cudaMemcpyAsync(c->d_off.p, off32.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, s));
-    EAST_CUDA(cudaMemcpyAsync(c->d_suf.p, suf_kp.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
-    EAST_CUDA(cudaMemcpyAsync(c->d_uniq_of.p, uniq_of.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
-    EAST_CUDA(cudaMemcpyAsync(c->d_uniq_rep.p, uniq_rep.data(), sizeof(int32_t) * (size_t)n_uniq, cudaMemcpyHostToDevice, s));
-    std::vector<uint8_t> q8, generic;
-    std::vector<int32_t> order;
+    std::vector<uint8_t> q8((size_t)total, 0), generic((size_t)total, 1);
+    std::vector<int32_t> order((size_t)n_uniq);
     if (fast) {
         // dense byte codes of the queries + per-suffix "contains a code point >= 0x0A00" flag
-        q8.resize((size_t)total); generic.resize((size_t)total);
         for (int32_t k = 0; k < K; ++k) {
             uint8_t weird = 0;
             for (int64_t p = kp_off[k + 1] - 1; p >= kp_off[k]; --p) {
@@ -668,8 +662,11 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
                 generic[(size_t)p] = weird;
             }
         }
-        // visit order of the distinct suffixes: counting sort by their first three dense symbols, so the
-        // threads of a warp walk neighbouring SA intervals (cache locality, less divergence)
+    }
+    if (fast && dedup) {
+        // visiting order of the distinct suffixes: counting sort by their first three dense symbols, so the
+        // threads of a warp walk neighbouring SA intervals (cache locality, less divergence).  (Without
+        // de-duplication the caller wants per-suffix results: they stay in suffix order.)
         const int b = idx->sym_bits;
         const int nsym = (3 * b <= 18) ? 3 : ((2 * b <= 18) ? 2 : 1);
         std::vector<uint32_t> bin((size_t)n_uniq);
@@ -682,19 +679,43 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
             ++count[key + 1];
         }
         for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
-        order.resize((size_t)n_uniq);
         for (int64_t u = 0; u < n_uniq; ++u) order[count[bin[(size_t)u]]++] = (int32_t)u;
-        c->d_order = DevBuf<int32_t>((size_t)n_uniq, s);
+    } else {
+        for (int64_t u = 0; u < n_uniq; ++u) order[(size_t)u] = (int32_t)u;
+    }
+    // one record per distinct suffix in visiting order; every suffix points at the position of its twin
+    std::vector<SufRec> recs((size_t)n_uniq);
+    std::vector<int32_t> pos_of((size_t)n_uniq);
+    for (int64_t pos = 0; pos < n_uniq; ++pos) {
+        const int32_t u = order[(size_t)pos];
+        const int64_t p = uniq_rep[(size_t)u], pe = kp_off[suf_kp[(size_t)p] + 1];
+        pos_of[(size_t)u] = (int32_t)pos;
+        SufRec r;
+        r.q8_first = 0;
+        for (int q = 0; q < 8 && p + q < pe; ++q) r.q8_first |= (uint64_t)q8[(size_t)(p + q)] << (8 * q);
+        r.sidx = (int32_t)p;
+        if (pe - p > 0xffff) throw Error(EAST_ERR_RANGE, "keyphrase longer than 65535 code points");
+        r.len = (uint16_t)(pe - p);
+        r.generic = generic[(size_t)p];
+        r.pad = 0;
+        recs[(size_t)pos] = r;
+    }
+    for (int64_t p = 0; p < total; ++p) uniq_of[(size_t)p] = pos_of[(size_t)uniq_of[(size_t)p]];
+    c->d_off = DevBuf<int32_t>(K + 1, s);
+    c->d_uniq_of = DevBuf<int32_t>((size_t)total, s);
+    c->d_recs = DevBuf<SufRec>((size_t)n_uniq, s);
+    EAST_CUDA(cudaMemcpyAsync(c->d_off.p, off32.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(c->d_uniq_of.p, uniq_of.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(c->d_recs.p, recs.data(), sizeof(SufRec) * (size_t)n_uniq, cudaMemcpyHostToDevice, s));
+    if (fast) {
         c->d_q8 = DevBuf<uint8_t>((size_t)total, s);
-        c->d_generic = DevBuf<uint8_t>((size_t)total, s);
-        EAST_CUDA(cudaMemcpyAsync(c->d_order.p, order.data(), sizeof(int32_t) * (size_t)n_uniq, cudaMemcpyHostToDevice, s));
         EAST_CUDA(cudaMemcpyAsync(c->d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));
-        EAST_CUDA(cudaMemcpyAsync(c->d_generic.p, generic.data(), (size_t)total, cudaMemcpyHostToDevice, s));
     }
     EAST_CUDA(cudaStreamSynchronize(s));   // the host staging vectors end here
     // the entry outlives this call: whoever drops it frees on the legacy stream (every call that used it has synchronised)
-    c->d_off.s = c->d_suf.s = c->d_uniq_of.s = c->d_uniq_rep.s = c->d_order.s = 0;
-    c->d_q8.s = c->d_generic.s = 0;
+    c->d_off.s = c->d_uniq_of.s = 0;
+    c->d_recs.s = 0;
+    c->d_q8.s = 0;
     c->kp = std::move(kp_host);
     return c;
 }
@@ -722,12 +743,11 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
     ScoreInput in;
     in.text = idx->text; in.sa = idx->sa;
     in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
-    in.kp = kp_dev; in.kp_off = kp->d_off.p; in.suf_kp = kp->d_suf.p; in.K = K; in.total_suffixes = (int32_t)total;
-    in.uniq_of = kp->d_uniq_of.p; in.uniq_rep = kp->d_uniq_rep.p; in.n_uniq = (int32_t)n_uniq;
+    in.kp = kp_dev; in.kp_off = kp->d_off.p; in.K = K; in.total_suffixes = (int32_t)total;
+    in.uniq_of = kp->d_uniq_of.p; in.recs = kp->d_recs.p; in.n_uniq = (int32_t)n_uniq;
     in.normalized = normalized ? 1 : 0;
     if (kp->fast) {
-        in.order = kp->d_order.p;
-        in.t8 = idx->t8; in.sk = idx->sk; in.q8 = kp->d_q8.p; in.suf_generic = kp->d_generic.p; in.sym_bits = idx->sym_bits;
+        in.t8 = idx->t8; in.sk = idx->sk; in.q8 = kp->d_q8.p; in.sym_bits = idx->sym_bits;
         in.bkt = idx->bkt + ((size_t)doc_begin << (2 * idx->sym_bits));
         if (idx->bkt3 && !get_option("score_no_bkt3", 0)) in.bkt3 = idx->bkt3 + ((size_t)doc_begin << (3 * idx->sym_bits));
     }

@@ -79,6 +79,14 @@ void build_lcp_tables(const uint32_t *text, const uint8_t *t8 /*or null*/, int t
                       int32_t *ann, StageTimer &tm, cudaStream_t s, int child_variant = 0);
 
 // batched scorer (easa.py:91-139)
+// one record per DISTINCT query suffix, in visiting order (thread order): everything a walk needs to start
+struct SufRec {
+    uint64_t q8_first;   // dense codes of the first 8 symbols (fast path; symbol d in byte d)
+    int32_t sidx;        // index of (one of) the suffix(es) in the concatenated keyphrases
+    uint16_t len;        // symbols to the end of its keyphrase
+    uint8_t generic;     // 1 = contains a code point >= 0x0A00 (or no fast path): generic walk on code points
+    uint8_t pad;
+};
 struct ScoreInput {
     const uint32_t *text;
     const int32_t *sa;
@@ -87,7 +95,6 @@ struct ScoreInput {
     int n_docs;
     const uint32_t *kp;        // device, concatenated queries
     const int32_t *kp_off;     // device, K + 1
-    const int32_t *suf_kp;     // device, total_suffixes: owning keyphrase of each suffix
     int32_t K;
     int32_t total_suffixes;
     int normalized;
@@ -97,11 +104,9 @@ struct ScoreInput {
     const uint32_t *bkt3 = nullptr;     // optional [n_docs << 3*sym_bits] + 1: depth 2 is a table lookup too
     const uint32_t *sk = nullptr;       // per rank: text bytes at offsets 2..5 of the suffix (saves the SA -> text hop)
     const uint8_t *q8 = nullptr;        // dense codes of kp (0 = symbol absent from the batch)
-    const uint8_t *suf_generic = nullptr;  // 1 = this suffix contains a code point >= 0x0A00: generic walk
-    const int32_t *order = nullptr;     // optional visit order of the distinct suffixes (a permutation of 0..n_uniq-1)
     // identical query suffixes (same code points to the end of their keyphrase) are walked once:
-    const int32_t *uniq_of = nullptr;   // device, total_suffixes: distinct-suffix id of every suffix
-    const int32_t *uniq_rep = nullptr;  // device, n_uniq: one suffix (index into kp) per distinct id
+    const int32_t *uniq_of = nullptr;   // device, total_suffixes: position (in visiting order) of the suffix's distinct twin
+    const SufRec *recs = nullptr;       // device, n_uniq: the distinct suffixes in visiting order
     int32_t n_uniq = 0;
     int sym_bits = 0;
     unsigned long long *probe_count = nullptr;  // device counter: run the probe-counting variant

@@ -97,14 +97,16 @@ template <bool PROBES>
 __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restrict__ T8, const int32_t *__restrict__ sa,
                                                         const uint32_t *__restrict__ sk, const uint32_t *__restrict__ row, const uint32_t *__restrict__ row3, int b,
                                                         int32_t start, int32_t end, int32_t m,
-                                                        const uint8_t *__restrict__ q, int32_t len, int normalized,
+                                                        const uint8_t *__restrict__ q, uint64_t qw, int32_t len, int normalized,
                                                         unsigned long long &probes) {
+    // query symbol at depth d: the first 8 travel in the suffix record, deeper ones are read from the byte-coded queries
+#define QSYM(d) ((d) < 8 ? (uint32_t)(qw >> (8 * (d))) & 0xffu : (uint32_t)q[d])
     // symbol of suffix rank r at depth d >= 2: depths 2..5 come from the per-rank key word (one load instead of
     // the dependent SA -> text pair), deeper ones from the text
 #define SYM8(r, d) (PROBES ? (probes += 5, (uint32_t)T8[sa[r] + (d)]) \
                            : ((sk != nullptr && (d) < 6) ? ((__ldg(sk + (r)) >> (8 * ((d) - 2))) & 0xffu) : (uint32_t)T8[sa[r] + (d)]))
     int32_t parent_f = (end - start) - m;
-    const uint32_t c0 = q[0];
+    const uint32_t c0 = QSYM(0);
     if (c0 == 0) return 0.0;
     int32_t lo = (int32_t)__ldg(row + (c0 << b));
     int32_t hi = (int32_t)__ldg(row + ((c0 + 1) << b)) - 1;
@@ -114,8 +116,8 @@ __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restric
     int32_t d = 1, nodes = 1;
     double frac = (double)size / (double)parent_f;
     parent_f = size;
-    if (len > 1 && q[1] != 0) {
-        const uint32_t x = (c0 << b) | q[1];
+    if (len > 1 && QSYM(1) != 0) {
+        const uint32_t x = (c0 << b) | QSYM(1);
         const int32_t nlo = (int32_t)__ldg(row + x), nhi = (int32_t)__ldg(row + x + 1) - 1;
         if (PROBES) probes += 8;
         if (nhi >= nlo) {
@@ -125,10 +127,10 @@ __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restric
                 frac = frac + (double)size / (double)parent_f;
             }
             lo = nlo; hi = nhi; parent_f = size; d = 2;
-            if (row3 != nullptr && d < len && q[2] != 0) {
+            if (row3 != nullptr && d < len && QSYM(2) != 0) {
                 // depth 2 from the 3-gram table of the per-document build (its buckets): one lookup instead of
                 // the binary search over the largest intervals of the walk
-                const uint32_t x3 = (x << b) | q[2];
+                const uint32_t x3 = (x << b) | QSYM(2);
                 const int32_t l3 = (int32_t)__ldg(row3 + x3), h3 = (int32_t)__ldg(row3 + x3 + 1) - 1;
                 if (PROBES) probes += 8;
                 if (h3 < l3) len = 2;   // no such 3-gram: the walk ends here
@@ -142,7 +144,7 @@ __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restric
                 }
             }
             while (d < len) {
-                const uint32_t c = q[d];
+                const uint32_t c = QSYM(d);
                 if (c == 0) break;
                 int32_t nl, nh;
                 if (lo == hi) {
@@ -187,6 +189,7 @@ __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restric
     if (normalized) r = r / (double)d;
     return r;
 #undef SYM8
+#undef QSYM
 }
 
 template <bool PROBES>
@@ -197,22 +200,24 @@ k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *pr
     const int64_t stride = (int64_t)gridDim.x * SC_THREADS;
     for (int64_t idx = (int64_t)blockIdx.x * SC_THREADS + threadIdx.x; idx < total; idx += stride) {
         const int32_t doc = (int32_t)(idx / in.n_uniq);
-        int32_t u = (int32_t)(idx - (int64_t)doc * in.n_uniq);
-        if (in.order) u = __ldg(in.order + u);
-        const int32_t sidx = __ldg(in.uniq_rep + u);   // one of the identical suffixes
-        const int32_t k = __ldg(in.suf_kp + sidx);
-        const int32_t qend = __ldg(in.kp_off + k + 1);
+        const int32_t u = (int32_t)(idx - (int64_t)doc * in.n_uniq);   // position in visiting order
+        // one coalesced 16-byte load: where the suffix is, how long, its first 8 symbols
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(in.recs) + u);
+        const uint64_t qw = ((uint64_t)raw.y << 32) | raw.x;
+        const int32_t sidx = (int32_t)raw.z;
+        const int32_t len = (int32_t)(raw.w & 0xffffu);
+        const bool generic = ((raw.w >> 16) & 0xffu) != 0u;
         const int32_t start = __ldg(in.doc_off + doc), end = __ldg(in.doc_off + doc + 1);
         double r;
-        if (in.bkt != nullptr && !__ldg(in.suf_generic + sidx)) {
+        if (in.bkt != nullptr && !generic) {
             r = score_one_suffix_fast<PROBES>(in.t8, in.sa, in.sk, in.bkt + ((size_t)doc << (2 * in.sym_bits)),
                                               in.bkt3 ? in.bkt3 + ((size_t)doc << (3 * in.sym_bits)) : nullptr, in.sym_bits, start, end,
-                                              __ldg(in.doc_m + doc), in.q8 + sidx, qend - sidx, in.normalized, probes);
+                                              __ldg(in.doc_m + doc), in.q8 + sidx, qw, len, in.normalized, probes);
         } else {
-            r = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx, qend - sidx,
+            r = score_one_suffix<PROBES>(in.text, in.sa, start, end, __ldg(in.doc_m + doc), in.kp + sidx, len,
                                          in.normalized, probes);
         }
-        tmp[(int64_t)doc * in.n_uniq + u] = r;
+        tmp[(int64_t)doc * in.n_uniq + u] = r;   // coalesced: results are stored in visiting order
     }
     if (PROBES) {
         for (int o = 16; o > 0; o >>= 1) probes += __shfl_down_sync(0xffffffffu, probes, o);
@@ -221,7 +226,7 @@ k_score_suffixes(ScoreInput in, double *__restrict__ tmp, unsigned long long *pr
 }
 
 // One thread per (document, keyphrase): adds up the results of the keyphrase's suffixes IN SUFFIX ORDER
-// (the reference's fp64 order, easa.py:127-134), each fetched through its distinct-suffix id from the
+// (the reference's fp64 order, easa.py:127-134), each fetched through the position of its distinct twin from the
 // document's row of tmp (L2-resident: the row was just written).  Adjacent threads own adjacent
 // keyphrases, so the id loads are contiguous across the warp.
 __global__ void __launch_bounds__(SC_THREADS)
