@@ -16,6 +16,7 @@
 //                          accumulate in TMEM, and tcgen05.commit signals an mbarrier so the
 //                          two-stage shared-memory ring can be refilled while the MMAs run.
 //                          Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> int32 stores.
+// C = B * B^T is symmetric: the CTAs below the diagonal exit at once, the others store their tile and its transpose.
 // Counts are exact: u8 products accumulated in int32 (D < 2^31).
 #include "sa_build.h"
 
@@ -81,7 +82,10 @@ k_cooc_umma(const uint8_t *__restrict__ Bm, int64_t Dp, int32_t Kp, int32_t K, i
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_tmem;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    // C is symmetric: only the tiles on and above the diagonal are computed, each is stored twice
+    if (blockIdx.x < blockIdx.y) return;
     const int32_t i0 = blockIdx.y * CT_TILE, j0 = blockIdx.x * CT_TILE;
+    const bool mirror = blockIdx.x != blockIdx.y;
 
     if (warp == 0) {
         // 128 TMEM columns x 128 lanes of 32-bit accumulators
@@ -173,6 +177,13 @@ k_cooc_umma(const uint8_t *__restrict__ Bm, int64_t Dp, int32_t Kp, int32_t K, i
                 const int32_t colj = j0 + cb + q;
                 if (colj < K) C[(int64_t)row * K + colj] = (int32_t)v[q];
             }
+            if (mirror) {   // the transposed tile: for a fixed q the 32 lanes write 32 consecutive ints
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int32_t colj = j0 + cb + q;
+                    if (colj < K) C[(int64_t)colj * K + row] = (int32_t)v[q];
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -180,22 +191,161 @@ k_cooc_umma(const uint8_t *__restrict__ Bm, int64_t Dp, int32_t Kp, int32_t K, i
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128));
 }
 
-void cooc_counts_tc(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s) {
+// ------------------------------------------------------------------------------------------
+// Pipelined version (default): 128 x 256 tile of C per CTA, warp-specialised.
+//   warps 0-3  producers: 16-byte cp.async copies of the A (128 rows) and B (256 rows) slices straight
+//              into the core-matrix layout of a 4-stage ring (48 KB per stage); completion is signalled
+//              with cp.async.mbarrier.arrive.noinc on the stage's "full" barrier.  Afterwards the same
+//              warps run the epilogue (TMEM lanes 32w..32w+31).
+//   warp 4     one elected thread waits for "full", issues four tcgen05.mma.kind::i8 (M = 128, N = 256,
+//              K = 32) per stage and commits to the stage's "empty" barrier, which releases the slot.
+// Operand traffic per output element is 0.75x that of the 128 x 128 kernel and the loads of stage
+// s+1..s+3 overlap the MMAs of stage s (the simple kernel serialised them with a block barrier).
+// ------------------------------------------------------------------------------------------
+constexpr int CP_TM = 128, CP_TN = 256, CP_BK = 128, CP_STAGES = 4;
+constexpr int CP_A_BYTES = CP_TM * CP_BK, CP_B_BYTES = CP_TN * CP_BK;
+constexpr int CP_STAGE_BYTES = CP_A_BYTES + CP_B_BYTES;   // 48 KB
+constexpr int CP_THREADS = 160;                            // 4 producer/epilogue warps + 1 MMA warp
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(CP_THREADS, 1)
+k_cooc_umma_pipe(const uint8_t *__restrict__ Bm, int64_t Dp, int32_t K, int32_t *__restrict__ C) {
+    extern __shared__ __align__(1024) uint8_t cp_smem[];
+    __shared__ __align__(8) uint64_t s_full[CP_STAGES], s_empty[CP_STAGES], s_done;
+    __shared__ uint32_t s_tmem;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int32_t i0 = blockIdx.y * CP_TM, j0 = blockIdx.x * CP_TN;
+    // symmetric result: a tile whose columns all lie left of its rows is covered by the transposed stores of another tile
+    if (j0 + CP_TN <= i0) return;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (t == 32) {
+        for (int i = 0; i < CP_STAGES; ++i) {
+            mbar_init(smem_u32(&s_full[i]), 128);   // one (non-incrementing) arrival per producer thread
+            mbar_init(smem_u32(&s_empty[i]), 1);    // one tcgen05.commit
+        }
+        mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+    const int chunks = (int)(Dp / CP_BK);
+
+    if (warp < 4) {
+        // ---- producers
+        for (int c = 0; c < chunks; ++c) {
+            const int st = c % CP_STAGES, round = c / CP_STAGES;
+            if (round > 0) mbar_wait(smem_u32(&s_empty[st]), (uint32_t)((round - 1) & 1));
+            const uint32_t sa = smem_u32(cp_smem + st * CP_STAGE_BYTES), sb = sa + CP_A_BYTES;
+            const int64_t col = (int64_t)c * CP_BK;
+#pragma unroll
+            for (int q = 0; q < (CP_TM * CP_BK / 16) / 128; ++q) {     // 8 pieces of A per thread
+                const int piece = q * 128 + t;
+                const int r = piece >> 3, kc = piece & 7;
+                cp_async16(sa + (uint32_t)((r >> 3) * 1024 + kc * 128 + (r & 7) * 16), Bm + (int64_t)(i0 + r) * Dp + col + kc * 16);
+            }
+#pragma unroll
+            for (int q = 0; q < (CP_TN * CP_BK / 16) / 128; ++q) {     // 16 pieces of B per thread
+                const int piece = q * 128 + t;
+                const int r = piece >> 3, kc = piece & 7;
+                cp_async16(sb + (uint32_t)((r >> 3) * 1024 + kc * 128 + (r & 7) * 16), Bm + (int64_t)(j0 + r) * Dp + col + kc * 16);
+            }
+            // arrives on "full" once all cp.async of this thread have landed
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_full[st])) : "memory");
+        }
+    } else if (lane == 0) {
+        // ---- MMA issuer
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(CP_TN >> 3) << 17) | ((uint32_t)(CP_TM >> 4) << 24);
+        for (int c = 0; c < chunks; ++c) {
+            const int st = c % CP_STAGES, round = c / CP_STAGES;
+            mbar_wait(smem_u32(&s_full[st]), (uint32_t)(round & 1));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> tensor-core reads
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t a_base = smem_u32(cp_smem + st * CP_STAGE_BYTES), b_base = a_base + CP_A_BYTES;
+#pragma unroll
+            for (int k = 0; k < CP_BK / 32; ++k) {
+                const uint64_t da = umma_desc(a_base + k * 256), db = umma_desc(b_base + k * 256);
+                const uint32_t accumulate = (c > 0 || k > 0) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+                    "}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                    : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_empty[st]))
+                         : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_done)) : "memory");
+    }
+
+    // ---- epilogue (warps 0-3): warp w owns TMEM lanes 32w..32w+31 = rows i0+32w.. of the tile
+    if (warp < 4) {
+        mbar_wait(smem_u32(&s_done), 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int32_t row = i0 + warp * 32 + lane;
+#pragma unroll 1
+        for (int cb = 0; cb < CP_TN; cb += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < K) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int32_t colj = j0 + cb + q;
+                    if (colj < K) {
+                        C[(int64_t)row * K + colj] = (int32_t)v[q];
+                        C[(int64_t)colj * K + row] = (int32_t)v[q];   // the transposed element (same value where tiles overlap)
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+}
+
+void cooc_counts_tc(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s, int simple) {
     const int64_t Dp = (D + CT_BK - 1) / CT_BK * CT_BK;
-    const int32_t Kp = (K + CT_TILE - 1) / CT_TILE * CT_TILE;
+    const int32_t Kp = (K + CP_TN - 1) / CP_TN * CP_TN;   // rows padded to the larger tile edge (256)
     DevBuf<uint8_t> Bm((size_t)Kp * (size_t)Dp, s);
     EAST_CUDA(cudaMemsetAsync(Bm.p, 0, (size_t)Kp * (size_t)Dp, s));  // padding rows / columns are zero
     dim3 tg((unsigned)((Dp + 31) / 32), (unsigned)((K + 31) / 32));
     EAST_BYTES(8.0 * (double)D * K + (double)K * Dp);
     EAST_LAUNCH(k_threshold_bytes, tg, 256, 0, s, S_DxK, D, K, threshold, Bm.p, Dp);
     static bool configured = false;
-    const int smem = 2 * CT_STAGE_BYTES + 1024;
+    const int smem = 2 * CT_STAGE_BYTES + 1024, smem_pipe = CP_STAGES * CP_STAGE_BYTES + 1024;
     if (!configured) {
         EAST_CUDA(cudaFuncSetAttribute(k_cooc_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        EAST_CUDA(cudaFuncSetAttribute(k_cooc_umma_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pipe));
         configured = true;
     }
-    dim3 grid(Kp / CT_TILE, Kp / CT_TILE);
-    EAST_LAUNCH(k_cooc_umma, grid, CT_THREADS, smem, s, Bm.p, Dp, Kp, K, C);
+    if (simple) {
+        dim3 grid(Kp / CT_TILE, Kp / CT_TILE);
+        EAST_LAUNCH(k_cooc_umma, grid, CT_THREADS, smem, s, Bm.p, Dp, Kp, K, C);
+    } else {
+        dim3 grid(Kp / CP_TN, Kp / CP_TM);
+        EAST_LAUNCH(k_cooc_umma_pipe, grid, CP_THREADS, smem_pipe, s, Bm.p, Dp, K, C);
+    }
 }
 
 }  // namespace east

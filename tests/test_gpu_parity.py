@@ -348,7 +348,7 @@ def test_multi_gpu_sharded_table_is_bit_identical(tmp_path):
         assert np.array_equal(got.view(np.uint64), expect.view(np.uint64))
 
 
-@pytest.mark.parametrize("K,D", [(5, 3), (130, 257), (300, 1000), (257, 4100)])
+@pytest.mark.parametrize("K,D", [(5, 3), (130, 257), (300, 1000), (257, 4100), (700, 900)])
 def test_cooccurrence_tensor_core_counts_are_exact(K, D):
     """C = B B^T on tcgen05 (u8 x u8 -> s32 in TMEM) against numpy and against the AND+POPC kernel."""
     capi = _capi()
@@ -357,11 +357,12 @@ def test_cooccurrence_tensor_core_counts_are_exact(K, D):
     S[rng.random((D, K)) < 0.3] = 0.25  # values exactly at the threshold count as present (>=)
     B = (S >= 0.25).astype(np.int64)
     expect = (B.T @ B).astype(np.int32)
-    got = capi.cooc_host(S, 0.25)
+    got = capi.cooc_host(S, 0.25)   # pipelined 128 x 256 tcgen05 kernel (cp.async ring, warp-specialised)
     assert np.array_equal(got, expect)
-    capi.set_option("cooc_variant", 1)
     try:
-        assert np.array_equal(capi.cooc_host(S, 0.25), expect)
+        for variant in (1, 2):      # AND+POPC cross-check, simple 128 x 128 tcgen05 kernel
+            capi.set_option("cooc_variant", variant)
+            assert np.array_equal(capi.cooc_host(S, 0.25), expect), variant
     finally:
         capi.set_option("cooc_variant", 0)
 
