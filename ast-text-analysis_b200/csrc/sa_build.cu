@@ -159,7 +159,7 @@ constexpr int ST_RESET = -1;  // scan state: a document started, no terminator s
 // (one ballot per 32 code points; global memory only for strings longer than the halo).
 __global__ void __launch_bounds__(256)
 k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict__ doc_off,
-            const int32_t *__restrict__ doc_m, int D, ScanResult *res) {
+            const int32_t *__restrict__ doc_m, int D, ScanResult *res, int tile_begin, int tile_end, int check_doc_ends) {
     __shared__ uint32_t s_present[EAST_TERM_BASE / 32];
     __shared__ uint32_t s_max, s_nterm, s_bad;
     __shared__ __align__(16) uint32_t s_t[ST_HALO + ST_TILE];
@@ -171,8 +171,9 @@ k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict
     for (int i = t; i < EAST_TERM_BASE / 32; i += 256) s_present[i] = 0;
     if (t == 0) { s_max = 0; s_nterm = 0; s_bad = 0; }
     uint32_t mx = 0, nt = 0, bad = 0;
-    const int num_tiles = (n + ST_TILE - 1) / ST_TILE;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // tiles [tile_begin, tile_end) of the text (a pipelined build scans what has arrived so far; a tile only
+    // looks backwards, at its halo)
+    for (int tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int64_t base = (int64_t)tile * ST_TILE;
         const int64_t win = base - ST_HALO;  // global position of s_t[0]
         const int tile_n = (int)min((int64_t)ST_TILE, (int64_t)n - base);
@@ -291,7 +292,7 @@ k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict
     }
     // every document must end with a terminator
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < D; d += stride) {
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; check_doc_ends && d < D; d += stride) {
         int32_t e = doc_off[d + 1];
         if (e <= doc_off[d] || T[e - 1] < EAST_TERM_BASE) bad = 1;
     }
@@ -880,6 +881,19 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
 
     DevBuf<uint8_t> t8;
     DevBuf<uint32_t> flags(2, s);   // [0] doc_sort overflow, [1] encode miss
+    // the validating scan follows the copies: after every run, the tiles of the text that are complete
+    EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
+    int tiles_done = 0;
+    const int tiles_all = (n + ST_TILE - 1) / ST_TILE;
+    auto scan_arrived = [&](int32_t arrived, bool last) {
+        const int tiles_to = last ? tiles_all : arrived / ST_TILE;
+        if (tiles_to > tiles_done || last) {
+            EAST_BYTES(4.0 * ST_TILE * (tiles_to - tiles_done));
+            EAST_LAUNCH(k_scan_text, grid_for((int64_t)(tiles_to - tiles_done) * ST_TILE, ST_TILE, 4), 256, 0, s, in.text, n,
+                        in.doc_off, in.doc_m, D, d_scan.p, tiles_done, tiles_to, last ? 1 : 0);
+            tiles_done = tiles_to;
+        }
+    };
     if (eligible) {
         tm.mark("doc_sort");
         DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
@@ -916,16 +930,15 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
                         (uint8_t)term, t8.p, flags.p + 1);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
                             out.bkt3.p, flags.p, s, nullptr, fuse ? &tables : nullptr, in.sk);
+            scan_arrived(e1, c + 1 == in.n_chunks);
         }
         out.tables_done = fuse ? 1 : 0;
     } else {
         for (int c = 1; c < in.n_chunks; ++c) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
+        scan_arrived(n, true);
     }
-    // the validating scan (also what the ordinary build starts with)
-    tm.mark("scan_text");
-    EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
-    EAST_BYTES(4.0 * n);
-    EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p);
+    // the validating scan is the ordinary build's first step, too
+    tm.mark("validate");
     uint32_t h_flags[2] = {0u, 0u};
     EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
     if (eligible) EAST_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
@@ -971,7 +984,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         tm.mark("scan_text");
         EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
         EAST_BYTES(4.0 * n);
-        EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p);
+        EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p, 0,
+                    (n + ST_TILE - 1) / ST_TILE, 1);
         EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
         EAST_CUDA(cudaStreamSynchronize(s));
     }
