@@ -108,17 +108,23 @@ __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restric
     int32_t parent_f = (end - start) - m;
     const uint32_t c0 = QSYM(0);
     if (c0 == 0) return 0.0;
-    int32_t lo = (int32_t)__ldg(row + (c0 << b));
-    int32_t hi = (int32_t)__ldg(row + ((c0 + 1) << b)) - 1;
+    // the table lookups of depths 0, 1 and 2 depend on the query only: all six loads are issued together
+    // (one memory round trip instead of three dependent ones), then the depths are replayed in order
+    const uint32_t c1 = len > 1 ? QSYM(1) : 0u, c2 = len > 2 ? QSYM(2) : 0u;
+    const uint32_t x = (c0 << b) | c1, x3 = (x << b) | c2;
+    const int32_t lo0 = (int32_t)__ldg(row + (c0 << b)), hi0 = (int32_t)__ldg(row + ((c0 + 1) << b)) - 1;
+    const int32_t lo1 = (int32_t)__ldg(row + x), hi1 = (int32_t)__ldg(row + x + 1) - 1;
+    int32_t lo2 = 0, hi2 = -1;
+    if (row3 != nullptr) { lo2 = (int32_t)__ldg(row3 + x3); hi2 = (int32_t)__ldg(row3 + x3 + 1) - 1; }
+    int32_t lo = lo0, hi = hi0;
     if (PROBES) probes += 8;
     if (hi < lo) return 0.0;
     int32_t size = hi - lo + 1;
     int32_t d = 1, nodes = 1;
     double frac = (double)size / (double)parent_f;
     parent_f = size;
-    if (len > 1 && QSYM(1) != 0) {
-        const uint32_t x = (c0 << b) | QSYM(1);
-        const int32_t nlo = (int32_t)__ldg(row + x), nhi = (int32_t)__ldg(row + x + 1) - 1;
+    if (c1 != 0) {
+        const int32_t nlo = lo1, nhi = hi1;
         if (PROBES) probes += 8;
         if (nhi >= nlo) {
             size = nhi - nlo + 1;
@@ -127,20 +133,18 @@ __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restric
                 frac = frac + (double)size / (double)parent_f;
             }
             lo = nlo; hi = nhi; parent_f = size; d = 2;
-            if (row3 != nullptr && d < len && QSYM(2) != 0) {
+            if (row3 != nullptr && c2 != 0) {
                 // depth 2 from the 3-gram table of the per-document build (its buckets): one lookup instead of
                 // the binary search over the largest intervals of the walk
-                const uint32_t x3 = (x << b) | QSYM(2);
-                const int32_t l3 = (int32_t)__ldg(row3 + x3), h3 = (int32_t)__ldg(row3 + x3 + 1) - 1;
                 if (PROBES) probes += 8;
-                if (h3 < l3) len = 2;   // no such 3-gram: the walk ends here
+                if (hi2 < lo2) len = 2;   // no such 3-gram: the walk ends here
                 else {
-                    size = h3 - l3 + 1;
+                    size = hi2 - lo2 + 1;
                     if (size != hi - lo + 1) {
                         ++nodes;
                         frac = frac + (double)size / (double)parent_f;
                     }
-                    lo = l3; hi = h3; parent_f = size; d = 3;
+                    lo = lo2; hi = hi2; parent_f = size; d = 3;
                 }
             }
             while (d < len) {
