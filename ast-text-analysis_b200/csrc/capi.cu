@@ -340,6 +340,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.doc_sort = (get_option("no_doc_sort", 0) || in.key_chars || in.rs_variant || in.sort_batch_elems ||
                        !in.segmented_sort || !in.local_group_sort) ? 0 : 1;
         in.want_bkt3 = get_option("no_bkt3", 0) ? 0 : 1;
+        in.light_scan = get_option("no_light_scan", 0) ? 0 : 1;
         if (!get_option("no_suffix_keys", 0)) {
             idx->sk = (uint32_t *)dev_alloc(sizeof(uint32_t) * (size_t)n, s);
             in.sk = idx->sk;

@@ -344,12 +344,15 @@ k_encode_text(const uint32_t *__restrict__ T, int32_t begin, int32_t end, const 
     if (missed && miss) atomicOr(miss, 1u);
 }
 
-// bitmap of the code points below 0x0A00 that occur in T[0, n): the speculative alphabet of a pipelined build
+// Light text scan: bitmap of the code points below 0x0A00 that occur in T[0, n), number of code points
+// >= 0x0A00 and the maximum code point -- everything k_scan_text reports except the validation of the
+// terminator layout, which the per-document kernel does itself.  Streams at HBM speed.
 __global__ void __launch_bounds__(256)
-k_alphabet(const uint32_t *__restrict__ T, int32_t n, uint32_t *present) {
+k_alphabet(const uint32_t *__restrict__ T, int32_t n, ScanResult *res) {
     __shared__ uint32_t s_present[EAST_TERM_BASE / 32];
     for (int i = threadIdx.x; i < (int)(EAST_TERM_BASE / 32); i += blockDim.x) s_present[i] = 0;
     __syncthreads();
+    uint32_t mx = 0, nt = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
         uint32_t c[4];
@@ -357,16 +360,22 @@ k_alphabet(const uint32_t *__restrict__ T, int32_t n, uint32_t *present) {
             uint4 v = *reinterpret_cast<const uint4 *>(T + i);
             c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
         } else {
-            for (int q = 0; q < 4; ++q) c[q] = (i + q < n) ? T[i + q] : EAST_TERM_BASE;
+            for (int q = 0; q < 4; ++q) c[q] = (i + q < n) ? T[i + q] : 0u;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (c[q] < EAST_TERM_BASE && !(((volatile uint32_t *)s_present)[c[q] >> 5] & (1u << (c[q] & 31))))
+        for (int q = 0; q < 4; ++q) {
+            mx = max(mx, c[q]);
+            if (c[q] >= EAST_TERM_BASE) ++nt;
+            else if (i + q < n && !(((volatile uint32_t *)s_present)[c[q] >> 5] & (1u << (c[q] & 31))))
                 atomicOr(&s_present[c[q] >> 5], 1u << (c[q] & 31));
+        }
     }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    nt = __reduce_add_sync(0xffffffffu, nt);
+    if ((threadIdx.x & 31) == 0) { atomicMax(&res->max_code, mx); if (nt) atomicAdd(&res->n_term, nt); }
     __syncthreads();
     for (int i = threadIdx.x; i < (int)(EAST_TERM_BASE / 32); i += blockDim.x)
-        if (s_present[i]) atomicOr(&present[i], s_present[i]);
+        if (s_present[i]) atomicOr(&res->present[i], s_present[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -863,14 +872,15 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     int32_t max_doc_n = 0;
     for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);
     tm.mark("alphabet");
-    DevBuf<uint32_t> d_present(EAST_TERM_BASE / 32, s);
-    EAST_CUDA(cudaMemsetAsync(d_present.p, 0, sizeof(uint32_t) * (EAST_TERM_BASE / 32), s));
+    DevBuf<ScanResult> d_first(1, s);
+    EAST_CUDA(cudaMemsetAsync(d_first.p, 0, sizeof(ScanResult), s));
     EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
     const int32_t n0 = in.doc_off_host[in.chunk_doc[1]];
-    EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_present.p);
-    uint32_t present[EAST_TERM_BASE / 32];
-    EAST_CUDA(cudaMemcpyAsync(present, d_present.p, sizeof(present), cudaMemcpyDeviceToHost, s));
+    EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_first.p);
+    ScanResult first;
+    EAST_CUDA(cudaMemcpyAsync(&first, d_first.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
     EAST_CUDA(cudaStreamSynchronize(s));
+    const uint32_t *present = first.present;
     int sigma = 0;
     std::vector<uint8_t> table(EAST_TERM_BASE, 0);
     for (uint32_t c = 0; c < EAST_TERM_BASE; ++c)
@@ -980,12 +990,22 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         scanned = true;                       // the validating scan is the ordinary build's first step
         if (out.doc_sort_overflow) allow_doc_sort = false;
     }
+    int32_t max_doc_n = 0;
+    for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);
+    // Batches of small documents start with the LIGHT scan (alphabet, counts): the per-document kernel
+    // validates the terminator layout of its document itself.  Whatever it cannot take (bad layout, a
+    // bucket too large, an alphabet too wide) is redone below with the validating scan.
+    const bool light = !scanned && allow_doc_sort && in.light_scan && !in.force_general && max_doc_n <= 65535;
     if (!scanned) {
         tm.mark("scan_text");
         EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
         EAST_BYTES(4.0 * n);
-        EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p, 0,
-                    (n + ST_TILE - 1) / ST_TILE, 1);
+        if (light) {
+            EAST_LAUNCH(k_alphabet, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_scan.p);
+        } else {
+            EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p, 0,
+                        (n + ST_TILE - 1) / ST_TILE, 1);
+        }
         EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
         EAST_CUDA(cudaStreamSynchronize(s));
     }
@@ -1042,9 +1062,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     out.term_code = fast ? (int)kp.term : 0;
 
     // ---- small documents: one CTA per document, everything in shared memory (doc_sort.cu)
+    uint32_t doc_sort_flags = 0;   // bit 0: a bucket too large, bit 1: bad terminator layout
     if (fast && allow_doc_sort) {
-        int32_t max_doc_n = 0;
-        for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);
         DocSortPlan plan;
         if (doc_sort_plan(sigma, max_doc_n, plan)) {
             tm.mark("doc_sort");
@@ -1100,11 +1119,22 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 out.t8 = std::move(t8);
                 return;
             }
-            out.doc_sort_overflow = 1;   // a bucket of > 8192 suffixes: the global sort below redoes the batch
+            doc_sort_flags = overflow;
+            out.doc_sort_overflow = (overflow & 1u) ? 1 : 0;   // a bucket of > 4096 suffixes: the global sort redoes the batch
             out.bkt = DevBuf<uint32_t>();
             out.bkt3 = DevBuf<uint32_t>();
             out.sym_bits = 0;
         }
+    }
+    if (light) {
+        // the global sort relies on the validated layout: start over with the full scan
+        SaInput again = in;
+        again.light_scan = 0;
+        if (doc_sort_flags & 1u) again.doc_sort = 0;
+        t8.release();
+        build_suffix_array(again, out, tm, s);
+        if (doc_sort_flags & 1u) out.doc_sort_overflow = 1;
+        return;
     }
 
     // buffers: ping-pong keys/values, active-list side arrays, histogram + look-back scratch

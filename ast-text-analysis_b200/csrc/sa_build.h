@@ -22,6 +22,7 @@ struct SaInput {
     // destination of the LCP / child / annotation tables: the per-document kernel fills them itself
     int32_t *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
     uint32_t *sk = nullptr;                 // destination of the scorer's per-rank key bytes (fast path only)
+    int light_scan = 1;                     // small documents: alphabet-only scan first (the per-document kernel validates)
     int want_bkt3 = 1;                      // per-document kernel: also keep its 3-gram bucket starts for the scorer
     // pipelined host build: the text arrives in n_chunks runs of whole documents; chunk c = documents
     // [chunk_doc[c], chunk_doc[c+1]) is resident once chunk_ready[c] has fired (recorded on the copy stream)

@@ -569,3 +569,26 @@ def test_duplicate_query_suffixes_are_scored_once_and_identically(oracle_mod):
         for d in range(3):
             exp = oracle_mod.OracleEASA(text=packed[d], m=ms[d]).score_many(codes, off, normalized)
             assert np.array_equal(table[d].view(np.uint64), exp.view(np.uint64))
+
+
+def test_terminator_layout_is_validated_by_the_document_kernel(oracle_mod, sa_path):
+    # Batches of small documents start with an alphabet-only scan; the per-document kernel itself checks that
+    # string k ends with 0x0A00 + k.  A text whose terminator COUNT is right but whose layout is not (swapped,
+    # repeated, missing at the end) must be caught there and take the general path: code point order, no
+    # terminator semantics -- exactly what the reference's DC3 does with such a string.
+    capi = _capi()
+    T = 0x0A00
+    good = np.array([65, 66, T, 67, T + 1], dtype=np.uint32)
+    for bad in ([65, T + 1, 66, T],            # swapped
+                [65, T, 66, T],                # repeated
+                [65, T, T + 1, 66],            # does not end with its last terminator
+                [T + 1, 65, 66, T]):           # starts with one
+        bad = np.array(bad, dtype=np.uint32)
+        idx = capi.DeviceIndex([good, bad, good], [2, 2, 2])
+        info = idx.info()
+        assert not info["fast_path"] and not info["doc_sorted"]
+        for d, text in enumerate((good, bad, good)):
+            o = oracle_mod.OracleEASA(text=text, m=2)
+            assert np.array_equal(idx.array(d, capi.SUFTAB), o.suftab), (bad.tolist(), d)
+            assert np.array_equal(idx.array(d, capi.LCPTAB), o.lcptab), (bad.tolist(), d)
+        idx.close()
