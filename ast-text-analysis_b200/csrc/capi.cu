@@ -352,6 +352,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
             in.n_chunks = (int)chunks->ready.size();
             in.chunk_doc = chunks->doc.data();
             in.chunk_ready = chunks->ready.data();
+            in.helper_stream = aux_stream(device);
         } else if (chunks) {   // the global sort needs the whole text: wait for every copy
             for (auto e : chunks->ready) EAST_CUDA(cudaStreamWaitEvent(s, e, 0));
         }
@@ -577,15 +578,19 @@ struct KpPrepared {
 };
 static thread_local std::unique_ptr<KpPrepared> g_kp_cache;
 
-static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
-                                      bool dedup, cudaStream_t s) {
+static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_dev, const uint32_t *kp_host_in,
+                                      const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s) {
     const int64_t total = kp_off[K];
     if (total >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "keyphrase buffer too large");
     for (int32_t k = 0; k < K; ++k)
         if (kp_off[k + 1] <= kp_off[k]) throw Error(EAST_ERR_ZERODIV, "empty query: float division by zero");
     std::vector<uint32_t> kp_host((size_t)total);
-    EAST_CUDA(cudaMemcpyAsync(kp_host.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
-    EAST_CUDA(cudaStreamSynchronize(s));
+    if (kp_host_in) {   // the caller's host copy (east_score_table_host): no round trip through the device
+        std::copy(kp_host_in, kp_host_in + total, kp_host.begin());
+    } else {
+        EAST_CUDA(cudaMemcpyAsync(kp_host.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+        EAST_CUDA(cudaStreamSynchronize(s));
+    }
     const bool fast = idx->bkt && idx->t8 && !get_option("score_generic", 0);
     KpPrepared *c = g_kp_cache.get();
     if (c && c->device == idx->device && c->dedup == dedup && c->fast == fast && (int64_t)c->off.size() == (int64_t)K + 1 &&
@@ -724,10 +729,11 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
 static void score_common(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
                          int normalized, double *out_dev, int32_t doc_begin, int32_t doc_count, cudaStream_t s,
                          double *suffix_out_dev /* optional: per-suffix results of the doc range */,
-                         int64_t *probes_out = nullptr /* optional: run the probe-counting scorer */) {
+                         int64_t *probes_out = nullptr /* optional: run the probe-counting scorer */,
+                         const uint32_t *kp_host = nullptr /* optional: the same code points on the host */) {
     // per-suffix results wanted (return_suffix_scores): every suffix is its own "distinct" suffix
     const bool dedup = !suffix_out_dev && !get_option("score_no_dedup", 0);
-    KpPrepared *kp = prepare_keyphrases(idx, kp_dev, kp_off, K, dedup, s);
+    KpPrepared *kp = prepare_keyphrases(idx, kp_dev, kp_host, kp_off, K, dedup, s);
     const int64_t total = kp_off[K], n_uniq = kp->n_uniq;
 
     // per-suffix results tmp[doc][distinct suffix] are produced and consumed tile by tile over the documents,
@@ -809,7 +815,7 @@ int east_score_table_host(const east_index *idx, const uint32_t *kp, const int64
     DevBuf<uint32_t> d_kp((size_t)kp_off[K], s);
     DevBuf<double> d_out((size_t)idx->n_docs * K, s);
     EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, s));
-    score_common(idx, d_kp.p, kp_off, K, normalized, d_out.p, 0, idx->n_docs, s, nullptr);
+    score_common(idx, d_kp.p, kp_off, K, normalized, d_out.p, 0, idx->n_docs, s, nullptr, nullptr, kp);
     EAST_CUDA(cudaMemcpy(out_DxK, d_out.p, sizeof(double) * (size_t)idx->n_docs * K, cudaMemcpyDeviceToHost));
     EAST_API_END
 }
@@ -825,7 +831,7 @@ int east_score_one(const east_index *idx, int32_t doc, const uint32_t *q, int32_
     DevBuf<uint32_t> d_q(len, s);
     DevBuf<double> d_out(1, s), d_suf(len, s);
     EAST_CUDA(cudaMemcpyAsync(d_q.p, q, sizeof(uint32_t) * len, cudaMemcpyHostToDevice, s));
-    score_common(idx, d_q.p, off, 1, normalized, d_out.p, doc, 1, s, d_suf.p);
+    score_common(idx, d_q.p, off, 1, normalized, d_out.p, doc, 1, s, d_suf.p, nullptr, q);
     EAST_CUDA(cudaMemcpy(score, d_out.p, sizeof(double), cudaMemcpyDeviceToHost));
     if (suffix_scores) EAST_CUDA(cudaMemcpy(suffix_scores, d_suf.p, sizeof(double) * len, cudaMemcpyDeviceToHost));
     EAST_API_END

@@ -931,17 +931,35 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
             EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
         }
+        // runs alternate between the main stream and a helper stream: a run is one wave of per-document CTAs,
+        // and on one stream the next wave could not start before the slowest CTA of the previous one ended
+        cudaStream_t lanes[2] = {s, in.helper_stream ? in.helper_stream : s};
+        cudaEvent_t ready_to_sort = nullptr, helper_done = nullptr;
+        if (lanes[1] != s) {
+            EAST_CUDA(cudaEventCreateWithFlags(&ready_to_sort, cudaEventDisableTiming));
+            EAST_CUDA(cudaEventCreateWithFlags(&helper_done, cudaEventDisableTiming));
+            EAST_CUDA(cudaEventRecord(ready_to_sort, s));           // table upload, memsets, flag reset
+            EAST_CUDA(cudaStreamWaitEvent(lanes[1], ready_to_sort, 0));
+        }
         for (int c = 0; c < in.n_chunks; ++c) {
             const int d0 = in.chunk_doc[c], d1 = in.chunk_doc[c + 1];
             const int32_t e0 = in.doc_off_host[d0], e1 = in.doc_off_host[d1];
-            if (c > 0) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
+            cudaStream_t ls = lanes[c & 1];
+            if (c > 0) EAST_CUDA(cudaStreamWaitEvent(ls, in.chunk_ready[c], 0));
             EAST_BYTES(5.0 * (e1 - e0));
-            EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, s, in.text, e0, e1, d_table.p,
+            EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, ls, in.text, e0, e1, d_table.p,
                         (uint8_t)term, t8.p, flags.p + 1);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
-                            out.bkt3.p, flags.p, s, nullptr, fuse ? &tables : nullptr, in.sk);
-            scan_arrived(e1, c + 1 == in.n_chunks);
+                            out.bkt3.p, flags.p, ls, nullptr, fuse ? &tables : nullptr, in.sk);
+            if (ls == s) scan_arrived(e1, false);   // validating scan of what has arrived (main stream only)
         }
+        if (lanes[1] != s) {
+            EAST_CUDA(cudaEventRecord(helper_done, lanes[1]));
+            EAST_CUDA(cudaStreamWaitEvent(s, helper_done, 0));
+            EAST_CUDA(cudaEventDestroy(ready_to_sort));
+            EAST_CUDA(cudaEventDestroy(helper_done));
+        }
+        scan_arrived(n, true);
         out.tables_done = fuse ? 1 : 0;
     } else {
         for (int c = 1; c < in.n_chunks; ++c) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));

@@ -29,6 +29,7 @@ struct SaInput {
     int n_chunks = 0;
     const int32_t *chunk_doc = nullptr;
     const cudaEvent_t *chunk_ready = nullptr;
+    cudaStream_t helper_stream = nullptr;   // odd runs are sorted here, so that consecutive one-wave kernels overlap their tails
 };
 
 struct SaOutput {
