@@ -836,36 +836,44 @@ k_doc_suffix_sort(DocSortParams p) {
         // at most 2 C iterations ("pop everything, then push" waited for the longest pop run of the 32
         // lanes at every rank).  Stack byte: offset in the chunk | 0x80 first l-index | 0x40 pushed on an
         // empty stack (PSE unknown).
+        // The top entry and its LCP value live in registers: shared memory is read only when a pop
+        // uncovers the entry below (which is also the popped rank's PSE).
         int r = c0;
         uint32_t l = (r < c1) ? s_lcp[r] : 0u;
+        uint32_t top = 0, top_l = 0;   // valid while depth > 0
+        int32_t *const ann_doc = p.ann + base, *const up_doc = p.up + base, *const down_doc = p.down + base,
+                *const next_doc = p.next + base;
         while (r < c1) {
-            uint32_t top = 0;
-            int t = 0;
-            bool pop = false;
-            if (depth > 0) {
-                top = stk[depth - 1];
-                t = c0 + (int)(top & 0x3fu);
-                pop = s_lcp[t] > l;
-            }
-            if (pop) {
+            if (depth > 0 && top_l > l) {
+                // pop: r is the NSV of the top
+                const uint32_t popped = top;
+                const int t = c0 + (int)(popped & 0x3fu);
                 --depth;
-                if (top & 0x40u) {
-                    if (nrec < R) { rec[2 * nrec] = (uint8_t)(top & 0x3fu); rec[2 * nrec + 1] = (uint8_t)(r - c0); ++nrec; }
+                uint32_t below = 0, below_l = 0;
+                if (depth > 0) { below = stk[depth - 1]; below_l = s_lcp[c0 + (int)(below & 0x3fu)]; }
+                if (popped & 0x40u) {
+                    if (nrec < R) { rec[2 * nrec] = (uint8_t)(popped & 0x3fu); rec[2 * nrec + 1] = (uint8_t)(r - c0); ++nrec; }
                     else resolve_outside(t, r);
-                } else if (top & 0x80u) {
-                    close_interval(t, c0 + (int)(stk[depth - 1] & 0x3fu), r, l);   // not the bottom: something is below
+                } else if (popped & 0x80u) {   // first l-index of [q .. r-1], q = the entry below (not the bottom: it exists)
+                    const int q = c0 + (int)(below & 0x3fu);
+                    ann_doc[t] = r - q;
+                    if (below_l <= l) up_doc[r] = t;      // r < c1 <= n: inside the document
+                    if (l <= below_l) down_doc[q] = t;
                 }
+                top = below; top_l = below_l;
             } else {
                 uint32_t flag = 0;
                 if (r == 0) {
-                    p.ann[base] = n - m;   // easa.py:329; rank 0 is nobody's first l-index and is never popped
+                    ann_doc[0] = n - m;   // easa.py:329; rank 0 is nobody's first l-index and is never popped
                 } else if (depth > 0) {
-                    if (s_lcp[t] == l) p.next[base + t] = r;
+                    if (top_l == l) next_doc[c0 + (int)(top & 0x3fu)] = r;
                     else flag = 0x80u;
                 } else {
                     flag = 0x40u;
                 }
-                stk[depth++] = (uint8_t)((uint32_t)(r - c0) | flag);
+                top = (uint32_t)(r - c0) | flag;
+                top_l = l;
+                stk[depth++] = (uint8_t)top;
                 ++r;
                 if (r < c1) l = s_lcp[r];
             }
