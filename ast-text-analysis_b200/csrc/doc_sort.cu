@@ -207,6 +207,44 @@ __device__ __forceinline__ void ds_rank_by_position(const DocCtx &c, const uint1
     }
 }
 
+// The same for buckets of <= 32 E members by ONE warp without the quadratic count: a bitonic sorting network
+// over E registers per lane (element e = r * 32 + lane; partners 32 or more apart are registers of the same
+// lane, closer ones come by shuffle).  Sorted positions leave as coalesced stores.
+template <int E>
+__device__ __forceinline__ void ds_sort_by_position(const DocCtx &c, const uint16_t *pos, int start, int size, int lane) {
+    uint32_t v[E];
+#pragma unroll
+    for (int r = 0; r < E; ++r) { const int e = r * 32 + lane; v[r] = e < size ? (uint32_t)pos[e] : 0xffffffffu; }
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    if ((r & jr) == 0) {
+                        const bool up = ((r * 32) & k) == 0;
+                        const uint32_t a = v[r], b = v[r | jr];
+                        v[r] = up ? min(a, b) : max(a, b);
+                        v[r | jr] = up ? max(a, b) : min(a, b);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const uint32_t o = __shfl_xor_sync(0xffffffffu, v[r], j);
+                    const bool up = (((r * 32) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    v[r] = (up == lower) ? min(v[r], o) : max(v[r], o);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < E; ++r) { const int e = r * 32 + lane; if (e < size) c.sa_doc[start + e] = c.base + (int32_t)v[r]; }
+}
+
 // symbols the members share beyond `depth` (DS_INF: all members are the same string tail), as seen
 // by this thread's members e = t, t + nthr, ...: compare everybody with member 0
 __device__ __forceinline__ int ds_common_prefix(const DocCtx &c, const uint16_t *pos, int size, int depth, int t, int nthr) {
@@ -249,7 +287,10 @@ __device__ void ds_refine_warp(const DocCtx &c, uint2 entry, int lane, uint8_t *
         else d2 = depth + cp;
     }
     if (terminal) {
-        ds_rank_by_position(c, wpos, start, size, lane, 32);
+        if (size <= 64) ds_sort_by_position<2>(c, wpos, start, size, lane);
+        else if (size <= 128) ds_sort_by_position<4>(c, wpos, start, size, lane);
+        else if (size <= 256) ds_sort_by_position<8>(c, wpos, start, size, lane);
+        else ds_rank_by_position(c, wpos, start, size, lane, 32);
         __syncwarp();
         return;
     }
