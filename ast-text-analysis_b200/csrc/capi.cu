@@ -685,7 +685,19 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
             ++count[key + 1];
         }
         for (size_t i = 1; i < count.size(); ++i) count[i] += count[i - 1];
+        std::vector<uint32_t> first(count.begin(), count.end() - 1);   // first position of every bin
         for (int64_t u = 0; u < n_uniq; ++u) order[count[bin[(size_t)u]]++] = (int32_t)u;
+        // inside a bin: full lexicographic order of the dense codes, so that the lanes of a warp share as
+        // long a prefix (= as much of their control flow and of their loads) as possible
+        auto lex_less = [&](int32_t a, int32_t b2) {
+            const int64_t pa = uniq_rep[(size_t)a], pb = uniq_rep[(size_t)b2];
+            const int64_t la = kp_off[suf_kp[(size_t)pa] + 1] - pa, lb = kp_off[suf_kp[(size_t)pb] + 1] - pb;
+            const int cmp = memcmp(q8.data() + pa, q8.data() + pb, (size_t)std::min(la, lb));
+            return cmp != 0 ? cmp < 0 : la < lb;
+        };
+        if (!get_option("score_bin_order", 0))
+            for (size_t x = 0; x < first.size(); ++x)
+                if (count[x] - first[x] > 1) std::sort(order.begin() + first[x], order.begin() + count[x], lex_less);
     } else {
         for (int64_t u = 0; u < n_uniq; ++u) order[(size_t)u] = (int32_t)u;
     }
