@@ -557,6 +557,7 @@ def test_duplicate_query_suffixes_are_scored_once_and_identically(oracle_mod):
     queries = [" ".join(rng.choice(words, size=int(rng.integers(1, 4)))) for _ in range(60)] + ["ALPHA", "ALPHA", "A"]
     from east import utils
     queries += [utils.prepare_text(k) for k in synth.keyphrases(30)] * 2
+    queries += ["QQQQQ7", "中文A", "A中", "ALPHA" * 8, "0", "ALPH", "ALPHAB"]   # absent symbols, code points >= 0x0A00, long
     codes, off = capi.pack_keyphrases(queries)
     for normalized in (True, False):
         table = idx.score_table(codes, off, normalized)
