@@ -593,3 +593,38 @@ def test_terminator_layout_is_validated_by_the_document_kernel(oracle_mod, sa_pa
             assert np.array_equal(idx.array(d, capi.SUFTAB), o.suftab), (bad.tolist(), d)
             assert np.array_equal(idx.array(d, capi.LCPTAB), o.lcptab), (bad.tolist(), d)
         idx.close()
+
+
+def test_document_sizes_around_the_kernel_limits(oracle_mod, sa_path):
+    # per-document kernel: 16-bit positions (n <= 65535), the fused LCP / child / annotation phases need the
+    # 16-bit LCP copy + pyramid to fit the scratch (n up to ~64.9 k), chunks of ceil(n / 1024) <= 64 ranks per
+    # thread in the stack walk; 65 536 code points and more take the global sort
+    import synth
+    capi = _capi()
+    rng = np.random.default_rng(17)
+    for target in (1023, 1025, 32768, 49000, 58000, 64800, 65535, 65536, 70000):
+        words = ["".join(rng.choice(list("ABCDEFGHIJKLMNOPQRSTUVWXYZ"), size=int(rng.integers(3, 9)))) for _ in range(400)]
+        strings, total = [], 0
+        while total < target:
+            s_ = "".join(rng.choice(words, size=3))
+            if total + len(s_) + 1 > target:
+                s_ = s_[: max(1, target - total - 1)]
+            strings.append(s_)
+            total += len(s_) + 1
+        if total != target:      # the last string was cut to 1 symbol but still overshoots by one: drop a symbol elsewhere
+            strings[0] = strings[0][: len(strings[0]) - (total - target)] or "A"
+        from east.asts import utils as au
+        packed = au.pack_strings_collection(strings)
+        idx = capi.DeviceIndex([packed], [len(strings)])
+        info = idx.info()
+        if sa_path.startswith("doc_sort"):
+            assert info["doc_sorted"] == (packed.size <= 65535), (target, packed.size)
+        _check_arrays(idx, 0, oracle_mod.OracleEASA(text=packed, m=len(strings)), target)
+        idx.close()
+    # thousands of tiny documents in one batch
+    tiny = [au.pack_strings_collection(["".join(rng.choice(list("AB "), size=int(rng.integers(1, 6)))) for _ in range(int(rng.integers(1, 4)))])
+            for _ in range(3000)]
+    tiny_m = [int((p >= 0x0A00).sum()) for p in tiny]
+    idx = capi.DeviceIndex(tiny, tiny_m)
+    for d in (0, 1, 1499, 2999):
+        _check_arrays(idx, d, oracle_mod.OracleEASA(text=tiny[d], m=tiny_m[d]), ("tiny", d))
