@@ -809,6 +809,16 @@ int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const in
     EAST_API_END
 }
 
+int east_score_range_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K, int normalized,
+                         int32_t doc_begin, int32_t doc_count, double *out_dev, void *stream) {
+    EAST_API_BEGIN
+    if (!idx || !kp_dev || !kp_off || !out_dev || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    if (doc_begin < 0 || doc_count <= 0 || doc_begin + doc_count > idx->n_docs) throw Error(EAST_ERR_INVALID, "bad document range");
+    EAST_CUDA(cudaSetDevice(idx->device));
+    score_common(idx, kp_dev, kp_off, K, normalized, out_dev, doc_begin, doc_count, (cudaStream_t)stream, nullptr);
+    EAST_API_END
+}
+
 int east_score_probes_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
                           double *out_DxK_dev, void *stream, int64_t *probes) {
     EAST_API_BEGIN

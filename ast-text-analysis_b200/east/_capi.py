@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "east_free", "east_index_info", "east_index_doc", "east_index_copy", "east_index_devptr",
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
     "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
-    "east_score_probes_dev", "east_index_stat",
+    "east_score_probes_dev", "east_index_stat", "east_score_range_dev",
 ]
 
 _lib = None
@@ -63,6 +63,7 @@ def load():
     L.east_index_devptr.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp)]
     L.east_score_table_host.argtypes = [_vp, _u32p, _i64p, ctypes.c_int32, ctypes.c_int, _f64p]
     L.east_score_table_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, _vp, _vp]
+    L.east_score_range_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
     L.east_score_probes_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, _vp, _vp, _i64p]
     L.east_score_one.argtypes = [_vp, ctypes.c_int32, _u32p, ctypes.c_int32, ctypes.c_int, _f64p, _f64p]
     L.east_cooc_dev.argtypes = [_vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_double, _vp, ctypes.c_int, _vp]
@@ -272,6 +273,13 @@ class DeviceIndex(object):
         kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
         _check(load().east_score_table_dev(self._h, _vp(kp_devptr), _ptr(kp_off, _i64p), len(kp_off) - 1,
                                            1 if normalized else 0, _vp(out_devptr), _vp(stream)))
+        self.score_timings = last_timings()
+
+    def score_range_dev(self, kp_devptr, kp_off, doc_begin, doc_count, out_devptr, normalized=True, stream=0):
+        """Rows of documents [doc_begin, doc_begin + doc_count) into out[doc_count, K] (device)."""
+        kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
+        _check(load().east_score_range_dev(self._h, _vp(kp_devptr), _ptr(kp_off, _i64p), len(kp_off) - 1,
+                                           1 if normalized else 0, int(doc_begin), int(doc_count), _vp(out_devptr), _vp(stream)))
         self.score_timings = last_timings()
 
     def score_probes_dev(self, kp_devptr, kp_off, out_devptr, stream=0):

@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--keyphrases", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--docs-total", type=int, default=100000, help="config4: documents of the whole job (sharded over the GPUs)")
+    ap.add_argument("--gather-tiles", type=int, default=1,
+                    help="config4: 1 = ONE all-gather after scoring (north_star); T > 1 = the table is scored in T document "
+                         "tiles and the all-gather of tile t overlaps the scoring of tile t+1")
     ap.add_argument("--workload", default="table", choices=["table", "single_doc", "config4"],
                     help="table = BASELINE configs[1] (headline); single_doc = configs[2]: SA+LCP+annotation build "
                          "throughput of ONE document of --doc-bytes (use 200000000), replicas only for N>1")
@@ -498,9 +501,19 @@ def run_config4(args):
         dist.init_process_group("nccl", device_id=dev)
     K = args.keyphrases if args.keyphrases != 1000 else 100000
     doc_bytes = args.doc_bytes if args.doc_bytes != 50000 else 10000
-    D = args.docs_total // world   # contiguous document range of this rank
+    D = args.docs_total // world   # documents of this rank
+    tiles = max(1, min(args.gather_tiles, D)) if world > 1 else 1
+    T = (D + tiles - 1) // tiles   # documents per tile
     t0 = time.perf_counter()
-    packed, ms, _ = synth.packed_collection(D, doc_bytes, first_seed=1 + rank * D)
+    # Document ids: with one all-gather rank r owns the contiguous range [r D, (r+1) D); with tiles the table is
+    # tile-major -- tile t holds documents t W T + r T + j -- so that every tile's all-gather output is one contiguous
+    # block AND the gathered table is in global document order.
+    packed, ms = [], []
+    for t in range(tiles):
+        cnt = min(T, D - t * T)
+        first = (rank * D if tiles == 1 else t * world * T + rank * T)
+        p_t, m_t, _ = synth.packed_collection(cnt, doc_bytes, first_seed=1 + first)
+        packed += list(p_t); ms += list(m_t)
     doc_m = np.array(ms, dtype=np.int32)
     doc_off = np.zeros(D + 1, dtype=np.int64)
     np.cumsum([len(p) for p in packed], out=doc_off[1:])
@@ -509,19 +522,37 @@ def run_config4(args):
     kp_codes, kp_off = _capi.pack_keyphrases(kps)
     kp_dev = torch.from_numpy(kp_codes.view(np.int32).copy()).to(dev)
     prep_s = time.perf_counter() - t0
-    out_dev = torch.empty(D * K, dtype=torch.float64, device=dev)
+    out_dev = torch.empty(D * K, dtype=torch.float64, device=dev) if tiles == 1 else None
+    bufs = [torch.empty(T * K, dtype=torch.float64, device=dev) for _ in range(2)] if tiles > 1 else None
     gathered = torch.empty(world * D * K, dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream()
 
     def step():
         idx = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream)
-        idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out_dev)
+        score_ms = 0.0
+        if tiles == 1:
+            idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
+            score_ms = dict(idx.score_timings).get("score", 0.0)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out_dev)
+                torch.cuda.synchronize()
+        else:
+            works, base = [], 0
+            for t in range(tiles):
+                cnt = min(T, D - t * T)
+                buf = bufs[t & 1]
+                if t >= 2:
+                    works[t - 2].wait()     # the collective that read this buffer two tiles ago
+                idx.score_range_dev(kp_dev.data_ptr(), kp_off, t * T, cnt, buf.data_ptr(), True, stream=stream.cuda_stream)
+                score_ms += dict(idx.score_timings).get("score", 0.0)
+                works.append(dist.all_gather_into_tensor(gathered[base: base + world * cnt * K], buf[: cnt * K], async_op=True))
+                base += world * cnt * K
+            for w in works:
+                w.wait()
             torch.cuda.synchronize()
-        t = idx.build_timings + idx.score_timings
+        build_t = dict(idx.build_timings)
         idx.close()
-        return dict(idx.build_timings), dict(t).get("score", 0.0)
+        return dict(idx.build_timings) or build_t, score_ms
 
     for _ in range(args.warmup):
         step()
@@ -542,6 +573,7 @@ def run_config4(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item())
     checksum = float((gathered if world > 1 else out_dev)[:: max(1, D * K // 4096)].sum().item())
+    full_sum = float((gathered if world > 1 else out_dev).sum().item())
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": world * D * K / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -551,8 +583,11 @@ def run_config4(args):
                                    "documents sharded over %d GPU(s), one NCCL all-gather of the [D_r, K] fp64 slices" % (
                                        K, world * D, doc_bytes // 1000, world),
                        "keyphrases": K, "docs_total": world * D, "docs_per_gpu": D, "doc_bytes": doc_bytes,
-                       "table_bytes": world * D * K * 8},
-            "breakdown": {"build_stages_ms": build_t, "score_ms": score_ms, "host_prep_s": prep_s, "checksum_sample": checksum}}))
+                       "table_bytes": world * D * K * 8,
+                       "gather": "one all-gather after scoring" if tiles == 1 else
+                                 "%d document tiles, all-gather of tile t overlaps the scoring of tile t+1" % tiles},
+            "breakdown": {"build_stages_ms": build_t, "score_ms": score_ms, "host_prep_s": prep_s, "checksum_sample": checksum,
+                          "table_sum": full_sum}}))
     if world > 1:
         dist.destroy_process_group()
 

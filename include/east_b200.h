@@ -93,6 +93,11 @@ int east_score_table_host(const east_index *idx, const uint32_t *kp, const int64
                           int32_t K, int normalized, double *out_DxK);
 int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
                          int32_t K, int normalized, double *out_DxK_dev, void *stream);
+/* the rows of documents [doc_begin, doc_begin + doc_count) only: out[(d - doc_begin) * K + k].  Lets a caller
+ * that shards documents over GPUs overlap the collective of one document tile with the scoring of the next. */
+int east_score_range_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
+                         int32_t K, int normalized, int32_t doc_begin, int32_t doc_count,
+                         double *out_dev, void *stream);
 /* same table through an instrumented scorer that also counts the algorithmic bytes it reads:
  * 8 per (SA word, text word) probe; on the fast path 5 per (SA word, text byte)
  * probe and 8 per 2-gram bucket lookup.  *probes receives that byte count. */
