@@ -348,11 +348,11 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         if (!get_option("no_fused_tables", 0)) {
             in.lcp = idx->lcp; in.up = idx->up; in.down = idx->down; in.next = idx->next; in.ann = idx->ann;
         }
+        in.helper_stream = aux_stream(device);
         if (chunks && in.doc_sort) {
             in.n_chunks = (int)chunks->ready.size();
             in.chunk_doc = chunks->doc.data();
             in.chunk_ready = chunks->ready.data();
-            in.helper_stream = aux_stream(device);
         } else if (chunks) {   // the global sort needs the whole text: wait for every copy
             for (auto e : chunks->ready) EAST_CUDA(cudaStreamWaitEvent(s, e, 0));
         }

@@ -1014,6 +1014,25 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     // validates the terminator layout of its document itself.  Whatever it cannot take (bad layout, a
     // bucket too large, an alphabet too wide) is redone below with the validating scan.
     const bool light = !scanned && allow_doc_sort && in.light_scan && !in.force_general && max_doc_n <= 65535;
+    // The per-document kernel stores the child table and the annotation sparsely into zero-filled arrays.  The
+    // four fills (16 bytes per code point) run on the helper stream from the start, under the text scan, the
+    // host's alphabet round trip and the encoding, instead of in front of the kernel.
+    cudaEvent_t tables_zeroed = nullptr;
+    if (!scanned && allow_doc_sort && in.lcp != nullptr && in.helper_stream != nullptr && in.helper_stream != s &&
+        max_doc_n <= 65535 && !in.force_general) {
+        cudaEvent_t fork;
+        EAST_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        EAST_CUDA(cudaEventRecord(fork, s));                       // the arrays were allocated on s
+        EAST_CUDA(cudaStreamWaitEvent(in.helper_stream, fork, 0));
+        EAST_CUDA(cudaEventDestroy(fork));
+        EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, in.helper_stream));
+        EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, in.helper_stream));
+        EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, in.helper_stream));
+        EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, in.helper_stream));
+        EAST_CUDA(cudaEventCreateWithFlags(&tables_zeroed, cudaEventDisableTiming));
+        EAST_CUDA(cudaEventRecord(tables_zeroed, in.helper_stream));
+    }
+    struct EventGuard { cudaEvent_t &e; ~EventGuard() { if (e) cudaEventDestroy(e); } } zero_guard{tables_zeroed};
     if (!scanned) {
         tm.mark("scan_text");
         EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
@@ -1108,7 +1127,9 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             }
             DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
             const bool fuse = in.lcp != nullptr && plan.tables_fit;
-            if (fuse) {
+            if (fuse && tables_zeroed) {
+                EAST_CUDA(cudaStreamWaitEvent(s, tables_zeroed, 0));
+            } else if (fuse) {
                 EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, s));
                 EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, s));
                 EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
@@ -1144,6 +1165,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             out.sym_bits = 0;
         }
     }
+    // whatever follows (the global sort and its table kernels) is ordered after the early zero-fills
+    if (tables_zeroed) EAST_CUDA(cudaStreamWaitEvent(s, tables_zeroed, 0));
     if (light) {
         // the global sort relies on the validated layout: start over with the full scan
         SaInput again = in;
