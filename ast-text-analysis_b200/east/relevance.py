@@ -17,6 +17,30 @@ from east.asts import easa
 from east.asts import utils as asts_utils
 
 
+SMALL_DOCUMENT_LIMIT = 65535   # code points: the per-document shared-memory kernel (csrc/doc_sort.cu) takes these
+MAX_BATCH_CODE_POINTS = 1 << 29   # one device index addresses < 2^30 code points (int32 ranks)
+
+
+def plan_batches(sizes, small_limit=SMALL_DOCUMENT_LIMIT, max_batch=MAX_BATCH_CODE_POINTS):
+    """Split a collection into device batches: documents the per-document kernel can take are kept apart from
+    larger ones (one large text would otherwise send the whole batch to the global sort), and no batch exceeds
+    what one index addresses.  Returns lists of document numbers, original order kept inside a batch."""
+    batches = []
+    for wanted_small in (True, False):
+        cur, cur_size = [], 0
+        for j, size in enumerate(sizes):
+            if (size <= small_limit) != wanted_small:
+                continue
+            if cur and cur_size + size > max_batch:
+                batches.append(cur)
+                cur, cur_size = [], 0
+            cur.append(j)
+            cur_size += size
+        if cur:
+            batches.append(cur)
+    return batches
+
+
 class RelevanceMeasure(object):
 
     def set_text_collection(self, texts, language=consts.Language.ENGLISH):
@@ -35,6 +59,7 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         self.device = device
         self.asts = []
         self._index = None
+        self._batches = []
 
     def set_text_collection(self, texts, language=consts.Language.ENGLISH):
         """relevance.py:34-49: one AST per text; here all of them in one batched build."""
@@ -42,6 +67,7 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         self.language = language
         self.asts = []
         self._index = None
+        self._batches = []
         total_texts = len(texts)
         if self.ast_algorithm not in tuple(consts.ASTAlgorithm):
             # other registered engines (none ship in this package) go through the registry
@@ -55,9 +81,13 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         if not collections:
             return
         packed = [asts_utils.pack_strings_collection(c) for c in collections]
-        self._index = _capi.DeviceIndex(packed, [len(c) for c in collections], device=self.device)
-        self.asts = [easa.EnhancedAnnotatedSuffixArray(c, _index=self._index, _doc=j)
-                     for j, c in enumerate(collections)]
+        self.asts = [None] * len(collections)
+        for docs in plan_batches([len(p) for p in packed]):
+            index = _capi.DeviceIndex([packed[j] for j in docs], [len(collections[j]) for j in docs], device=self.device)
+            self._batches.append((index, docs))
+            for local, j in enumerate(docs):
+                self.asts[j] = easa.EnhancedAnnotatedSuffixArray(collections[j], _index=index, _doc=local)
+        self._index = self._batches[0][0]
 
     def relevance(self, keyphrase, text, synonimizer=None):
         return self.asts[text].score(keyphrase, normalized=self.normalized, synonimizer=synonimizer)
@@ -68,4 +98,9 @@ class ASTRelevanceMeasure(RelevanceMeasure):
             return np.array([[ast.score(kp, normalized=self.normalized) for kp in prepared_keyphrases]
                              for ast in self.asts], dtype=np.float64)
         codes, off = _capi.pack_keyphrases(prepared_keyphrases)
-        return self._index.score_table(codes, off, normalized=self.normalized)
+        if len(self._batches) == 1:
+            return self._index.score_table(codes, off, normalized=self.normalized)
+        table = np.empty((len(self.asts), len(prepared_keyphrases)), dtype=np.float64)
+        for index, docs in self._batches:
+            table[docs] = index.score_table(codes, off, normalized=self.normalized)
+        return table

@@ -628,3 +628,27 @@ def test_document_sizes_around_the_kernel_limits(oracle_mod, sa_path):
     idx = capi.DeviceIndex(tiny, tiny_m)
     for d in (0, 1, 1499, 2999):
         _check_arrays(idx, d, oracle_mod.OracleEASA(text=tiny[d], m=tiny_m[d]), ("tiny", d))
+
+
+def test_collections_mixing_small_and_large_documents(oracle_mod, sa_path):
+    # east.relevance splits a collection into device batches: documents the per-document kernel takes, and larger ones
+    from east import applications, relevance, utils
+    import synth
+    docs = synth.documents(5, 3000, first_seed=300)
+    docs.insert(2, synth.documents(1, 90000, first_seed=400)[0])   # ~82 k code points: global sort
+    texts = {"t%d" % i: d for i, d in enumerate(docs)}
+    kps = synth.keyphrases(12)
+    measure = relevance.ASTRelevanceMeasure("easa", True)
+    table = applications.keyphrases_table(kps, texts, measure)
+    assert len(measure._batches) == 2
+    assert measure._batches[0][0].info()["doc_sorted"] == sa_path.startswith("doc_sort")
+    assert not measure._batches[1][0].info()["doc_sorted"]
+    names = list(texts.keys())
+    for i, name in enumerate(names):
+        o = oracle_mod.OracleEASA(utils.text_to_strings_collection(texts[name]))
+        for kp in kps:
+            q = utils.prepare_text(kp).replace(" ", "")
+            from east.asts.utils import codepoints
+            codes = np.ascontiguousarray(codepoints(q), dtype=np.uint32)
+            exp = o.score_many(codes, np.array([0, len(codes)], dtype=np.int64), True)[0]
+            assert float(table[kp][name]).hex() == float(exp).hex(), (name, kp)

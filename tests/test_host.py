@@ -113,3 +113,14 @@ def test_synthetic_generator_is_deterministic():
     col = utils.text_to_strings_collection(d1)
     n = sum(len(s) for s in col) + len(col)
     assert 0.85 < n / 10000.0 < 0.97  # n ~ 0.911 x bytes
+
+
+def test_plan_batches_separates_large_documents_and_bounds_the_batch():
+    from east.relevance import plan_batches
+    sizes = [100, 70000, 200, 300, 65535, 65536, 50]
+    assert plan_batches(sizes) == [[0, 2, 3, 4, 6], [1, 5]]
+    assert plan_batches([10, 20, 30, 40], small_limit=100, max_batch=50) == [[0, 1], [2], [3]]
+    assert plan_batches([500, 10, 500], small_limit=100, max_batch=600) == [[1], [0], [2]]
+    assert plan_batches([]) == []
+    flat = sorted(j for b in plan_batches(list(range(1, 200)), small_limit=50, max_batch=300) for j in b)
+    assert flat == list(range(199))
