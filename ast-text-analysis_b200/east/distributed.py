@@ -84,9 +84,13 @@ def relevance_table_sharded(texts, prepared_keyphrases, normalized=True, device=
     if end > begin:
         cols = [utils.text_to_strings_collection(t) for t in texts[begin:end]]
         packed = [asts_utils.pack_strings_collection(c) for c in cols]
-        index = _capi.DeviceIndex(packed, [len(c) for c in cols], device=device)
-        local = torch.from_numpy(index.score_table(codes, off, normalized)).to("cuda:%d" % device)
-        index.close()
+        from east.relevance import plan_batches
+        table = np.empty((len(cols), K), dtype=np.float64)
+        for docs in plan_batches([len(p) for p in packed]):   # small documents apart from large ones, bounded batches
+            index = _capi.DeviceIndex([packed[j] for j in docs], [len(cols[j]) for j in docs], device=device)
+            table[docs] = index.score_table(codes, off, normalized)
+            index.close()
+        local = torch.from_numpy(table).to("cuda:%d" % device)
     else:
         local = torch.zeros((0, K), dtype=torch.float64, device="cuda:%d" % device)
     return gather_score_slices(local, ranges, group)
