@@ -1,9 +1,10 @@
-// doc_sort.cu -- suffix array of every SMALL document by one CTA that keeps the document in
-// shared memory (B200: 227 KB per CTA hold the text, the bucket counters and the sort scratch).
+// doc_sort.cu -- suffix array, LCP, child table and annotation of every SMALL document by one CTA that keeps
+// the document in shared memory (B200: 227 KB per CTA hold the text, the bucket counters and the scratch).
 //
-// Replaces east/asts/easa.py:141-245 (_compute_suftab) for batches whose documents have at most
-// 65 535 code points each (BASELINE configs 1, 2, 4, 5: 10-50 KB texts) on the terminator-class
-// fast path.  Larger documents keep the global prefix-doubling sort of sa_build.cu.
+// Replaces east/asts/easa.py:141-331 (_compute_suftab, _compute_lcptab, _compute_childtab,
+// _compute_childtab_next_l_index, _compute_anntab) for batches whose documents have at most 65 535 code
+// points each (BASELINE configs 1, 2, 4, 5: 10-50 KB texts) on the terminator-class fast path.  Larger
+// documents keep the global prefix-doubling sort of sa_build.cu and the table kernels of tables.cu.
 //
 // Order being computed (equal to the code point order of the reference because dense codes are
 // monotone and every terminator 0x0A00+i sorts above all text): compare symbol by symbol, all
@@ -11,23 +12,28 @@
 // terminator differ only in WHICH terminator they reach = string index = text position.
 //
 // Phases of one CTA (document of n code points, b bits per symbol, G = symbols per bucket id):
-//   1  stage the byte-coded text in shared memory (128-bit loads)
+//   1  stage the byte-coded text in shared memory (128-bit loads); the suffixes that ARE a terminator form
+//      the last bucket and are placed at once (rank = string index); the terminator layout the later phases
+//      rely on is validated here (a bad one raises flag bit 1: the host takes the general path)
 //   2  histogram of the G-gram bucket ids (window cut after the first terminator): packed 16-bit
-//      shared-memory counters
-//   3  exclusive scan -> bucket starts; bitmap of the ranks where a bucket starts; work list of the
-//      buckets larger than a warp; the scorer's 2-gram table (first rank of every 2-gram)
+//      shared-memory counters, 8 consecutive suffixes per 16-byte window
+//   3  warp-cooperative exclusive scan -> bucket starts; bitmap of the ranks where a bucket starts; work
+//      list of the buckets larger than a warp; the scorer's 2-gram and 3-gram tables (first ranks)
 //   4  scatter every suffix into its bucket (shared-memory cursor atomics, 4-byte global stores
-//      that stay in L2); the bucket of the bare terminators is final at once (rank = string index)
-//   5  refine the buckets of more than 32 suffixes, level by level, by groups of 4 warps: skip the
-//      prefix all members share (SWAR compare against the first member), counting-sort the members
-//      on the next S2 symbols in shared memory, mark the new bucket starts, queue what is still
-//      larger than a warp; a bucket whose members are identical up to their terminator is ranked by
-//      position
-//   6  buckets of <= 32 suffixes: one warp per window of 32 ranks ranks every suffix inside its own
-//      bucket by counting the smaller ones; keys are the next 8 symbols (raw bytes, byte-reversed),
-//      ties go to a byte-wise SWAR comparison of the shared-memory text.
-// A bucket of more than 4096 suffixes raises the overflow flag: the host redoes the batch with the
-// global sort.
+//      that stay in L2)
+//   5  refine the buckets of more than 32 suffixes level by level: a warp takes a bucket (<= 1024; larger
+//      ones a group of 4 warps) from a shared work counter, skips the prefix all members share (SWAR compare
+//      against the first member), counting-sorts the members on the first symbol that differs, marks the new
+//      bucket starts and queues what is still larger than a warp; a bucket whose members are identical up to
+//      their terminator is sorted by position (register bitonic network)
+//   6  buckets of <= 32 suffixes: a warp takes a window of 32 ranks and every suffix ranks itself inside its
+//      own bucket by counting the smaller members; keys are the next 8 symbols (raw bytes, byte-reversed),
+//      ties go to a byte-wise SWAR comparison of the shared-memory text (or to the position)
+//   7  LCP of neighbouring suffixes (SWAR on the staged text), 16-bit copy + min-pyramid in the freed scratch,
+//      per-rank key bytes for the scorer
+//   8  child table and annotation: per-thread chunks walked with the reference's stack discipline, what lies
+//      outside a chunk searched in the pyramid (farthest first, so that the lanes' long searches coincide).
+// A bucket of more than 4096 suffixes raises flag bit 0: the host redoes the batch with the global sort.
 #include "sa_build.h"
 
 namespace east {
