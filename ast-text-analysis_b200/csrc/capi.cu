@@ -726,7 +726,8 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
     EAST_CUDA(cudaMemcpyAsync(c->d_uniq_of.p, uniq_of.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
     EAST_CUDA(cudaMemcpyAsync(c->d_recs.p, recs.data(), sizeof(SufRec) * (size_t)n_uniq, cudaMemcpyHostToDevice, s));
     if (fast) {
-        c->d_q8 = DevBuf<uint8_t>((size_t)total, s);
+        c->d_q8 = DevBuf<uint8_t>((size_t)total + 16, s);   // the scorer reads the queries 8 bytes at a time
+        EAST_CUDA(cudaMemsetAsync(c->d_q8.p + total, 0, 16, s));
         EAST_CUDA(cudaMemcpyAsync(c->d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));
     }
     EAST_CUDA(cudaStreamSynchronize(s));   // the host staging vectors end here

@@ -21,6 +21,16 @@ namespace east {
 constexpr int SC_THREADS = 128;
 
 
+// 8 bytes at an arbitrary global address (two aligned 64-bit loads + funnel shift; the buffers carry slack)
+__device__ __forceinline__ uint64_t load8u(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint64_t *q = (const uint64_t *)(a & ~(uintptr_t)7);
+    const int sh = (int)(a & 7) * 8;
+    const uint64_t lo = q[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (q[1] << (64 - sh));
+}
+
 // character of suffix rank r at depth d as a comparable value: 0 = "no character" (sorts first)
 __device__ __forceinline__ uint64_t sym_at_(const uint32_t *__restrict__ T, const int32_t *__restrict__ sa,
                                            int32_t r, int32_t d, int32_t end) {
@@ -152,6 +162,19 @@ __device__ __forceinline__ double score_one_suffix_fast(const uint8_t *__restric
                 if (c == 0) break;
                 int32_t nl, nh;
                 if (lo == hi) {
+                    if (!PROBES) {
+                        // One suffix left: every further depth keeps the interval (no new node, frac unchanged), so
+                        // the rest of the walk is the length of the common prefix of the query and that suffix --
+                        // one SA load and 8 symbols per step instead of one probe per depth.
+                        const uint8_t *tp = T8 + sa[lo];
+                        while (d < len) {
+                            const uint64_t diff = load8u(tp + d) ^ load8u(q + d);
+                            const int same = diff ? ((__ffsll((long long)diff) - 1) >> 3) : 8;
+                            d += min(same, len - d);
+                            if (same < 8) break;
+                        }
+                        break;
+                    }
                     if (SYM8(lo, d) != c) break;
                     nl = lo; nh = hi;
                 } else {
