@@ -58,6 +58,14 @@ def parse_args():
     return ap.parse_args()
 
 
+def apply_env_options(_capi):
+    """Tuning experiments: EAST_BENCH_OPTS="name=value,..." sets library options (east_set_option)."""
+    for kv in os.environ.get("EAST_BENCH_OPTS", "").split(","):
+        if "=" in kv:
+            name, value = kv.split("=")
+            _capi.set_option(name, int(value))
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -251,10 +259,7 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     debug = bool(os.environ.get("EAST_BENCH_DEBUG"))
-    for kv in os.environ.get("EAST_BENCH_OPTS", "").split(","):   # tuning experiments: "name=value,..."
-        if "=" in kv:
-            name, value = kv.split("=")
-            _capi.set_option(name, int(value))
+    apply_env_options(_capi)
 
     def step_device():
         ta = time.perf_counter()
@@ -436,6 +441,7 @@ def run_single_doc(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     rank = int(os.environ.get("RANK", "0"))
     torch.cuda.set_device(local_rank)
+    apply_env_options(_capi)
     packed, m, text_bytes, _ = synth.packed_big_document(args.doc_bytes, seed=3 + rank)
     n = int(packed.size)
     doc_off = np.array([0, n], dtype=np.int64)
@@ -499,6 +505,7 @@ def run_config4(args):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join("/tmp", "nccl_%h_%p.log"))
         dist.init_process_group("nccl", device_id=dev)
+    apply_env_options(_capi)
     K = args.keyphrases if args.keyphrases != 1000 else 100000
     doc_bytes = args.doc_bytes if args.doc_bytes != 50000 else 10000
     D = args.docs_total // world   # documents of this rank
