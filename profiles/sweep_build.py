@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Tuning sweep on the bench workload (1000 docs x 50 KB): radix-sort kernel shape (rs_variant) and
-round-0 window (key_chars).  Prints per-stage device ms (CUDA events) of the best of 3 builds.
+"""Tuning sweep of the GLOBAL prefix-doubling sort (option no_doc_sort = 1) on the bench workload
+(1000 docs x 50 KB): radix-sort kernel shape (rs_variant) and round-0 window (key_chars).  Prints per-stage device ms (CUDA events) of the best of 3 builds.
 usage (GPU box): python profiles/sweep_build.py [--docs 1000] [--doc-bytes 50000]"""
 import argparse, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,6 +20,7 @@ packed, ms, _ = synth.packed_collection(a.docs, a.doc_bytes)
 doc_off = np.zeros(a.docs + 1, dtype=np.int64); np.cumsum([len(p) for p in packed], out=doc_off[1:])
 doc_m = np.array(ms, dtype=np.int32)
 dev = torch.from_numpy(np.concatenate(packed).view(np.int32)).cuda()
+_capi.set_option("no_doc_sort", 1)
 for _ in range(3):
     _capi.DeviceIndex.build_dev(dev.data_ptr(), doc_off, doc_m).close()
 import itertools
