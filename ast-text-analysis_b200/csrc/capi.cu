@@ -37,10 +37,17 @@ void ktime_begin(const char *name, cudaStream_t s) {
 }
 void ktime_end(cudaStream_t s) { EAST_CUDA(cudaEventRecord(g_pending.back().b, s)); }
 void ktime_collect() {
+    // EAST_DEBUG_TIMELINE (with option time_kernels): start offset of every launch from the first one collected
+    static const bool timeline = getenv("EAST_DEBUG_TIMELINE") != nullptr;
     std::vector<PendingLaunch> still;
     for (auto &p : g_pending) {
         float ms = 0.f;
         cudaError_t e = cudaEventElapsedTime(&ms, p.a, p.b);
+        if (timeline && e == cudaSuccess) {
+            float off = 0.f;
+            if (cudaEventElapsedTime(&off, g_pending.front().a, p.a) != cudaSuccess) cudaGetLastError();
+            fprintf(stderr, "[east] timeline %8.3f ms  +%7.3f ms  %s\n", off, ms, p.name.c_str());
+        }
         if (e == cudaErrorNotReady) {  // launched on the auxiliary stream and not finished yet: keep for later
             cudaGetLastError();
             still.push_back(p);
@@ -172,6 +179,21 @@ static cudaStream_t aux_stream(int device) {
     return st;
 }
 
+// per-device high-priority stream: small preparatory kernels of the pipelined build
+static cudaStream_t prep_stream(int device) {
+    static std::mutex m;
+    static std::map<int, cudaStream_t> streams;
+    std::lock_guard<std::mutex> g(m);
+    auto it = streams.find(device);
+    if (it != streams.end()) return it->second;
+    int least = 0, greatest = 0;
+    EAST_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    cudaStream_t st;
+    EAST_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest));
+    streams[device] = st;
+    return st;
+}
+
 // per-device copy stream of the pipelined host build
 static cudaStream_t copy_stream(int device) {
     static std::mutex m;
@@ -288,8 +310,18 @@ struct ChunkPlan {   // pipelined host build: runs of whole documents and the ev
     ~ChunkPlan() { for (auto e : ready) cudaEventDestroy(e); }
 };
 
+// what east_table_host hangs on the pipelined build: a hook called after every run of documents, and where
+// to publish the index under construction (its text / suffix-array / offset pointers are final from the start)
+struct RunHook {
+    void (*begin)(void *ctx, const RunReady &run, DocScore &score) = nullptr;
+    void (*fn)(void *ctx, const RunReady &run, int in_kernel) = nullptr;
+    void *ctx = nullptr;
+    const east_index **building = nullptr;
+};
+
 static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t *doc_off, const int32_t *doc_m,
-                        int32_t n_docs, int device, cudaStream_t s, east_index **out, const ChunkPlan *chunks = nullptr) {
+                        int32_t n_docs, int device, cudaStream_t s, east_index **out, const ChunkPlan *chunks = nullptr,
+                        const RunHook *hook = nullptr) {
     std::unique_ptr<east_index, void (*)(east_index *)> idx(new east_index(), free_index);
     // pipelined build: whatever happens, the copy stream must be done with the text before the index
     // (declared above, destroyed after this guard) can free it
@@ -349,6 +381,11 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
             in.lcp = idx->lcp; in.up = idx->up; in.down = idx->down; in.next = idx->next; in.ann = idx->ann;
         }
         in.helper_stream = aux_stream(device);
+        if (!get_option("no_prep_stream", 0)) in.prep_stream = prep_stream(device);
+        if (hook && hook->fn) {
+            in.run_begin = hook->begin; in.run_hook = hook->fn; in.run_ctx = hook->ctx;
+            if (hook->building) *hook->building = idx.get();
+        }
         if (chunks && in.doc_sort) {
             in.n_chunks = (int)chunks->ready.size();
             in.chunk_doc = chunks->doc.data();
@@ -417,9 +454,8 @@ static void check_build_args(const void *text, const int64_t *doc_off, const int
     if (doc_off[n_docs] >= (1ll << 30)) throw Error(EAST_ERR_RANGE, "more than 2^30 code points in one index; split the batch");
 }
 
-int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
-                    int device, east_index **out) {
-    EAST_API_BEGIN
+static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                            int device, east_index **out, const RunHook *hook) {
     static const bool debug = getenv("EAST_DEBUG_TIMING") != nullptr;
     if (debug) fprintf(stderr, "[east] host %.3f ms  east_build_host enter\n", host_now_ms());
     check_build_args(text, doc_off, doc_m, n_docs, out);
@@ -471,9 +507,15 @@ int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t 
             throw;
         }
         if (debug) fprintf(stderr, "[east] host %.3f ms  copies queued\n", host_now_ms());
-        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, &plan);
+        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, &plan, hook);
         if (debug) fprintf(stderr, "[east] host %.3f ms  build_common done\n", host_now_ms());
     }
+}
+
+int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                    int device, east_index **out) {
+    EAST_API_BEGIN
+    build_host_impl(text, doc_off, doc_m, n_docs, device, out, nullptr);
     EAST_API_END
 }
 
@@ -578,12 +620,18 @@ struct KpPrepared {
 };
 static thread_local std::unique_ptr<KpPrepared> g_kp_cache;
 
+static void check_keyphrases(const int64_t *kp_off, int32_t K) {
+    if (kp_off[K] >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "keyphrase buffer too large");
+    for (int32_t k = 0; k < K; ++k) {
+        if (kp_off[k + 1] <= kp_off[k]) throw Error(EAST_ERR_ZERODIV, "empty query: float division by zero");
+        if (kp_off[k + 1] - kp_off[k] > 0xffff) throw Error(EAST_ERR_RANGE, "keyphrase longer than 65535 code points");
+    }
+}
+
 static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_dev, const uint32_t *kp_host_in,
                                       const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s) {
     const int64_t total = kp_off[K];
-    if (total >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "keyphrase buffer too large");
-    for (int32_t k = 0; k < K; ++k)
-        if (kp_off[k + 1] <= kp_off[k]) throw Error(EAST_ERR_ZERODIV, "empty query: float division by zero");
+    check_keyphrases(kp_off, K);
     std::vector<uint32_t> kp_host((size_t)total);
     if (kp_host_in) {   // the caller's host copy (east_score_table_host): no round trip through the device
         std::copy(kp_host_in, kp_host_in + total, kp_host.begin());
@@ -739,6 +787,36 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
     return c;
 }
 
+// The launches that score documents [doc_begin, doc_begin + doc_count) of `idx` (tile_docs at a time through the
+// scratch tmp[tile_docs][n_uniq]) into out_dev[(d - doc_begin) * K + k]; nothing here waits for the device.
+static void score_enqueue(const east_index *idx, const KpPrepared *kp, const uint32_t *kp_dev, int64_t total, int32_t K,
+                          int normalized, double *out_dev, int32_t doc_begin, int32_t doc_count, cudaStream_t s,
+                          double *tmp, int32_t tile_docs, unsigned long long *probe_count) {
+    ScoreInput in;
+    in.text = idx->text; in.sa = idx->sa;
+    in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
+    in.kp = kp_dev; in.kp_off = kp->d_off.p; in.K = K; in.total_suffixes = (int32_t)total;
+    in.uniq_of = kp->d_uniq_of.p; in.recs = kp->d_recs.p; in.n_uniq = (int32_t)kp->n_uniq;
+    in.normalized = normalized ? 1 : 0;
+    if (kp->fast) {
+        in.t8 = idx->t8; in.sk = idx->sk; in.q8 = kp->d_q8.p; in.sym_bits = idx->sym_bits;
+        in.bkt = idx->bkt + ((size_t)doc_begin << (2 * idx->sym_bits));
+        if (idx->bkt3 && !get_option("score_no_bkt3", 0)) in.bkt3 = idx->bkt3 + ((size_t)doc_begin << (3 * idx->sym_bits));
+    }
+    in.algorithmic_bytes = (double)get_option("score_bytes", 0);
+    in.probe_count = probe_count;
+    for (int32_t d0 = 0; d0 < doc_count; d0 += tile_docs) {
+        ScoreInput part = in;
+        part.n_docs = std::min(tile_docs, doc_count - d0);
+        part.doc_off = in.doc_off + d0;
+        part.doc_m = in.doc_m + d0;
+        if (in.bkt) part.bkt = in.bkt + ((size_t)d0 << (2 * in.sym_bits));
+        if (in.bkt3) part.bkt3 = in.bkt3 + ((size_t)d0 << (3 * in.sym_bits));
+        part.algorithmic_bytes = in.algorithmic_bytes * ((double)part.n_docs / (double)doc_count);
+        score_table(part, tmp, out_dev + (size_t)d0 * K, s);
+    }
+}
+
 static void score_common(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K,
                          int normalized, double *out_dev, int32_t doc_begin, int32_t doc_count, cudaStream_t s,
                          double *suffix_out_dev /* optional: per-suffix results of the doc range */,
@@ -760,36 +838,14 @@ static void score_common(const east_index *idx, const uint32_t *kp_dev, const in
         tmp_own = DevBuf<double>((size_t)tile_docs * (size_t)n_uniq, s);
         tmp = tmp_own.p;
     }
-    ScoreInput in;
-    in.text = idx->text; in.sa = idx->sa;
-    in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
-    in.kp = kp_dev; in.kp_off = kp->d_off.p; in.K = K; in.total_suffixes = (int32_t)total;
-    in.uniq_of = kp->d_uniq_of.p; in.recs = kp->d_recs.p; in.n_uniq = (int32_t)n_uniq;
-    in.normalized = normalized ? 1 : 0;
-    if (kp->fast) {
-        in.t8 = idx->t8; in.sk = idx->sk; in.q8 = kp->d_q8.p; in.sym_bits = idx->sym_bits;
-        in.bkt = idx->bkt + ((size_t)doc_begin << (2 * idx->sym_bits));
-        if (idx->bkt3 && !get_option("score_no_bkt3", 0)) in.bkt3 = idx->bkt3 + ((size_t)doc_begin << (3 * idx->sym_bits));
-    }
-    in.algorithmic_bytes = (double)get_option("score_bytes", 0);
     DevBuf<unsigned long long> d_probes;
     if (probes_out) {
         d_probes = DevBuf<unsigned long long>(1, s);
         EAST_CUDA(cudaMemsetAsync(d_probes.p, 0, sizeof(unsigned long long), s));
-        in.probe_count = d_probes.p;
     }
     StageTimer tm(s);
     tm.mark("score");
-    for (int32_t d0 = 0; d0 < doc_count; d0 += tile_docs) {
-        ScoreInput part = in;
-        part.n_docs = std::min(tile_docs, doc_count - d0);
-        part.doc_off = in.doc_off + d0;
-        part.doc_m = in.doc_m + d0;
-        if (in.bkt) part.bkt = in.bkt + ((size_t)d0 << (2 * in.sym_bits));
-        if (in.bkt3) part.bkt3 = in.bkt3 + ((size_t)d0 << (3 * in.sym_bits));
-        part.algorithmic_bytes = in.algorithmic_bytes * ((double)part.n_docs / (double)doc_count);
-        score_table(part, tmp, out_dev + (size_t)d0 * K, s);
-    }
+    score_enqueue(idx, kp, kp_dev, total, K, normalized, out_dev, doc_begin, doc_count, s, tmp, tile_docs, d_probes.p);
     tm.finish();
     if (probes_out) {
         unsigned long long h = 0;
@@ -840,6 +896,158 @@ int east_score_table_host(const east_index *idx, const uint32_t *kp, const int64
     EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, s));
     score_common(idx, d_kp.p, kp_off, K, normalized, d_out.p, 0, idx->n_docs, s, nullptr, nullptr, kp);
     EAST_CUDA(cudaMemcpy(out_DxK, d_out.p, sizeof(double) * (size_t)idx->n_docs * K, cudaMemcpyDeviceToHost));
+    EAST_API_END
+}
+
+// ---- build + score in one call ------------------------------------------------------------
+// applications.keyphrases_table (applications.py:43-52) builds the structure of a text and scores every
+// keyphrase against it, text after text.  Here: while the pipelined host build is still receiving the
+// later runs of documents, the runs that are already sorted are scored on the stream that sorted them
+// and their rows of the table go back to the host -- copy-in, sort, score and copy-out overlap.
+struct TableRun {
+    const east_index *building = nullptr;
+    const uint32_t *kp_host = nullptr, *d_kp = nullptr;
+    const int64_t *kp_off = nullptr;
+    int32_t K = 0;
+    int normalized = 0;
+    double *d_out = nullptr, *host_out = nullptr;   // host_out NULL: the table stays on the device
+    KpPrepared *kp = nullptr;
+    east_index view;                 // non-owning: the pointers of the index under construction + the run's tables
+    cudaStream_t lane[2] = {nullptr, nullptr};
+    bool lane_used[2] = {false, false};
+    DevBuf<double> tmp[2];           // per-stream scratch of the scorer: [documents of a run][distinct suffixes]
+    int64_t tmp_docs[2] = {0, 0};
+    int32_t docs_scored = 0;         // of the current pass over the batch (a pass starts with document 0)
+    int final_pass = 0;              // the last pass was not speculative
+    bool failed = false;
+};
+
+static int table_lane(TableRun &t, cudaStream_t s) {
+    for (int i = 0; i < 2; ++i)
+        if (t.lane_used[i] && t.lane[i] == s) return i;
+    for (int i = 0; i < 2; ++i)
+        if (!t.lane_used[i]) { t.lane_used[i] = true; t.lane[i] = s; return i; }
+    throw Error(EAST_ERR_INVALID, "the build used more than two streams");
+}
+
+// before the per-document kernel of a run is launched: have it score the run itself when the scratch fits
+static void table_run_begin(void *vctx, const RunReady &r, DocScore &score) {
+    TableRun &t = *static_cast<TableRun *>(vctx);
+    try {
+        if (r.doc_begin == 0) {   // a new pass over the batch (the first, or the ordinary build after a failed speculation)
+            t.failed = false;
+            t.docs_scored = 0;
+            t.final_pass = r.speculative ? 0 : 1;
+            const east_index *b = t.building;
+            east_index &v = t.view;
+            v.device = b->device; v.n_docs = b->n_docs; v.n = b->n;
+            v.text = b->text; v.sa = b->sa; v.sk = b->sk; v.d_doc_off = b->d_doc_off; v.d_doc_m = b->d_doc_m;
+            v.t8 = const_cast<uint8_t *>(r.t8);
+            v.bkt = const_cast<uint32_t *>(r.bkt);
+            v.bkt3 = const_cast<uint32_t *>(r.bkt3);
+            v.sym_bits = r.sym_bits;
+            v.code_table = *r.code_table;
+            t.kp = prepare_keyphrases(&v, t.d_kp, t.kp_host, t.kp_off, t.K, !get_option("score_no_dedup", 0), r.stream);
+        }
+        if (t.failed || !t.kp) return;
+        const int li = table_lane(t, r.stream);
+        const int64_t n_uniq = std::max<int64_t>(1, t.kp->n_uniq);
+        const int64_t budget = get_option("score_tmp_doubles", (int64_t)1 << 27);
+        const bool in_kernel = t.kp->fast && (int64_t)r.doc_count * n_uniq <= budget && !get_option("no_fused_score", 0);
+        const int64_t want = in_kernel ? r.doc_count : std::max<int64_t>(1, std::min<int64_t>(r.doc_count, budget / n_uniq));
+        if (t.tmp_docs[li] < want) {
+            t.tmp[li] = DevBuf<double>((size_t)want * (size_t)n_uniq, r.stream);
+            t.tmp_docs[li] = want;
+        }
+        if (in_kernel) {
+            score.recs = t.kp->d_recs.p; score.n_uniq = (int32_t)t.kp->n_uniq; score.q8 = t.kp->d_q8.p; score.kp = t.d_kp;
+            score.tmp = t.tmp[li].p; score.normalized = t.normalized ? 1 : 0;
+            score.kp_off = t.kp->d_off.p; score.uniq_of = t.kp->d_uniq_of.p; score.K = t.K;
+            score.out = t.d_out + (size_t)r.doc_begin * t.K;
+            score.algorithmic_bytes = (double)get_option("score_bytes", 0) * ((double)r.doc_count / (double)t.view.n_docs);
+        }
+    } catch (...) {
+        t.failed = true;   // the ordinary score call after the build reports whatever this was
+    }
+}
+
+// after the launch: the batched scorer if the kernel did not score the run itself, and the rows of the table on
+// their way to the host
+static void table_run_done(void *vctx, const RunReady &r, int in_kernel) {
+    TableRun &t = *static_cast<TableRun *>(vctx);
+    if (t.failed || !t.kp) return;
+    try {
+        const int li = table_lane(t, r.stream);
+        double *rows = t.d_out + (size_t)r.doc_begin * t.K;
+        if (!in_kernel) {
+            score_enqueue(&t.view, t.kp, t.d_kp, t.kp_off[t.K], t.K, t.normalized, rows, r.doc_begin, r.doc_count, r.stream,
+                          t.tmp[li].p, (int32_t)t.tmp_docs[li], nullptr);
+        }
+        if (t.host_out)
+            EAST_CUDA(cudaMemcpyAsync(t.host_out + (size_t)r.doc_begin * t.K, rows, sizeof(double) * (size_t)r.doc_count * t.K,
+                                      cudaMemcpyDeviceToHost, r.stream));
+        t.docs_scored += r.doc_count;
+    } catch (...) {
+        t.failed = true;
+    }
+}
+
+int east_table_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
+                    const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized, double *out_DxK,
+                    east_index **out_idx) {
+    EAST_API_BEGIN
+    if (!kp || !kp_off || !out_DxK || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    east_index *built = nullptr;
+    check_build_args(text, doc_off, doc_m, n_docs, &built);
+    check_keyphrases(kp_off, K);
+    use_device(device);
+    cudaStream_t s = 0;
+    DevBuf<uint32_t> d_kp((size_t)kp_off[K], s);
+    DevBuf<double> d_out((size_t)n_docs * K, s);
+    EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, s));
+    TableRun run;
+    run.kp_host = kp; run.d_kp = d_kp.p; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
+    run.d_out = d_out.p; run.host_out = out_DxK;
+    RunHook hook;
+    hook.begin = table_run_begin; hook.fn = table_run_done; hook.ctx = &run; hook.building = &run.building;
+    build_host_impl(text, doc_off, doc_m, n_docs, device, &built, &hook);
+    std::unique_ptr<east_index, void (*)(east_index *)> guard(built, free_index);
+    // Rows scored on the way stand if the pass that produced them is the one the index came from: the speculative
+    // pipelined pass (pipelined = 1: the build ended on a host sync after both streams, the rows are in out_DxK)
+    // or the ordinary per-document pass (its copy is still in flight on stream s).
+    const bool stands = !run.failed && run.docs_scored == n_docs &&
+                        ((built->pipelined && !run.final_pass) || (built->doc_sorted && !built->pipelined && run.final_pass));
+    if (stands) {
+        EAST_CUDA(cudaStreamSynchronize(s));
+    } else {
+        score_common(built, d_kp.p, kp_off, K, normalized, d_out.p, 0, n_docs, s, nullptr, nullptr, kp);
+        EAST_CUDA(cudaMemcpy(out_DxK, d_out.p, sizeof(double) * (size_t)n_docs * K, cudaMemcpyDeviceToHost));
+    }
+    if (out_idx) *out_idx = guard.release();
+    EAST_API_END
+}
+
+int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
+                   const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, int normalized,
+                   double *out_DxK_dev, void *stream, east_index **out_idx) {
+    EAST_API_BEGIN
+    if (!kp_dev || !kp_off || !out_DxK_dev || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    east_index *built = nullptr;
+    check_build_args(text_dev, doc_off, doc_m, n_docs, &built);
+    check_keyphrases(kp_off, K);
+    use_device(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    TableRun run;
+    run.kp_host = kp_host; run.d_kp = kp_dev; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
+    run.d_out = out_DxK_dev; run.host_out = nullptr;
+    RunHook hook;
+    hook.begin = table_run_begin; hook.fn = table_run_done; hook.ctx = &run; hook.building = &run.building;
+    build_common(text_dev, false, doc_off, doc_m, n_docs, device, s, &built, nullptr, &hook);
+    std::unique_ptr<east_index, void (*)(east_index *)> guard(built, free_index);
+    const bool stands = !run.failed && run.docs_scored == n_docs && built->doc_sorted && run.final_pass;
+    if (stands) EAST_CUDA(cudaStreamSynchronize(s));
+    else score_common(built, kp_dev, kp_off, K, normalized, out_DxK_dev, 0, n_docs, s, nullptr, nullptr, kp_host);
+    if (out_idx) *out_idx = guard.release();
     EAST_API_END
 }
 

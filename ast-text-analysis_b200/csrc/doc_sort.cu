@@ -35,6 +35,7 @@
 //      outside a chunk searched in the pyramid (farthest first, so that the lanes' long searches coincide).
 // A bucket of more than 4096 suffixes raises flag bit 0: the host redoes the batch with the global sort.
 #include "sa_build.h"
+#include "score_walk.cuh"
 
 namespace east {
 
@@ -73,6 +74,7 @@ struct DocSortParams {
     // up/down/next/ann must be zero-filled by the caller, lcp is written for every rank
     int32_t *lcp, *up, *down, *next, *ann;
     uint32_t *sk;             // optional: the 4 text bytes at offsets 2..5 of every suffix, in rank order (scorer)
+    DocScore score;           // optional (recs != nullptr; needs bkt and sk): score the keyphrases against the document
 };
 
 // 8 bytes of shared memory at an arbitrary byte offset from a 16-byte aligned base: three aligned
@@ -468,6 +470,75 @@ found:
     return j;
 }
 
+// empty 2-gram / 3-gram bucket tables of a document the kernel gives up on
+__device__ __forceinline__ void ds_clear_tables(const DocSortParams &p, int doc, int b, int tid) {
+    if (p.bkt) {
+        uint32_t *row = p.bkt + ((size_t)doc << (2 * b));
+        for (int i = tid; i < (1 << (2 * b)); i += DS_THREADS) row[i] = 0u;
+    }
+    if (p.bkt3) {
+        uint32_t *row = p.bkt3 + ((size_t)doc << (3 * b));
+        for (int i = tid; i < (1 << (3 * b)); i += DS_THREADS) row[i] = 0u;
+    }
+}
+
+// ---- phase 9 (optional): score the keyphrases against the document this CTA has just indexed
+// (EnhancedAnnotatedSuffixArray._score, easa.py:91-139, for every distinct query suffix; score_walk.cuh).
+// The CTA's shared memory is free again: the byte text and the suffix array (16-bit local positions) of the
+// document are staged there, so every probe of a walk -- the binary searches over (rank -> symbol at depth d)
+// -- is two shared-memory loads instead of dependent L2 / HBM round trips.  Only the bucket-table lookups that
+// open a walk (one batch of loads per suffix) and the suffix records go to global memory.
+__device__ __forceinline__ void ds_score_document(const DocSortParams &p, uint8_t *smem, int smem_bytes, int doc, int32_t base, int n, int tid) {
+    if (p.score.recs == nullptr) return;
+    __syncthreads();   // every rank of sa and every bucket start of this document is in place; shared memory is free
+    const int b = p.b;
+    const uint32_t *row = p.bkt + ((size_t)doc << (2 * b));
+    const uint32_t *row3 = p.bkt3 ? p.bkt3 + ((size_t)doc << (3 * b)) : nullptr;
+    const int32_t m = p.doc_m[doc];
+    double *out = p.score.tmp + (size_t)(doc - p.doc_begin) * (size_t)p.score.n_uniq;
+    const int32_t a0 = base & ~15;
+    const int shift = base - a0;
+    const int text_bytes = (shift + n + 48 + 15) & ~15;   // as staged in phase 1: the walks read 8 bytes at a time
+    const bool staged = text_bytes + 2 * n <= smem_bytes;
+    const uint8_t *s_text = smem + shift;
+    uint16_t *s_sa = reinterpret_cast<uint16_t *>(smem + text_bytes);
+    if (staged) {
+        for (int o = tid * 16; o < text_bytes; o += DS_THREADS * 16)
+            *reinterpret_cast<uint4 *>(smem + o) = *reinterpret_cast<const uint4 *>(p.t8 + a0 + o);
+        const int32_t *sa_doc = p.sa + base;
+        for (int r = tid; r < n; r += DS_THREADS) s_sa[r] = (uint16_t)(sa_doc[r] - base);
+        __syncthreads();
+    }
+    unsigned long long probes = 0;
+    for (int u = tid; u < p.score.n_uniq; u += DS_THREADS) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(p.score.recs) + u);
+        const uint64_t qw = ((uint64_t)raw.y << 32) | raw.x;
+        const int32_t sidx = (int32_t)raw.z;
+        const int32_t len = (int32_t)(raw.w & 0xffffu);
+        const bool generic = ((raw.w >> 16) & 0xffu) != 0u;
+        double r;
+        if (generic)
+            r = score_one_suffix<false, false>(p.text, p.sa, base, base + n, m, p.score.kp + sidx, len, p.score.normalized, probes);
+        else if (staged)
+            r = score_one_suffix_fast<false, false, uint16_t>(s_text, s_sa, nullptr, row, row3, b, base, base + n, m,
+                                                              p.score.q8 + sidx, qw, len, p.score.normalized, probes, base);
+        else
+            r = score_one_suffix_fast<false, false>(p.t8, p.sa, p.sk, row, row3, b, base, base + n, m, p.score.q8 + sidx, qw, len,
+                                                    p.score.normalized, probes);
+        out[u] = r;
+    }
+    // the keyphrase sums: the results of the keyphrase's suffixes IN SUFFIX ORDER (the reference's fp64 order,
+    // easa.py:127-134), each fetched through the position of its distinct twin -- k_score_combine's arithmetic
+    __syncthreads();
+    double *table_row = p.score.out + (size_t)(doc - p.doc_begin) * (size_t)p.score.K;
+    for (int k = tid; k < p.score.K; k += DS_THREADS) {
+        const int32_t sb = __ldg(p.score.kp_off + k), se = __ldg(p.score.kp_off + k + 1);
+        double result = 0.0;
+        for (int32_t x = sb; x < se; ++x) result = result + __ldcg(out + __ldg(p.score.uniq_of + x));
+        table_row[k] = result / (double)(se - sb);
+    }
+}
+
 __global__ void __launch_bounds__(DS_THREADS, 1)
 k_doc_suffix_sort(DocSortParams p) {
     extern __shared__ __align__(16) uint8_t ds_smem[];
@@ -479,6 +550,7 @@ k_doc_suffix_sort(DocSortParams p) {
     __shared__ uint32_t s_warp_sum[DS_WARPS];
     __shared__ uint32_t s_nlist[2];
     __shared__ uint32_t s_work;
+    __shared__ uint32_t s_fail;   // this document cannot be sorted here (a bucket too large)
     __shared__ int s_gmin[DS_NGROUPS];
     __shared__ uint32_t s_gw[DS_NGROUPS * DS_GWARPS];
 
@@ -514,7 +586,7 @@ k_doc_suffix_sort(DocSortParams p) {
         for (int i = tid; i < NW; i += DS_THREADS) s_scr[i] = 0;
         for (int i = tid; i < p.bits_words; i += DS_THREADS) s_bits[i] = 0;
         if (tid < 2) s_nlist[tid] = 0;
-        if (tid == 0) s_work = 0;   // here: number of terminator codes seen
+        if (tid == 0) { s_work = 0; s_fail = 0; }   // s_work here: number of terminator codes seen
         __syncthreads();
         int bad = 0;
         for (int o = tid * 16; o < nbytes; o += DS_THREADS * 16) {
@@ -549,6 +621,11 @@ k_doc_suffix_sort(DocSortParams p) {
         }
         if (__syncthreads_or(bad)) {
             if (tid == 0) atomicOr(p.overflow, 2u);
+            // Nothing of this document is usable.  A caller that scores speculatively (east_table_host scores a
+            // run before the host has seen the flag) must still stay inside the arrays: empty bucket tables end
+            // every fast walk before its first suffix-array read, an in-range suffix array bounds the generic walk.
+            for (int r = tid; r < n; r += DS_THREADS) sa_doc[r] = base + r;
+            ds_clear_tables(p, doc, b, tid);
             return;
         }
     }
@@ -607,7 +684,7 @@ k_doc_suffix_sort(DocSortParams p) {
                     if (cnt) {
                         atomicOr(&s_bits[st >> 5], 1u << (st & 31));
                         if (cnt > 32u && id != term_bucket) {
-                            if (cnt > (uint32_t)DS_REFINE_MAX) atomicOr(p.overflow, 1u);
+                            if (cnt > (uint32_t)DS_REFINE_MAX) { atomicOr(p.overflow, 1u); s_fail = 1u; }
                             else {
                                 const uint32_t slot = atomicAdd(&s_nlist[0], 1u);
                                 const uint32_t term_flag = ds_id_has_term(id, G, b, p.term) ? 1u : 0u;
@@ -622,6 +699,7 @@ k_doc_suffix_sort(DocSortParams p) {
         if (tid == 0) atomicOr(&s_bits[n >> 5], 1u << (n & 31));  // sentinel: "a bucket starts at rank n"
     }
     __syncthreads();
+    if (s_fail) ds_clear_tables(p, doc, b, tid);   // the suffix array stays a permutation, but not a sorted one: see phase 1
     DS_STAMP(2);
 
     // ---- phase 4: scatter the suffixes into their buckets (arbitrary order inside a bucket)
@@ -770,6 +848,7 @@ k_doc_suffix_sort(DocSortParams p) {
             __syncthreads();
             for (int r = tid; r < n; r += DS_THREADS) p.sk[base + r] = ds_lds4(s_raw, shift + (sa_doc[r] - base) + 2);
         }
+        ds_score_document(p, ds_smem, p.text_cap + DS_SCR_BYTES + 4 * p.bits_words + 2 * (int)sizeof(uint2) * DS_LIST_CAP, doc, base, n, tid);
         return;
     }
 
@@ -943,6 +1022,9 @@ k_doc_suffix_sort(DocSortParams p) {
     }
     if (p.phase_clk) __syncthreads();
     DS_STAMP(8);
+    ds_score_document(p, ds_smem, p.text_cap + DS_SCR_BYTES + 4 * p.bits_words + 2 * (int)sizeof(uint2) * DS_LIST_CAP, doc, base, n, tid);
+    if (p.phase_clk) __syncthreads();
+    DS_STAMP(9);
 #undef DS_STAMP
 }
 
@@ -972,7 +1054,7 @@ bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan) {
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
                      const int32_t *doc_m, int doc_begin, int n_docs,
                      int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *bkt3, uint32_t *overflow, cudaStream_t s,
-                     unsigned long long *phase_clk, const DocSortTables *tables, uint32_t *sk) {
+                     unsigned long long *phase_clk, const DocSortTables *tables, uint32_t *sk, const DocScore *score) {
     static bool configured = false;
     if (!configured) {
         EAST_CUDA(cudaFuncSetAttribute(k_doc_suffix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -985,11 +1067,13 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     p.phase_clk = phase_clk;
     p.doc_begin = doc_begin;
     p.sk = sk;
+    if (score && score->recs && bkt && sk) p.score = *score;
     p.lcp = p.up = p.down = p.next = p.ann = nullptr;
     if (tables && plan.tables_fit) { p.lcp = tables->lcp; p.up = tables->up; p.down = tables->down; p.next = tables->next; p.ann = tables->ann; }
     // algorithmic bytes per code point: 1 (byte text in) + 4 (suffix array out), with the fused tables + 5 x 4
-    // (LCP, up, down, next, annotation out)
-    EAST_BYTES((p.lcp ? 25.0 : 5.0) * (double)n_total);
+    // (LCP, up, down, next, annotation out); with the scorer inside, plus the bytes of its walks (counted by the
+    // instrumented scorer, option score_bytes)
+    EAST_BYTES((p.lcp ? 25.0 : 5.0) * (double)n_total + (p.score.recs ? p.score.algorithmic_bytes : 0.0));
     EAST_LAUNCH(k_doc_suffix_sort, n_docs, DS_THREADS, plan.smem, s, p);
 }
 

@@ -310,6 +310,18 @@ k_scan_text(const uint32_t *__restrict__ T, int32_t n, const int32_t *__restrict
     }
 }
 
+// Four code points T[i .. i+3] (i a multiple of 4) as one 128-bit load when they all lie in [lo, hi),
+// else element by element with `fill` outside the range
+__device__ __forceinline__ uint4 load4_guarded(const uint32_t *__restrict__ T, int64_t i, int64_t lo, int64_t hi, uint32_t fill) {
+    if (i >= lo && i + 3 < hi) return *reinterpret_cast<const uint4 *>(T + i);
+    uint4 v;
+    v.x = (i >= lo && i < hi) ? T[i] : fill;
+    v.y = (i + 1 >= lo && i + 1 < hi) ? T[i + 1] : fill;
+    v.z = (i + 2 >= lo && i + 2 < hi) ? T[i + 2] : fill;
+    v.w = (i + 3 >= lo && i + 3 < hi) ? T[i + 3] : fill;
+    return v;
+}
+
 // dense byte codes: 1..sigma for present code points < 0x0A00, sigma+1 for every terminator.
 // Encodes [begin, end) (begin a multiple of 4 or a document start handled by the scalar edges);
 // *miss is set when a code point below 0x0A00 has no code (speculative alphabet, see below).
@@ -322,27 +334,54 @@ k_encode_text(const uint32_t *__restrict__ T, int32_t begin, int32_t end, const 
     const int32_t a0 = begin & ~3;   // groups of 4 aligned code points; the edges are masked
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     bool missed = false;
-    for (int64_t i = a0 + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < end; i += stride) {
-        const bool full = i >= begin && i + 3 < end;
-        uint32_t c[4];
-        if (full) {
-            uint4 v = *reinterpret_cast<const uint4 *>(T + i);  // 128-bit load
-            c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
-        } else {
-            for (int q = 0; q < 4; ++q) c[q] = (i + q >= begin && i + q < end) ? T[i + q] : EAST_TERM_BASE;
-        }
-        uint32_t packed = 0;
+    constexpr int U = 4;   // independent 128-bit loads in flight per thread (one alone left HBM at ~40 %)
+    for (int64_t i0 = a0 + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < end; i0 += U * stride) {
+        uint4 v[U];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint32_t e = (c[q] < EAST_TERM_BASE) ? s_code[c[q]] : term_code;
-            missed = missed || e == 0u;
-            packed |= e << (8 * q);
+        for (int u = 0; u < U; ++u) v[u] = load4_guarded(T, i0 + u * stride, begin, end, EAST_TERM_BASE);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= end) break;
+            const uint32_t c[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            uint32_t packed = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t e = (c[q] < EAST_TERM_BASE) ? s_code[c[q]] : term_code;
+                missed = missed || e == 0u;
+                packed |= e << (8 * q);
+            }
+            if (i >= begin && i + 3 < end) *reinterpret_cast<uint32_t *>(T8 + i) = packed;
+            else for (int q = 0; q < 4; ++q) if (i + q >= begin && i + q < end) T8[i + q] = (uint8_t)(packed >> (8 * q));
         }
-        if (full) *reinterpret_cast<uint32_t *>(T8 + i) = packed;
-        else for (int q = 0; q < 4; ++q) if (i + q >= begin && i + q < end) T8[i + q] = (uint8_t)(packed >> (8 * q));
     }
     if (missed && miss) atomicOr(miss, 1u);
 }
+
+// The dense-code table (code point < 0x0A00 -> 1..sigma in code point order, 0 = absent) from the scan's
+// presence bitmap, on the device: the host derives the same table for itself, and a host-to-device upload here
+// would queue behind the bulk text copies of a pipelined build (one copy engine per direction).
+__global__ void __launch_bounds__(128)
+k_code_table(const ScanResult *__restrict__ res, uint8_t *__restrict__ table) {
+    constexpr int W = EAST_TERM_BASE / 32;
+    __shared__ uint32_t s_before[W];
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < W; ++w) { s_before[w] = run; run += __popc(res->present[w]); }
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        const uint32_t bits = res->present[w];
+        uint32_t code = s_before[w];
+        for (int k = 0; k < 32; ++k) {
+            const bool on = (bits >> k) & 1u;
+            if (on) ++code;
+            table[32 * w + k] = on ? (uint8_t)(code & 0xffu) : (uint8_t)0;
+        }
+    }
+}
+
+__global__ void k_store_u32(uint32_t *dst, uint32_t value) { *dst = value; }
 
 // Light text scan: bitmap of the code points below 0x0A00 that occur in T[0, n), number of code points
 // >= 0x0A00 and the maximum code point -- everything k_scan_text reports except the validation of the
@@ -354,20 +393,23 @@ k_alphabet(const uint32_t *__restrict__ T, int32_t n, ScanResult *res) {
     __syncthreads();
     uint32_t mx = 0, nt = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
-    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-        uint32_t c[4];
-        if (i + 3 < n) {
-            uint4 v = *reinterpret_cast<const uint4 *>(T + i);
-            c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
-        } else {
-            for (int q = 0; q < 4; ++q) c[q] = (i + q < n) ? T[i + q] : 0u;
-        }
+    constexpr int U = 4;   // independent 128-bit loads in flight per thread
+    for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += U * stride) {
+        uint4 v[U];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            mx = max(mx, c[q]);
-            if (c[q] >= EAST_TERM_BASE) ++nt;
-            else if (i + q < n && !(((volatile uint32_t *)s_present)[c[q] >> 5] & (1u << (c[q] & 31))))
-                atomicOr(&s_present[c[q] >> 5], 1u << (c[q] & 31));
+        for (int u = 0; u < U; ++u) v[u] = load4_guarded(T, i0 + u * stride, 0, n, 0u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= n) break;
+            const uint32_t c[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                mx = max(mx, c[q]);
+                if (c[q] >= EAST_TERM_BASE) ++nt;
+                else if (i + q < n && !(((volatile uint32_t *)s_present)[c[q] >> 5] & (1u << (c[q] & 31))))
+                    atomicOr(&s_present[c[q] >> 5], 1u << (c[q] & 31));
+            }
         }
     }
     mx = __reduce_max_sync(0xffffffffu, mx);
@@ -863,10 +905,12 @@ k_bucket_fill(uint32_t *__restrict__ bkt, int entries, const int32_t *__restrict
 // Pipelined host build (east_build_host on a large batch of small documents): the text arrives chunk
 // by chunk on a copy stream.  The alphabet is taken from chunk 0 (speculation: later chunks use no
 // other code point below 0x0A00), every chunk is encoded and sorted by the per-document kernel as soon
-// as it is resident, and ONE validating scan of the whole text at the end confirms the alphabet and the
-// terminator layout.  If it does not, nothing is kept and the ordinary build runs on the resident text.
-static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s, ScanResult &scan,
-                            DevBuf<ScanResult> &d_scan) {
+// as it is resident.  Two flags confirm the speculation at the end, with no further pass over the text: the
+// encoder reports a code point below 0x0A00 that the alphabet of chunk 0 lacks (the only way the alphabets can
+// differ: chunk 0 is part of the text), and the per-document kernel validates the terminator layout of its
+// document (count, values, order, last position).  If either is set, nothing is kept and the ordinary build
+// runs on the resident text.
+static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s, uint32_t &doc_sort_flags) {
     const int32_t n = in.n;
     const int D = in.n_docs;
     int32_t max_doc_n = 0;
@@ -874,6 +918,14 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     tm.mark("alphabet");
     DevBuf<ScanResult> d_first(1, s);
     EAST_CUDA(cudaMemsetAsync(d_first.p, 0, sizeof(ScanResult), s));
+    if (in.lcp != nullptr) {
+        // the per-document kernel stores child table and annotation sparsely into zero-filled arrays: the fills
+        // (16 bytes per code point) run now, while the device has nothing else to do but wait for the first run
+        EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, s));
+        EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, s));
+        EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
+        EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
+    }
     EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
     const int32_t n0 = in.doc_off_host[in.chunk_doc[1]];
     EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_first.p);
@@ -891,67 +943,65 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
 
     DevBuf<uint8_t> t8;
     DevBuf<uint32_t> flags(2, s);   // [0] doc_sort overflow, [1] encode miss
-    // the validating scan follows the copies: after every run, the tiles of the text that are complete
-    EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
-    int tiles_done = 0;
-    const int tiles_all = (n + ST_TILE - 1) / ST_TILE;
-    auto scan_arrived = [&](int32_t arrived, bool last) {
-        const int tiles_to = last ? tiles_all : arrived / ST_TILE;
-        if (tiles_to > tiles_done || last) {
-            EAST_BYTES(4.0 * ST_TILE * (tiles_to - tiles_done));
-            EAST_LAUNCH(k_scan_text, grid_for((int64_t)(tiles_to - tiles_done) * ST_TILE, ST_TILE, 4), 256, 0, s, in.text, n,
-                        in.doc_off, in.doc_m, D, d_scan.p, tiles_done, tiles_to, last ? 1 : 0);
-            tiles_done = tiles_to;
-        }
-    };
     if (eligible) {
         tm.mark("doc_sort");
         DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
-        EAST_CUDA(cudaMemcpyAsync(d_table.p, table.data(), EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
+        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_first.p, d_table.p);
         t8 = DevBuf<uint8_t>((size_t)n + 128, s);
         EAST_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(uint32_t), s));
         if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
             const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
             out.bkt = DevBuf<uint32_t>(entries, s);
-            EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt.p + entries - 1, (uint32_t)n);
             out.sym_bits = plan.b;
             if (in.want_bkt3 && plan.G == 3 && ((size_t)D << (3 * plan.b)) * sizeof(uint32_t) <= ((size_t)8 << 30)) {
                 // the kernel's buckets ARE the 3-grams: their first ranks cost one more coalesced store and turn
                 // the scorer's depth-2 narrowing (a binary search over the largest intervals) into a lookup
                 const size_t e3 = ((size_t)D << (3 * plan.b)) + 1;
                 out.bkt3 = DevBuf<uint32_t>(e3, s);
-                EAST_CUDA(cudaMemcpyAsync(out.bkt3.p + e3 - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+                EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt3.p + e3 - 1, (uint32_t)n);
             }
         }
         DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
         const bool fuse = in.lcp != nullptr && plan.tables_fit;
-        if (fuse) {
-            EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, s));
-            EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, s));
-            EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
-            EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
-        }
         // runs alternate between the main stream and a helper stream: a run is one wave of per-document CTAs,
         // and on one stream the next wave could not start before the slowest CTA of the previous one ended
         cudaStream_t lanes[2] = {s, in.helper_stream ? in.helper_stream : s};
+        // the byte-coding of a run needs a few microseconds of the machine, but a per-document CTA owns its SM: on
+        // the lane that sorts the run it would start only when the other lane's wave drains, right in front of
+        // the kernel that waits for it.  On a high-priority stream of its own it is done long before.
+        cudaStream_t prep = (in.prep_stream && lanes[1] != s) ? in.prep_stream : nullptr;
         cudaEvent_t ready_to_sort = nullptr, helper_done = nullptr;
         if (lanes[1] != s) {
             EAST_CUDA(cudaEventCreateWithFlags(&ready_to_sort, cudaEventDisableTiming));
             EAST_CUDA(cudaEventCreateWithFlags(&helper_done, cudaEventDisableTiming));
-            EAST_CUDA(cudaEventRecord(ready_to_sort, s));           // table upload, memsets, flag reset
+            EAST_CUDA(cudaEventRecord(ready_to_sort, s));           // code table, flag reset, allocations
             EAST_CUDA(cudaStreamWaitEvent(lanes[1], ready_to_sort, 0));
+            if (prep) EAST_CUDA(cudaStreamWaitEvent(prep, ready_to_sort, 0));
         }
         for (int c = 0; c < in.n_chunks; ++c) {
             const int d0 = in.chunk_doc[c], d1 = in.chunk_doc[c + 1];
             const int32_t e0 = in.doc_off_host[d0], e1 = in.doc_off_host[d1];
             cudaStream_t ls = lanes[c & 1];
-            if (c > 0) EAST_CUDA(cudaStreamWaitEvent(ls, in.chunk_ready[c], 0));
+            cudaStream_t es = prep ? prep : ls;
+            if (c > 0) EAST_CUDA(cudaStreamWaitEvent(es, in.chunk_ready[c], 0));
             EAST_BYTES(5.0 * (e1 - e0));
-            EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, ls, in.text, e0, e1, d_table.p,
+            EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, es, in.text, e0, e1, d_table.p,
                         (uint8_t)term, t8.p, flags.p + 1);
+            if (prep) {
+                cudaEvent_t coded;
+                EAST_CUDA(cudaEventCreateWithFlags(&coded, cudaEventDisableTiming));
+                EAST_CUDA(cudaEventRecord(coded, prep));
+                EAST_CUDA(cudaStreamWaitEvent(ls, coded, 0));
+                EAST_CUDA(cudaEventDestroy(coded));   // released once it has fired
+            }
+            const bool hooks = out.bkt.p && in.sk;
+            const RunReady run{d0, d1 - d0, ls, t8.p, out.bkt.p, out.bkt3.p, out.sym_bits, &table, 1};
+            DocScore score;
+            if (hooks && in.run_begin) in.run_begin(in.run_ctx, run, score);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
-                            out.bkt3.p, flags.p, ls, nullptr, fuse ? &tables : nullptr, in.sk);
-            if (ls == s) scan_arrived(e1, false);   // validating scan of what has arrived (main stream only)
+                            out.bkt3.p, flags.p, ls, nullptr, fuse ? &tables : nullptr, in.sk, &score);
+            if (hooks && in.run_hook) in.run_hook(in.run_ctx, run, score.recs != nullptr ? 1 : 0);
         }
         if (lanes[1] != s) {
             EAST_CUDA(cudaEventRecord(helper_done, lanes[1]));
@@ -959,20 +1009,16 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             EAST_CUDA(cudaEventDestroy(ready_to_sort));
             EAST_CUDA(cudaEventDestroy(helper_done));
         }
-        scan_arrived(n, true);
         out.tables_done = fuse ? 1 : 0;
     } else {
         for (int c = 1; c < in.n_chunks; ++c) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
-        scan_arrived(n, true);
     }
-    // the validating scan is the ordinary build's first step, too
     tm.mark("validate");
     uint32_t h_flags[2] = {0u, 0u};
-    EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
     if (eligible) EAST_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
     EAST_CUDA(cudaStreamSynchronize(s));
-    bool ok = eligible && !scan.bad && scan.n_term == (uint32_t)in.m_total && !h_flags[0] && !h_flags[1];
-    for (int w = 0; ok && w < (int)(EAST_TERM_BASE / 32); ++w) ok = scan.present[w] == present[w];
+    const bool ok = eligible && !h_flags[0] && !h_flags[1];
+    doc_sort_flags = h_flags[0];
     if (!ok) {
         out.pipeline_miss = eligible ? 1 : 0;
         out.doc_sort_overflow = (h_flags[0] & 1u) ? 1 : 0;
@@ -1001,24 +1047,23 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     const int D = in.n_docs;
     DevBuf<ScanResult> d_scan(1, s);
     ScanResult scan;
-    bool scanned = false;
     bool allow_doc_sort = in.doc_sort != 0;
     if (in.n_chunks > 0) {
-        if (build_pipelined(in, out, tm, s, scan, d_scan)) return;
-        scanned = true;                       // the validating scan is the ordinary build's first step
-        if (out.doc_sort_overflow) allow_doc_sort = false;
+        uint32_t refused = 0;   // what the per-document kernel reported: bit 0 a bucket too large, bit 1 a bad layout
+        if (build_pipelined(in, out, tm, s, refused)) return;
+        if (refused) allow_doc_sort = false;  // it would refuse again: full scan, global sort
     }
     int32_t max_doc_n = 0;
     for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);
     // Batches of small documents start with the LIGHT scan (alphabet, counts): the per-document kernel
     // validates the terminator layout of its document itself.  Whatever it cannot take (bad layout, a
     // bucket too large, an alphabet too wide) is redone below with the validating scan.
-    const bool light = !scanned && allow_doc_sort && in.light_scan && !in.force_general && max_doc_n <= 65535;
+    const bool light = allow_doc_sort && in.light_scan && !in.force_general && max_doc_n <= 65535;
     // The per-document kernel stores the child table and the annotation sparsely into zero-filled arrays.  The
     // four fills (16 bytes per code point) run on the helper stream from the start, under the text scan, the
     // host's alphabet round trip and the encoding, instead of in front of the kernel.
     cudaEvent_t tables_zeroed = nullptr;
-    if (!scanned && allow_doc_sort && in.lcp != nullptr && in.helper_stream != nullptr && in.helper_stream != s &&
+    if (allow_doc_sort && in.lcp != nullptr && in.helper_stream != nullptr && in.helper_stream != s &&
         max_doc_n <= 65535 && !in.force_general) {
         cudaEvent_t fork;
         EAST_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
@@ -1033,19 +1078,17 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         EAST_CUDA(cudaEventRecord(tables_zeroed, in.helper_stream));
     }
     struct EventGuard { cudaEvent_t &e; ~EventGuard() { if (e) cudaEventDestroy(e); } } zero_guard{tables_zeroed};
-    if (!scanned) {
-        tm.mark("scan_text");
-        EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
-        EAST_BYTES(4.0 * n);
-        if (light) {
-            EAST_LAUNCH(k_alphabet, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_scan.p);
-        } else {
-            EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p, 0,
-                        (n + ST_TILE - 1) / ST_TILE, 1);
-        }
-        EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
-        EAST_CUDA(cudaStreamSynchronize(s));
+    tm.mark("scan_text");
+    EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
+    EAST_BYTES(4.0 * n);
+    if (light) {
+        EAST_LAUNCH(k_alphabet, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_scan.p);
+    } else {
+        EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p, 0,
+                    (n + ST_TILE - 1) / ST_TILE, 1);
     }
+    EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
+    EAST_CUDA(cudaStreamSynchronize(s));
 
     int sigma = 0;
     std::vector<uint8_t> table(EAST_TERM_BASE, 0);
@@ -1089,7 +1132,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     DevBuf<uint8_t> t8;
     if (fast) {
         DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
-        EAST_CUDA(cudaMemcpyAsync(d_table.p, table.data(), EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
+        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p);
         t8 = DevBuf<uint8_t>((size_t)n + 128, s);
         EAST_BYTES(5.0 * n);
         EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, 0, n, d_table.p,
@@ -1109,14 +1152,14 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
                 const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
                 out.bkt = DevBuf<uint32_t>(entries, s);
-                EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+                EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt.p + entries - 1, (uint32_t)n);
                 out.sym_bits = plan.b;
                 if (in.want_bkt3 && plan.G == 3 && ((size_t)D << (3 * plan.b)) * sizeof(uint32_t) <= ((size_t)8 << 30)) {
                     // the kernel's buckets ARE the 3-grams: their first ranks cost one more coalesced store and turn
                     // the scorer's depth-2 narrowing (a binary search over the largest intervals) into a lookup
                     const size_t e3 = ((size_t)D << (3 * plan.b)) + 1;
                     out.bkt3 = DevBuf<uint32_t>(e3, s);
-                    EAST_CUDA(cudaMemcpyAsync(out.bkt3.p + e3 - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+                    EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt3.p + e3 - 1, (uint32_t)n);
                 }
             }
             static const bool profile = getenv("EAST_DOC_SORT_PROFILE") != nullptr;
@@ -1135,20 +1178,25 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
                 EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
             }
+            const bool hooks = out.bkt.p && in.sk;
+            const RunReady run{0, D, s, t8.p, out.bkt.p, out.bkt3.p, out.sym_bits, &table, 0};
+            DocScore score;
+            if (hooks && in.run_begin) in.run_begin(in.run_ctx, run, score);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, 0, D, n, kp.term, out.sa, out.bkt.p, out.bkt3.p, flag.p, s, clk.p,
-                            fuse ? &tables : nullptr, in.sk);
+                            fuse ? &tables : nullptr, in.sk, &score);
             uint32_t overflow = 0;
             EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             EAST_CUDA(cudaStreamSynchronize(s));
             if (profile) {
                 unsigned long long h[16];
                 EAST_CUDA(cudaMemcpy(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost));
-                static const char *names[9] = {"load", "hist", "scan", "scatter", "refine", "windows", "lcp", "stack_walk", "beyond_chunk"};
+                static const char *names[10] = {"load", "hist", "scan", "scatter", "refine", "windows", "lcp", "stack_walk", "beyond_chunk", "score"};
                 fprintf(stderr, "[east] doc_sort phases, kilo-cycles per document:");
-                for (int k = 0; k < 9; ++k) fprintf(stderr, " %s %.1f", names[k], (double)h[k] / D / 1e3);
+                for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1f", names[k], (double)h[k] / D / 1e3);
                 fprintf(stderr, "\n");
             }
             if (!overflow) {
+                if (hooks && in.run_hook) in.run_hook(in.run_ctx, run, score.recs != nullptr ? 1 : 0);
                 out.doc_sorted = 1;
                 out.tables_done = fuse ? 1 : 0;
                 out.sk_done = in.sk ? 1 : 0;
@@ -1259,7 +1307,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         const size_t entries = ((size_t)D << (2 * kp.b)) + 1;
         out.bkt = DevBuf<uint32_t>(entries, s);
         EAST_CUDA(cudaMemsetAsync(out.bkt.p, 0xff, sizeof(uint32_t) * (entries - 1), s));
-        EAST_CUDA(cudaMemcpyAsync(out.bkt.p + entries - 1, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt.p + entries - 1, (uint32_t)n);
         out.sym_bits = kp.b;
     }
     tm.mark("rerank0");

@@ -4,6 +4,38 @@
 
 namespace east {
 
+struct SufRec;
+// Keyphrases to score INSIDE the per-document kernel: once a CTA has indexed its document it walks every distinct
+// query suffix (score_walk.cuh) while suffix array, key words and bucket rows are still hot in L2, and stores the
+// per-suffix results to tmp[(document - doc_begin) * n_uniq + position], then adds them up per keyphrase.
+struct DocScore {
+    const SufRec *recs = nullptr;     // distinct query suffixes in visiting order
+    int32_t n_uniq = 0;
+    const uint8_t *q8 = nullptr;      // dense byte codes of the concatenated keyphrases
+    const uint32_t *kp = nullptr;     // their code points (walks of suffixes with code points >= 0x0A00)
+    double *tmp = nullptr;
+    int normalized = 0;
+    // the keyphrase sums (k_score_combine's arithmetic) are taken by the same CTA: out[(document - doc_begin) * K + k]
+    const int32_t *kp_off = nullptr;  // K + 1
+    const int32_t *uniq_of = nullptr; // per suffix of the concatenated keyphrases: position of its distinct twin
+    int32_t K = 0;
+    double *out = nullptr;
+    double algorithmic_bytes = 0.0;   // of the walks of this launch (measurement only: added to the kernel's byte count)
+};
+
+// What a caller-supplied hook sees once the per-document kernel of one run of
+// documents has been queued on `stream` -- everything the scorer needs for these documents is ordered
+// before whatever the hook queues on the same stream (east_table_host scores the run there).
+struct RunReady {
+    int32_t doc_begin, doc_count;
+    cudaStream_t stream;
+    const uint8_t *t8;
+    const uint32_t *bkt, *bkt3;   // whole-batch tables (row of document 0 first); bkt3 may be NULL
+    int sym_bits;
+    const std::vector<uint8_t> *code_table;
+    int speculative;              // 1 = pipelined host build: the run stands only if the build ends with pipelined = 1
+};
+
 struct SaInput {
     const uint32_t *text;     // device, n code points (packed documents, concatenated)
     const int32_t *doc_off;   // device, n_docs + 1
@@ -30,6 +62,14 @@ struct SaInput {
     const int32_t *chunk_doc = nullptr;
     const cudaEvent_t *chunk_ready = nullptr;
     cudaStream_t helper_stream = nullptr;   // odd runs are sorted here, so that consecutive one-wave kernels overlap their tails
+    cudaStream_t prep_stream = nullptr;     // pipelined build: the runs are byte-coded here (high priority) as soon as they arrive
+    // Hooks around every launch of the per-document kernel (each run of the pipelined build; the whole batch
+    // otherwise), only when the 2-gram table and the key words exist.  run_begin may fill `score` to have the
+    // kernel score the documents; run_hook is called after the launch (in the ordinary build: after the launch
+    // is known to have succeeded) with in_kernel = whether that happened.
+    void (*run_begin)(void *ctx, const RunReady &run, DocScore &score) = nullptr;
+    void (*run_hook)(void *ctx, const RunReady &run, int in_kernel) = nullptr;
+    void *run_ctx = nullptr;
 };
 
 struct SaOutput {
@@ -72,7 +112,8 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
                      int64_t n_total /* code points of these documents */, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *bkt3, uint32_t *overflow, cudaStream_t s,
                      unsigned long long *phase_clk = nullptr /* profiling: 8 cycle counters */,
                      const DocSortTables *tables = nullptr /* also produce LCP, child table, annotation */,
-                     uint32_t *sk = nullptr /* also produce the scorer's per-rank key bytes */);
+                     uint32_t *sk = nullptr /* also produce the scorer's per-rank key bytes */,
+                     const DocScore *score = nullptr /* also score keyphrases (needs bkt and sk) */);
 
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch
@@ -114,6 +155,8 @@ struct ScoreInput {
     unsigned long long *probe_count = nullptr;  // device counter: run the probe-counting variant
     double algorithmic_bytes = 0.0;             // 8 B x probes of this workload, if known (roofline numerator)
 };
+// the second half of score_table alone: tmp[doc][distinct suffix] (here: written by the per-document kernel) -> out[doc][k]
+void score_combine(const ScoreInput &in, const double *suffix_tmp, double *out_DxK, cudaStream_t s);
 void score_table(const ScoreInput &in, double *suffix_tmp /*n_docs x n_uniq*/, double *out_DxK,
                  cudaStream_t s);
 

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "east_free", "east_index_info", "east_index_doc", "east_index_copy", "east_index_devptr",
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
     "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
-    "east_score_probes_dev", "east_index_stat", "east_score_range_dev",
+    "east_score_probes_dev", "east_index_stat", "east_score_range_dev", "east_table_host", "east_table_dev",
 ]
 
 _lib = None
@@ -63,6 +63,10 @@ def load():
     L.east_index_devptr.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp)]
     L.east_score_table_host.argtypes = [_vp, _u32p, _i64p, ctypes.c_int32, ctypes.c_int, _f64p]
     L.east_score_table_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, _vp, _vp]
+    L.east_table_host.argtypes = [_u32p, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _u32p, _i64p, ctypes.c_int32,
+                                  ctypes.c_int, _f64p, ctypes.POINTER(_vp)]
+    L.east_table_dev.argtypes = [_vp, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _vp, _u32p, _i64p, ctypes.c_int32,
+                                 ctypes.c_int, _vp, _vp, ctypes.POINTER(_vp)]
     L.east_score_range_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
     L.east_score_probes_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, _vp, _vp, _i64p]
     L.east_score_one.argtypes = [_vp, ctypes.c_int32, _u32p, ctypes.c_int32, ctypes.c_int, _f64p, _f64p]
@@ -184,6 +188,45 @@ class DeviceIndex(object):
         h = _vp()
         _check(L.east_build_host(_ptr(text, _u32p), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m),
                                  int(device), ctypes.byref(h)))
+        return cls.from_handle(h, doc_off, doc_m, int(device))
+
+    @classmethod
+    def build_host_and_score(cls, text, doc_off, doc_m, kp_codes, kp_off, out, normalized=True, device=0):
+        """build_host() + score_table_into() as ONE engine call (east_table_host): on a large batch of small
+        documents the runs of documents already sorted are scored, and their rows of `out` copied back, while
+        the rest of the text is still on its way to the device.  Returns the index; `out` ([n_docs, K] float64,
+        may be pinned) holds the table."""
+        L = load()
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
+        doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
+        kp_codes = np.ascontiguousarray(kp_codes, dtype=np.uint32)
+        kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
+        K = len(kp_off) - 1
+        assert text.dtype == np.uint32 and text.flags["C_CONTIGUOUS"]
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == len(doc_m) * K
+        h = _vp()
+        _check(L.east_table_host(_ptr(text, _u32p), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m), int(device),
+                                 _ptr(kp_codes, _u32p), _ptr(kp_off, _i64p), K, 1 if normalized else 0,
+                                 _ptr(out, _f64p), ctypes.byref(h)))
+        return cls.from_handle(h, doc_off, doc_m, int(device))
+
+    @classmethod
+    def build_dev_and_score(cls, text_devptr, doc_off, doc_m, kp_devptr, kp_codes, kp_off, out_devptr, normalized=True,
+                            device=0, stream=0):
+        """build_dev() + score_table_dev() as ONE engine call (east_table_dev): the per-document kernel scores every
+        document right after indexing it.  kp_codes: host copy of the keyphrase code points (or None)."""
+        L = load()
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
+        doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
+        kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
+        kp_host = None
+        if kp_codes is not None:
+            kp_codes = np.ascontiguousarray(kp_codes, dtype=np.uint32)
+            kp_host = _ptr(kp_codes, _u32p)
+        h = _vp()
+        _check(L.east_table_dev(_vp(text_devptr), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m), int(device),
+                                _vp(kp_devptr), kp_host, _ptr(kp_off, _i64p), len(kp_off) - 1, 1 if normalized else 0,
+                                _vp(out_devptr), _vp(stream), ctypes.byref(h)))
         return cls.from_handle(h, doc_off, doc_m, int(device))
 
     def score_table_into(self, kp_codes, kp_off, out, normalized=True):

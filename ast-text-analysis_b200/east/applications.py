@@ -22,9 +22,13 @@ def _score_matrix(keyphrases, texts, similarity_measure, synonimizer, language):
     similarity_measure = similarity_measure or relevance.ASTRelevanceMeasure()
     text_titles = list(texts.keys())
     text_collection = list(texts.values())
-    similarity_measure.set_text_collection(text_collection, language)
     kept = [kp for kp in keyphrases if kp]  # empty keyphrases are skipped (applications.py:44-45)
     prepared = [utils.prepare_text(kp) for kp in kept]
+    if synonimizer is None and isinstance(similarity_measure, relevance.ASTRelevanceMeasure) and prepared:
+        # the measure scores the keyphrases while it indexes the collection (one overlapped engine call)
+        similarity_measure.set_text_collection(text_collection, language, prepared_keyphrases=prepared)
+    else:
+        similarity_measure.set_text_collection(text_collection, language)
     if not kept or not text_titles:
         return kept, text_titles, np.zeros((len(text_titles), len(kept)))
     if synonimizer is None and hasattr(similarity_measure, "relevance_table"):

@@ -60,14 +60,22 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         self.asts = []
         self._index = None
         self._batches = []
+        self._table = None
+        self._table_keyphrases = None
 
-    def set_text_collection(self, texts, language=consts.Language.ENGLISH):
-        """relevance.py:34-49: one AST per text; here all of them in one batched build."""
+    def set_text_collection(self, texts, language=consts.Language.ENGLISH, prepared_keyphrases=None):
+        """relevance.py:34-49: one AST per text; here all of them in one batched build.
+
+        prepared_keyphrases (optional, what keyphrases_table passes): the keyphrases relevance_table() is
+        going to be asked for.  Each batch is then built AND scored by one engine call, which overlaps the
+        scoring of the documents already indexed with the transfer of the rest (east_table_host)."""
         self.texts = texts
         self.language = language
         self.asts = []
         self._index = None
         self._batches = []
+        self._table = None
+        self._table_keyphrases = None
         total_texts = len(texts)
         if self.ast_algorithm not in tuple(consts.ASTAlgorithm):
             # other registered engines (none ship in this package) go through the registry
@@ -82,8 +90,23 @@ class ASTRelevanceMeasure(RelevanceMeasure):
             return
         packed = [asts_utils.pack_strings_collection(c) for c in collections]
         self.asts = [None] * len(collections)
+        fused = None
+        if prepared_keyphrases:
+            fused = _capi.pack_keyphrases(prepared_keyphrases)
+            self._table = np.empty((len(collections), len(prepared_keyphrases)), dtype=np.float64)
+            self._table_keyphrases = list(prepared_keyphrases)
         for docs in plan_batches([len(p) for p in packed]):
-            index = _capi.DeviceIndex([packed[j] for j in docs], [len(collections[j]) for j in docs], device=self.device)
+            if fused is None:
+                index = _capi.DeviceIndex([packed[j] for j in docs], [len(collections[j]) for j in docs], device=self.device)
+            else:
+                doc_off = np.zeros(len(docs) + 1, dtype=np.int64)
+                np.cumsum([len(packed[j]) for j in docs], out=doc_off[1:])
+                text = np.ascontiguousarray(np.concatenate([packed[j] for j in docs]), dtype=np.uint32)
+                rows = np.empty((len(docs), len(prepared_keyphrases)), dtype=np.float64)
+                index = _capi.DeviceIndex.build_host_and_score(text, doc_off, [len(collections[j]) for j in docs],
+                                                               fused[0], fused[1], rows, normalized=self.normalized,
+                                                               device=self.device)
+                self._table[docs] = rows
             self._batches.append((index, docs))
             for local, j in enumerate(docs):
                 self.asts[j] = easa.EnhancedAnnotatedSuffixArray(collections[j], _index=index, _doc=local)
@@ -97,6 +120,8 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         if self._index is None:
             return np.array([[ast.score(kp, normalized=self.normalized) for kp in prepared_keyphrases]
                              for ast in self.asts], dtype=np.float64)
+        if self._table is not None and list(prepared_keyphrases) == self._table_keyphrases:
+            return self._table   # scored while the collection was being indexed
         codes, off = _capi.pack_keyphrases(prepared_keyphrases)
         if len(self._batches) == 1:
             return self._index.score_table(codes, off, normalized=self.normalized)

@@ -12,7 +12,8 @@ Workload at N=1: BASELINE.json configs[1]: 1 000 keyphrases x 1 000 synthetic Zi
 joined with one NCCL all-gather inside the timed step.
 
   value      device-timed (CUDA events), inputs resident in HBM, max over ranks
-  e2e        same step through the host-buffer C-ABI calls (east_build_host / east_score_table_host):
+  e2e        same step through the host-buffer C-ABI call behind applications.keyphrases_table (east_table_host =
+             build + score; EAST_BENCH_E2E=two_calls: east_build_host then east_score_table_host):
              pinned host text -> device, table -> host, inside the timed region
   roofline   dominant kernel of the step: algorithmic bytes / its event-timed duration vs measured HBM peak
   cpu_baseline  the reference's own Python code (or the C port when oracle/_ref is absent) on a bounded sample
@@ -261,12 +262,21 @@ def run_b200(args):
     debug = bool(os.environ.get("EAST_BENCH_DEBUG"))
     apply_env_options(_capi)
 
+    # A/B: EAST_BENCH_E2E=two_calls times east_build_* followed by east_score_table_* instead of the one-call entries
+    two_calls = os.environ.get("EAST_BENCH_E2E", "") == "two_calls"
+
     def step_device():
         ta = time.perf_counter()
-        idx = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank,
-                                          stream=stream.cuda_stream)
-        tb = time.perf_counter()
-        idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
+        if two_calls:
+            idx = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank,
+                                              stream=stream.cuda_stream)
+            tb = time.perf_counter()
+            idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
+        else:   # east_table_dev: build + score, the per-document kernel scores its document itself
+            idx = _capi.DeviceIndex.build_dev_and_score(text_dev.data_ptr(), doc_off, doc_m, kp_dev.data_ptr(), kp_codes,
+                                                        kp_off, out_dev.data_ptr(), True, device=local_rank,
+                                                        stream=stream.cuda_stream)
+            tb = time.perf_counter()
         tc = time.perf_counter()
         if world > 1:
             # the step ends when the gathered [N*D, K] table is complete on this rank (without this
@@ -276,7 +286,7 @@ def run_b200(args):
         td = time.perf_counter()
         info = idx.info()
         idx.close()  # waits for the LCP / child / annotation kernels that overlapped the scorer
-        timings = idx.build_timings + idx.score_timings
+        timings = idx.build_timings + getattr(idx, "score_timings", [])
         if debug:
             sys.stderr.write("[rank %d] dev step: build %.2f ms, score %.2f ms, gather %.2f ms, close %.2f ms\n" % (
                 rank, (tb - ta) * 1e3, (tc - tb) * 1e3, (td - tc) * 1e3, (time.perf_counter() - td) * 1e3))
@@ -284,9 +294,14 @@ def run_b200(args):
 
     def step_e2e():
         ta = time.perf_counter()
-        idx = _capi.DeviceIndex.build_host(host_text_np, doc_off, doc_m, device=local_rank)
-        tb = time.perf_counter()
-        idx.score_table_into(kp_codes, kp_off, host_out_np, True)
+        if two_calls:
+            idx = _capi.DeviceIndex.build_host(host_text_np, doc_off, doc_m, device=local_rank)
+            tb = time.perf_counter()
+            idx.score_table_into(kp_codes, kp_off, host_out_np, True)
+        else:   # east_table_host: the call behind applications.keyphrases_table (build + score, overlapped)
+            idx = _capi.DeviceIndex.build_host_and_score(host_text_np, doc_off, doc_m, kp_codes, kp_off, host_out_np,
+                                                         True, device=local_rank)
+            tb = time.perf_counter()
         tc = time.perf_counter()
         pipelined = idx.stat("pipelined")
         if world > 1:
@@ -394,7 +409,8 @@ def run_b200(args):
         "config": workload_config(args, n_gpus),
         "e2e": {"value": n_gpus * D * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_total * 4 + doc_off.nbytes + doc_m.nbytes + kp_codes.nbytes + kp_off.nbytes),
-                "d2h_bytes_per_step": int(D * K * 8)},
+                "d2h_bytes_per_step": int(D * K * 8),
+                "call": "east_build_host+east_score_table_host" if two_calls else "east_table_host"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -404,7 +420,8 @@ def run_b200(args):
                      "launches_per_step": dom["launches"] / args.steps, "ms_per_launch": per_launch_ms,
                      "algorithmic_bytes_per_launch": per_launch_bytes,
                      "share_of_step": dom["ms"] / args.steps / dev_ms},
-        "breakdown": {"build_ms": build_ms, "score_ms": score_ms,
+        "breakdown": {"device_call": "east_build_dev+east_score_table_dev" if two_calls else "east_table_dev",
+                      "build_ms": build_ms, "score_ms": score_ms,
                       "sa_build_MB_per_s": text_mb / (build_ms * 1e-3) if build_ms > 0 else None,
                       "build_codepoints_per_s": n_total / (build_ms * 1e-3) if build_ms > 0 else None,
                       "score_only_scores_per_s": D * K / (score_ms * 1e-3) if score_ms > 0 else None,

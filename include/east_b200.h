@@ -93,6 +93,20 @@ int east_score_table_host(const east_index *idx, const uint32_t *kp, const int64
                           int32_t K, int normalized, double *out_DxK);
 int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
                          int32_t K, int normalized, double *out_DxK_dev, void *stream);
+/* Build and score in ONE call: what applications.keyphrases_table does per text (build the structure,
+ * applications.py:25 -> relevance.py:34-49, then score every keyphrase, applications.py:43-52), for the
+ * whole collection.  Arguments as in east_build_host + east_score_table_host.  On a large batch of small
+ * documents the text is copied in runs of whole documents; each run is sorted and scored, and its rows of
+ * out_DxK copied back, while the later runs are still arriving.  Results are identical to the two calls.
+ * out_idx may be NULL; otherwise it receives the index (east_free it). */
+int east_table_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                    int device, const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized,
+                    double *out_DxK, east_index **out_idx);
+/* the same with text, keyphrases and table resident on the device (kp_host: optional host copy of the
+ * keyphrase code points, saves a device-to-host round trip; may be NULL) */
+int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                   int device, const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K,
+                   int normalized, double *out_DxK_dev, void *stream, east_index **out_idx);
 /* the rows of documents [doc_begin, doc_begin + doc_count) only: out[(d - doc_begin) * K + k].  Lets a caller
  * that shards documents over GPUs overlap the collective of one document tile with the scoring of the next. */
 int east_score_range_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,

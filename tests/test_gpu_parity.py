@@ -545,6 +545,95 @@ def test_pipelined_host_build_matches_and_recovers(oracle_mod, sa_path):
         capi.set_option("no_pipeline", 0)
 
 
+def test_build_and_score_in_one_call_matches_the_two_calls(oracle_mod, sa_path):
+    # east_table_host scores every run of documents as soon as the per-document kernel has sorted it, while later
+    # runs are still being copied; whatever happens to the speculation the table equals build + score
+    import synth
+    from east import utils
+    from east.asts import utils as au
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(400, 1200, first_seed=170)
+    kps = [utils.prepare_text(k) for k in synth.keyphrases(40)] + ["QQQQQ7", "中文A", "A中", "E", "TH"]
+    codes, off = capi.pack_keyphrases(kps)
+
+    def both(packed_docs, doc_m, normalized):
+        doc_off = np.zeros(len(packed_docs) + 1, dtype=np.int64)
+        np.cumsum([len(p) for p in packed_docs], out=doc_off[1:])
+        text = np.ascontiguousarray(np.concatenate(packed_docs), dtype=np.uint32)
+        out = np.full((len(packed_docs), len(kps)), -1.0)
+        idx = capi.DeviceIndex.build_host_and_score(text, doc_off, doc_m, codes, off, out, normalized)
+        try:
+            capi.set_option("no_pipeline", 1)
+            ref = capi.DeviceIndex(packed_docs, doc_m)
+            exp = ref.score_table(codes, off, normalized)
+        finally:
+            capi.set_option("no_pipeline", 0)
+        assert np.array_equal(out.view(np.uint64), exp.view(np.uint64))
+        # the index that comes back is a complete one
+        again = idx.score_table(codes, off, normalized)
+        assert np.array_equal(again.view(np.uint64), exp.view(np.uint64))
+        # the same with everything resident on the device (east_table_dev), and the two-call device entries
+        import torch
+        text_t = torch.from_numpy(text.view(np.int32)).cuda()
+        kp_t = torch.from_numpy(codes.view(np.int32).copy()).cuda()
+        out_t = torch.full((len(packed_docs), len(kps)), -1.0, dtype=torch.float64, device="cuda")
+        for host_copy in (codes, None):
+            out_t.fill_(-1.0)
+            dev = capi.DeviceIndex.build_dev_and_score(text_t.data_ptr(), doc_off, doc_m, kp_t.data_ptr(), host_copy, off,
+                                                       out_t.data_ptr(), normalized)
+            assert np.array_equal(out_t.cpu().numpy().view(np.uint64), exp.view(np.uint64))
+        out_t.fill_(-1.0)
+        dev.score_table_dev(kp_t.data_ptr(), off, out_t.data_ptr(), normalized)
+        assert np.array_equal(out_t.cpu().numpy().view(np.uint64), exp.view(np.uint64))
+        if len(packed_docs) > 4:
+            part = torch.full((3, len(kps)), -1.0, dtype=torch.float64, device="cuda")
+            dev.score_range_dev(kp_t.data_ptr(), off, 2, 3, part.data_ptr(), normalized)
+            assert np.array_equal(part.cpu().numpy().view(np.uint64), exp[2:5].view(np.uint64))
+        dev.close()
+        return idx, out
+
+    try:
+        capi.set_option("pipeline_chunk", 40000)   # 3 runs of 148, 148, 104 documents
+        # the per-document kernel scores its document itself (default); the batched scorer after each run
+        # (option, or a scratch budget too small for a run) must give the same table
+        capi.set_option("no_fused_score", 1)
+        both(packed, ms, True)
+        capi.set_option("no_fused_score", 0)
+        capi.set_option("score_tmp_doubles", 20000)
+        both(packed, ms, True)
+        capi.set_option("score_tmp_doubles", 0)
+        for normalized in (True, False):
+            idx, out = both(packed, ms, normalized)
+            if sa_path != "global_sort":
+                assert idx.stat("pipelined") == 1
+            for d in (0, 148, 399):
+                exp = oracle_mod.OracleEASA(text=packed[d], m=ms[d]).score_many(codes, off, normalized)
+                assert np.array_equal(out[d].view(np.uint64), exp.view(np.uint64))
+                _check_arrays(idx, d, oracle_mod.OracleEASA(text=packed[d], m=ms[d]), ("fused", d))
+        # runs scored speculatively and then discarded: a new symbol, a broken layout, a bucket too large (late runs)
+        late = au.pack_strings_collection(["0123456789 QUIZ", "ZEBRA9"])
+        idx, _ = both(list(packed) + [late], list(ms) + [2], True)
+        if sa_path != "global_sort":
+            assert idx.stat("pipeline_miss") == 1 and idx.stat("pipelined") == 0
+        weird = au.pack_strings_collection(["中文", "AB"])
+        idx, _ = both(list(packed) + [weird], list(ms) + [2], True)
+        assert idx.stat("pipelined") == 0
+        runs = au.pack_strings_collection(["E" * 6000, "THE END"])
+        idx, _ = both(list(packed) + [runs], list(ms) + [2], True)
+        assert idx.stat("pipelined") == 0
+        # a batch too small to be pipelined: plain build + score inside the call
+        both(packed[:5], ms[:5], True)
+    finally:
+        capi.set_option("pipeline_chunk", 0)
+        capi.set_option("no_pipeline", 0)
+        capi.set_option("no_fused_score", 0)
+        capi.set_option("score_tmp_doubles", 0)
+    with pytest.raises(ZeroDivisionError):
+        c2, o2 = capi.pack_keyphrases(["A", ""])
+        capi.DeviceIndex.build_host_and_score(np.ascontiguousarray(packed[0], dtype=np.uint32), np.array([0, len(packed[0])]),
+                                              [ms[0]], c2, o2, np.zeros((1, 2)))
+
+
 def test_duplicate_query_suffixes_are_scored_once_and_identically(oracle_mod):
     # identical query suffixes (same tail of the same word, repeated keyphrases) are walked once; the table
     # must not depend on that (option score_no_dedup walks every suffix)
