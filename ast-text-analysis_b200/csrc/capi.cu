@@ -490,9 +490,13 @@ static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const 
             // runs of whole documents, a multiple of the SM count each: one per-document CTA per SM and wave,
             // so a run costs exactly its waves (10 runs of 100 documents on 148 SMs would cost 10 waves, not 7)
             const int32_t per_run = (int32_t)(((int64_t)(n_docs + want - 1) / want + EAST_NUM_SMS - 1) / EAST_NUM_SMS) * EAST_NUM_SMS;
+            // the device idles until the first run is resident and its alphabet known: the first wave's documents
+            // come as a short run (a quarter of the SMs) followed by the rest of the wave
+            const int32_t lead = get_option("no_lead_run", 0) ? 0 : EAST_NUM_SMS / 4;
             plan.doc.push_back(0);
-            for (int32_t d = 0; d < n_docs; d += per_run) {
-                const int32_t d1 = std::min(n_docs, d + per_run);
+            for (int32_t d = 0; d < n_docs;) {
+                const int32_t step = (lead > 0 && d == 0) ? lead : ((lead > 0 && d == lead) ? per_run - lead : per_run);
+                const int32_t d1 = std::min(n_docs, d + step);
                 const int64_t e0 = doc_off[d], e1 = doc_off[d1];
                 EAST_CUDA(cudaMemcpyAsync(d_text + e0, text + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, cs));
                 cudaEvent_t ev;
@@ -500,6 +504,7 @@ static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const 
                 plan.ready.push_back(ev);
                 EAST_CUDA(cudaEventRecord(ev, cs));
                 plan.doc.push_back(d1);
+                d = d1;
             }
         } catch (...) {
             cudaStreamSynchronize(cs);

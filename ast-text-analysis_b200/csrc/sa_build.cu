@@ -918,13 +918,28 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     tm.mark("alphabet");
     DevBuf<ScanResult> d_first(1, s);
     EAST_CUDA(cudaMemsetAsync(d_first.p, 0, sizeof(ScanResult), s));
+    cudaEvent_t tables_zeroed = nullptr;
+    struct EventGuard { cudaEvent_t &e; ~EventGuard() { if (e) cudaEventDestroy(e); } } zero_guard{tables_zeroed};
     if (in.lcp != nullptr) {
         // the per-document kernel stores child table and annotation sparsely into zero-filled arrays: the fills
-        // (16 bytes per code point) run now, while the device has nothing else to do but wait for the first run
-        EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, s));
-        EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, s));
-        EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
-        EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
+        // (16 bytes per code point) run now, on the helper stream, while the first run arrives and its alphabet
+        // makes the round trip to the host
+        cudaStream_t zs = (in.helper_stream && in.helper_stream != s) ? in.helper_stream : s;
+        if (zs != s) {
+            cudaEvent_t fork;
+            EAST_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+            EAST_CUDA(cudaEventRecord(fork, s));                       // the arrays were allocated on s
+            EAST_CUDA(cudaStreamWaitEvent(zs, fork, 0));
+            EAST_CUDA(cudaEventDestroy(fork));
+        }
+        EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, zs));
+        EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, zs));
+        EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, zs));
+        EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, zs));
+        if (zs != s) {
+            EAST_CUDA(cudaEventCreateWithFlags(&tables_zeroed, cudaEventDisableTiming));
+            EAST_CUDA(cudaEventRecord(tables_zeroed, zs));
+        }
     }
     EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
     const int32_t n0 = in.doc_off_host[in.chunk_doc[1]];
@@ -979,6 +994,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             EAST_CUDA(cudaStreamWaitEvent(lanes[1], ready_to_sort, 0));
             if (prep) EAST_CUDA(cudaStreamWaitEvent(prep, ready_to_sort, 0));
         }
+        if (tables_zeroed) EAST_CUDA(cudaStreamWaitEvent(s, tables_zeroed, 0));   // (the helper stream did the fills itself)
         for (int c = 0; c < in.n_chunks; ++c) {
             const int d0 = in.chunk_doc[c], d1 = in.chunk_doc[c + 1];
             const int32_t e0 = in.doc_off_host[d0], e1 = in.doc_off_host[d1];
@@ -1013,6 +1029,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     } else {
         for (int c = 1; c < in.n_chunks; ++c) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
     }
+    if (tables_zeroed) EAST_CUDA(cudaStreamWaitEvent(s, tables_zeroed, 0));   // whatever follows on s comes after the fills
     tm.mark("validate");
     uint32_t h_flags[2] = {0u, 0u};
     if (eligible) EAST_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, s));

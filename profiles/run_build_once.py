@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Build (and score) the bench workload a few times: a short target for ncu captures.
-usage: python profiles/run_build_once.py [docs] [doc_bytes] [iters] [option=value ...]"""
+usage: python profiles/run_build_once.py [docs] [doc_bytes] [iters] [option=value ...]
+(EAST_BENCH_E2E=two_calls: east_build_dev + east_score_table_dev instead of east_table_dev)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "ast-text-analysis_b200")); sys.path.insert(0, ROOT)
@@ -21,9 +22,13 @@ kps = [utils.prepare_text(k) for k in synth.keyphrases(1000)]
 codes, off = _capi.pack_keyphrases(kps)
 kp_dev = torch.from_numpy(codes.view(np.int32).copy()).cuda()
 out = torch.empty(docs * 1000, dtype=torch.float64, device="cuda")
+two_calls = os.environ.get("EAST_BENCH_E2E", "") == "two_calls"
 for _ in range(iters):
-    idx = _capi.DeviceIndex.build_dev(dev.data_ptr(), doc_off, doc_m)
-    idx.score_table_dev(kp_dev.data_ptr(), off, out.data_ptr(), True)
+    if two_calls:
+        idx = _capi.DeviceIndex.build_dev(dev.data_ptr(), doc_off, doc_m)
+        idx.score_table_dev(kp_dev.data_ptr(), off, out.data_ptr(), True)
+    else:   # east_table_dev: the per-document kernel scores its document itself
+        idx = _capi.DeviceIndex.build_dev_and_score(dev.data_ptr(), doc_off, doc_m, kp_dev.data_ptr(), codes, off, out.data_ptr(), True)
     info = idx.info(); idx.close()
-    print(info, [(n, round(m, 3)) for n, m in idx.build_timings + idx.score_timings])
+    print(info, [(n, round(m, 3)) for n, m in idx.build_timings + getattr(idx, "score_timings", [])])
 torch.cuda.synchronize()

@@ -11,7 +11,7 @@ def f(x):
 cur_file = ""
 per = {}   # (file, line) -> [samples, exec, source]
 for r in rows:
-    if len(r) == 2 and r[0] == "File Name":
+    if len(r) == 2 and r[0] in ("File Name", "File Path"):
         cur_file = r[1]; continue
     if len(r) < 8 or r[0] == "Line No": continue
     line, src, addr = r[0], r[1], r[2]
