@@ -618,6 +618,13 @@ def run_config4(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: whatever a library prints there on its own (NCCL's version line under
+    # NCCL_DEBUG=VERSION, for one) is sent to stderr -- the process's descriptor 1 points at stderr while the run lasts,
+    # and print() below writes to a copy of the real one
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.workload == "config4" and args.impl == "b200":
         return run_config4(args)
     if args.workload == "single_doc" and args.impl == "b200":
