@@ -787,57 +787,67 @@ k_doc_suffix_sort(DocSortParams p) {
             if (r1 - last_start > 32) { r1 = last_start; --nseg; }  // a bucket of > 32 identical tails: already in position order
             const int len = r1 - r0;   // <= 63
             if (len <= nseg) continue; // only singletons
-            uint64_t key[2];
-            int li[2], sb[2], se[2];
+            // per slot (lane, lane + 32): bucket [sb, se) of the member, packed -- what else the ranking needs (key,
+            // position) is re-read from the window scratch instead of being kept in registers across the loops
+            uint32_t seg[2];
             const int nslots = len > 32 ? 2 : 1;   // warp-uniform: the second slot only exists for ranges of 33..63
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int x = lane + 32 * s;
-                key[s] = 0; li[s] = 0; sb[s] = 0; se[s] = 0;
+                seg[s] = 0;
                 if (s < nslots && x < len) {
                     const int r = r0 + x;
-                    li[s] = sa_doc[r] - base;
+                    const int li = sa_doc[r] - base;
                     const int wp = r - 32 * w;  // 0..63
                     const uint32_t le = (wp < 32) ? (word & (0xffffffffu >> (31 - wp))) : word;
-                    sb[s] = 32 * w + (31 - __clz(le)) - r0;
+                    const int sb = 32 * w + (31 - __clz(le)) - r0;
                     const uint32_t gt = (wp < 31) ? (word & (0xfffffffeu << wp)) : 0u;
-                    se[s] = gt ? (32 * w + (__ffs(gt) - 1) - r0) : len;
-                    if (se[s] > len) se[s] = len;
-                    if (se[s] - sb[s] > 1) {
-                        key[s] = ds_key8(s_raw, shift + li[s], term8, G);
-                        wkeys[x] = key[s];
+                    int se = gt ? (32 * w + (__ffs(gt) - 1) - r0) : len;
+                    if (se > len) se = len;
+                    if (se - sb > 1) {
+                        wkeys[x] = ds_key8(s_raw, shift + li, term8, G);
+                        seg[s] = (uint32_t)sb | ((uint32_t)se << 8);
                     }
-                    wpos[x] = (uint32_t)li[s];
+                    wpos[x] = (uint32_t)li;
                 }
             }
             __syncwarp();
-            int out[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int x = lane + 32 * s;
-                out[s] = x;
-                if (s < nslots && x < len && se[s] - sb[s] > 1) {
+                if (s < nslots && seg[s] != 0u) {
+                    const int q0 = (int)(seg[s] & 0xffu), q1 = (int)(seg[s] >> 8);
+                    const uint64_t key = wkeys[x];
+                    const uint32_t li = wpos[x];
                     int below = 0;
-                    const uint32_t last = (uint32_t)key[s] & 0xffu;
+                    const uint32_t last = (uint32_t)key & 0xffu;
                     const bool by_pos = last == 0u || last == p.term;   // the window reaches the terminator
-                    for (int q = sb[s]; q < se[s]; ++q) {
+                    // members with a smaller key are counted in a branch-free loop; the members with an EQUAL key
+                    // are only noted (a bucket has at most 32 members: one bit each) and resolved afterwards, so
+                    // that the expensive comparison runs as often as the lane with the most ties needs it, not
+                    // in every iteration in which some lane of the warp meets one
+                    uint32_t ties = 0;
+#pragma unroll 4
+                    for (int q = q0; q < q1; ++q) {
                         const uint64_t kq = wkeys[q];
-                        bool less = kq < key[s];
-                        if (kq == key[s] && q != x) {
-                            const uint32_t pq = wpos[q];
-                            less = by_pos ? (pq < (uint32_t)li[s])
-                                          : ds_deep_less(s_raw, shift + (int)pq, shift + li[s], G + 8, term8);
-                        }
+                        below += (kq < key) ? 1 : 0;
+                        ties |= (kq == key ? 1u : 0u) << (q - q0);
+                    }
+                    ties &= ~(1u << (x - q0));
+                    while (ties) {
+                        const uint32_t pq = wpos[q0 + __ffs(ties) - 1];
+                        ties &= ties - 1u;
+                        const bool less = by_pos ? (pq < li) : ds_deep_less(s_raw, shift + (int)pq, shift + (int)li, G + 8, term8);
                         below += less ? 1 : 0;
                     }
-                    out[s] = sb[s] + below;
+                    seg[s] = (uint32_t)(q0 + below) | 0x100u;   // final offset in the range (< 64), bit 8 = "moved"
                 }
             }
             __syncwarp();
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 const int x = lane + 32 * s;
-                if (s < nslots && x < len && se[s] - sb[s] > 1) sa_doc[r0 + out[s]] = base + li[s];
+                if (s < nslots && seg[s] != 0u) sa_doc[r0 + (int)(seg[s] & 0xffu)] = base + (int32_t)wpos[x];
             }
             __syncwarp();
         }
