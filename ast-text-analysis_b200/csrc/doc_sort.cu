@@ -71,7 +71,7 @@ struct DocSortParams {
     int doc_begin;            // first document of this launch (CTA x sorts document doc_begin + x)
     unsigned long long *phase_clk;  // optional (profiling): SM cycles per phase, summed over the CTAs
     // optional fused tables (all or none): LCP (easa.py:247-266), child table (:268-304), annotation (:306-331);
-    // up/down/next/ann must be zero-filled by the caller, lcp is written for every rank
+    // every entry of the documents of the launch is written (the kernel zero-fills what phase 8 does not set)
     int32_t *lcp, *up, *down, *next, *ann;
     uint32_t *sk;             // optional: the 4 text bytes at offsets 2..5 of every suffix, in rank order (scorer)
     DocScore score;           // optional (recs != nullptr; needs bkt and sk): score the keyphrases against the document
@@ -880,6 +880,13 @@ k_doc_suffix_sort(DocSortParams p) {
         s_pyr_levels = levels;
     }
     __syncthreads();
+    // child table and annotation are stored sparsely in phase 8: their slices of this document are zero-filled
+    // here, by the CTA itself -- the stores drain under the LCP computation and the sparse stores that follow find
+    // the lines in L2 (host-side fills of the whole batch made the kernel wait for them and went to HBM twice)
+    {
+        int32_t *const up_doc = p.up + base, *const down_doc = p.down + base, *const next_doc = p.next + base, *const ann_doc = p.ann + base;
+        for (int r = tid; r < n; r += DS_THREADS) { up_doc[r] = 0; down_doc[r] = 0; next_doc[r] = 0; ann_doc[r] = 0; }
+    }
     SPyr M;
     M.lcp = s_lcp; M.off = s_pyr_off; M.size_ = s_pyr_size; M.levels = s_pyr_levels;
     uint16_t *s_lv1 = s_lcp + s_pyr_off[1];
@@ -935,7 +942,7 @@ k_doc_suffix_sort(DocSortParams p) {
     // stack, e of the ranks still stacked at the end -- comes from the min-pyramid.  Closed forms as
     // in tables.cu: lcp[q] == l -> next[q] = r; else r is the first l-index of [q .. e-1]:
     // ann[r] = e - q, up[e] = r if lcp[q] <= lcp[e], down[q] = r if lcp[e] <= lcp[q] (e inside the
-    // document).  Values are ranks local to the document, 0 = none (arrays zero-filled by the host).
+    // document).  Values are ranks local to the document, 0 = none (the arrays were zero-filled at the start of phase 7).
     // The stacks (one byte per entry: offset in the chunk | 0x80 = first l-index) reuse the text area.
     {
         const int m = p.doc_m[doc];

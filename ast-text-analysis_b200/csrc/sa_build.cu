@@ -918,29 +918,6 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     tm.mark("alphabet");
     DevBuf<ScanResult> d_first(1, s);
     EAST_CUDA(cudaMemsetAsync(d_first.p, 0, sizeof(ScanResult), s));
-    cudaEvent_t tables_zeroed = nullptr;
-    struct EventGuard { cudaEvent_t &e; ~EventGuard() { if (e) cudaEventDestroy(e); } } zero_guard{tables_zeroed};
-    if (in.lcp != nullptr) {
-        // the per-document kernel stores child table and annotation sparsely into zero-filled arrays: the fills
-        // (16 bytes per code point) run now, on the helper stream, while the first run arrives and its alphabet
-        // makes the round trip to the host
-        cudaStream_t zs = (in.helper_stream && in.helper_stream != s) ? in.helper_stream : s;
-        if (zs != s) {
-            cudaEvent_t fork;
-            EAST_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-            EAST_CUDA(cudaEventRecord(fork, s));                       // the arrays were allocated on s
-            EAST_CUDA(cudaStreamWaitEvent(zs, fork, 0));
-            EAST_CUDA(cudaEventDestroy(fork));
-        }
-        EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, zs));
-        EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, zs));
-        EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, zs));
-        EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, zs));
-        if (zs != s) {
-            EAST_CUDA(cudaEventCreateWithFlags(&tables_zeroed, cudaEventDisableTiming));
-            EAST_CUDA(cudaEventRecord(tables_zeroed, zs));
-        }
-    }
     EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
     const int32_t n0 = in.doc_off_host[in.chunk_doc[1]];
     EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_first.p);
@@ -994,7 +971,6 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             EAST_CUDA(cudaStreamWaitEvent(lanes[1], ready_to_sort, 0));
             if (prep) EAST_CUDA(cudaStreamWaitEvent(prep, ready_to_sort, 0));
         }
-        if (tables_zeroed) EAST_CUDA(cudaStreamWaitEvent(s, tables_zeroed, 0));   // (the helper stream did the fills itself)
         for (int c = 0; c < in.n_chunks; ++c) {
             const int d0 = in.chunk_doc[c], d1 = in.chunk_doc[c + 1];
             const int32_t e0 = in.doc_off_host[d0], e1 = in.doc_off_host[d1];
@@ -1029,7 +1005,6 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     } else {
         for (int c = 1; c < in.n_chunks; ++c) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
     }
-    if (tables_zeroed) EAST_CUDA(cudaStreamWaitEvent(s, tables_zeroed, 0));   // whatever follows on s comes after the fills
     tm.mark("validate");
     uint32_t h_flags[2] = {0u, 0u};
     if (eligible) EAST_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, s));
@@ -1076,25 +1051,6 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     // validates the terminator layout of its document itself.  Whatever it cannot take (bad layout, a
     // bucket too large, an alphabet too wide) is redone below with the validating scan.
     const bool light = allow_doc_sort && in.light_scan && !in.force_general && max_doc_n <= 65535;
-    // The per-document kernel stores the child table and the annotation sparsely into zero-filled arrays.  The
-    // four fills (16 bytes per code point) run on the helper stream from the start, under the text scan, the
-    // host's alphabet round trip and the encoding, instead of in front of the kernel.
-    cudaEvent_t tables_zeroed = nullptr;
-    if (allow_doc_sort && in.lcp != nullptr && in.helper_stream != nullptr && in.helper_stream != s &&
-        max_doc_n <= 65535 && !in.force_general) {
-        cudaEvent_t fork;
-        EAST_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        EAST_CUDA(cudaEventRecord(fork, s));                       // the arrays were allocated on s
-        EAST_CUDA(cudaStreamWaitEvent(in.helper_stream, fork, 0));
-        EAST_CUDA(cudaEventDestroy(fork));
-        EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, in.helper_stream));
-        EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, in.helper_stream));
-        EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, in.helper_stream));
-        EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, in.helper_stream));
-        EAST_CUDA(cudaEventCreateWithFlags(&tables_zeroed, cudaEventDisableTiming));
-        EAST_CUDA(cudaEventRecord(tables_zeroed, in.helper_stream));
-    }
-    struct EventGuard { cudaEvent_t &e; ~EventGuard() { if (e) cudaEventDestroy(e); } } zero_guard{tables_zeroed};
     tm.mark("scan_text");
     EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
     EAST_BYTES(4.0 * n);
@@ -1187,14 +1143,6 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             }
             DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
             const bool fuse = in.lcp != nullptr && plan.tables_fit;
-            if (fuse && tables_zeroed) {
-                EAST_CUDA(cudaStreamWaitEvent(s, tables_zeroed, 0));
-            } else if (fuse) {
-                EAST_CUDA(cudaMemsetAsync(in.up, 0, sizeof(int32_t) * (size_t)n, s));
-                EAST_CUDA(cudaMemsetAsync(in.down, 0, sizeof(int32_t) * (size_t)n, s));
-                EAST_CUDA(cudaMemsetAsync(in.next, 0, sizeof(int32_t) * (size_t)n, s));
-                EAST_CUDA(cudaMemsetAsync(in.ann, 0, sizeof(int32_t) * (size_t)n, s));
-            }
             const bool hooks = out.bkt.p && in.sk;
             const RunReady run{0, D, s, t8.p, out.bkt.p, out.bkt3.p, out.sym_bits, &table, 0};
             DocScore score;
@@ -1230,8 +1178,6 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             out.sym_bits = 0;
         }
     }
-    // whatever follows (the global sort and its table kernels) is ordered after the early zero-fills
-    if (tables_zeroed) EAST_CUDA(cudaStreamWaitEvent(s, tables_zeroed, 0));
     if (light) {
         // the global sort relies on the validated layout: start over with the full scan
         SaInput again = in;

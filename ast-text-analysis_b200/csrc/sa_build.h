@@ -105,7 +105,7 @@ struct DocSortPlan {
     size_t smem = 0;
     int tables_fit = 0;         // the fused LCP / child / annotation phases fit the shared memory too
 };
-struct DocSortTables { int32_t *lcp, *up, *down, *next, *ann; };   // up/down/next zero-filled by the caller
+struct DocSortTables { int32_t *lcp, *up, *down, *next, *ann; };   // every entry of the launched documents is written
 bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan);
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
                      const int32_t *doc_m, int doc_begin, int n_docs,
