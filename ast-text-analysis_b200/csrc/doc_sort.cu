@@ -1,4 +1,4 @@
-// doc_sort.cu -- suffix array, LCP, child table and annotation of every SMALL document by one CTA that keeps
+// doc_sort.cu -- suffix array, LCP, child table, annotation (and keyphrase scores) of every SMALL document by one CTA that keeps
 // the document in shared memory (B200: 227 KB per CTA hold the text, the bucket counters and the scratch).
 //
 // Replaces east/asts/easa.py:141-331 (_compute_suftab, _compute_lcptab, _compute_childtab,
@@ -29,11 +29,17 @@
 //   6  buckets of <= 32 suffixes: a warp takes a window of 32 ranks and every suffix ranks itself inside its
 //      own bucket by counting the smaller members; keys are the next 8 symbols (raw bytes, byte-reversed),
 //      ties go to a byte-wise SWAR comparison of the shared-memory text (or to the position)
-//   7  LCP of neighbouring suffixes (SWAR on the staged text), 16-bit copy + min-pyramid in the freed scratch,
+//   7  zero-fill the document's slices of the child / annotation arrays (phase 8 stores sparsely); LCP of
+//      neighbouring suffixes (SWAR on the staged text), 16-bit copy + min-pyramid in the freed scratch,
 //      per-rank key bytes for the scorer
 //   8  child table and annotation: per-thread chunks walked with the reference's stack discipline, what lies
-//      outside a chunk searched in the pyramid (farthest first, so that the lanes' long searches coincide).
-// A bucket of more than 4096 suffixes raises flag bit 0: the host redoes the batch with the global sort.
+//      outside a chunk searched in the pyramid (farthest first, so that the lanes' long searches coincide)
+//   9  (optional: east_table_host / east_table_dev) score every distinct query suffix against the document
+//      (easa.py:91-139; walks of score_walk.cuh) from a copy of text + suffix array in the freed shared memory,
+//      then add the results up per keyphrase: the CTA writes its row of the score table.
+// A bucket of more than 4096 suffixes raises flag bit 0: the host redoes the batch with the global sort.  A
+// document the kernel gives up on gets empty bucket rows (and, for a bad layout, an in-range suffix array), so
+// that a caller that scores speculatively stays inside the arrays.
 #include "sa_build.h"
 #include "score_walk.cuh"
 
