@@ -373,6 +373,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
                        !in.segmented_sort || !in.local_group_sort) ? 0 : 1;
         in.want_bkt3 = get_option("no_bkt3", 0) ? 0 : 1;
         in.light_scan = get_option("no_light_scan", 0) ? 0 : 1;
+        in.fused_encode = get_option("no_fused_encode", 0) ? 0 : 1;
         if (!get_option("no_suffix_keys", 0)) {
             idx->sk = (uint32_t *)dev_alloc(sizeof(uint32_t) * (size_t)n, s);
             in.sk = idx->sk;

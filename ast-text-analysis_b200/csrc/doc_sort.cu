@@ -81,6 +81,12 @@ struct DocSortParams {
     int32_t *lcp, *up, *down, *next, *ann;
     uint32_t *sk;             // optional: the 4 text bytes at offsets 2..5 of every suffix, in rank order (scorer)
     DocScore score;           // optional (recs != nullptr; needs bkt and sk): score the keyphrases against the document
+    // optional (code_table != nullptr): the kernel byte-codes its document itself from the code points (phase 1)
+    // and writes the codes to t8_out = t8; *miss is set when a code point below 0x0A00 has no code
+    const uint8_t *code_table;
+    uint8_t *t8_out;
+    uint32_t *miss;
+    int64_t text_len;         // code points of the whole batch (bound of the 128-bit loads)
 };
 
 // 8 bytes of shared memory at an arbitrary byte offset from a 16-byte aligned base: three aligned
@@ -557,6 +563,7 @@ k_doc_suffix_sort(DocSortParams p) {
     __shared__ uint32_t s_nlist[2];
     __shared__ uint32_t s_work;
     __shared__ uint32_t s_fail;   // this document cannot be sorted here (a bucket too large)
+    __shared__ uint8_t s_code[EAST_TERM_BASE];   // code point -> dense code (only when the kernel byte-codes its document)
     __shared__ int s_gmin[DS_NGROUPS];
     __shared__ uint32_t s_gw[DS_NGROUPS * DS_GWARPS];
 
@@ -593,10 +600,51 @@ k_doc_suffix_sort(DocSortParams p) {
         for (int i = tid; i < p.bits_words; i += DS_THREADS) s_bits[i] = 0;
         if (tid < 2) s_nlist[tid] = 0;
         if (tid == 0) { s_work = 0; s_fail = 0; }   // s_work here: number of terminator codes seen
+        const bool encode = p.code_table != nullptr;
+        if (encode)
+            for (int i = tid; i < (int)EAST_TERM_BASE; i += DS_THREADS) s_code[i] = p.code_table[i];
         __syncthreads();
-        int bad = 0;
+        int bad = 0, missed = 0;
         for (int o = tid * 16; o < nbytes; o += DS_THREADS * 16) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(p.t8 + a0 + o);
+            uint4 v;
+            if (!encode) {
+                v = *reinterpret_cast<const uint4 *>(p.t8 + a0 + o);
+            } else {
+                // 16 code points -> 16 byte codes (k_encode_text's mapping); only the document's own positions
+                // count for the miss flag and are written back: its neighbours may not even be resident yet
+                uint32_t w[4];
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    const int64_t g = (int64_t)a0 + o + 4 * wi;
+                    uint4 c4;
+                    if (g + 3 < p.text_len) c4 = *reinterpret_cast<const uint4 *>(p.text + g);
+                    else {
+                        c4.x = g < p.text_len ? p.text[g] : EAST_TERM_BASE;
+                        c4.y = g + 1 < p.text_len ? p.text[g + 1] : EAST_TERM_BASE;
+                        c4.z = g + 2 < p.text_len ? p.text[g + 2] : EAST_TERM_BASE;
+                        c4.w = EAST_TERM_BASE;
+                    }
+                    const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t e = c[j] < EAST_TERM_BASE ? (uint32_t)s_code[c[j]] : p.term;
+                        const int i = o + 4 * wi + j - shift;
+                        if (e == 0u && i >= 0 && i < n) missed = 1;
+                        packed |= e << (8 * j);
+                    }
+                    w[wi] = packed;
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+                const int i0 = o - shift;
+                if (i0 >= 0 && i0 + 15 < n) {
+                    *reinterpret_cast<uint4 *>(p.t8_out + a0 + o) = v;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (i0 + j >= 0 && i0 + j < n) p.t8_out[base + i0 + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+                }
+            }
             *reinterpret_cast<uint4 *>(s_raw + o) = v;
             // the suffixes that ARE a terminator form the last bucket (term is the top code) and are
             // ordered by string index = terminator value - 0x0A00: final right here, while the
@@ -616,6 +664,7 @@ k_doc_suffix_sort(DocSortParams p) {
                 }
             }
         }
+        if (missed) atomicOr(p.miss, 1u);
         __syncthreads();
         // The layout every later phase relies on (east/asts/utils.py:25-40): exactly m terminator codes,
         // string k ends with 0x0A00 + k, the document ends with its last terminator.  A build that
@@ -1077,7 +1126,8 @@ bool doc_sort_plan(int sigma, int32_t max_doc_n, DocSortPlan &plan) {
 void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t *text, const int32_t *doc_off,
                      const int32_t *doc_m, int doc_begin, int n_docs,
                      int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *bkt3, uint32_t *overflow, cudaStream_t s,
-                     unsigned long long *phase_clk, const DocSortTables *tables, uint32_t *sk, const DocScore *score) {
+                     unsigned long long *phase_clk, const DocSortTables *tables, uint32_t *sk, const DocScore *score,
+                     const uint8_t *code_table, uint32_t *miss, int64_t text_len) {
     static bool configured = false;
     if (!configured) {
         EAST_CUDA(cudaFuncSetAttribute(k_doc_suffix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -1091,12 +1141,15 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     p.doc_begin = doc_begin;
     p.sk = sk;
     if (score && score->recs && bkt && sk) p.score = *score;
+    p.code_table = (code_table && miss) ? code_table : nullptr;
+    p.t8_out = const_cast<uint8_t *>(t8); p.miss = miss; p.text_len = text_len;
     p.lcp = p.up = p.down = p.next = p.ann = nullptr;
     if (tables && plan.tables_fit) { p.lcp = tables->lcp; p.up = tables->up; p.down = tables->down; p.next = tables->next; p.ann = tables->ann; }
     // algorithmic bytes per code point: 1 (byte text in) + 4 (suffix array out), with the fused tables + 5 x 4
-    // (LCP, up, down, next, annotation out); with the scorer inside, plus the bytes of its walks (counted by the
+    // (LCP, up, down, next, annotation out), + 4 when the kernel byte-codes the text itself (code points in);
+    // with the scorer inside, plus the bytes of its walks (counted by the
     // instrumented scorer, option score_bytes)
-    EAST_BYTES((p.lcp ? 25.0 : 5.0) * (double)n_total + (p.score.recs ? p.score.algorithmic_bytes : 0.0));
+    EAST_BYTES(((p.lcp ? 25.0 : 5.0) + (p.code_table ? 4.0 : 0.0)) * (double)n_total + (p.score.recs ? p.score.algorithmic_bytes : 0.0));
     EAST_LAUNCH(k_doc_suffix_sort, n_docs, DS_THREADS, plan.smem, s, p);
 }
 

@@ -975,12 +975,14 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             const int d0 = in.chunk_doc[c], d1 = in.chunk_doc[c + 1];
             const int32_t e0 = in.doc_off_host[d0], e1 = in.doc_off_host[d1];
             cudaStream_t ls = lanes[c & 1];
-            cudaStream_t es = prep ? prep : ls;
+            cudaStream_t es = (prep && !in.fused_encode) ? prep : ls;
             if (c > 0) EAST_CUDA(cudaStreamWaitEvent(es, in.chunk_ready[c], 0));
-            EAST_BYTES(5.0 * (e1 - e0));
-            EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, es, in.text, e0, e1, d_table.p,
-                        (uint8_t)term, t8.p, flags.p + 1);
-            if (prep) {
+            if (!in.fused_encode) {
+                EAST_BYTES(5.0 * (e1 - e0));
+                EAST_LAUNCH(k_encode_text, grid_for(e1 - e0, 256 * 4 * 4, 4), 256, 0, es, in.text, e0, e1, d_table.p,
+                            (uint8_t)term, t8.p, flags.p + 1);
+            }
+            if (prep && !in.fused_encode) {
                 cudaEvent_t coded;
                 EAST_CUDA(cudaEventCreateWithFlags(&coded, cudaEventDisableTiming));
                 EAST_CUDA(cudaEventRecord(coded, prep));
@@ -992,7 +994,8 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             DocScore score;
             if (hooks && in.run_begin) in.run_begin(in.run_ctx, run, score);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
-                            out.bkt3.p, flags.p, ls, nullptr, fuse ? &tables : nullptr, in.sk, &score);
+                            out.bkt3.p, flags.p, ls, nullptr, fuse ? &tables : nullptr, in.sk, &score,
+                            in.fused_encode ? d_table.p : nullptr, flags.p + 1, n);
             if (hooks && in.run_hook) in.run_hook(in.run_ctx, run, score.recs != nullptr ? 1 : 0);
         }
         if (lanes[1] != s) {
@@ -1102,26 +1105,34 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     out.key_bits = key_bits;
 
     tm.mark("encode");
-    DevBuf<uint8_t> t8;
-    if (fast) {
-        DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
-        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p);
-        t8 = DevBuf<uint8_t>((size_t)n + 128, s);
+    DevBuf<uint8_t> t8, d_table;
+    // the per-document kernel byte-codes its document itself: the separate pass only runs for the global sort
+    DocSortPlan doc_plan;
+    const bool try_doc_sort = fast && allow_doc_sort && doc_sort_plan(sigma, max_doc_n, doc_plan);
+    bool coded = false;
+    auto encode_all = [&]() {
         EAST_BYTES(5.0 * n);
         EAST_LAUNCH(k_encode_text, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, 0, n, d_table.p,
                     (uint8_t)kp.term, t8.p, (uint32_t *)nullptr);
+        coded = true;
+    };
+    if (fast) {
+        d_table = DevBuf<uint8_t>(EAST_TERM_BASE, s);
+        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p);
+        t8 = DevBuf<uint8_t>((size_t)n + 128, s);
+        if (!(try_doc_sort && in.fused_encode)) encode_all();
     }
     out.code_table = table;
     out.term_code = fast ? (int)kp.term : 0;
 
     // ---- small documents: one CTA per document, everything in shared memory (doc_sort.cu)
     uint32_t doc_sort_flags = 0;   // bit 0: a bucket too large, bit 1: bad terminator layout
-    if (fast && allow_doc_sort) {
-        DocSortPlan plan;
-        if (doc_sort_plan(sigma, max_doc_n, plan)) {
+    if (try_doc_sort) {
+        const DocSortPlan &plan = doc_plan;
+        {
             tm.mark("doc_sort");
-            DevBuf<uint32_t> flag(1, s);
-            EAST_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), s));
+            DevBuf<uint32_t> flag(2, s);   // [0] the kernel's flags, [1] encoder miss (cannot happen here: the alphabet is complete)
+            EAST_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(uint32_t), s));
             if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
                 const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
                 out.bkt = DevBuf<uint32_t>(entries, s);
@@ -1148,7 +1159,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             DocScore score;
             if (hooks && in.run_begin) in.run_begin(in.run_ctx, run, score);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, 0, D, n, kp.term, out.sa, out.bkt.p, out.bkt3.p, flag.p, s, clk.p,
-                            fuse ? &tables : nullptr, in.sk, &score);
+                            fuse ? &tables : nullptr, in.sk, &score, coded ? nullptr : d_table.p, flag.p + 1, n);
             uint32_t overflow = 0;
             EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
             EAST_CUDA(cudaStreamSynchronize(s));
@@ -1178,6 +1189,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             out.sym_bits = 0;
         }
     }
+    if (fast && !coded && !light) encode_all();   // the global sort reads the whole byte text
     if (light) {
         // the global sort relies on the validated layout: start over with the full scan
         SaInput again = in;

@@ -56,6 +56,7 @@ struct SaInput {
     uint32_t *sk = nullptr;                 // destination of the scorer's per-rank key bytes (fast path only)
     int light_scan = 1;                     // small documents: alphabet-only scan first (the per-document kernel validates)
     int want_bkt3 = 1;                      // per-document kernel: also keep its 3-gram bucket starts for the scorer
+    int fused_encode = 1;                   // per-document kernel: byte-code the text itself (no separate k_encode_text pass)
     // pipelined host build: the text arrives in n_chunks runs of whole documents; chunk c = documents
     // [chunk_doc[c], chunk_doc[c+1]) is resident once chunk_ready[c] has fired (recorded on the copy stream)
     int n_chunks = 0;
@@ -113,7 +114,9 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
                      unsigned long long *phase_clk = nullptr /* profiling: 8 cycle counters */,
                      const DocSortTables *tables = nullptr /* also produce LCP, child table, annotation */,
                      uint32_t *sk = nullptr /* also produce the scorer's per-rank key bytes */,
-                     const DocScore *score = nullptr /* also score keyphrases (needs bkt and sk) */);
+                     const DocScore *score = nullptr /* also score keyphrases (needs bkt and sk) */,
+                     const uint8_t *code_table = nullptr /* byte-code the text in the kernel (writes t8, sets *miss) */,
+                     uint32_t *miss = nullptr, int64_t text_len = 0 /* code points of the whole batch */);
 
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch
