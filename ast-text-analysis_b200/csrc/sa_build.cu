@@ -362,16 +362,21 @@ k_encode_text(const uint32_t *__restrict__ T, int32_t begin, int32_t end, const 
 // presence bitmap, on the device: the host derives the same table for itself, and a host-to-device upload here
 // would queue behind the bulk text copies of a pipelined build (one copy engine per direction).
 __global__ void __launch_bounds__(128)
-k_code_table(const ScanResult *__restrict__ res, uint8_t *__restrict__ table) {
+k_code_table(const ScanResult *__restrict__ res, uint8_t *__restrict__ table, uint4 extra) {
+    // extra: code points below 128 that get a code although the scan did not meet them (pipelined build)
     constexpr int W = EAST_TERM_BASE / 32;
+    __shared__ uint32_t s_bits[W];
     __shared__ uint32_t s_before[W];
+    const uint32_t ex[4] = {extra.x, extra.y, extra.z, extra.w};
+    for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = res->present[w] | (w < 4 ? ex[w] : 0u);
+    __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t run = 0;
-        for (int w = 0; w < W; ++w) { s_before[w] = run; run += __popc(res->present[w]); }
+        for (int w = 0; w < W; ++w) { s_before[w] = run; run += __popc(s_bits[w]); }
     }
     __syncthreads();
     for (int w = threadIdx.x; w < W; w += blockDim.x) {
-        const uint32_t bits = res->present[w];
+        const uint32_t bits = s_bits[w];
         uint32_t code = s_before[w];
         for (int k = 0; k < 32; ++k) {
             const bool on = (bits >> k) & 1u;
@@ -924,7 +929,27 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     ScanResult first;
     EAST_CUDA(cudaMemcpyAsync(&first, d_first.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
     EAST_CUDA(cudaStreamSynchronize(s));
-    const uint32_t *present = first.present;
+    // The alphabet of run 0 (a few dozen documents) may lack a rare letter or digit that later runs use, and a miss
+    // costs a second, ordinary build.  A code that the text never uses costs nothing as long as the symbol width
+    // stays the same: a class of ASCII symbols (A-Z, a-z, 0-9) that run 0 has met at all is completed when that fits.
+    uint32_t *present = first.present;
+    uint32_t extra[4] = {0u, 0u, 0u, 0u};
+    {
+        int seen = 0;
+        for (int w = 0; w < (int)(EAST_TERM_BASE / 32); ++w) seen += __builtin_popcount(present[w]);
+        const int width = bits_for((uint64_t)seen + 1);
+        int room = (1 << width) - 1 - (seen + 1);   // codes 1..sigma and sigma + 1 for the terminators must fit `width` bits
+        const int classes[3][2] = {{'A', 'Z'}, {'a', 'z'}, {'0', '9'}};
+        for (auto &cl : classes) {
+            int have = 0, lack = 0;
+            for (int c = cl[0]; c <= cl[1]; ++c) (present[c >> 5] & (1u << (c & 31))) ? ++have : ++lack;
+            if (have == 0 || lack == 0 || lack > room) continue;
+            for (int c = cl[0]; c <= cl[1]; ++c)
+                if (!(present[c >> 5] & (1u << (c & 31)))) extra[c >> 5] |= 1u << (c & 31);
+            room -= lack;
+        }
+        for (int w = 0; w < 4; ++w) present[w] |= extra[w];
+    }
     int sigma = 0;
     std::vector<uint8_t> table(EAST_TERM_BASE, 0);
     for (uint32_t c = 0; c < EAST_TERM_BASE; ++c)
@@ -938,7 +963,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     if (eligible) {
         tm.mark("doc_sort");
         DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
-        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_first.p, d_table.p);
+        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_first.p, d_table.p, make_uint4(extra[0], extra[1], extra[2], extra[3]));
         t8 = DevBuf<uint8_t>((size_t)n + 128, s);
         EAST_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(uint32_t), s));
         if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
@@ -1118,7 +1143,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     };
     if (fast) {
         d_table = DevBuf<uint8_t>(EAST_TERM_BASE, s);
-        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p);
+        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p, make_uint4(0u, 0u, 0u, 0u));
         t8 = DevBuf<uint8_t>((size_t)n + 128, s);
         if (!(try_doc_sort && in.fused_encode)) encode_all();
     }

@@ -304,6 +304,9 @@ def run_b200(args):
             tb = time.perf_counter()
         tc = time.perf_counter()
         pipelined = idx.stat("pipelined")
+        if debug:
+            sys.stderr.write("e2e index: pipelined=%d miss=%d doc_sorted=%d overflow=%d\n" % (
+                pipelined, idx.stat("pipeline_miss"), idx.stat("doc_sorted"), idx.stat("doc_sort_overflow")))
         if world > 1:
             out_dev.copy_(host_out.view(-1), non_blocking=True)   # gather the table this step produced
             dist.all_gather_into_tensor(gathered, out_dev)
