@@ -101,6 +101,14 @@ def test_argument_validation_needs_no_gpu():
                            off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                            m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 1, 0, ctypes.byref(h))
     assert rc == -1 and b"empty document" in L.east_last_error()
+    # the one-call entry validates the documents AND the keyphrases before it touches the device: an empty
+    # query is the reference's ZeroDivisionError (easa.py:134), whatever else would happen later
+    out = np.zeros((1, 2))
+    with pytest.raises(ValueError):
+        _capi.DeviceIndex.build_host_and_score(text, off, m, np.array([65], dtype=np.uint32), np.array([0, 1, 1]), out)
+    good_off = np.array([0, 2], dtype=np.int64)
+    with pytest.raises(ZeroDivisionError):
+        _capi.DeviceIndex.build_host_and_score(text, good_off, m, np.array([65], dtype=np.uint32), np.array([0, 1, 1]), out)
 
 
 def test_synthetic_generator_is_deterministic():
