@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -83,6 +85,19 @@ static inline int bits_for(uint64_t v) {  // number of bits needed to represent 
     int b = 0;
     while (v) { ++b; v >>= 1; }
     return b;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: a process that indexes on several devices
+// (the `device` argument of the C ABI) must opt in on each of them, once
+static inline void ensure_dynamic_smem(const void *kernel, int bytes) {
+    static std::mutex m;
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    EAST_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(m);
+    if (done.count({kernel, dev})) return;
+    EAST_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.insert({kernel, dev});
 }
 
 static inline int grid_for(int64_t work_items, int per_block, int max_waves = 8) {

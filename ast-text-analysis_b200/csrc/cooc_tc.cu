@@ -332,13 +332,9 @@ void cooc_counts_tc(const double *S_DxK, int64_t D, int32_t K, double threshold,
     dim3 tg((unsigned)((Dp + 31) / 32), (unsigned)((K + 31) / 32));
     EAST_BYTES(8.0 * (double)D * K + (double)K * Dp);
     EAST_LAUNCH(k_threshold_bytes, tg, 256, 0, s, S_DxK, D, K, threshold, Bm.p, Dp);
-    static bool configured = false;
     const int smem = 2 * CT_STAGE_BYTES + 1024, smem_pipe = CP_STAGES * CP_STAGE_BYTES + 1024;
-    if (!configured) {
-        EAST_CUDA(cudaFuncSetAttribute(k_cooc_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        EAST_CUDA(cudaFuncSetAttribute(k_cooc_umma_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pipe));
-        configured = true;
-    }
+    ensure_dynamic_smem((const void *)k_cooc_umma, smem);
+    ensure_dynamic_smem((const void *)k_cooc_umma_pipe, smem_pipe);
     if (simple) {
         dim3 grid(Kp / CT_TILE, Kp / CT_TILE);
         EAST_LAUNCH(k_cooc_umma, grid, CT_THREADS, smem, s, Bm.p, Dp, Kp, K, C);

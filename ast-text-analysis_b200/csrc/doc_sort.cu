@@ -1128,11 +1128,7 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
                      int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *bkt3, uint32_t *overflow, cudaStream_t s,
                      unsigned long long *phase_clk, const DocSortTables *tables, uint32_t *sk, const DocScore *score,
                      const uint8_t *code_table, uint32_t *miss, int64_t text_len) {
-    static bool configured = false;
-    if (!configured) {
-        EAST_CUDA(cudaFuncSetAttribute(k_doc_suffix_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        configured = true;
-    }
+    ensure_dynamic_smem((const void *)k_doc_suffix_sort, 220 * 1024);
     DocSortParams p;
     p.t8 = t8; p.text = text; p.doc_off = doc_off; p.doc_m = doc_m; p.sa = sa; p.bkt = bkt; p.bkt3 = (plan.G == 3) ? bkt3 : nullptr; p.overflow = overflow;
     p.b = plan.b; p.G = plan.G; p.S2 = plan.S2; p.term = term;

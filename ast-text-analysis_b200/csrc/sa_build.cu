@@ -34,12 +34,8 @@ static void launch_onesweep(const uint64_t *kin, uint64_t *kout, const uint32_t 
                             int shift, const uint32_t *hist_excl, uint32_t *status, uint32_t *ticket,
                             cudaStream_t s) {
     using Cfg = RsCfg<THREADS, ITEMS>;
-    static bool configured = false;
     auto kern = k_rs_onesweep<THREADS, ITEMS, MINB>;
-    if (!configured) {
-        EAST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        configured = true;
-    }
+    ensure_dynamic_smem((const void *)kern, Cfg::SMEM);
     const int tiles = rs_num_tiles(n, Cfg::TILE);
     EAST_BYTES(24.0 * n);  // read + write of an 8-byte key and a 4-byte value per element
     if (g_time_kernels) ktime_begin("k_rs_onesweep", s);
@@ -103,11 +99,7 @@ int radix_sort_pairs_segmented(uint64_t *ka, uint64_t *kb, uint32_t *va, uint32_
     using Cfg = RsCfg<256, 16>;
     static_assert(Cfg::TILE == RS_SEG_TILE, "tile descriptors are built for the 256 x 16 kernel");
     auto kern = k_rs_onesweep<256, 16, 3>;
-    static bool configured = false;
-    if (!configured) {
-        EAST_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        configured = true;
-    }
+    ensure_dynamic_smem((const void *)kern, Cfg::SMEM);
     // exclusive scan of every (segment, pass) row of 256 bins
     EAST_LAUNCH(k_rs_scan_hist, n_seg * passes, 256, 0, s, hist);
     const size_t status_words = (size_t)num_tiles * 256;
