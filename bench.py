@@ -625,7 +625,7 @@ def main():
     # NCCL_DEBUG=VERSION, for one) is sent to stderr -- the process's descriptor 1 points at stderr while the run lasts,
     # and print() below writes to a copy of the real one
     sys.stdout.flush()
-    real_stdout = os.fdopen(os.dup(1), "w")
+    real_stdout = os.fdopen(os.dup(1), "w", buffering=1)   # line-buffered: the JSON line leaves with its newline
     os.dup2(2, 1)
     sys.stdout = real_stdout
     if args.workload == "config4" and args.impl == "b200":
