@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -11,6 +12,7 @@
 
 #include "../../include/east_b200.h"
 #include "sa_build.h"
+#include "kp_prep.h"
 
 namespace east {
 
@@ -87,7 +89,13 @@ void *dev_alloc(size_t bytes, cudaStream_t s) {
     }
     return p;
 }
-void dev_free(void *p, cudaStream_t s) { if (p) cudaFreeAsync(p, s); }
+void dev_free(void *p, cudaStream_t s) {
+    if (!p) return;
+    // an exception is unwinding the build: kernels that use the buffer may still run on the auxiliary, helper, prep or
+    // copy streams (non-blocking: `s` does not order them) -- let the device finish before anything goes back to the pool
+    if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();
+    cudaFreeAsync(p, s);
+}
 
 static double host_now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -293,6 +301,7 @@ int east_kernel_stats(char *names, int32_t names_cap, double *ms, int64_t *launc
 static void free_index(east_index *idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
+    if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();   // error path: see dev_free
     if (idx->tables_pending) { cudaEventSynchronize(idx->ev_tables); idx->tables_pending = false; }
     if (idx->build_timer) { try { idx->build_timer->collect(); } catch (...) {} idx->build_timer.reset(); }
     if (idx->ev_tables) cudaEventDestroy(idx->ev_tables);
@@ -477,7 +486,7 @@ static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const 
     if (!pipelined) {
         e = cudaMemcpyAsync(d_text, text, bytes, cudaMemcpyHostToDevice, 0);
         if (e != cudaSuccess) { dev_free(d_text, 0); throw Error(EAST_ERR_CUDA, cudaGetErrorString(e)); }
-        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out);  // owns d_text from here on
+        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, nullptr, hook);  // owns d_text from here on
     } else {
         ChunkPlan plan;
         cudaStream_t cs = copy_stream(device);
@@ -614,15 +623,13 @@ int east_index_devptr(const east_index *idx, int which, const void **ptr) {
 // other (document tiles, ranks, benchmark steps).  A hit is confirmed by comparing the code points.
 struct KpPrepared {
     int device = -1;
-    bool dedup = false, fast = false;
+    bool dedup = false, fast = false, finished = false;
     int sym_bits = 0;
-    std::vector<uint32_t> kp;          // host copy of the code points (cache key)
+    std::vector<uint32_t> kp;          // host copy of the code points (cache key; host preparation)
     std::vector<int64_t> off;          // K + 1 offsets (cache key)
     std::vector<uint8_t> code_table;   // alphabet of the index the dense codes were made for (cache key)
     int64_t n_uniq = 0;
-    DevBuf<int32_t> d_off, d_uniq_of;
-    DevBuf<SufRec> d_recs;
-    DevBuf<uint8_t> d_q8;
+    KpDevice dev;                      // d_off, d_uniq_of, d_recs, d_q8: filled by kp_prep.cu (or by the host variant)
 };
 static thread_local std::unique_ptr<KpPrepared> g_kp_cache;
 
@@ -634,29 +641,14 @@ static void check_keyphrases(const int64_t *kp_off, int32_t K) {
     }
 }
 
-static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_dev, const uint32_t *kp_host_in,
-                                      const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s) {
+// The host variant of kp_prep.cu (round 1; option "kp_prep_host" = 1, kept as the cross-check of the device pipeline):
+// hashing, sorting and coding on the host, four uploads and a stream sync.
+static void prepare_keyphrases_host(KpPrepared *c, bool fast, int sym_bits, const std::vector<uint8_t> &code_table,
+                                    const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s) {
     const int64_t total = kp_off[K];
-    check_keyphrases(kp_off, K);
-    std::vector<uint32_t> kp_host((size_t)total);
-    if (kp_host_in) {   // the caller's host copy (east_score_table_host): no round trip through the device
-        std::copy(kp_host_in, kp_host_in + total, kp_host.begin());
-    } else {
-        EAST_CUDA(cudaMemcpyAsync(kp_host.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
-        EAST_CUDA(cudaStreamSynchronize(s));
-    }
-    const bool fast = idx->bkt && idx->t8 && !get_option("score_generic", 0);
-    KpPrepared *c = g_kp_cache.get();
-    if (c && c->device == idx->device && c->dedup == dedup && c->fast == fast && (int64_t)c->off.size() == (int64_t)K + 1 &&
-        c->kp == kp_host && std::equal(c->off.begin(), c->off.end(), kp_off) &&
-        (!fast || (c->sym_bits == idx->sym_bits && c->code_table == idx->code_table)))
-        return c;
-    g_kp_cache.reset(new KpPrepared());
-    c = g_kp_cache.get();
-    c->device = idx->device; c->dedup = dedup; c->fast = fast; c->sym_bits = idx->sym_bits;
-    c->off.assign(kp_off, kp_off + K + 1);
-    if (fast) c->code_table = idx->code_table;
-
+    const std::vector<uint32_t> &kp_host = c->kp;
+    struct { const std::vector<uint8_t> &code_table; int sym_bits; } view{code_table, sym_bits};
+    auto *idx = &view;
     std::vector<int32_t> off32(K + 1), suf_kp((size_t)total);
     for (int32_t k = 0; k <= K; ++k) off32[k] = (int32_t)kp_off[k];
     for (int32_t k = 0; k < K; ++k)
@@ -773,23 +765,85 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
         recs[(size_t)pos] = r;
     }
     for (int64_t p = 0; p < total; ++p) uniq_of[(size_t)p] = pos_of[(size_t)uniq_of[(size_t)p]];
-    c->d_off = DevBuf<int32_t>(K + 1, s);
-    c->d_uniq_of = DevBuf<int32_t>((size_t)total, s);
-    c->d_recs = DevBuf<SufRec>((size_t)n_uniq, s);
-    EAST_CUDA(cudaMemcpyAsync(c->d_off.p, off32.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, s));
-    EAST_CUDA(cudaMemcpyAsync(c->d_uniq_of.p, uniq_of.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
-    EAST_CUDA(cudaMemcpyAsync(c->d_recs.p, recs.data(), sizeof(SufRec) * (size_t)n_uniq, cudaMemcpyHostToDevice, s));
+    KpDevice &d = c->dev;
+    d.total = (int32_t)total; d.K = K; d.dedup = dedup;
+    d.d_off = DevBuf<int32_t>(K + 1, s);
+    d.d_uniq_of = DevBuf<int32_t>((size_t)total, s);
+    d.d_recs = DevBuf<SufRec>((size_t)n_uniq, s);
+    EAST_CUDA(cudaMemcpyAsync(d.d_off.p, off32.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(d.d_uniq_of.p, uniq_of.data(), sizeof(int32_t) * (size_t)total, cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(d.d_recs.p, recs.data(), sizeof(SufRec) * (size_t)n_uniq, cudaMemcpyHostToDevice, s));
     if (fast) {
-        c->d_q8 = DevBuf<uint8_t>((size_t)total + 16, s);   // the scorer reads the queries 8 bytes at a time
-        EAST_CUDA(cudaMemsetAsync(c->d_q8.p + total, 0, 16, s));
-        EAST_CUDA(cudaMemcpyAsync(c->d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));
+        d.d_q8 = DevBuf<uint8_t>((size_t)total + 16, s);   // the scorer reads the queries 8 bytes at a time
+        EAST_CUDA(cudaMemsetAsync(d.d_q8.p + total, 0, 16, s));
+        EAST_CUDA(cudaMemcpyAsync(d.d_q8.p, q8.data(), (size_t)total, cudaMemcpyHostToDevice, s));
     }
     EAST_CUDA(cudaStreamSynchronize(s));   // the host staging vectors end here
-    // the entry outlives this call: whoever drops it frees on the legacy stream (every call that used it has synchronised)
-    c->d_off.s = c->d_uniq_of.s = 0;
-    c->d_recs.s = 0;
-    c->d_q8.s = 0;
-    c->kp = std::move(kp_host);
+}
+
+// Keyphrase preparation in two steps.  kp_begin: everything that does not depend on an index (queued on `s`, nothing
+// waits: east_table_host runs it on a side stream under the transfer of the text).  kp_finish: the dense codes for the
+// alphabet of an index, queued on `s`; returns with n_uniq known.  kp_finish may be repeated for another alphabet.
+static std::unique_ptr<KpPrepared> kp_begin(int device, const uint32_t *kp_dev, const uint32_t *kp_host_in, const int64_t *kp_off,
+                                            int32_t K, bool dedup, bool keep_host_copy, cudaStream_t s) {
+    std::unique_ptr<KpPrepared> c(new KpPrepared());
+    const int64_t total = kp_off[K];
+    const bool host_prep = get_option("kp_prep_host", 0) != 0;
+    c->device = device; c->dedup = dedup;
+    c->off.assign(kp_off, kp_off + K + 1);
+    if (keep_host_copy || host_prep) {
+        c->kp.resize((size_t)total);
+        if (kp_host_in) {   // the caller's host copy: no round trip through the device
+            std::copy(kp_host_in, kp_host_in + total, c->kp.begin());
+        } else {
+            EAST_CUDA(cudaMemcpyAsync(c->kp.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+            EAST_CUDA(cudaStreamSynchronize(s));
+        }
+    }
+    if (!host_prep) kp_stage1(c->dev, kp_dev, kp_off, K, dedup, s);
+    return c;
+}
+
+static void kp_finish(KpPrepared *c, const uint32_t *kp_dev, bool fast, int sym_bits, const std::vector<uint8_t> &code_table,
+                      cudaStream_t s) {
+    const int32_t K = (int32_t)c->off.size() - 1;
+    c->fast = fast; c->sym_bits = sym_bits;
+    if (fast) c->code_table = code_table; else c->code_table.clear();
+    if (get_option("kp_prep_host", 0) != 0 || !c->dev.done) {
+        prepare_keyphrases_host(c, fast, sym_bits, code_table, c->off.data(), K, c->dedup, s);
+    } else {
+        kp_stage2(c->dev, kp_dev, fast ? code_table.data() : nullptr, s);
+        c->n_uniq = c->dev.n_uniq;
+    }
+    c->finished = true;
+}
+
+// score calls on an existing index: what was prepared for the previous call is kept (exact match of the code points)
+static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_dev, const uint32_t *kp_host_in,
+                                      const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s) {
+    check_keyphrases(kp_off, K);
+    const int64_t total = kp_off[K];
+    const bool fast = idx->bkt && idx->t8 && !get_option("score_generic", 0);
+    std::vector<uint32_t> kp_host;
+    const uint32_t *kh = kp_host_in;
+    if (!kh) {
+        kp_host.resize((size_t)total);
+        EAST_CUDA(cudaMemcpyAsync(kp_host.data(), kp_dev, sizeof(uint32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+        EAST_CUDA(cudaStreamSynchronize(s));
+        kh = kp_host.data();
+    }
+    KpPrepared *c = g_kp_cache.get();
+    if (c && c->finished && c->device == idx->device && c->dedup == dedup && c->fast == fast && (int64_t)c->off.size() == (int64_t)K + 1 &&
+        (int64_t)c->kp.size() == total && std::equal(c->kp.begin(), c->kp.end(), kh) && std::equal(c->off.begin(), c->off.end(), kp_off) &&
+        (!fast || (c->sym_bits == idx->sym_bits && c->code_table == idx->code_table)))
+        return c;
+    if (c) { cudaSetDevice(c->device); cudaDeviceSynchronize(); g_kp_cache.reset(); cudaSetDevice(idx->device); }
+    g_kp_cache = kp_begin(idx->device, kp_dev, kh, kp_off, K, dedup, true, s);
+    c = g_kp_cache.get();
+    kp_finish(c, kp_dev, fast, idx->sym_bits, idx->code_table, s);
+    EAST_CUDA(cudaStreamSynchronize(s));
+    // the entry outlives this call: whoever drops it frees on the legacy stream of its device, after a device sync
+    for (cudaStream_t *ps : {&c->dev.d_off.s, &c->dev.d_uniq_of.s, &c->dev.d_recs.s, &c->dev.d_q8.s, &c->dev.d_table.s, &c->dev.d_n_uniq.s}) *ps = 0;
     return c;
 }
 
@@ -801,11 +855,11 @@ static void score_enqueue(const east_index *idx, const KpPrepared *kp, const uin
     ScoreInput in;
     in.text = idx->text; in.sa = idx->sa;
     in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
-    in.kp = kp_dev; in.kp_off = kp->d_off.p; in.K = K; in.total_suffixes = (int32_t)total;
-    in.uniq_of = kp->d_uniq_of.p; in.recs = kp->d_recs.p; in.n_uniq = (int32_t)kp->n_uniq;
+    in.kp = kp_dev; in.kp_off = kp->dev.d_off.p; in.K = K; in.total_suffixes = (int32_t)total;
+    in.uniq_of = kp->dev.d_uniq_of.p; in.recs = kp->dev.d_recs.p; in.n_uniq = (int32_t)kp->n_uniq;
     in.normalized = normalized ? 1 : 0;
     if (kp->fast) {
-        in.t8 = idx->t8; in.sk = idx->sk; in.q8 = kp->d_q8.p; in.sym_bits = idx->sym_bits;
+        in.t8 = idx->t8; in.sk = idx->sk; in.q8 = kp->dev.d_q8.p; in.sym_bits = idx->sym_bits;
         in.bkt = idx->bkt + ((size_t)doc_begin << (2 * idx->sym_bits));
         if (idx->bkt3 && !get_option("score_no_bkt3", 0)) in.bkt3 = idx->bkt3 + ((size_t)doc_begin << (3 * idx->sym_bits));
     }
@@ -917,6 +971,8 @@ struct TableRun {
     int32_t K = 0;
     int normalized = 0;
     double *d_out = nullptr, *host_out = nullptr;   // host_out NULL: the table stays on the device
+    std::unique_ptr<KpPrepared> kp_own;   // prepared for this call only (a table call is made once per collection)
+    cudaEvent_t kp_ready = nullptr;       // dense codes of the current pass queued
     KpPrepared *kp = nullptr;
     east_index view;                 // non-owning: the pointers of the index under construction + the run's tables
     cudaStream_t lane[2] = {nullptr, nullptr};
@@ -926,6 +982,7 @@ struct TableRun {
     int32_t docs_scored = 0;         // of the current pass over the batch (a pass starts with document 0)
     int final_pass = 0;              // the last pass was not speculative
     bool failed = false;
+    ~TableRun() { if (kp_ready) cudaEventDestroy(kp_ready); }
 };
 
 static int table_lane(TableRun &t, cudaStream_t s) {
@@ -953,9 +1010,14 @@ static void table_run_begin(void *vctx, const RunReady &r, DocScore &score) {
             v.bkt3 = const_cast<uint32_t *>(r.bkt3);
             v.sym_bits = r.sym_bits;
             v.code_table = *r.code_table;
-            t.kp = prepare_keyphrases(&v, t.d_kp, t.kp_host, t.kp_off, t.K, !get_option("score_no_dedup", 0), r.stream);
+            const bool fast = v.bkt && v.t8 && !get_option("score_generic", 0);
+            kp_finish(t.kp_own.get(), t.d_kp, fast, v.sym_bits, v.code_table, r.stream);
+            t.kp = t.kp_own.get();
+            if (!t.kp_ready) EAST_CUDA(cudaEventCreateWithFlags(&t.kp_ready, cudaEventDisableTiming));
+            EAST_CUDA(cudaEventRecord(t.kp_ready, r.stream));
         }
         if (t.failed || !t.kp) return;
+        EAST_CUDA(cudaStreamWaitEvent(r.stream, t.kp_ready, 0));   // the other lane: the dense codes were queued on the first
         const int li = table_lane(t, r.stream);
         const int64_t n_uniq = std::max<int64_t>(1, t.kp->n_uniq);
         const int64_t budget = get_option("score_tmp_doubles", (int64_t)1 << 27);
@@ -966,9 +1028,9 @@ static void table_run_begin(void *vctx, const RunReady &r, DocScore &score) {
             t.tmp_docs[li] = want;
         }
         if (in_kernel) {
-            score.recs = t.kp->d_recs.p; score.n_uniq = (int32_t)t.kp->n_uniq; score.q8 = t.kp->d_q8.p; score.kp = t.d_kp;
+            score.recs = t.kp->dev.d_recs.p; score.n_uniq = (int32_t)t.kp->n_uniq; score.q8 = t.kp->dev.d_q8.p; score.kp = t.d_kp;
             score.tmp = t.tmp[li].p; score.normalized = t.normalized ? 1 : 0;
-            score.kp_off = t.kp->d_off.p; score.uniq_of = t.kp->d_uniq_of.p; score.K = t.K;
+            score.kp_off = t.kp->dev.d_off.p; score.uniq_of = t.kp->dev.d_uniq_of.p; score.K = t.K;
             score.out = t.d_out + (size_t)r.doc_begin * t.K;
             score.algorithmic_bytes = (double)get_option("score_bytes", 0) * ((double)r.doc_count / (double)t.view.n_docs);
         }
@@ -1008,10 +1070,14 @@ int east_table_host(const uint32_t *text, const int64_t *doc_off, const int32_t 
     check_keyphrases(kp_off, K);
     use_device(device);
     cudaStream_t s = 0;
-    DevBuf<uint32_t> d_kp((size_t)kp_off[K], s);
+    // the keyphrases go first, on a side stream: hashing, ordering and de-duplication of their suffixes (kp_prep.cu)
+    // run there while the text is on its way
+    cudaStream_t ps = prep_stream(device);
+    DevBuf<uint32_t> d_kp((size_t)kp_off[K], ps);
     DevBuf<double> d_out((size_t)n_docs * K, s);
-    EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, ps));
     TableRun run;
+    run.kp_own = kp_begin(device, d_kp.p, kp, kp_off, K, !get_option("score_no_dedup", 0), false, ps);
     run.kp_host = kp; run.d_kp = d_kp.p; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
     run.d_out = d_out.p; run.host_out = out_DxK;
     RunHook hook;
@@ -1044,6 +1110,7 @@ int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32
     use_device(device);
     cudaStream_t s = (cudaStream_t)stream;
     TableRun run;
+    run.kp_own = kp_begin(device, kp_dev, kp_host, kp_off, K, !get_option("score_no_dedup", 0), false, s);
     run.kp_host = kp_host; run.d_kp = kp_dev; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
     run.d_out = out_DxK_dev; run.host_out = nullptr;
     RunHook hook;

@@ -78,7 +78,7 @@ __device__ __forceinline__ void rs_hist_flush(const uint32_t *s_hist, uint32_t *
 }
 
 // exclusive scan of each pass' 256 bins, in place.  grid = passes, block = 256
-__global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t *hist) {
+static __global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t *hist) {
     __shared__ uint32_t s_warp[8];
     uint32_t *h = hist + blockIdx.x * 256;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) k_rs_scan_hist(uint32_t *hist) {
 }
 
 // standalone histogram (used when keys were not produced by a fused generator)
-__global__ void __launch_bounds__(256) k_rs_hist(const uint64_t *__restrict__ keys, int32_t n,
+static __global__ void __launch_bounds__(256) k_rs_hist(const uint64_t *__restrict__ keys, int32_t n,
                                                  int passes, uint32_t *g_hist) {
     __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
     for (int i = threadIdx.x; i < passes * 256; i += blockDim.x) s_hist[i] = 0;

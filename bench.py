@@ -284,8 +284,8 @@ def run_b200(args):
             dist.all_gather_into_tensor(gathered, out_dev)
             torch.cuda.synchronize()
         td = time.perf_counter()
-        info = idx.info()
         idx.close()  # waits for the LCP / child / annotation kernels that overlapped the scorer
+        info = None
         timings = idx.build_timings + getattr(idx, "score_timings", [])
         if debug:
             sys.stderr.write("[rank %d] dev step: build %.2f ms, score %.2f ms, gather %.2f ms, close %.2f ms\n" % (
@@ -323,6 +323,26 @@ def run_b200(args):
     info0 = idx0.info()
     idx0.close()
     _capi.set_option("score_bytes", probes)  # the instrumented scorer counts bytes
+
+    # ---- keyphrase preparation (hashing / ordering / de-duplication of the query suffixes, kp_prep.cu): every
+    # east_table_* call does it from scratch (one call per collection: there is nothing to reuse); the score calls
+    # on an existing index keep it.  Its cost = a score call with new keyphrases minus the same call repeated.
+    def timed_score(idx_, codes_):
+        kd = torch.from_numpy(codes_.view(np.int32).copy()).to(dev)
+        torch.cuda.synchronize()
+        t_a = time.perf_counter()
+        idx_.score_table_dev(kd.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t_a) * 1e3
+    idx1 = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream)
+    cold, warm = [], []
+    for i in range(5):
+        varied = kp_codes.copy()
+        varied[:: max(1, varied.size // 7)] = ord("A") + i     # other keyphrases of the same shape: a miss
+        cold.append(timed_score(idx1, varied))
+        warm.append(timed_score(idx1, varied))
+    idx1.close()
+    kp_prep_ms = max(0.0, sorted(cold)[len(cold) // 2] - sorted(warm)[len(warm) // 2])
 
     def barrier():
         if world > 1:
@@ -377,6 +397,38 @@ def run_b200(args):
     e2e_ms = float(t.item())
     checksum = float(host_out_np.sum())
 
+    # ---- untimed self-check: rows of the table the LAST timed end-to-end step produced (and, at N > 1, rows of the
+    # gathered table that other ranks produced) against the CPU oracle, bit for bit
+    parity = {"checked": False}
+    if rank == 0 and not os.environ.get("EAST_BENCH_NO_PARITY"):
+        try:
+            from oracle import oracle as oracle_mod
+            oracle_mod.build()
+            rows = sorted(set([0, 1, D // 2, D - 1] + list(range(3, D, max(1, D // 14)))))[:18]
+            bad = 0
+            for d in rows:
+                exp = oracle_mod.OracleEASA(text=packed[d], m=int(doc_m[d])).score_many(kp_codes, kp_off, True)
+                bad += int(not np.array_equal(exp.view(np.uint64), host_out_np[d].view(np.uint64)))
+            other = 0
+            if world > 1:
+                g = gathered.view(world, D, K)
+                for r in sorted(set([1, world - 1])):
+                    for j in (0, D - 1):
+                        col = utils.text_to_strings_collection(synth.documents(1, args.doc_bytes, first_seed=1 + r * args.docs + j)[0])
+                        exp = oracle_mod.OracleEASA(col).score_many(kp_codes, kp_off, True)
+                        bad += int(not np.array_equal(exp.view(np.uint64), g[r, j].cpu().numpy().view(np.uint64)))
+                        other += 1
+            parity = {"checked": True, "rows_vs_oracle": len(rows), "rows_of_other_ranks": other, "mismatching_rows": bad,
+                      "how": "bit-exact comparison of fp64 rows with oracle/east_oracle.c after the timed region"}
+        except Exception as e:  # noqa: BLE001
+            parity = {"checked": False, "error": repr(e)}
+    if world > 1:
+        gathered_sum = float(gathered.sum().item())
+        local = torch.tensor([float(out_dev.sum().item())], dtype=torch.float64, device=dev)
+        dist.all_reduce(local)
+        parity["gathered_sum"] = gathered_sum
+        parity["sum_of_rank_sums"] = float(local.item())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -413,7 +465,11 @@ def run_b200(args):
         "e2e": {"value": n_gpus * D * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_total * 4 + doc_off.nbytes + doc_m.nbytes + kp_codes.nbytes + kp_off.nbytes),
                 "d2h_bytes_per_step": int(D * K * 8),
-                "call": "east_build_host+east_score_table_host" if two_calls else "east_table_host"},
+                "call": "east_build_host+east_score_table_host" if two_calls else "east_table_host",
+                "keyphrase_preparation": "inside every call (device, kp_prep.cu): nothing is cached between table calls",
+                "kp_prep_ms": kp_prep_ms},
+        "parity_checked": bool(parity.get("checked") and parity.get("mismatching_rows") == 0),
+        "parity": parity,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -430,7 +486,7 @@ def run_b200(args):
                       "score_only_scores_per_s": D * K / (score_ms * 1e-3) if score_ms > 0 else None,
                       "stages_ms": {k: v / args.steps for k, v in stage_ms.items()},
                       "kernels": kernel_table, "scorer_algorithmic_bytes": probes,
-                      "index": info0, "n_codepoints": n_total, "checksum": checksum,
+                      "index": info0, "n_codepoints": n_total, "checksum": checksum, "kp_prep_ms": kp_prep_ms,
                       "host_prep_s": {"generate": t1 - t0, "tokenize_pack": t2 - t1}},
     }
     if not args.no_cpu_baseline and n_gpus == 1:

@@ -1,0 +1,183 @@
+"""GPU: parity of the ONE-CALL entries (east_table_host / east_table_dev -- the path bench.py times) at the sizes
+the benchmark runs them: ~50 KB documents x 1 000 keyphrases, the pipelined host build, documents at the limits of
+the per-document kernel, and the device-side keyphrase preparation against its host variant.  All bit-exact
+against the CPU oracle (oracle/east_oracle.c), through the C ABI."""
+import numpy as np
+import pytest
+
+from conftest import ARRAY_NAMES
+
+pytestmark = pytest.mark.gpu
+
+
+def _capi():
+    from east import _capi
+    return _capi
+
+
+def _concat(packed):
+    doc_off = np.zeros(len(packed) + 1, dtype=np.int64)
+    np.cumsum([len(p) for p in packed], out=doc_off[1:])
+    return np.ascontiguousarray(np.concatenate(packed), dtype=np.uint32), doc_off
+
+
+def _keyphrases(K, extra=()):
+    import synth
+    from east import utils
+    kps = [utils.prepare_text(k) for k in synth.keyphrases(K)] + list(extra)
+    return _capi().pack_keyphrases(kps)
+
+
+def _table_host(packed, ms, codes, off, normalized=True):
+    text, doc_off = _concat(packed)
+    out = np.full((len(packed), len(off) - 1), -1.0)
+    idx = _capi().DeviceIndex.build_host_and_score(text, doc_off, ms, codes, off, out, normalized)
+    return idx, out
+
+
+def _table_dev(packed, ms, codes, off, normalized=True, host_copy=True):
+    import torch
+    text, doc_off = _concat(packed)
+    text_t = torch.from_numpy(text.view(np.int32)).cuda()
+    kp_t = torch.from_numpy(codes.view(np.int32).copy()).cuda()
+    out_t = torch.full((len(packed), len(off) - 1), -1.0, dtype=torch.float64, device="cuda")
+    idx = _capi().DeviceIndex.build_dev_and_score(text_t.data_ptr(), doc_off, ms, kp_t.data_ptr(), codes if host_copy else None,
+                                                  off, out_t.data_ptr(), normalized)
+    torch.cuda.synchronize()
+    return idx, out_t.cpu().numpy()
+
+
+def _oracle_rows(oracle_mod, packed, ms, docs, codes, off, normalized=True):
+    return {d: oracle_mod.OracleEASA(text=packed[d], m=ms[d]).score_many(codes, off, normalized) for d in docs}
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def _check_arrays(idx, doc, o, tag):
+    capi = _capi()
+    for which, name in zip(range(6), ARRAY_NAMES):
+        got = idx.array(doc, which)
+        exp = getattr(o, name)
+        assert np.array_equal(got, exp), (tag, name, np.nonzero(got != exp)[0][:5])
+
+
+def test_one_call_entries_at_benchmark_document_size(oracle_mod):
+    # BASELINE configs[1] shape, 8 documents of it: every row of both one-call entries against the oracle
+    import synth
+    packed, ms, _ = synth.packed_collection(8, 50000, first_seed=1)
+    codes, off = _keyphrases(1000)
+    exp = _oracle_rows(oracle_mod, packed, ms, range(8), codes, off)
+    for normalized in (True, False):
+        if not normalized:
+            exp = _oracle_rows(oracle_mod, packed, ms, range(8), codes, off, False)
+        idx, out = _table_host(packed, ms, codes, off, normalized)
+        assert idx.info()["doc_sorted"] and idx.stat("tables_fused") == 1
+        for d in range(8):
+            assert np.array_equal(_bits(out[d]), _bits(exp[d])), ("host", normalized, d)
+        if normalized:
+            for d in (0, 7):
+                _check_arrays(idx, d, oracle_mod.OracleEASA(text=packed[d], m=ms[d]), ("host", d))
+        idx.close()
+        idx, out = _table_dev(packed, ms, codes, off, normalized)
+        for d in range(8):
+            assert np.array_equal(_bits(out[d]), _bits(exp[d])), ("dev", normalized, d)
+        idx.close()
+
+
+def test_pipelined_one_call_at_benchmark_size(oracle_mod):
+    # 300 documents x 50 KB: large enough for the pipelined host build (runs of whole documents copied, indexed and
+    # scored while the rest is in flight).  Sampled rows against the oracle, every row against the two-call path.
+    import synth
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(300, 50000, first_seed=1001)
+    codes, off = _keyphrases(1000)
+    idx, out = _table_host(packed, ms, codes, off)
+    assert idx.stat("pipelined") == 1 and idx.stat("pipeline_miss") == 0
+    sample = [0, 1, 36, 37, 147, 148, 149, 295, 296, 299] + list(range(60, 300, 47))
+    exp = _oracle_rows(oracle_mod, packed, ms, sample, codes, off)
+    for d in sample:
+        assert np.array_equal(_bits(out[d]), _bits(exp[d])), d
+    for d in (36, 37, 299):
+        _check_arrays(idx, d, oracle_mod.OracleEASA(text=packed[d], m=ms[d]), ("pipelined", d))
+    again = idx.score_table(codes, off, True)     # the batched scorer kernels on the finished index
+    assert np.array_equal(_bits(again), _bits(out))
+    idx.close()
+    idx, out_dev = _table_dev(packed, ms, codes, off, host_copy=False)
+    assert np.array_equal(_bits(out_dev), _bits(out))
+    idx.close()
+    try:   # the host variant of the keyphrase preparation gives the same table (another visiting order, same values)
+        capi.set_option("kp_prep_host", 1)
+        idx, out_h = _table_host(packed, ms, codes, off)
+        assert np.array_equal(_bits(out_h), _bits(out))
+        idx.close()
+    finally:
+        capi.set_option("kp_prep_host", 0)
+
+
+def _document_of(rng, target):
+    """A strings collection whose packed form has exactly `target` code points."""
+    words = ["".join(rng.choice(list("ABCDEFGHIJKLMNOPQRSTUVWXYZ"), size=int(rng.integers(3, 9)))) for _ in range(2000)]
+    p = 1.0 / np.arange(1, len(words) + 1)
+    p /= p.sum()
+    strings, total = [], 0
+    while total < target:
+        s_ = "".join(rng.choice(words, size=3, p=p))
+        if total + len(s_) + 1 > target:
+            s_ = s_[: max(1, target - total - 1)]
+        strings.append(s_)
+        total += len(s_) + 1
+    if total != target:
+        strings[0] = strings[0][: len(strings[0]) - (total - target)] or "A"
+    return strings
+
+
+def test_documents_at_the_kernel_limits_are_indexed_and_scored_in_one_call(oracle_mod):
+    # documents of 58 000 / 64 800 / 65 535 code points: the scorer phase of the per-document kernel stages text and
+    # suffix array in what the sort left of the shared memory; the fused table phases stop fitting near 64.9 k
+    from east.asts import utils as au
+    rng = np.random.default_rng(5)
+    codes, off = _keyphrases(300, extra=["QZX", "E", "A" * 40])
+    for group in ((58000, 1200), (64800, 30000), (65535, 64800, 58000, 700)):
+        cols = [_document_of(rng, t) for t in group]
+        packed = [au.pack_strings_collection(c) for c in cols]
+        assert [p.size for p in packed] == list(group)
+        ms = [len(c) for c in cols]
+        exp = _oracle_rows(oracle_mod, packed, ms, range(len(group)), codes, off)
+        for fn in (_table_host, _table_dev):
+            idx, out = fn(packed, ms, codes, off)
+            assert idx.info()["doc_sorted"]
+            for d in range(len(group)):
+                assert np.array_equal(_bits(out[d]), _bits(exp[d])), (fn.__name__, group, d)
+                _check_arrays(idx, d, oracle_mod.OracleEASA(text=packed[d], m=ms[d]), (fn.__name__, group, d))
+            idx.close()
+
+
+def test_keyphrase_preparation_on_the_device_equals_the_host_variant(oracle_mod):
+    # duplicates, shared tails, one-symbol and long keyphrases, code points outside the alphabet and in the terminator
+    # range: the table must not depend on where (or in which order) the distinct suffixes were found
+    import synth
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(5, 4000, first_seed=31)
+    extra = ["E", "E", "THE", "THETHE", "ATHE", "中文A", "A中", "਀", "ABਁC", "Q" * 300, "Q" * 299, "ABCDEFGHIJKLMNOPQRSTUVWXYZ" * 9,
+             "ABCDEFGHIJKLMNOPQRSTUVWXYZ" * 9 + "A", "XYZABCDEFGHIJ", "WXYZABCDEFGHIJ", "ZABCDEFGHIJK"]
+    for K in (1, 7, 1000):
+        codes, off = _keyphrases(K, extra=extra if K > 1 else ())
+        exp = _oracle_rows(oracle_mod, packed, ms, range(5), codes, off)
+        for host_prep in (0, 1):
+            try:
+                capi.set_option("kp_prep_host", host_prep)
+                idx, out = _table_host(packed, ms, codes, off)
+                two = idx.score_table(codes, off, True)
+                idx.close()
+            finally:
+                capi.set_option("kp_prep_host", 0)
+            for d in range(5):
+                assert np.array_equal(_bits(out[d]), _bits(exp[d])), (K, host_prep, d)
+            assert np.array_equal(_bits(two), _bits(out)), (K, host_prep)
+    # per-suffix results (return_suffix_scores): every suffix is its own group, in suffix order
+    from east.asts import base
+    ast = base.AST.get_ast(["XABXAC", "HI"])
+    s, per = ast.score("ABCIAB", return_suffix_scores=True)
+    assert list(per.keys()) == ["ABCIAB", "BCIAB", "CIAB", "IAB", "AB", "B"]
