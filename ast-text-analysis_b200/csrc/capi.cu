@@ -330,7 +330,7 @@ struct RunHook {
 
 static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t *doc_off, const int32_t *doc_m,
                         int32_t n_docs, int device, cudaStream_t s, east_index **out, const ChunkPlan *chunks = nullptr,
-                        const RunHook *hook = nullptr) {
+                        const RunHook *hook = nullptr, const uint8_t *text8_dev = nullptr /* one byte per code point: text_dev is filled from it */) {
     std::unique_ptr<east_index, void (*)(east_index *)> idx(new east_index(), free_index);
     // pipelined build: whatever happens, the copy stream must be done with the text before the index
     // (declared above, destroyed after this guard) can free it
@@ -362,6 +362,15 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
     idx->next = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
     idx->ann = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
 
+    if (text8_dev && !chunks) {   // not pipelined: the code points first, then the ordinary build
+        DevBuf<uint32_t> bad(1, s);
+        EAST_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(uint32_t), s));
+        expand_text8(text8_dev, idx->d_doc_off, idx->d_doc_m, n_docs, idx->text, bad.p, s);
+        uint32_t h_bad = 0;
+        EAST_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        EAST_CUDA(cudaStreamSynchronize(s));
+        if (h_bad) throw Error(EAST_ERR_INVALID, "one-byte text: a document does not hold exactly doc_m string ends (0xFF) or does not end with one");
+    }
     idx->build_timer.reset(new StageTimer(s));
     StageTimer &tm = *idx->build_timer;
     const bool overlap = get_option("sync_build", 0) == 0;
@@ -395,6 +404,10 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         if (hook && hook->fn) {
             in.run_begin = hook->begin; in.run_hook = hook->fn; in.run_ctx = hook->ctx;
             if (hook->building) *hook->building = idx.get();
+        }
+        if (chunks && text8_dev) {
+            if (!in.doc_sort || !in.fused_encode) throw Error(EAST_ERR_INVALID, "internal: the one-byte pipelined build needs the per-document kernel");
+            in.text8 = text8_dev;
         }
         if (chunks && in.doc_sort) {
             in.n_chunks = (int)chunks->ready.size();
@@ -464,15 +477,23 @@ static void check_build_args(const void *text, const int64_t *doc_off, const int
     if (doc_off[n_docs] >= (1ll << 30)) throw Error(EAST_ERR_RANGE, "more than 2^30 code points in one index; split the batch");
 }
 
-static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+static void build_host_impl(const void *text_any, int width /* bytes per code point on the host: 4, or 1 (0xFF = end of a string) */,
+                            const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
                             int device, east_index **out, const RunHook *hook) {
+    const uint32_t *text = static_cast<const uint32_t *>(text_any);
+    const uint8_t *text8 = static_cast<const uint8_t *>(text_any);
     static const bool debug = getenv("EAST_DEBUG_TIMING") != nullptr;
     if (debug) fprintf(stderr, "[east] host %.3f ms  east_build_host enter\n", host_now_ms());
-    check_build_args(text, doc_off, doc_m, n_docs, out);
+    check_build_args(text_any, doc_off, doc_m, n_docs, out);
     use_device(device);
     const int64_t n = doc_off[n_docs];
     const size_t bytes = sizeof(uint32_t) * (size_t)n;
     // stream-ordered pool allocation (cudaMalloc/cudaFree take device-wide locks and synchronise)
+    DevBuf<uint8_t> d_text8;
+    if (width == 1) {
+        d_text8 = DevBuf<uint8_t>((size_t)n + 256, 0);   // the per-document kernel reads whole 16-byte groups
+        EAST_CUDA(cudaMemsetAsync(d_text8.p + n, 0, 256, 0));
+    }
     uint32_t *d_text = (uint32_t *)dev_alloc(bytes, 0);
     // Large batches of small documents: copy in runs of whole documents on a copy stream so that the
     // per-document kernels of run c overlap the copy of run c+1 (worth it with pinned host memory)
@@ -480,13 +501,17 @@ static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const 
     for (int32_t d = 0; d < n_docs; ++d) max_doc = std::max(max_doc, doc_off[d + 1] - doc_off[d]);
     const int64_t chunk_target = get_option("pipeline_chunk", (int64_t)1 << 22);
     int want = (int)std::min<int64_t>(16, n / chunk_target);
+    if (width == 1) want = (int)std::min<int64_t>(16, n / (chunk_target / 4));   // the same runs of documents for a quarter of the bytes
+    const bool tuned_sort = get_option("key_chars", 0) || get_option("rs_variant", 0) || get_option("sort_batch_elems", 0) ||
+                            get_option("global_sort", 0) || get_option("doubling_radix", 0);
     const bool pipelined = want >= 2 && n_docs >= 2 * EAST_NUM_SMS && max_doc <= 65535 && !get_option("no_pipeline", 0) &&
-                           !get_option("no_doc_sort", 0);
+                           !get_option("no_doc_sort", 0) && (width == 4 || (!get_option("no_fused_encode", 0) && !tuned_sort));
     cudaError_t e = cudaSuccess;
     if (!pipelined) {
-        e = cudaMemcpyAsync(d_text, text, bytes, cudaMemcpyHostToDevice, 0);
+        e = width == 1 ? cudaMemcpyAsync(d_text8.p, text8, (size_t)n, cudaMemcpyHostToDevice, 0)
+                       : cudaMemcpyAsync(d_text, text, bytes, cudaMemcpyHostToDevice, 0);
         if (e != cudaSuccess) { dev_free(d_text, 0); throw Error(EAST_ERR_CUDA, cudaGetErrorString(e)); }
-        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, nullptr, hook);  // owns d_text from here on
+        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, nullptr, hook, d_text8.p);  // owns d_text from here on
     } else {
         ChunkPlan plan;
         cudaStream_t cs = copy_stream(device);
@@ -508,7 +533,8 @@ static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const 
                 const int32_t step = (lead > 0 && d == 0) ? lead : ((lead > 0 && d == lead) ? per_run - lead : per_run);
                 const int32_t d1 = std::min(n_docs, d + step);
                 const int64_t e0 = doc_off[d], e1 = doc_off[d1];
-                EAST_CUDA(cudaMemcpyAsync(d_text + e0, text + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, cs));
+                if (width == 1) EAST_CUDA(cudaMemcpyAsync(d_text8.p + e0, text8 + e0, (size_t)(e1 - e0), cudaMemcpyHostToDevice, cs));
+                else EAST_CUDA(cudaMemcpyAsync(d_text + e0, text + e0, sizeof(uint32_t) * (size_t)(e1 - e0), cudaMemcpyHostToDevice, cs));
                 cudaEvent_t ev;
                 EAST_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                 plan.ready.push_back(ev);
@@ -522,7 +548,7 @@ static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const 
             throw;
         }
         if (debug) fprintf(stderr, "[east] host %.3f ms  copies queued\n", host_now_ms());
-        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, &plan, hook);
+        build_common(d_text, true, doc_off, doc_m, n_docs, device, 0, out, &plan, hook, d_text8.p);
         if (debug) fprintf(stderr, "[east] host %.3f ms  build_common done\n", host_now_ms());
     }
 }
@@ -530,7 +556,14 @@ static void build_host_impl(const uint32_t *text, const int64_t *doc_off, const 
 int east_build_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
                     int device, east_index **out) {
     EAST_API_BEGIN
-    build_host_impl(text, doc_off, doc_m, n_docs, device, out, nullptr);
+    build_host_impl(text, 4, doc_off, doc_m, n_docs, device, out, nullptr);
+    EAST_API_END
+}
+
+int east_build_host_u8(const uint8_t *text8, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                       int device, east_index **out) {
+    EAST_API_BEGIN
+    build_host_impl(text8, 1, doc_off, doc_m, n_docs, device, out, nullptr);
     EAST_API_END
 }
 
@@ -800,7 +833,7 @@ static std::unique_ptr<KpPrepared> kp_begin(int device, const uint32_t *kp_dev, 
             EAST_CUDA(cudaStreamSynchronize(s));
         }
     }
-    if (!host_prep) kp_stage1(c->dev, kp_dev, kp_off, K, dedup, s);
+    if (!host_prep) kp_stage1(c->dev, kp_dev, kp_host_in, kp_off, K, dedup, s);
     return c;
 }
 
@@ -1060,10 +1093,9 @@ static void table_run_done(void *vctx, const RunReady &r, int in_kernel) {
     }
 }
 
-int east_table_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
-                    const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized, double *out_DxK,
-                    east_index **out_idx) {
-    EAST_API_BEGIN
+static void table_host_impl(const void *text, int width, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
+                            const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized, double *out_DxK,
+                            east_index **out_idx) {
     if (!kp || !kp_off || !out_DxK || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
     east_index *built = nullptr;
     check_build_args(text, doc_off, doc_m, n_docs, &built);
@@ -1082,7 +1114,7 @@ int east_table_host(const uint32_t *text, const int64_t *doc_off, const int32_t 
     run.d_out = d_out.p; run.host_out = out_DxK;
     RunHook hook;
     hook.begin = table_run_begin; hook.fn = table_run_done; hook.ctx = &run; hook.building = &run.building;
-    build_host_impl(text, doc_off, doc_m, n_docs, device, &built, &hook);
+    build_host_impl(text, width, doc_off, doc_m, n_docs, device, &built, &hook);
     std::unique_ptr<east_index, void (*)(east_index *)> guard(built, free_index);
     // Rows scored on the way stand if the pass that produced them is the one the index came from: the speculative
     // pipelined pass (pipelined = 1: the build ended on a host sync after both streams, the rows are in out_DxK)
@@ -1096,6 +1128,21 @@ int east_table_host(const uint32_t *text, const int64_t *doc_off, const int32_t 
         EAST_CUDA(cudaMemcpy(out_DxK, d_out.p, sizeof(double) * (size_t)n_docs * K, cudaMemcpyDeviceToHost));
     }
     if (out_idx) *out_idx = guard.release();
+}
+
+int east_table_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
+                    const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized, double *out_DxK,
+                    east_index **out_idx) {
+    EAST_API_BEGIN
+    table_host_impl(text, 4, doc_off, doc_m, n_docs, device, kp, kp_off, K, normalized, out_DxK, out_idx);
+    EAST_API_END
+}
+
+int east_table_host_u8(const uint8_t *text8, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
+                       const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized, double *out_DxK,
+                       east_index **out_idx) {
+    EAST_API_BEGIN
+    table_host_impl(text8, 1, doc_off, doc_m, n_docs, device, kp, kp_off, K, normalized, out_DxK, out_idx);
     EAST_API_END
 }
 
@@ -1110,7 +1157,15 @@ int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32
     use_device(device);
     cudaStream_t s = (cudaStream_t)stream;
     TableRun run;
-    run.kp_own = kp_begin(device, kp_dev, kp_host, kp_off, K, !get_option("score_no_dedup", 0), false, s);
+    {   // keyphrase preparation on a side stream, under the alphabet scan of the text and its round trip to the host
+        cudaStream_t ps = prep_stream(device);
+        cudaEvent_t inputs_ready;
+        EAST_CUDA(cudaEventCreateWithFlags(&inputs_ready, cudaEventDisableTiming));
+        EAST_CUDA(cudaEventRecord(inputs_ready, s));
+        EAST_CUDA(cudaStreamWaitEvent(ps, inputs_ready, 0));
+        EAST_CUDA(cudaEventDestroy(inputs_ready));
+        run.kp_own = kp_begin(device, kp_dev, kp_host, kp_off, K, !get_option("score_no_dedup", 0), false, ps);
+    }
     run.kp_host = kp_host; run.d_kp = kp_dev; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
     run.d_out = out_DxK_dev; run.host_out = nullptr;
     RunHook hook;

@@ -87,6 +87,11 @@ struct DocSortParams {
     uint8_t *t8_out;
     uint32_t *miss;
     int64_t text_len;         // code points of the whole batch (bound of the 128-bit loads)
+    // optional (with code_table): the text arrives as ONE BYTE per code point (east_*_host_u8: code points < 0xFF as
+    // themselves, 0xFF = end of a string); the kernel byte-codes from it and writes the code points -- the k-th 0xFF of
+    // the document becomes the terminator 0x0A00 + k -- to text_out (= text) for the later readers of the index
+    const uint8_t *text8;
+    uint32_t *text_out;
 };
 
 // 8 bytes of shared memory at an arbitrary byte offset from a 16-byte aligned base: three aligned
@@ -601,6 +606,10 @@ k_doc_suffix_sort(DocSortParams p) {
         if (tid < 2) s_nlist[tid] = 0;
         if (tid == 0) { s_work = 0; s_fail = 0; }   // s_work here: number of terminator codes seen
         const bool encode = p.code_table != nullptr;
+        const bool from8 = encode && p.text8 != nullptr;
+        // from8: terminators of the document inside every 16-byte chunk, then their exclusive prefix (the work lists
+        // are not in use yet)
+        uint16_t *s_tc = reinterpret_cast<uint16_t *>(s_list0);
         if (encode)
             for (int i = tid; i < (int)EAST_TERM_BASE; i += DS_THREADS) s_code[i] = p.code_table[i];
         __syncthreads();
@@ -609,6 +618,36 @@ k_doc_suffix_sort(DocSortParams p) {
             uint4 v;
             if (!encode) {
                 v = *reinterpret_cast<const uint4 *>(p.t8 + a0 + o);
+            } else if (from8) {
+                const uint4 raw = *reinterpret_cast<const uint4 *>(p.text8 + a0 + o);   // 16 code points in one load
+                const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+                uint32_t w[4];
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t c = (rw[wi] >> (8 * j)) & 0xffu;
+                        const uint32_t e = c == 0xffu ? p.term : (uint32_t)s_code[c];
+                        const int i = o + 4 * wi + j - shift;
+                        const bool inside = i >= 0 && i < n;
+                        if (e == 0u && inside) missed = 1;
+                        if (c == 0xffu && inside) ++cnt;
+                        packed |= e << (8 * j);
+                    }
+                    w[wi] = packed;
+                }
+                s_tc[o >> 4] = (uint16_t)cnt;
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+                const int i0 = o - shift;
+                if (i0 >= 0 && i0 + 15 < n) {
+                    *reinterpret_cast<uint4 *>(p.t8_out + a0 + o) = v;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (i0 + j >= 0 && i0 + j < n) p.t8_out[base + i0 + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+                }
             } else {
                 // 16 code points -> 16 byte codes (k_encode_text's mapping); only the document's own positions
                 // count for the miss flag and are written back: its neighbours may not even be resident yet
@@ -650,6 +689,7 @@ k_doc_suffix_sort(DocSortParams p) {
             // ordered by string index = terminator value - 0x0A00: final right here, while the
             // loads of the code points overlap the staging
             const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+            if (from8) continue;   // placed below, once the string index of every terminator is known
 #pragma unroll
             for (int wi = 0; wi < 4; ++wi) {
                 uint32_t z = ds_zero4(wv[wi] ^ term4);
@@ -666,6 +706,57 @@ k_doc_suffix_sort(DocSortParams p) {
         }
         if (missed) atomicOr(p.miss, 1u);
         __syncthreads();
+        if (from8) {
+            // string index of a terminator = number of terminators of the document before it: block-wide exclusive
+            // scan of the per-chunk counts, then a second pass places the terminators (rank = string index) and
+            // writes the code points of the document
+            const int nch = nbytes >> 4;
+            const int per = (nch + DS_THREADS - 1) / DS_THREADS;
+            const int c0 = min(nch, tid * per), c1 = min(nch, c0 + per);
+            uint32_t sum = 0;
+            for (int c = c0; c < c1; ++c) sum += s_tc[c];
+            uint32_t x = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            if (lane == 31) s_warp_sum[warp] = x;
+            __syncthreads();
+            uint32_t run = x - sum;
+            for (int i = 0; i < warp; ++i) run += s_warp_sum[i];
+            for (int c = c0; c < c1; ++c) { const uint32_t cv = s_tc[c]; s_tc[c] = (uint16_t)run; run += cv; }
+            if (tid == DS_THREADS - 1) s_work = run;
+            __syncthreads();
+            for (int o = tid * 16; o < nbytes; o += DS_THREADS * 16) {
+                const uint4 raw = *reinterpret_cast<const uint4 *>(p.text8 + a0 + o);
+                const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+                uint32_t k = s_tc[o >> 4];
+                uint32_t cp[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t c = (rw[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    const int i = o + j - shift;
+                    cp[j] = c;
+                    if (c == 0xffu && i >= 0 && i < n) {
+                        if (k < (uint32_t)m) sa_doc[n - m + (int)k] = base + i; else bad = 1;
+                        cp[j] = EAST_TERM_BASE + k;
+                        ++k;
+                    }
+                }
+                const int i0 = o - shift;
+                if (i0 >= 0 && i0 + 15 < n) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4 *>(p.text_out + a0 + o + 4 * q) = make_uint4(cp[4 * q], cp[4 * q + 1], cp[4 * q + 2], cp[4 * q + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (i0 + j >= 0 && i0 + j < n) p.text_out[base + i0 + j] = cp[j];
+                }
+            }
+            __syncthreads();
+        }
         // The layout every later phase relies on (east/asts/utils.py:25-40): exactly m terminator codes,
         // string k ends with 0x0A00 + k, the document ends with its last terminator.  A build that
         // runs ahead of the validating text scan (pipelined host build) finds out here.
@@ -1127,7 +1218,7 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
                      const int32_t *doc_m, int doc_begin, int n_docs,
                      int64_t n_total, uint32_t term, int32_t *sa, uint32_t *bkt, uint32_t *bkt3, uint32_t *overflow, cudaStream_t s,
                      unsigned long long *phase_clk, const DocSortTables *tables, uint32_t *sk, const DocScore *score,
-                     const uint8_t *code_table, uint32_t *miss, int64_t text_len) {
+                     const uint8_t *code_table, uint32_t *miss, int64_t text_len, const uint8_t *text8) {
     ensure_dynamic_smem((const void *)k_doc_suffix_sort, 220 * 1024);
     DocSortParams p;
     p.t8 = t8; p.text = text; p.doc_off = doc_off; p.doc_m = doc_m; p.sa = sa; p.bkt = bkt; p.bkt3 = (plan.G == 3) ? bkt3 : nullptr; p.overflow = overflow;
@@ -1139,13 +1230,14 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     if (score && score->recs && bkt && sk) p.score = *score;
     p.code_table = (code_table && miss) ? code_table : nullptr;
     p.t8_out = const_cast<uint8_t *>(t8); p.miss = miss; p.text_len = text_len;
+    p.text8 = p.code_table ? text8 : nullptr; p.text_out = const_cast<uint32_t *>(text);
     p.lcp = p.up = p.down = p.next = p.ann = nullptr;
     if (tables && plan.tables_fit) { p.lcp = tables->lcp; p.up = tables->up; p.down = tables->down; p.next = tables->next; p.ann = tables->ann; }
     // algorithmic bytes per code point: 1 (byte text in) + 4 (suffix array out), with the fused tables + 5 x 4
     // (LCP, up, down, next, annotation out), + 4 when the kernel byte-codes the text itself (code points in);
     // with the scorer inside, plus the bytes of its walks (counted by the
     // instrumented scorer, option score_bytes)
-    EAST_BYTES(((p.lcp ? 25.0 : 5.0) + (p.code_table ? 4.0 : 0.0)) * (double)n_total + (p.score.recs ? p.score.algorithmic_bytes : 0.0));
+    EAST_BYTES(((p.lcp ? 25.0 : 5.0) + (p.code_table ? (p.text8 ? 5.0 : 4.0) : 0.0)) * (double)n_total + (p.score.recs ? p.score.algorithmic_bytes : 0.0));
     EAST_LAUNCH(k_doc_suffix_sort, n_docs, DS_THREADS, plan.smem, s, p);
 }
 

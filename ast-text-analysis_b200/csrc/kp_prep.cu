@@ -9,9 +9,10 @@
 //
 //   k_kp_suffix_keys   one thread per keyphrase, backwards: 64-bit hash of every suffix, "contains a code point
 //                      >= 0x0A00" flag, end of the suffix
-//   k_kp_lexkeys       one thread per suffix: its first 10 symbols as two 60-bit words (12 bits per code point)
-//   radix sort x 3     the library's own onesweep LSD sort, stable: by hash, then by symbols 5..9, then by symbols
-//                      0..4 -> lexicographic by the first 10 symbols, identical suffixes adjacent (equal hash)
+//   k_kp_lexkeys       one thread per suffix: its first symbols as one 64-bit word (9 symbols of 7 bits for A-Z) or,
+//                      for wide alphabets, two (12 bits per code point: 2 x 5 symbols)
+//   radix sort x 2-3   the library's own onesweep LSD sort, stable: by 32 hash bits, then by the symbol word(s)
+//                      -> lexicographic by the first symbols, identical suffixes adjacent (equal hash)
 //   k_kp_mark          a suffix that equals its predecessor code point by code point (hash, length and a full
 //                      comparison: a hash collision only costs a redundant walk, never a wrong twin) is a
 //                      duplicate; every other one is the head of a group of identical suffixes
@@ -28,8 +29,7 @@
 namespace east {
 
 constexpr int KP_THREADS = 1024;
-constexpr int KP_LEX_SYMS = 5;     // symbols per 64-bit lexicographic word
-constexpr int KP_LEX_BITS = 12;    // bits per symbol: code point + 1, clamped (code points of the texts are < 0x0A00)
+constexpr int KP_MAX_SYM_BITS = 12;   // code points of the texts are < 0x0A00: 12 bits hold code point + 1, larger ones are clamped
 
 __global__ void __launch_bounds__(256)
 k_kp_suffix_keys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ off, int32_t K, uint64_t *__restrict__ hash,
@@ -43,7 +43,7 @@ k_kp_suffix_keys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ of
             h = h * 0x100000001b3ull + (uint64_t)cp + 0x632be59bd9b4e019ull;
             h ^= h >> 29;
             if (cp >= EAST_TERM_BASE) w = 1;
-            hash[p] = h;
+            hash[p] = h >> 32;     // 32 bits order the groups; identity is decided by comparing the code points
             vals[p] = (uint32_t)p;
             send[p] = e;
             weird[p] = w;
@@ -51,20 +51,19 @@ k_kp_suffix_keys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ of
     }
 }
 
+// the first 2 * per_word symbols of every suffix as two words of per_word symbols, sym_bits bits each (symbol = code
+// point + 1, clamped; 0 = past the end of the keyphrase)
 __global__ void __launch_bounds__(256)
-k_kp_lexkeys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ send, int32_t total, uint64_t *__restrict__ lex0,
-             uint64_t *__restrict__ lex1) {
+k_kp_lexkeys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ send, int32_t total, int sym_bits, int per_word,
+             uint64_t *__restrict__ lex0, uint64_t *__restrict__ lex1) {
+    const uint32_t top = (1u << sym_bits) - 1u;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
         const int32_t e = send[p];
-        uint64_t w[2] = {0ull, 0ull};
-#pragma unroll
-        for (int q = 0; q < 2 * KP_LEX_SYMS; ++q) {
-            uint64_t sym = 0;
-            if (p + q < e) sym = min(kp[p + q] + 1u, (1u << KP_LEX_BITS) - 1u);
-            w[q / KP_LEX_SYMS] = (w[q / KP_LEX_SYMS] << KP_LEX_BITS) | sym;
-        }
-        lex0[p] = w[0];
-        lex1[p] = w[1];
+        uint64_t w0 = 0ull, w1 = 0ull;
+        for (int q = 0; q < per_word; ++q) w0 = (w0 << sym_bits) | (uint64_t)((p + q < e) ? min(kp[p + q] + 1u, top) : 0u);
+        if (lex1) for (int q = per_word; q < 2 * per_word; ++q) w1 = (w1 << sym_bits) | (uint64_t)((p + q < e) ? min(kp[p + q] + 1u, top) : 0u);
+        lex0[p] = w0;
+        if (lex1) lex1[p] = w1;
     }
 }
 
@@ -190,7 +189,7 @@ k_kp_encode(const uint32_t *__restrict__ kp, int32_t total, const uint8_t *__res
 
 static thread_local uint32_t *g_pinned_word = nullptr;
 
-void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s) {
+void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s) {
     const int64_t total64 = kp_off[K];
     const int32_t total = (int32_t)total64;
     kp.total = total; kp.K = K; kp.dedup = dedup; kp.n_uniq = -1;
@@ -211,16 +210,28 @@ void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const int64_t *kp_off, int3
     EAST_LAUNCH(k_kp_suffix_keys, grid_for(K, 256, 8), 256, 0, s, kp_dev, kp.d_off.p, K, hash.p, vals_a.p, send.p, weird.p);
     const uint32_t *order = vals_a.p;
     if (dedup) {
-        lex0 = DevBuf<uint64_t>((size_t)total, s); lex1 = DevBuf<uint64_t>((size_t)total, s);
+        // symbol width from the largest code point (the host has the keyphrases; without a host copy: the full 12 bits).
+        // Narrow symbols (7 bits for A-Z) put 9 of them into ONE 64-bit word: two sorts instead of three.
+        int sym_bits = KP_MAX_SYM_BITS;
+        if (kp_host) {
+            uint32_t mx = 0;
+            for (int32_t p = 0; p < total; ++p) mx = std::max(mx, kp_host[p]);
+            sym_bits = std::min(KP_MAX_SYM_BITS, std::max(1, bits_for((uint64_t)mx + 1)));
+        }
+        const int per_word = 64 / sym_bits;
+        const bool two_words = per_word < 8;
+        lex0 = DevBuf<uint64_t>((size_t)total, s);
+        if (two_words) lex1 = DevBuf<uint64_t>((size_t)total, s);
         keys_a = DevBuf<uint64_t>((size_t)total, s); keys_b = DevBuf<uint64_t>((size_t)total, s);
         vals_b = DevBuf<uint32_t>((size_t)total, s);
         DevBuf<uint32_t> hist(256 * RS_MAX_PASSES, s);
         DevBuf<uint8_t> scratch(rs_scratch_bytes(total, RS_MAX_PASSES), s);
-        EAST_LAUNCH(k_kp_lexkeys, grid_for(total, 256, 8), 256, 0, s, kp_dev, send.p, total, lex0.p, lex1.p);
+        EAST_LAUNCH(k_kp_lexkeys, grid_for(total, 256, 8), 256, 0, s, kp_dev, send.p, total, sym_bits, per_word, lex0.p, lex1.p);
         uint32_t *va = vals_a.p, *vb = vals_b.p;
         const uint64_t *srcs[3] = {hash.p, lex1.p, lex0.p};
-        const int bits[3] = {64, KP_LEX_SYMS * KP_LEX_BITS, KP_LEX_SYMS * KP_LEX_BITS};
+        const int bits[3] = {32, per_word * sym_bits, per_word * sym_bits};
         for (int round = 0; round < 3; ++round) {
+            if (!srcs[round]) continue;
             EAST_LAUNCH(k_kp_gather, grid_for(total, 256, 8), 256, 0, s, srcs[round], va, total, keys_a.p);
             const int cur = radix_sort_pairs(keys_a.p, keys_b.p, va, vb, total, bits[round], hist.p, false, scratch.p, s);
             if (cur) std::swap(va, vb);

@@ -417,6 +417,84 @@ k_alphabet(const uint32_t *__restrict__ T, int32_t n, ScanResult *res) {
         if (s_present[i]) atomicOr(&res->present[i], s_present[i]);
 }
 
+// The same for a text that arrives as one byte per code point (east_*_host_u8): bytes below 0xFF are code points,
+// 0xFF ends a string.
+__global__ void __launch_bounds__(256)
+k_alphabet8(const uint8_t *__restrict__ T8, int32_t n, ScanResult *res) {
+    __shared__ uint32_t s_present[8];
+    if (threadIdx.x < 8) s_present[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t seen[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    uint32_t nt = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+    for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i0 < n; i0 += stride) {
+        uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (i0 + 15 < n) v = *reinterpret_cast<const uint4 *>(T8 + i0);   // the buffer starts 256-byte aligned
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            if (i0 + 15 >= n) { if (i0 + j >= n) continue; c = T8[i0 + j]; }
+            if (c == 0xffu) ++nt;
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if ((int)(c >> 5) == q) seen[q] |= 1u << (c & 31);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t s = __reduce_or_sync(0xffffffffu, seen[q]);
+        if ((threadIdx.x & 31) == 0 && s) atomicOr(&s_present[q], s);
+    }
+    nt = __reduce_add_sync(0xffffffffu, nt);
+    if ((threadIdx.x & 31) == 0 && nt) atomicAdd(&res->n_term, nt);
+    __syncthreads();
+    if (threadIdx.x < 8 && s_present[threadIdx.x]) atomicOr(&res->present[threadIdx.x], s_present[threadIdx.x]);
+    if (threadIdx.x == 0) atomicMax(&res->max_code, 0xfeu);
+}
+
+// one byte per code point -> code points: CTA d expands document d, the k-th 0xFF of the document becomes the terminator
+// 0x0A00 + k (east/asts/utils.py:35-39).  *bad is set when a document does not hold exactly doc_m terminators or does not
+// end with one.  (Batches that do not take the pipelined per-document path.)
+__global__ void __launch_bounds__(256)
+k_expand_text8(const uint8_t *__restrict__ T8, const int32_t *__restrict__ doc_off, const int32_t *__restrict__ doc_m,
+               uint32_t *__restrict__ T, uint32_t *bad) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_run;
+    const int d = blockIdx.x;
+    const int32_t b = doc_off[d], e = doc_off[d + 1];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) s_run = 0;
+    __syncthreads();
+    for (int32_t i0 = b; i0 < e; i0 += 256 * 8) {
+        // thread t owns 8 consecutive bytes of the tile
+        const int32_t p0 = i0 + t * 8;
+        uint32_t c[8], cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = (p0 + j < e) ? T8[p0 + j] : 0u; cnt += (p0 + j < e && c[j] == 0xffu) ? 1u : 0u; }
+        uint32_t x = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[w] = x;
+        __syncthreads();
+        uint32_t k = s_run + x - cnt;
+        for (int i = 0; i < w; ++i) k += s_warp[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (p0 + j < e) T[p0 + j] = (c[j] == 0xffu) ? EAST_TERM_BASE + k++ : c[j];
+        __syncthreads();
+        if (t == 255) s_run = k;
+        __syncthreads();
+    }
+    if (t == 0 && (s_run != (uint32_t)doc_m[d] || T8[e - 1] != 0xffu)) atomicOr(bad, 1u);
+}
+
+void expand_text8(const uint8_t *text8, const int32_t *doc_off, const int32_t *doc_m, int n_docs, uint32_t *text, uint32_t *bad,
+                  cudaStream_t s) {
+    EAST_LAUNCH(k_expand_text8, n_docs, 256, 0, s, text8, doc_off, doc_m, text, bad);
+}
+
 // ------------------------------------------------------------------------------------------
 // round 0 key generation (+ fused digit histograms of all passes)
 // ------------------------------------------------------------------------------------------
@@ -917,7 +995,8 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     EAST_CUDA(cudaMemsetAsync(d_first.p, 0, sizeof(ScanResult), s));
     EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
     const int32_t n0 = in.doc_off_host[in.chunk_doc[1]];
-    EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_first.p);
+    if (in.text8) EAST_LAUNCH(k_alphabet8, grid_for(n0, 256 * 16, 4), 256, 0, s, in.text8, n0, d_first.p);
+    else EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_first.p);
     ScanResult first;
     EAST_CUDA(cudaMemcpyAsync(&first, d_first.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
     EAST_CUDA(cudaStreamSynchronize(s));
@@ -1013,7 +1092,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             if (hooks && in.run_begin) in.run_begin(in.run_ctx, run, score);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
                             out.bkt3.p, flags.p, ls, nullptr, fuse ? &tables : nullptr, in.sk, &score,
-                            in.fused_encode ? d_table.p : nullptr, flags.p + 1, n);
+                            in.fused_encode ? d_table.p : nullptr, flags.p + 1, n, in.text8);
             if (hooks && in.run_hook) in.run_hook(in.run_ctx, run, score.recs != nullptr ? 1 : 0);
         }
         if (lanes[1] != s) {
@@ -1065,6 +1144,17 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         uint32_t refused = 0;   // what the per-document kernel reported: bit 0 a bucket too large, bit 1 a bad layout
         if (build_pipelined(in, out, tm, s, refused)) return;
         if (refused) allow_doc_sort = false;  // it would refuse again: full scan, global sort
+        if (in.text8) {
+            // the runs were byte-coded from the one-byte text; what follows reads code points: expand the whole batch
+            // (every run has arrived: build_pipelined ended on a host sync after the last one)
+            DevBuf<uint32_t> bad(1, s);
+            EAST_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(uint32_t), s));
+            expand_text8(in.text8, in.doc_off, in.doc_m, D, const_cast<uint32_t *>(in.text), bad.p, s);
+            uint32_t h_bad = 0;
+            EAST_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            EAST_CUDA(cudaStreamSynchronize(s));
+            if (h_bad) throw Error(-1, "one-byte text: a document does not hold exactly doc_m string ends (0xFF) or does not end with one");
+        }
     }
     int32_t max_doc_n = 0;
     for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);

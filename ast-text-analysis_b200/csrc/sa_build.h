@@ -38,6 +38,9 @@ struct RunReady {
 
 struct SaInput {
     const uint32_t *text;     // device, n code points (packed documents, concatenated)
+    // pipelined host build of east_*_host_u8: the text arrives as one byte per code point (0xFF = end of a string);
+    // `text` is then an OUTPUT of the per-document kernel (the code points with their terminators 0x0A00 + k)
+    const uint8_t *text8 = nullptr;
     const int32_t *doc_off;   // device, n_docs + 1
     const int32_t *doc_m;     // device, n_docs
     int32_t n;
@@ -98,6 +101,10 @@ struct SaOutput {
 };
 
 void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s);
+// one byte per code point (0xFF = end of a string) -> packed code points with terminators 0x0A00 + k; *bad |= 1 when a
+// document does not hold exactly doc_m terminators or does not end with one
+void expand_text8(const uint8_t *text8, const int32_t *doc_off, const int32_t *doc_m, int n_docs, uint32_t *text, uint32_t *bad,
+                  cudaStream_t s);
 
 // per-document shared-memory suffix sort (doc_sort.cu)
 struct DocSortPlan {
@@ -116,7 +123,8 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
                      uint32_t *sk = nullptr /* also produce the scorer's per-rank key bytes */,
                      const DocScore *score = nullptr /* also score keyphrases (needs bkt and sk) */,
                      const uint8_t *code_table = nullptr /* byte-code the text in the kernel (writes t8, sets *miss) */,
-                     uint32_t *miss = nullptr, int64_t text_len = 0 /* code points of the whole batch */);
+                     uint32_t *miss = nullptr, int64_t text_len = 0 /* code points of the whole batch */,
+                     const uint8_t *text8 = nullptr /* with code_table: one byte per code point in, code points out to `text` */);
 
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch

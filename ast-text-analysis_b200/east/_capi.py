@@ -27,11 +27,13 @@ EXPORTED_SYMBOLS = [
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
     "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
     "east_score_probes_dev", "east_index_stat", "east_score_range_dev", "east_table_host", "east_table_dev",
+    "east_build_host_u8", "east_table_host_u8",
 ]
 
 _lib = None
 
 _u32p = ctypes.POINTER(ctypes.c_uint32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _i64p = ctypes.POINTER(ctypes.c_int64)
 _f64p = ctypes.POINTER(ctypes.c_double)
@@ -65,6 +67,9 @@ def load():
     L.east_score_table_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, _vp, _vp]
     L.east_table_host.argtypes = [_u32p, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _u32p, _i64p, ctypes.c_int32,
                                   ctypes.c_int, _f64p, ctypes.POINTER(_vp)]
+    L.east_build_host_u8.argtypes = [_u8p, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, ctypes.POINTER(_vp)]
+    L.east_table_host_u8.argtypes = [_u8p, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _u32p, _i64p, ctypes.c_int32,
+                                     ctypes.c_int, _f64p, ctypes.POINTER(_vp)]
     L.east_table_dev.argtypes = [_vp, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _vp, _u32p, _i64p, ctypes.c_int32,
                                  ctypes.c_int, _vp, _vp, ctypes.POINTER(_vp)]
     L.east_score_range_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
@@ -191,6 +196,18 @@ class DeviceIndex(object):
         return cls.from_handle(h, doc_off, doc_m, int(device))
 
     @classmethod
+    def build_host_u8(cls, text8, doc_off, doc_m, device=0):
+        """build_host() for a text shipped as one byte per code point (pack_strings_collection_u8)."""
+        L = load()
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
+        doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
+        assert text8.dtype == np.uint8 and text8.flags["C_CONTIGUOUS"]
+        h = _vp()
+        _check(L.east_build_host_u8(_ptr(text8, _u8p), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m),
+                                    int(device), ctypes.byref(h)))
+        return cls.from_handle(h, doc_off, doc_m, int(device))
+
+    @classmethod
     def build_host_and_score(cls, text, doc_off, doc_m, kp_codes, kp_off, out, normalized=True, device=0):
         """build_host() + score_table_into() as ONE engine call (east_table_host): on a large batch of small
         documents the runs of documents already sorted are scored, and their rows of `out` copied back, while
@@ -202,9 +219,14 @@ class DeviceIndex(object):
         kp_codes = np.ascontiguousarray(kp_codes, dtype=np.uint32)
         kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
         K = len(kp_off) - 1
-        assert text.dtype == np.uint32 and text.flags["C_CONTIGUOUS"]
+        assert text.dtype in (np.uint32, np.uint8) and text.flags["C_CONTIGUOUS"]
         assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == len(doc_m) * K
         h = _vp()
+        if text.dtype == np.uint8:   # one byte per code point, 0xFF ends a string (pack_strings_collection_u8)
+            _check(L.east_table_host_u8(_ptr(text, _u8p), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m), int(device),
+                                        _ptr(kp_codes, _u32p), _ptr(kp_off, _i64p), K, 1 if normalized else 0,
+                                        _ptr(out, _f64p), ctypes.byref(h)))
+            return cls.from_handle(h, doc_off, doc_m, int(device))
         _check(L.east_table_host(_ptr(text, _u32p), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m), int(device),
                                  _ptr(kp_codes, _u32p), _ptr(kp_off, _i64p), K, 1 if normalized else 0,
                                  _ptr(out, _f64p), ctypes.byref(h)))

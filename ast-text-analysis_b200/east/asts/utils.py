@@ -52,3 +52,17 @@ def pack_strings_collection(strings_collection):
     out[is_char] = chars
     out[term_pos] = consts.String.UNICODE_SPECIAL_SYMBOLS_START + np.arange(m, dtype=np.uint32)
     return out
+
+
+def pack_strings_collection_u8(strings_collection):
+    """The same packed document as ONE BYTE per code point, for collections whose code points are all below 0xFF (ASCII,
+    Latin-1): every string followed by the byte 0xFF, which stands for its terminator 0x0A00 + i (the engine restores the
+    code points on the device).  A quarter of the bytes of pack_strings_collection() over the host link.  Returns None
+    when a code point does not fit."""
+    try:
+        data = ("\xff".join(strings_collection) + "\xff").encode("latin-1")
+    except UnicodeEncodeError:
+        return None
+    if data.count(b"\xff") != len(strings_collection):
+        return None   # a string contains U+00FF itself
+    return np.frombuffer(data, dtype=np.uint8)

@@ -88,29 +88,37 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         collections = [utils.text_to_strings_collection(text) for text in texts]
         if not collections:
             return
-        packed = [asts_utils.pack_strings_collection(c) for c in collections]
-        self.asts = [None] * len(collections)
-        fused = None
-        if prepared_keyphrases:
-            fused = _capi.pack_keyphrases(prepared_keyphrases)
-            self._table = np.empty((len(collections), len(prepared_keyphrases)), dtype=np.float64)
-            self._table_keyphrases = list(prepared_keyphrases)
+        # one byte per code point where the text allows it (ASCII / Latin-1: a quarter of the bytes over the host link),
+        # uint32 code points otherwise; both have one entry per code point + one per string
+        packed = [asts_utils.pack_strings_collection_u8(c) for c in collections]
+        packed = [p if p is not None else asts_utils.pack_strings_collection(c) for p, c in zip(packed, collections)]
+        fused = _capi.pack_keyphrases(prepared_keyphrases) if prepared_keyphrases else None
+        # everything is built into locals: a batch that raises leaves the measure empty, not half-initialised
+        asts = [None] * len(collections)
+        batches = []
+        table = np.empty((len(collections), len(prepared_keyphrases)), dtype=np.float64) if fused else None
         for docs in plan_batches([len(p) for p in packed]):
+            narrow = all(packed[j].dtype == np.uint8 for j in docs)
+            parts = [packed[j] if narrow or packed[j].dtype == np.uint32 else asts_utils.pack_strings_collection(collections[j])
+                     for j in docs]
+            doc_off = np.zeros(len(docs) + 1, dtype=np.int64)
+            np.cumsum([len(p) for p in parts], out=doc_off[1:])
+            text = np.ascontiguousarray(np.concatenate(parts) if len(parts) > 1 else parts[0])
+            doc_m = [len(collections[j]) for j in docs]
             if fused is None:
-                index = _capi.DeviceIndex([packed[j] for j in docs], [len(collections[j]) for j in docs], device=self.device)
+                build = _capi.DeviceIndex.build_host_u8 if narrow else _capi.DeviceIndex.build_host
+                index = build(text, doc_off, doc_m, device=self.device)
             else:
-                doc_off = np.zeros(len(docs) + 1, dtype=np.int64)
-                np.cumsum([len(packed[j]) for j in docs], out=doc_off[1:])
-                text = np.ascontiguousarray(np.concatenate([packed[j] for j in docs]), dtype=np.uint32)
                 rows = np.empty((len(docs), len(prepared_keyphrases)), dtype=np.float64)
-                index = _capi.DeviceIndex.build_host_and_score(text, doc_off, [len(collections[j]) for j in docs],
-                                                               fused[0], fused[1], rows, normalized=self.normalized,
-                                                               device=self.device)
-                self._table[docs] = rows
-            self._batches.append((index, docs))
+                index = _capi.DeviceIndex.build_host_and_score(text, doc_off, doc_m, fused[0], fused[1], rows,
+                                                               normalized=self.normalized, device=self.device)
+                table[docs] = rows
+            batches.append((index, docs))
             for local, j in enumerate(docs):
-                self.asts[j] = easa.EnhancedAnnotatedSuffixArray(collections[j], _index=index, _doc=local)
-        self._index = self._batches[0][0]
+                asts[j] = easa.EnhancedAnnotatedSuffixArray(collections[j], _index=index, _doc=local)
+        self.asts, self._batches, self._index = asts, batches, batches[0][0]
+        if fused:
+            self._table, self._table_keyphrases = table, list(prepared_keyphrases)
 
     def relevance(self, keyphrase, text, synonimizer=None):
         return self.asts[text].score(keyphrase, normalized=self.normalized, synonimizer=synonimizer)

@@ -102,6 +102,19 @@ int east_score_table_dev(const east_index *idx, const uint32_t *kp_dev, const in
 int east_table_host(const uint32_t *text, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
                     int device, const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized,
                     double *out_DxK, east_index **out_idx);
+/* The same two host entries for a text shipped as ONE BYTE per code point -- four times fewer bytes over the host link.
+ * text8: the code points of string 0 (each < 0xFF, as themselves), then 0xFF, the code points of string 1, then 0xFF, ...:
+ * the k-th 0xFF of a document stands for the terminator 0x0A00 + k of east/asts/utils.py:35-39; doc_off / doc_m as above
+ * (offsets in code points = bytes).  Texts with a code point >= 0xFF (Cyrillic, CJK) use the uint32 entries.  On a large
+ * batch of small documents the per-document kernel byte-codes straight from these bytes and writes the uint32 code
+ * points of the index itself; otherwise they are expanded on the device first.  Results are identical to the uint32
+ * entries on the equivalent packed text.  EAST_ERR_INVALID when a document does not hold exactly doc_m bytes 0xFF or does
+ * not end with one. */
+int east_build_host_u8(const uint8_t *text8, const int64_t *doc_off, const int32_t *doc_m,
+                       int32_t n_docs, int device, east_index **out);
+int east_table_host_u8(const uint8_t *text8, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                       int device, const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized,
+                       double *out_DxK, east_index **out_idx);
 /* the same with text, keyphrases and table resident on the device (kp_host: optional host copy of the
  * keyphrase code points, saves a device-to-host round trip; may be NULL) */
 int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,

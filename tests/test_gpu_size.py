@@ -181,3 +181,71 @@ def test_keyphrase_preparation_on_the_device_equals_the_host_variant(oracle_mod)
     ast = base.AST.get_ast(["XABXAC", "HI"])
     s, per = ast.score("ABCIAB", return_suffix_scores=True)
     assert list(per.keys()) == ["ABCIAB", "BCIAB", "CIAB", "IAB", "AB", "B"]
+
+
+def test_one_byte_text_entries_equal_the_uint32_entries(oracle_mod):
+    # east_*_host_u8: the text crosses the host link as one byte per code point (0xFF = end of a string); the
+    # per-document kernel byte-codes from it and restores the code points (terminators 0x0A00 + k) itself
+    import synth
+    from east.asts import utils as au
+    capi = _capi()
+    packed, ms, cols = synth.packed_collection(320, 10000, first_seed=501)
+    packed8 = [au.pack_strings_collection_u8(c) for c in cols]
+    assert all(p8 is not None and p8.size == p.size for p8, p in zip(packed8, packed))
+    codes, off = _keyphrases(200, extra=["ABਁC", "਀", "E", "Zਁ"])   # code points in the terminator range: the generic
+    text8, doc_off = _concat(packed8)                                 # walk reads the restored uint32 text
+    text8 = np.ascontiguousarray(text8, dtype=np.uint8)
+
+    def table8(t8, d_off, d_m):
+        out = np.full((len(d_m), len(off) - 1), -1.0)
+        return capi.DeviceIndex.build_host_and_score(t8, d_off, d_m, codes, off, out, True), out
+
+    idx32, exp = _table_host(packed, ms, codes, off)
+    idx8, out = table8(text8, doc_off, ms)
+    assert idx8.stat("pipelined") == 1 and idx8.info()["doc_sorted"]
+    assert np.array_equal(_bits(out), _bits(exp))
+    for d in (0, 36, 37, 148, 319):
+        o = oracle_mod.OracleEASA(text=packed[d], m=ms[d])
+        _check_arrays(idx8, d, o, ("u8", d))
+        assert np.array_equal(_bits(out[d]), _bits(o.score_many(codes, off, True)))
+    assert np.array_equal(_bits(idx8.score_table(codes, off, True)), _bits(exp))   # the index that comes back is complete
+    idx8.close(); idx32.close()
+    # build only
+    idx8 = capi.DeviceIndex.build_host_u8(text8, doc_off, ms)
+    assert idx8.stat("pipelined") == 1
+    assert np.array_equal(_bits(idx8.score_table(codes, off, True)), _bits(exp))
+    idx8.close()
+    # a batch too small for the pipelined build, and one with a document the per-document kernel cannot take: expanded
+    # on the device, then the ordinary build
+    t5, o5 = _concat(packed8[:5])
+    idx8, out5 = table8(np.ascontiguousarray(t5, dtype=np.uint8), o5, ms[:5])
+    assert idx8.stat("pipelined") == 0
+    assert np.array_equal(_bits(out5), _bits(exp[:5]))
+    idx8.close()
+    big, big_m, big_cols = synth.packed_collection(1, 90000, first_seed=77)
+    mix8 = packed8[:3] + [au.pack_strings_collection_u8(big_cols[0])]
+    tm, om = _concat(mix8)
+    idx8, outm = table8(np.ascontiguousarray(tm, dtype=np.uint8), om, ms[:3] + big_m)
+    assert not idx8.info()["doc_sorted"]
+    o = oracle_mod.OracleEASA(text=big[0], m=big_m[0])
+    assert np.array_equal(_bits(outm[3]), _bits(o.score_many(codes, off, True)))
+    _check_arrays(idx8, 3, o, "u8 big")
+    idx8.close()
+    # a symbol that first appears in a late run: the speculation fails, the batch is expanded and rebuilt
+    late_col = ["0123456789 QUIZ", "ZEBRA9"]
+    late8, late32 = au.pack_strings_collection_u8(late_col), au.pack_strings_collection(late_col)
+    tl, ol = _concat(packed8 + [late8])
+    idx8, outl = table8(np.ascontiguousarray(tl, dtype=np.uint8), ol, ms + [2])
+    assert idx8.stat("pipeline_miss") == 1 and idx8.stat("pipelined") == 0
+    assert np.array_equal(_bits(outl[:320]), _bits(exp))
+    assert np.array_equal(_bits(outl[320]), _bits(oracle_mod.OracleEASA(text=late32, m=2).score_many(codes, off, True)))
+    idx8.close()
+    # malformed: a document that does not end with 0xFF / holds another number of string ends than doc_m says
+    broken = text8.copy()
+    broken[doc_off[200 + 1] - 1] = ord("A")
+    with pytest.raises(ValueError):
+        table8(broken, doc_off, ms)
+    with pytest.raises(ValueError):
+        table8(np.ascontiguousarray(t5, dtype=np.uint8), o5, [m_ + 1 for m_ in ms[:5]])
+    # the Python layer takes the narrow form on its own when the text allows it
+    assert au.pack_strings_collection_u8(["ÿ"]) is None and au.pack_strings_collection_u8(["Я"]) is None
