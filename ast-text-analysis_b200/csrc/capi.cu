@@ -1004,6 +1004,9 @@ struct TableRun {
     int32_t K = 0;
     int normalized = 0;
     double *d_out = nullptr, *host_out = nullptr;   // host_out NULL: the table stays on the device
+    double *const *peer_rows = nullptr;             // sharded table: where this rank's rows start in every other rank's table
+    int32_t n_peers = 0;
+    int32_t docs_sent = 0;                          // documents whose rows have reached the peers (current pass)
     std::unique_ptr<KpPrepared> kp_own;   // prepared for this call only (a table call is made once per collection)
     cudaEvent_t kp_ready = nullptr;       // dense codes of the current pass queued
     KpPrepared *kp = nullptr;
@@ -1033,6 +1036,7 @@ static void table_run_begin(void *vctx, const RunReady &r, DocScore &score) {
         if (r.doc_begin == 0) {   // a new pass over the batch (the first, or the ordinary build after a failed speculation)
             t.failed = false;
             t.docs_scored = 0;
+            t.docs_sent = 0;
             t.final_pass = r.speculative ? 0 : 1;
             const east_index *b = t.building;
             east_index &v = t.view;
@@ -1065,6 +1069,8 @@ static void table_run_begin(void *vctx, const RunReady &r, DocScore &score) {
             score.tmp = t.tmp[li].p; score.normalized = t.normalized ? 1 : 0;
             score.kp_off = t.kp->dev.d_off.p; score.uniq_of = t.kp->dev.d_uniq_of.p; score.K = t.K;
             score.out = t.d_out + (size_t)r.doc_begin * t.K;
+            score.n_peers = t.n_peers;
+            for (int32_t pi = 0; pi < t.n_peers; ++pi) score.peer_out[pi] = t.peer_rows[pi] + (size_t)r.doc_begin * t.K;
             score.algorithmic_bytes = (double)get_option("score_bytes", 0) * ((double)r.doc_count / (double)t.view.n_docs);
         }
     } catch (...) {
@@ -1083,6 +1089,8 @@ static void table_run_done(void *vctx, const RunReady &r, int in_kernel) {
         if (!in_kernel) {
             score_enqueue(&t.view, t.kp, t.d_kp, t.kp_off[t.K], t.K, t.normalized, rows, r.doc_begin, r.doc_count, r.stream,
                           t.tmp[li].p, (int32_t)t.tmp_docs[li], nullptr);
+        } else {
+            t.docs_sent += r.doc_count;   // the kernel stores its rows to the peers itself
         }
         if (t.host_out)
             EAST_CUDA(cudaMemcpyAsync(t.host_out + (size_t)r.doc_begin * t.K, rows, sizeof(double) * (size_t)r.doc_count * t.K,
@@ -1146,11 +1154,11 @@ int east_table_host_u8(const uint8_t *text8, const int64_t *doc_off, const int32
     EAST_API_END
 }
 
-int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
-                   const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, int normalized,
-                   double *out_DxK_dev, void *stream, east_index **out_idx) {
-    EAST_API_BEGIN
+static void table_dev_impl(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
+                           const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, int normalized,
+                           double *out_DxK_dev, double *const *peer_rows, int32_t n_peers, void *stream, east_index **out_idx) {
     if (!kp_dev || !kp_off || !out_DxK_dev || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    if (n_peers < 0 || n_peers > DocScore::MAX_PEERS || (n_peers > 0 && !peer_rows)) throw Error(EAST_ERR_INVALID, "bad peer list");
     east_index *built = nullptr;
     check_build_args(text_dev, doc_off, doc_m, n_docs, &built);
     check_keyphrases(kp_off, K);
@@ -1168,14 +1176,37 @@ int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32
     }
     run.kp_host = kp_host; run.d_kp = kp_dev; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
     run.d_out = out_DxK_dev; run.host_out = nullptr;
+    run.peer_rows = peer_rows; run.n_peers = n_peers;
     RunHook hook;
     hook.begin = table_run_begin; hook.fn = table_run_done; hook.ctx = &run; hook.building = &run.building;
     build_common(text_dev, false, doc_off, doc_m, n_docs, device, s, &built, nullptr, &hook);
     std::unique_ptr<east_index, void (*)(east_index *)> guard(built, free_index);
     const bool stands = !run.failed && run.docs_scored == n_docs && built->doc_sorted && run.final_pass;
-    if (stands) EAST_CUDA(cudaStreamSynchronize(s));
-    else score_common(built, kp_dev, kp_off, K, normalized, out_DxK_dev, 0, n_docs, s, nullptr, nullptr, kp_host);
+    if (!stands) score_common(built, kp_dev, kp_off, K, normalized, out_DxK_dev, 0, n_docs, s, nullptr, nullptr, kp_host);
+    if (n_peers > 0 && !(stands && run.docs_sent == n_docs)) {
+        // the rows were (also) produced by the batched scorer: plain peer copies of the slice
+        for (int32_t pi = 0; pi < n_peers; ++pi)
+            EAST_CUDA(cudaMemcpyAsync(peer_rows[pi], out_DxK_dev, sizeof(double) * (size_t)n_docs * K, cudaMemcpyDefault, s));
+    }
+    EAST_CUDA(cudaStreamSynchronize(s));
     if (out_idx) *out_idx = guard.release();
+}
+
+int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
+                   const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, int normalized,
+                   double *out_DxK_dev, void *stream, east_index **out_idx) {
+    EAST_API_BEGIN
+    table_dev_impl(text_dev, doc_off, doc_m, n_docs, device, kp_dev, kp_host, kp_off, K, normalized, out_DxK_dev, nullptr, 0,
+                   stream, out_idx);
+    EAST_API_END
+}
+
+int east_table_dev_gather(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
+                          const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, int normalized,
+                          double *out_DxK_dev, double *const *peer_rows, int32_t n_peers, void *stream, east_index **out_idx) {
+    EAST_API_BEGIN
+    table_dev_impl(text_dev, doc_off, doc_m, n_docs, device, kp_dev, kp_host, kp_off, K, normalized, out_DxK_dev, peer_rows,
+                   n_peers, stream, out_idx);
     EAST_API_END
 }
 

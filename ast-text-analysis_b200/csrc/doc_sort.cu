@@ -552,8 +552,14 @@ __device__ __forceinline__ void ds_score_document(const DocSortParams &p, uint8_
         const int32_t sb = __ldg(p.score.kp_off + k), se = __ldg(p.score.kp_off + k + 1);
         double result = 0.0;
         for (int32_t x = sb; x < se; ++x) result = result + __ldcg(out + __ldg(p.score.uniq_of + x));
-        table_row[k] = result / (double)(se - sb);
+        const double v = result / (double)(se - sb);
+        table_row[k] = v;
+        // sharded table: the row goes to the other ranks' gathered tables as well (peer memory over NVLink) -- the
+        // all-gather happens here, row by row, under the indexing of the documents still to come
+        const size_t cell = (size_t)(doc - p.doc_begin) * (size_t)p.score.K + (size_t)k;
+        for (int pi = 0; pi < p.score.n_peers; ++pi) p.score.peer_out[pi][cell] = v;
     }
+    if (p.score.n_peers > 0) __threadfence_system();
 }
 
 __global__ void __launch_bounds__(DS_THREADS, 1)

@@ -20,6 +20,11 @@ struct DocScore {
     const int32_t *uniq_of = nullptr; // per suffix of the concatenated keyphrases: position of its distinct twin
     int32_t K = 0;
     double *out = nullptr;
+    // the all-gather of a documents-sharded table, fused: every row is also stored into the gathered tables of the other
+    // ranks (their memory mapped into this process: NVLink peer stores), at the same row offset as `out`
+    static constexpr int MAX_PEERS = 15;
+    double *peer_out[MAX_PEERS] = {};
+    int32_t n_peers = 0;
     double algorithmic_bytes = 0.0;   // of the walks of this launch (measurement only: added to the kernel's byte count)
 };
 

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
     "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
     "east_score_probes_dev", "east_index_stat", "east_score_range_dev", "east_table_host", "east_table_dev",
-    "east_build_host_u8", "east_table_host_u8",
+    "east_build_host_u8", "east_table_host_u8", "east_table_dev_gather",
 ]
 
 _lib = None
@@ -72,6 +72,8 @@ def load():
                                      ctypes.c_int, _f64p, ctypes.POINTER(_vp)]
     L.east_table_dev.argtypes = [_vp, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _vp, _u32p, _i64p, ctypes.c_int32,
                                  ctypes.c_int, _vp, _vp, ctypes.POINTER(_vp)]
+    L.east_table_dev_gather.argtypes = [_vp, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _vp, _u32p, _i64p, ctypes.c_int32,
+                                        ctypes.c_int, _vp, ctypes.POINTER(_vp), ctypes.c_int32, _vp, ctypes.POINTER(_vp)]
     L.east_score_range_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
     L.east_score_probes_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, _vp, _vp, _i64p]
     L.east_score_one.argtypes = [_vp, ctypes.c_int32, _u32p, ctypes.c_int32, ctypes.c_int, _f64p, _f64p]
@@ -234,9 +236,11 @@ class DeviceIndex(object):
 
     @classmethod
     def build_dev_and_score(cls, text_devptr, doc_off, doc_m, kp_devptr, kp_codes, kp_off, out_devptr, normalized=True,
-                            device=0, stream=0):
+                            device=0, stream=0, peer_rows=None):
         """build_dev() + score_table_dev() as ONE engine call (east_table_dev): the per-document kernel scores every
-        document right after indexing it.  kp_codes: host copy of the keyphrase code points (or None)."""
+        document right after indexing it.  kp_codes: host copy of the keyphrase code points (or None).
+        peer_rows: device addresses in the OTHER ranks' gathered tables where this rank's rows start (mapped peer
+        memory): the kernel stores every row there too (east_table_dev_gather, the fused all-gather)."""
         L = load()
         doc_off = np.ascontiguousarray(doc_off, dtype=np.int64)
         doc_m = np.ascontiguousarray(doc_m, dtype=np.int32)
@@ -246,6 +250,13 @@ class DeviceIndex(object):
             kp_codes = np.ascontiguousarray(kp_codes, dtype=np.uint32)
             kp_host = _ptr(kp_codes, _u32p)
         h = _vp()
+        if peer_rows:
+            peers = (_vp * len(peer_rows))(*[int(a) for a in peer_rows])
+            _check(L.east_table_dev_gather(_vp(text_devptr), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m), int(device),
+                                           _vp(kp_devptr), kp_host, _ptr(kp_off, _i64p), len(kp_off) - 1,
+                                           1 if normalized else 0, _vp(out_devptr), peers, len(peer_rows), _vp(stream),
+                                           ctypes.byref(h)))
+            return cls.from_handle(h, doc_off, doc_m, int(device))
         _check(L.east_table_dev(_vp(text_devptr), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m), int(device),
                                 _vp(kp_devptr), kp_host, _ptr(kp_off, _i64p), len(kp_off) - 1, 1 if normalized else 0,
                                 _vp(out_devptr), _vp(stream), ctypes.byref(h)))

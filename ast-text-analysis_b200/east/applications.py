@@ -67,16 +67,22 @@ def keyphrases_graph(keyphrases, texts, referral_confidence=0.6, relevance_thres
     |T1 & T2| / max(|T1|, 1) reaches referral_confidence.
     """
     kept, titles, scores = _score_matrix(keyphrases, texts, similarity_measure, synonimizer, language)
+    if scores.size:
+        cooc = _capi.cooc_host(scores, relevance_threshold)
+    else:
+        cooc = np.zeros((len(kept), len(kept)), dtype=np.int32)
+    return graph_from_cooccurrence(keyphrases, kept, cooc, referral_confidence, relevance_threshold, support_threshold)
+
+
+def graph_from_cooccurrence(keyphrases, kept, cooc, referral_confidence, relevance_threshold, support_threshold):
+    """The graph dict of east/applications.py:115-149 from the co-occurrence counts cooc[k1][k2] = number of texts
+    in which both kept keyphrases k1 and k2 reach the relevance threshold (diagonal: the support)."""
     column_of = {}
     for k, kp in enumerate(kept):
         column_of[kp] = k  # duplicate keyphrases share one table row (last wins, like a dict)
     for kp in keyphrases:
         if kp not in column_of:
             raise KeyError(kp)  # the reference indexes table[keyphrase] for skipped empty keyphrases
-    if scores.size:
-        cooc = _capi.cooc_host(scores, relevance_threshold)
-    else:
-        cooc = np.zeros((len(kept), len(kept)), dtype=np.int32)
     support = {kp: int(cooc[column_of[kp], column_of[kp]]) for kp in keyphrases}
 
     graph = {

@@ -126,7 +126,8 @@ def workload_config(args, n_gpus):
     return {"workload": "keyphrases_table: %d keyphrases x %d synthetic Zipf docs x ~%d KB per GPU (BASELINE configs[1]), "
                         "build (SA+LCP+child+annotation) + score, normalized" % (args.keyphrases, args.docs, args.doc_bytes // 1000),
             "keyphrases": args.keyphrases, "docs_per_gpu": args.docs, "doc_bytes": args.doc_bytes,
-            "parallelism": "documents sharded over %d GPU(s), all-gather of score slices" % n_gpus,
+            "parallelism": "documents sharded over %d GPU(s), all-gather of score slices (%s)" % (
+                n_gpus, os.environ.get("EAST_GATHER_USED", "n/a")),
             "l2": "inputs larger than L2: packed text + sort buffers of a step are > 1 GB"}
 
 
@@ -258,10 +259,31 @@ def run_b200(args):
     text_dev = host_text.to(dev)
     kp_dev = torch.from_numpy(kp_codes.view(np.int32).copy()).to(dev)
     out_dev = torch.empty(D * K, dtype=torch.float64, device=dev)
-    gathered = torch.empty(world * D * K, dtype=torch.float64, device=dev) if world > 1 else None
+    # N > 1: the gathered [N*D, K] table.  Default: symmetric memory, every rank's kernel stores its rows straight into
+    # the tables of its peers (east_table_dev_gather: the all-gather is fused into the scoring kernel, NVLink peer
+    # stores) and one symmetric-memory barrier ends the step.  EAST_BENCH_GATHER=nccl (or no symmetric memory): one
+    # NCCL all_gather_into_tensor per step.
+    gathered, symm = None, None
+    if world > 1:
+        from east import distributed as east_dist
+        ok = 0
+        if os.environ.get("EAST_BENCH_GATHER", "fused") == "fused" and east_dist.symmetric_memory_available():
+            try:
+                symm = east_dist.SymmetricTable(world * D, K, local_rank)
+                ok = 1
+            except Exception as e:  # noqa: BLE001
+                sys.stderr.write("[rank %d] symmetric memory unavailable (%r): NCCL all-gather\n" % (rank, e))
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if not bool(flag.item()):
+            symm = None
+        gathered = symm.tensor.view(-1) if symm is not None else torch.empty(world * D * K, dtype=torch.float64, device=dev)
     host_out = torch.empty(D * K, dtype=torch.float64).pin_memory()
     host_out_np = host_out.numpy().reshape(D, K)
     torch.cuda.synchronize()
+    os.environ["EAST_GATHER_USED"] = ("none: one GPU" if world == 1 else
+                                      "fused into the scoring kernel: NVLink peer stores into symmetric memory + one barrier"
+                                      if symm is not None else "one NCCL all_gather_into_tensor per step")
 
     debug = bool(os.environ.get("EAST_BENCH_DEBUG"))
     apply_env_options(_capi)
@@ -276,13 +298,21 @@ def run_b200(args):
                                               stream=stream.cuda_stream)
             tb = time.perf_counter()
             idx.score_table_dev(kp_dev.data_ptr(), kp_off, out_dev.data_ptr(), True, stream=stream.cuda_stream)
+        elif symm is not None:   # east_table_dev_gather: build + score + the all-gather in one kernel
+            idx = _capi.DeviceIndex.build_dev_and_score(text_dev.data_ptr(), doc_off, doc_m, kp_dev.data_ptr(), kp_codes,
+                                                        kp_off, symm.own_rows(rank * D), True, device=local_rank,
+                                                        stream=stream.cuda_stream, peer_rows=symm.peer_rows(rank * D))
+            tb = time.perf_counter()
         else:   # east_table_dev: build + score, the per-document kernel scores its document itself
             idx = _capi.DeviceIndex.build_dev_and_score(text_dev.data_ptr(), doc_off, doc_m, kp_dev.data_ptr(), kp_codes,
                                                         kp_off, out_dev.data_ptr(), True, device=local_rank,
                                                         stream=stream.cuda_stream)
             tb = time.perf_counter()
         tc = time.perf_counter()
-        if world > 1:
+        if symm is not None and not two_calls:
+            symm.barrier()             # every rank's rows have reached every table
+            torch.cuda.synchronize()
+        elif world > 1:
             # the step ends when the gathered [N*D, K] table is complete on this rank (without this
             # host sync the NCCL kernel of step i overlaps the build of step i+1 and both crawl)
             dist.all_gather_into_tensor(gathered, out_dev)

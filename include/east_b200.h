@@ -120,6 +120,17 @@ int east_table_host_u8(const uint8_t *text8, const int64_t *doc_off, const int32
 int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
                    int device, const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K,
                    int normalized, double *out_DxK_dev, void *stream, east_index **out_idx);
+/* east_table_dev for a table whose documents are sharded over several GPUs (one process per GPU; the documents are
+ * independent: east/relevance.py:41-47), with the all-gather of the per-rank slices fused into the scoring kernel:
+ * every row this rank produces is also stored, by the CTA that computed it, at peer_rows[i] + the same row offset --
+ * peer_rows[i] = where this rank's slice starts in the gathered table of the i-th other rank, a pointer into that rank's
+ * memory mapped into this process (CUDA peer access / torch symmetric memory: the stores travel over NVLink).  The call
+ * returns when this rank's kernels are done and its stores are fenced system-wide; the caller then runs a barrier
+ * across ranks, after which every rank holds the whole table.  n_peers <= 15.  Without peers it is east_table_dev. */
+int east_table_dev_gather(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                          int device, const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K,
+                          int normalized, double *out_DxK_dev, double *const *peer_rows, int32_t n_peers, void *stream,
+                          east_index **out_idx);
 /* the rows of documents [doc_begin, doc_begin + doc_count) only: out[(d - doc_begin) * K + k].  Lets a caller
  * that shards documents over GPUs overlap the collective of one document tile with the scoring of the next. */
 int east_score_range_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,

@@ -230,7 +230,32 @@ def test_hse_table_and_graph(golden):
         assert np.array_equal(cooc, (B.T.astype(np.int64) @ B.astype(np.int64)).astype(np.int32))
         support = np.diag(cooc)
         assert [n["support"] for n in g["nodes"]] == [int(support[n["id"]]) for n in g["nodes"]]
-    del measure, texts
+        # nodes and EVERY edge (order, endpoints, confidence bit for bit) as the reference built them
+        graph = applications.graph_from_cooccurrence(kps, kps, cooc, g["c"], g["r"], g["p"])
+        assert graph["nodes"] == g["nodes"]
+        assert [(e["source"], e["target"], float(e["confidence"]).hex()) for e in graph["edges"]] == \
+               [(e["source"], e["target"], e["confidence"]) for e in g["edges"]]
+    del measure
+    # the same through the public API (applications.keyphrases_graph -> ASTRelevanceMeasure -> one-call engine entry):
+    # the goldens hold the strings collections, so the preprocessing step hands them out for marker texts
+    from east import utils as east_utils
+    real = east_utils.text_to_strings_collection
+    try:
+        east_utils.text_to_strings_collection = lambda text: cols[int(text[2:])]
+        marker_texts = {d["name"]: "@@%d" % j for j, d in enumerate(hse["docs"])}
+        for g in hse["graphs"]:
+            graph = applications.keyphrases_graph(kps, marker_texts, referral_confidence=g["c"], relevance_threshold=g["r"],
+                                                  support_threshold=g["p"],
+                                                  similarity_measure=relevance.ASTRelevanceMeasure("easa", normalized=True))
+            assert graph["nodes"] == g["nodes"], (g["c"], g["r"], g["p"])
+            assert [(e["source"], e["target"], float(e["confidence"]).hex()) for e in graph["edges"]] == \
+                   [(e["source"], e["target"], e["confidence"]) for e in g["edges"]]
+        tab = applications.keyphrases_table(kps, marker_texts, relevance.ASTRelevanceMeasure("easa", normalized=True))
+        for kp in kps:
+            for d in hse["docs"]:
+                assert float(tab[kp][d["name"]]).hex() == hse["table_norm"][kp][d["name"]]
+    finally:
+        east_utils.text_to_strings_collection = real
 
 
 def test_applications_api_end_to_end(golden, oracle_mod):
@@ -320,6 +345,17 @@ def _nccl_worker(rank, world, port, out_dir):
         kps = [utils.prepare_text(k) for k in synth.keyphrases(9)]
         full = distributed.relevance_table_sharded(docs, kps, True, device=rank)
         np.save(os.path.join(out_dir, "rank%d.npy" % rank), full.cpu().numpy())
+        plain = distributed.relevance_table_sharded(docs, kps, True, device=rank, fused_gather=False)
+        np.save(os.path.join(out_dir, "plain%d.npy" % rank), plain.cpu().numpy())
+        # a ragged collection (one document the per-document kernel cannot take): several device batches per rank
+        ragged = docs[:3] + [synth.document(90000, 999)] + docs[3:]
+        rag = distributed.relevance_table_sharded(ragged, kps, True, device=rank)
+        np.save(os.path.join(out_dir, "ragged%d.npy" % rank), rag.cpu().numpy())
+        names = synth.keyphrases(9)
+        graph = distributed.keyphrases_graph_sharded(names, {"t%d" % j: d for j, d in enumerate(docs)}, 0.5, 0.1, 1, device=rank)
+        import json
+        with open(os.path.join(out_dir, "graph%d.json" % rank), "w") as f:
+            json.dump(graph, f)
     finally:
         dist.destroy_process_group()
 
@@ -343,9 +379,23 @@ def test_multi_gpu_sharded_table_is_bit_identical(tmp_path):
     idx = _build(cols)
     codes, off = capi.pack_keyphrases(kps)
     expect = idx.score_table(codes, off, True)
+    from east import applications, relevance
+    names = synth.keyphrases(9)
+    graph1 = applications.keyphrases_graph(names, {"t%d" % j: d for j, d in enumerate(docs)}, 0.5, 0.1, 1,
+                                           similarity_measure=relevance.ASTRelevanceMeasure("easa", True))
+    ragged = docs[:3] + [synth.document(90000, 999)] + docs[3:]
+    big = _build([utils.text_to_strings_collection(ragged[3])])
+    expect_ragged = np.concatenate([expect[:3], big.score_table(codes, off, True), expect[3:]])
+    import json
     for r in range(2):
         got = np.load(str(tmp_path / ("rank%d.npy" % r)))
         assert np.array_equal(got.view(np.uint64), expect.view(np.uint64))
+        got = np.load(str(tmp_path / ("plain%d.npy" % r)))
+        assert np.array_equal(got.view(np.uint64), expect.view(np.uint64))
+        got = np.load(str(tmp_path / ("ragged%d.npy" % r)))
+        assert np.array_equal(got.view(np.uint64), expect_ragged.view(np.uint64))
+        with open(str(tmp_path / ("graph%d.json" % r))) as f:
+            assert json.load(f) == json.loads(json.dumps(graph1))
 
 
 @pytest.mark.parametrize("K,D", [(5, 3), (130, 257), (300, 1000), (257, 4100), (700, 900)])
