@@ -1,5 +1,6 @@
 // capi.cu -- the C ABI of libeast_b200.so (declared in include/east_b200.h).
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -79,13 +80,120 @@ static int64_t get_option(const char *name, int64_t dflt) {
     return (it == g_options.end() || it->second == 0) ? dflt : it->second;
 }
 
-void *dev_alloc(size_t bytes, cudaStream_t s) {
+// two library-private pools per device: [0] scratch, [1] large repeating blocks (index arenas, text buffers)
+static std::mutex g_pool_mutex;
+static std::map<int, std::array<cudaMemPool_t, 2>> g_pools;
+
+static cudaMemPool_t pool_for(bool big) {
+    int dev = 0;
+    EAST_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    auto it = g_pools.find(dev);
+    if (it == g_pools.end()) {
+        std::array<cudaMemPool_t, 2> pools{};
+        size_t free_b = 0, total_b = 0;
+        EAST_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        for (int k = 0; k < 2; ++k) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            EAST_CUDA(cudaMemPoolCreate(&pools[k], &props));
+            // freed blocks stay for the next call up to this much (build/score steps reuse them); east_trim() drops them
+            uint64_t thr = k ? (uint64_t)total_b / 4 : (uint64_t)total_b / 16;
+            EAST_CUDA(cudaMemPoolSetAttribute(pools[k], cudaMemPoolAttrReleaseThreshold, &thr));
+        }
+        it = g_pools.emplace(dev, pools).first;
+    }
+    return it->second[big ? 1 : 0];
+}
+
+// Large blocks (index arenas, text buffers) are kept by the library itself when they are freed and handed out again to
+// the next request of (nearly) the same size: measured on B200, a 2 GB cudaMallocFromPoolAsync costs 0.3-0.55 ms of host
+// time even when the pool holds a free block of exactly that size -- a tenth of a whole table call.  A cached block
+// carries the event after which its previous user is done with it.
+struct BigBlock { void *p; size_t bytes; cudaEvent_t idle; };
+static std::map<int, std::vector<BigBlock>> g_big_cache;     // per device, free blocks
+static std::map<const void *, size_t> g_big_live;            // blocks handed out: size
+static const size_t BIG_CACHE_BLOCKS = 6;
+
+static void *big_cache_take(size_t bytes, cudaStream_t s) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    BigBlock hit{nullptr, 0, nullptr};
+    {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        auto &v = g_big_cache[dev];
+        size_t best = v.size();
+        for (size_t i = 0; i < v.size(); ++i)
+            if (v[i].bytes >= bytes && v[i].bytes - bytes <= bytes / 8 && (best == v.size() || v[i].bytes < v[best].bytes)) best = i;
+        if (best == v.size()) return nullptr;
+        hit = v[best];
+        v.erase(v.begin() + best);
+        g_big_live[hit.p] = hit.bytes;
+    }
+    cudaStreamWaitEvent(s, hit.idle, 0);
+    cudaEventDestroy(hit.idle);
+    return hit.p;
+}
+
+// true: the block was kept (or freed) here
+static bool big_cache_put(void *p, cudaStream_t s) {
+    int dev = 0;
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        auto it = g_big_live.find(p);
+        if (it == g_big_live.end()) return false;
+        bytes = it->second;
+        g_big_live.erase(it);
+    }
+    cudaEvent_t ev = nullptr;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventRecord(ev, s) != cudaSuccess) {
+        cudaGetLastError();
+        if (ev) cudaEventDestroy(ev);
+        cudaFreeAsync(p, s);
+        return true;
+    }
+    BigBlock evict{nullptr, 0, nullptr};
+    {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        auto &v = g_big_cache[dev];
+        v.push_back(BigBlock{p, bytes, ev});
+        if (v.size() > BIG_CACHE_BLOCKS) { evict = v.front(); v.erase(v.begin()); }   // the oldest goes back to the pool
+    }
+    if (evict.p) { cudaStreamWaitEvent(s, evict.idle, 0); cudaEventDestroy(evict.idle); cudaFreeAsync(evict.p, s); }
+    return true;
+}
+
+static void big_cache_drop(int dev) {
+    std::vector<BigBlock> v;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mutex);
+        v.swap(g_big_cache[dev]);
+    }
+    for (auto &b : v) { cudaEventDestroy(b.idle); cudaFreeAsync(b.p, 0); }
+}
+
+void *dev_alloc(size_t bytes, cudaStream_t s, bool big) {
     void *p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, bytes, s);
+    if (big && (p = big_cache_take(bytes, s)) != nullptr) return p;
+    cudaError_t e = cudaMallocFromPoolAsync(&p, bytes, pool_for(big), s);
+    if (e == cudaErrorMemoryAllocation && big) {   // give the cached blocks back and try once more
+        cudaGetLastError();
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceSynchronize();
+        big_cache_drop(dev);
+        e = cudaMallocFromPoolAsync(&p, bytes, pool_for(big), s);
+    }
+    if (e == cudaSuccess && big) { std::lock_guard<std::mutex> g(g_pool_mutex); g_big_live[p] = bytes; }
     if (e != cudaSuccess) {
         cudaGetLastError();
         throw Error(e == cudaErrorMemoryAllocation ? -3 : -2,
-                    std::string("cudaMallocAsync(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+                    std::string("cudaMallocFromPoolAsync(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
     }
     return p;
 }
@@ -94,11 +202,16 @@ void dev_free(void *p, cudaStream_t s) {
     // an exception is unwinding the build: kernels that use the buffer may still run on the auxiliary, helper, prep or
     // copy streams (non-blocking: `s` does not order them) -- let the device finish before anything goes back to the pool
     if (std::uncaught_exceptions() > 0) cudaDeviceSynchronize();
+    if (big_cache_put(p, s)) return;
     cudaFreeAsync(p, s);
 }
 
 static double host_now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+void host_debug_mark(const char *what) {
+    static const bool debug = getenv("EAST_DEBUG_TIMING") != nullptr;
+    if (debug) fprintf(stderr, "[east] host %.3f ms  . %s\n", host_now_ms(), what);
 }
 void StageTimer::mark(const char *name) {
     static const bool debug = getenv("EAST_DEBUG_TIMING") != nullptr;
@@ -132,16 +245,6 @@ static void use_device(int device) {
     }
     if (device < 0 || device >= cnt) throw Error(-1, "bad device ordinal");
     EAST_CUDA(cudaSetDevice(device));
-    static std::mutex m;
-    static std::map<int, bool> tuned;
-    std::lock_guard<std::mutex> g(m);
-    if (!tuned[device]) {
-        cudaMemPool_t pool;
-        EAST_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t thr = ~0ull;  // keep freed blocks in the pool: build/score steps reuse them
-        EAST_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-        tuned[device] = true;
-    }
 }
 
 }  // namespace east
@@ -155,6 +258,7 @@ struct east_index {
     int64_t m_total = 0;
     std::vector<int32_t> doc_off;  // host copies
     std::vector<int32_t> doc_m;
+    Arena arena;                    // one allocation: every array below except an owned text
     bool owns_text = false;
     uint32_t *text = nullptr;
     int32_t *d_doc_off = nullptr, *d_doc_m = nullptr;
@@ -305,11 +409,12 @@ static void free_index(east_index *idx) {
     if (idx->tables_pending) { cudaEventSynchronize(idx->ev_tables); idx->tables_pending = false; }
     if (idx->build_timer) { try { idx->build_timer->collect(); } catch (...) {} idx->build_timer.reset(); }
     if (idx->ev_tables) cudaEventDestroy(idx->ev_tables);
-    if (idx->owns_text && idx->text) cudaFreeAsync(idx->text, 0);
+    if (idx->owns_text && idx->text) dev_free(idx->text, 0);
     for (void *p : {(void *)idx->d_doc_off, (void *)idx->d_doc_m, (void *)idx->sa, (void *)idx->lcp,
                     (void *)idx->up, (void *)idx->down, (void *)idx->next, (void *)idx->ann, (void *)idx->t8,
                     (void *)idx->bkt, (void *)idx->bkt3, (void *)idx->sk})
-        if (p) cudaFreeAsync(p, 0);
+        if (p && !idx->arena.holds(p)) cudaFreeAsync(p, 0);   // a slice the arena had no room for
+    if (idx->arena.base) dev_free(idx->arena.base, 0);
     delete idx;
 }
 
@@ -350,17 +455,36 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
     for (int i = 0; i <= n_docs; ++i) idx->doc_off[i] = (int32_t)doc_off[i];
     for (int i = 0; i < n_docs; ++i) idx->m_total += doc_m[i];
 
-    idx->d_doc_off = (int32_t *)dev_alloc(sizeof(int32_t) * (n_docs + 1), s);
-    idx->d_doc_m = (int32_t *)dev_alloc(sizeof(int32_t) * n_docs, s);
+    // ---- one arena for everything the index keeps: an upper bound that does not depend on the alphabet
+    int32_t max_doc_n = 0;
+    for (int i = 0; i < n_docs; ++i) max_doc_n = std::max<int32_t>(max_doc_n, (int32_t)(doc_off[i + 1] - doc_off[i]));
+    if (!get_option("no_arena", 0)) {
+        const size_t words = sizeof(int32_t) * (size_t)n;
+        size_t need = Arena::padded(sizeof(int32_t) * ((size_t)n_docs + 1)) + Arena::padded(sizeof(int32_t) * (size_t)n_docs) +
+                      7 * Arena::padded(words) + Arena::padded((size_t)n + 128);
+        // 2-gram table: n_docs << 2b entries with b <= 7, kept only up to 2n + 4096; 3-gram table: the per-document
+        // kernel with 3 symbols per bucket id (b = 4, 5), kept up to 8 GB
+        need += Arena::padded(sizeof(uint32_t) * (std::min<size_t>((size_t)n_docs << 14, (size_t)2 * n + 4096) + 1));
+        const size_t e3 = ((size_t)n_docs << 15) + 1;
+        if (max_doc_n <= 65535 && !get_option("no_doc_sort", 0) && !get_option("no_bkt3", 0) && e3 * sizeof(uint32_t) <= ((size_t)8 << 30) + 4)
+            need += Arena::padded(sizeof(uint32_t) * e3);
+        host_debug_mark("arena alloc");
+        idx->arena.base = (uint8_t *)dev_alloc(need, s, true);
+        idx->arena.cap = need;
+        host_debug_mark("arena alloc done");
+    }
+    auto take32 = [&](size_t count) { DevBuf<int32_t> b = idx->arena.take<int32_t>(count, s); int32_t *p = b.p; b.p = nullptr; return p; };
+    idx->d_doc_off = take32((size_t)n_docs + 1);
+    idx->d_doc_m = take32((size_t)n_docs);
     EAST_CUDA(cudaMemcpyAsync(idx->d_doc_off, idx->doc_off.data(), sizeof(int32_t) * (n_docs + 1),
                               cudaMemcpyHostToDevice, s));
     EAST_CUDA(cudaMemcpyAsync(idx->d_doc_m, idx->doc_m.data(), sizeof(int32_t) * n_docs, cudaMemcpyHostToDevice, s));
-    idx->sa = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
-    idx->lcp = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
-    idx->up = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
-    idx->down = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
-    idx->next = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
-    idx->ann = (int32_t *)dev_alloc(sizeof(int32_t) * (size_t)n, s);
+    idx->sa = take32((size_t)n);
+    idx->lcp = take32((size_t)n);
+    idx->up = take32((size_t)n);
+    idx->down = take32((size_t)n);
+    idx->next = take32((size_t)n);
+    idx->ann = take32((size_t)n);
 
     if (text8_dev && !chunks) {   // not pipelined: the code points first, then the ordinary build
         DevBuf<uint32_t> bad(1, s);
@@ -393,12 +517,13 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.light_scan = get_option("no_light_scan", 0) ? 0 : 1;
         in.fused_encode = get_option("no_fused_encode", 0) ? 0 : 1;
         if (!get_option("no_suffix_keys", 0)) {
-            idx->sk = (uint32_t *)dev_alloc(sizeof(uint32_t) * (size_t)n, s);
+            idx->sk = (uint32_t *)take32((size_t)n);
             in.sk = idx->sk;
         }
         if (!get_option("no_fused_tables", 0)) {
             in.lcp = idx->lcp; in.up = idx->up; in.down = idx->down; in.next = idx->next; in.ann = idx->ann;
         }
+        in.arena = idx->arena.base ? &idx->arena : nullptr;
         in.helper_stream = aux_stream(device);
         if (!get_option("no_prep_stream", 0)) in.prep_stream = prep_stream(device);
         if (hook && hook->fn) {
@@ -430,7 +555,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         idx->tables_fused = so.tables_done;
         if (idx->sk && !so.sk_done) {
             if (idx->t8) fill_suffix_keys(idx->t8, idx->sa, n, idx->sk, s);    // global sort, fast path
-            else { dev_free(idx->sk, s); idx->sk = nullptr; }                  // general path: no byte text
+            else { if (!idx->arena.holds(idx->sk)) dev_free(idx->sk, s); idx->sk = nullptr; }   // general path: no byte text
         }
         if (so.tables_done) {
             tm.finish();   // the per-document kernel produced every table: nothing is pending
@@ -491,10 +616,13 @@ static void build_host_impl(const void *text_any, int width /* bytes per code po
     // stream-ordered pool allocation (cudaMalloc/cudaFree take device-wide locks and synchronise)
     DevBuf<uint8_t> d_text8;
     if (width == 1) {
-        d_text8 = DevBuf<uint8_t>((size_t)n + 256, 0);   // the per-document kernel reads whole 16-byte groups
+        d_text8 = DevBuf<uint8_t>((uint8_t *)dev_alloc((size_t)n + 256, 0, true), (size_t)n + 256);   // 16-byte groups are read whole
+        d_text8.owned = true;
         EAST_CUDA(cudaMemsetAsync(d_text8.p + n, 0, 256, 0));
     }
-    uint32_t *d_text = (uint32_t *)dev_alloc(bytes, 0);
+    host_debug_mark("text alloc");
+    uint32_t *d_text = (uint32_t *)dev_alloc(bytes, 0, true);
+    host_debug_mark("text alloc done");
     // Large batches of small documents: copy in runs of whole documents on a copy stream so that the
     // per-document kernels of run c overlap the copy of run c+1 (worth it with pinned host memory)
     int64_t max_doc = 0;
@@ -1048,10 +1176,12 @@ static void table_run_begin(void *vctx, const RunReady &r, DocScore &score) {
             v.sym_bits = r.sym_bits;
             v.code_table = *r.code_table;
             const bool fast = v.bkt && v.t8 && !get_option("score_generic", 0);
+            host_debug_mark("kp_finish begin");
             kp_finish(t.kp_own.get(), t.d_kp, fast, v.sym_bits, v.code_table, r.stream);
             t.kp = t.kp_own.get();
             if (!t.kp_ready) EAST_CUDA(cudaEventCreateWithFlags(&t.kp_ready, cudaEventDisableTiming));
             EAST_CUDA(cudaEventRecord(t.kp_ready, r.stream));
+            host_debug_mark("kp_finish end");
         }
         if (t.failed || !t.kp) return;
         EAST_CUDA(cudaStreamWaitEvent(r.stream, t.kp_ready, 0));   // the other lane: the dense codes were queued on the first
@@ -1255,6 +1385,20 @@ int east_cooc_host(const double *S_DxK, int64_t D, int32_t K, double threshold, 
     if (get_option("cooc_variant", 0) == 1) cooc_counts(d_S.p, D, K, threshold, d_C.p, s);
     else cooc_counts_tc(d_S.p, D, K, threshold, d_C.p, s, get_option("cooc_variant", 0) == 2);
     EAST_CUDA(cudaMemcpy(C_KxK, d_C.p, sizeof(int32_t) * (size_t)K * K, cudaMemcpyDeviceToHost));
+    EAST_API_END
+}
+
+int east_trim(int device) {
+    EAST_API_BEGIN
+    use_device(device);
+    EAST_CUDA(cudaDeviceSynchronize());
+    g_kp_cache.reset();
+    big_cache_drop(device);
+    EAST_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> g(g_pool_mutex);
+    auto it = g_pools.find(device);
+    if (it != g_pools.end())
+        for (cudaMemPool_t pool : it->second) EAST_CUDA(cudaMemPoolTrimTo(pool, 0));
     EAST_API_END
 }
 

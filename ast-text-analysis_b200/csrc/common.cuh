@@ -30,7 +30,8 @@ extern thread_local int g_time_kernels;     // option "time_kernels": CUDA event
 extern thread_local double g_next_bytes;    // algorithmic bytes of the next launch (roofline numerator)
 void ktime_begin(const char *name, cudaStream_t s);
 void ktime_end(cudaStream_t s);
-void ktime_collect();  // after a stream sync: fold the pending event pairs into the per-kernel table
+void ktime_collect();
+void host_debug_mark(const char *what);   // EAST_DEBUG_TIMING: host timestamp on stderr  // after a stream sync: fold the pending event pairs into the per-kernel table
 
 // every kernel launch of the library goes through this macro so bench.py can report
 // "gpu_launches" from a real count and per-kernel device time measured live with CUDA events
@@ -47,8 +48,12 @@ void ktime_collect();  // after a stream sync: fold the pending event pairs into
     } while (0)
 #define EAST_BYTES(b) (::east::g_next_bytes = (double)(b))
 
-// stream-ordered allocations from the device's default pool (release threshold raised once)
-void *dev_alloc(size_t bytes, cudaStream_t s);
+// Stream-ordered allocations from two library-private memory pools per device (the device's default pool and its
+// attributes are left alone: the caller's framework allocates there).  `big`: the arena of an index and the text
+// buffers -- a few large blocks whose sizes repeat from call to call, so a freed block is reused whole; everything else
+// (scratch of a build or score call) comes from the other pool.  Both keep freed memory up to a bounded release
+// threshold; east_trim() gives it back.
+void *dev_alloc(size_t bytes, cudaStream_t s, bool big = false);
 void dev_free(void *p, cudaStream_t s);
 
 template <typename T>
@@ -56,17 +61,39 @@ struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
     cudaStream_t s = 0;
+    bool owned = true;   // false: a slice of an index arena (freed with the arena)
     DevBuf() {}
     DevBuf(size_t n_, cudaStream_t s_) : n(n_), s(s_) { p = (T *)dev_alloc(sizeof(T) * (n_ ? n_ : 1), s_); }
+    DevBuf(T *slice, size_t n_) : p(slice), n(n_), owned(false) {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s), owned(o.owned) { o.p = nullptr; }
     DevBuf &operator=(DevBuf &&o) noexcept {
-        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; }
+        if (this != &o) { release(); p = o.p; n = o.n; s = o.s; owned = o.owned; o.p = nullptr; }
         return *this;
     }
-    void release() { if (p) { dev_free(p, s); p = nullptr; } }
+    void release() { if (p) { if (owned) dev_free(p, s); p = nullptr; } }
     ~DevBuf() { release(); }
+};
+
+// One allocation that holds every array of an index (suffix array, tables, byte text, bucket tables ...): a bump
+// allocator over an upper bound computed before the build.  take() falls back to an allocation of its own when the
+// bound turns out too small; rewind() gives back what a failed pass (speculative pipelined build, bucket overflow) took.
+struct Arena {
+    uint8_t *base = nullptr;
+    size_t cap = 0, used = 0;
+    template <typename T>
+    DevBuf<T> take(size_t count, cudaStream_t s) {
+        const size_t bytes = (sizeof(T) * (count ? count : 1) + 255) & ~(size_t)255;
+        if (base && used + bytes <= cap) {
+            T *p = reinterpret_cast<T *>(base + used);
+            used += bytes;
+            return DevBuf<T>(p, count);
+        }
+        return DevBuf<T>(count, s);
+    }
+    bool holds(const void *p) const { return base && (const uint8_t *)p >= base && (const uint8_t *)p < base + cap; }
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 };
 
 // per-stage device timing with CUDA events on the launching stream

@@ -985,6 +985,12 @@ k_bucket_fill(uint32_t *__restrict__ bkt, int entries, const int32_t *__restrict
 // differ: chunk 0 is part of the text), and the per-document kernel validates the terminator layout of its
 // document (count, values, order, last position).  If either is set, nothing is kept and the ordinary build
 // runs on the resident text.
+// arrays that stay with the index come from its arena (one allocation per index), scratch from the pool
+template <typename T>
+static DevBuf<T> take(const SaInput &in, size_t count, cudaStream_t s) {
+    return in.arena ? in.arena->take<T>(count, s) : DevBuf<T>(count, s);
+}
+
 static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s, uint32_t &doc_sort_flags) {
     const int32_t n = in.n;
     const int D = in.n_docs;
@@ -1035,18 +1041,18 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
         tm.mark("doc_sort");
         DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
         EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_first.p, d_table.p, make_uint4(extra[0], extra[1], extra[2], extra[3]));
-        t8 = DevBuf<uint8_t>((size_t)n + 128, s);
+        t8 = take<uint8_t>(in, (size_t)n + 128, s);
         EAST_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(uint32_t), s));
         if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
             const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
-            out.bkt = DevBuf<uint32_t>(entries, s);
+            out.bkt = take<uint32_t>(in, entries, s);
             EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt.p + entries - 1, (uint32_t)n);
             out.sym_bits = plan.b;
             if (in.want_bkt3 && plan.G == 3 && ((size_t)D << (3 * plan.b)) * sizeof(uint32_t) <= ((size_t)8 << 30)) {
                 // the kernel's buckets ARE the 3-grams: their first ranks cost one more coalesced store and turn
                 // the scorer's depth-2 narrowing (a binary search over the largest intervals) into a lookup
                 const size_t e3 = ((size_t)D << (3 * plan.b)) + 1;
-                out.bkt3 = DevBuf<uint32_t>(e3, s);
+                out.bkt3 = take<uint32_t>(in, e3, s);
                 EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt3.p + e3 - 1, (uint32_t)n);
             }
         }
@@ -1089,7 +1095,9 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
             const bool hooks = out.bkt.p && in.sk;
             const RunReady run{d0, d1 - d0, ls, t8.p, out.bkt.p, out.bkt3.p, out.sym_bits, &table, 1};
             DocScore score;
+            host_debug_mark("run begin");
             if (hooks && in.run_begin) in.run_begin(in.run_ctx, run, score);
+            host_debug_mark("run launch");
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, d0, d1 - d0, e1 - e0, term, out.sa, out.bkt.p,
                             out.bkt3.p, flags.p, ls, nullptr, fuse ? &tables : nullptr, in.sk, &score,
                             in.fused_encode ? d_table.p : nullptr, flags.p + 1, n, in.text8);
@@ -1140,9 +1148,11 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     DevBuf<ScanResult> d_scan(1, s);
     ScanResult scan;
     bool allow_doc_sort = in.doc_sort != 0;
+    const size_t arena_mark = in.arena ? in.arena->used : 0;   // a pass that fails gives its slices back
     if (in.n_chunks > 0) {
         uint32_t refused = 0;   // what the per-document kernel reported: bit 0 a bucket too large, bit 1 a bad layout
         if (build_pipelined(in, out, tm, s, refused)) return;
+        if (in.arena) in.arena->used = arena_mark;
         if (refused) allow_doc_sort = false;  // it would refuse again: full scan, global sort
         if (in.text8) {
             // the runs were byte-coded from the one-byte text; what follows reads code points: expand the whole batch
@@ -1214,6 +1224,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
 
     tm.mark("encode");
     DevBuf<uint8_t> t8, d_table;
+    size_t arena_after_t8 = arena_mark;
     // the per-document kernel byte-codes its document itself: the separate pass only runs for the global sort
     DocSortPlan doc_plan;
     const bool try_doc_sort = fast && allow_doc_sort && doc_sort_plan(sigma, max_doc_n, doc_plan);
@@ -1227,7 +1238,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     if (fast) {
         d_table = DevBuf<uint8_t>(EAST_TERM_BASE, s);
         EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p, make_uint4(0u, 0u, 0u, 0u));
-        t8 = DevBuf<uint8_t>((size_t)n + 128, s);
+        t8 = take<uint8_t>(in, (size_t)n + 128, s);
+        arena_after_t8 = in.arena ? in.arena->used : 0;
         if (!(try_doc_sort && in.fused_encode)) encode_all();
     }
     out.code_table = table;
@@ -1243,14 +1255,14 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             EAST_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(uint32_t), s));
             if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
                 const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
-                out.bkt = DevBuf<uint32_t>(entries, s);
+                out.bkt = take<uint32_t>(in, entries, s);
                 EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt.p + entries - 1, (uint32_t)n);
                 out.sym_bits = plan.b;
                 if (in.want_bkt3 && plan.G == 3 && ((size_t)D << (3 * plan.b)) * sizeof(uint32_t) <= ((size_t)8 << 30)) {
                     // the kernel's buckets ARE the 3-grams: their first ranks cost one more coalesced store and turn
                     // the scorer's depth-2 narrowing (a binary search over the largest intervals) into a lookup
                     const size_t e3 = ((size_t)D << (3 * plan.b)) + 1;
-                    out.bkt3 = DevBuf<uint32_t>(e3, s);
+                    out.bkt3 = take<uint32_t>(in, e3, s);
                     EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt3.p + e3 - 1, (uint32_t)n);
                 }
             }
@@ -1295,6 +1307,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             out.bkt = DevBuf<uint32_t>();
             out.bkt3 = DevBuf<uint32_t>();
             out.sym_bits = 0;
+            if (in.arena) in.arena->used = arena_after_t8;   // the byte text stays
         }
     }
     if (fast && !coded && !light) encode_all();   // the global sort reads the whole byte text
@@ -1304,6 +1317,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         again.light_scan = 0;
         if (doc_sort_flags & 1u) again.doc_sort = 0;
         t8.release();
+        if (in.arena) in.arena->used = arena_mark;
         build_suffix_array(again, out, tm, s);
         if (doc_sort_flags & 1u) out.doc_sort_overflow = 1;
         return;
@@ -1388,7 +1402,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     // scorer acceleration (fast path): first ranks of all (document, 2-gram) buckets
     if (fast && kc >= 2 && ((size_t)D << (2 * kp.b)) <= (size_t)2 * n + 4096) {
         const size_t entries = ((size_t)D << (2 * kp.b)) + 1;
-        out.bkt = DevBuf<uint32_t>(entries, s);
+        out.bkt = take<uint32_t>(in, entries, s);
         EAST_CUDA(cudaMemsetAsync(out.bkt.p, 0xff, sizeof(uint32_t) * (entries - 1), s));
         EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt.p + entries - 1, (uint32_t)n);
         out.sym_bits = kp.b;

@@ -79,6 +79,7 @@ struct SaInput {
     void (*run_begin)(void *ctx, const RunReady &run, DocScore &score) = nullptr;
     void (*run_hook)(void *ctx, const RunReady &run, int in_kernel) = nullptr;
     void *run_ctx = nullptr;
+    Arena *arena = nullptr;   // where the arrays that stay with the index (byte text, bucket tables) are taken from
 };
 
 struct SaOutput {

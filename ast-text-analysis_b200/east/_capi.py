@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
     "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
     "east_score_probes_dev", "east_index_stat", "east_score_range_dev", "east_table_host", "east_table_dev",
-    "east_build_host_u8", "east_table_host_u8", "east_table_dev_gather",
+    "east_build_host_u8", "east_table_host_u8", "east_table_dev_gather", "east_trim",
 ]
 
 _lib = None
@@ -107,6 +107,11 @@ def _ptr(a, t):
 
 def device_count():
     return load().east_device_count()
+
+
+def trim(device=0):
+    """Return the memory the library keeps for reuse (its private pools) to the driver."""
+    _check(load().east_trim(int(device)))
 
 
 def set_option(name, value):

@@ -165,6 +165,10 @@ int east_kernel_stats(char *names, int32_t names_cap, double *ms, int64_t *launc
                       int32_t cap);
 /* number of kernel launches issued by the library on this thread since the last reset */
 int64_t east_launch_count(int reset);
+/* The library allocates from two private stream-ordered memory pools per device (the device's default pool is not
+ * touched) and keeps freed blocks for the next call, up to a quarter of the device memory.  east_trim waits for the
+ * device and returns everything that is not in use to the driver (also drops the cached keyphrase preparation). */
+int east_trim(int device);
 /* tuning knobs (0 = default): "key_chars" (round-0 window), "score_block", ... */
 int east_set_option(const char *name, int64_t value);
 

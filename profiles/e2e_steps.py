@@ -1,24 +1,23 @@
 #!/usr/bin/env python3
-"""Launch timeline of ONE end-to-end step (east_table_host, pinned host text -> table on the host) of the bench
-workload: start offset and duration of every kernel, from the library's own event pairs.
-usage (GPU box): EAST_DEBUG_TIMELINE=1 python profiles/timeline_e2e.py [--docs 1000] [--doc-bytes 50000] 2> timeline.txt
-(the events sit between the kernels of a stream: the step runs ~3 % slower than untimed)"""
+"""Wall time of consecutive end-to-end steps (east_table_host / east_table_host_u8) of the bench workload, one line per step.
+usage (GPU box): python profiles/e2e_steps.py [--width 1|4] [--steps 12]"""
 import argparse, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "ast-text-analysis_b200")); sys.path.insert(0, ROOT)
 import numpy as np, torch
 import synth
 from east import _capi, utils
+from east.asts import utils as au
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--docs", type=int, default=1000)
 ap.add_argument("--doc-bytes", type=int, default=50000)
 ap.add_argument("--keyphrases", type=int, default=1000)
-ap.add_argument("--width", type=int, default=1, help="bytes per code point over the host link: 1 (east_table_host_u8) or 4")
+ap.add_argument("--width", type=int, default=1)
+ap.add_argument("--steps", type=int, default=12)
 a = ap.parse_args()
 packed, ms, cols = synth.packed_collection(a.docs, a.doc_bytes)
 if a.width == 1:
-    from east.asts import utils as au
     packed = [au.pack_strings_collection_u8(c) for c in cols]
 doc_off = np.zeros(a.docs + 1, dtype=np.int64); np.cumsum([len(p) for p in packed], out=doc_off[1:])
 doc_m = np.array(ms, dtype=np.int32)
@@ -28,12 +27,10 @@ text[:] = np.concatenate(packed)
 codes, off = _capi.pack_keyphrases([utils.prepare_text(k) for k in synth.keyphrases(a.keyphrases)])
 out_t = torch.empty(a.docs * a.keyphrases, dtype=torch.float64).pin_memory()
 out = out_t.numpy().reshape(a.docs, a.keyphrases)
-for _ in range(4):
-    _capi.DeviceIndex.build_host_and_score(text, doc_off, doc_m, codes, off, out).close()
-_capi.set_option("time_kernels", 1)
-t0 = time.perf_counter()
-idx = _capi.DeviceIndex.build_host_and_score(text, doc_off, doc_m, codes, off, out)
-t1 = time.perf_counter()
-idx.close()
-_capi.set_option("time_kernels", 0)
-sys.stderr.write("[east] step wall %.3f ms (with event pairs)\n" % ((t1 - t0) * 1e3))
+for i in range(a.steps):
+    t0 = time.perf_counter()
+    idx = _capi.DeviceIndex.build_host_and_score(text, doc_off, doc_m, codes, off, out)
+    t1 = time.perf_counter()
+    idx.close()
+    t2 = time.perf_counter()
+    print("step %2d: call %.3f ms, close %.3f ms, pipelined=%s" % (i, (t1 - t0) * 1e3, (t2 - t1) * 1e3, "?"))
