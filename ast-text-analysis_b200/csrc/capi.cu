@@ -101,7 +101,7 @@ static cudaMemPool_t pool_for(bool big) {
             props.location.id = dev;
             EAST_CUDA(cudaMemPoolCreate(&pools[k], &props));
             // freed blocks stay for the next call up to this much (build/score steps reuse them); east_trim() drops them
-            uint64_t thr = k ? (uint64_t)total_b / 4 : (uint64_t)total_b / 16;
+            uint64_t thr = (uint64_t)total_b / 4;
             EAST_CUDA(cudaMemPoolSetAttribute(pools[k], cudaMemPoolAttrReleaseThreshold, &thr));
         }
         it = g_pools.emplace(dev, pools).first;
@@ -116,7 +116,8 @@ static cudaMemPool_t pool_for(bool big) {
 struct BigBlock { void *p; size_t bytes; cudaEvent_t idle; };
 static std::map<int, std::vector<BigBlock>> g_big_cache;     // per device, free blocks
 static std::map<const void *, size_t> g_big_live;            // blocks handed out: size
-static const size_t BIG_CACHE_BLOCKS = 6;
+static std::map<int, size_t> g_big_cached_bytes;             // per device, bytes held by the free blocks
+static const size_t BIG_CACHE_BLOCKS = 48;                   // and at most a third of the device memory
 
 static void *big_cache_take(size_t bytes, cudaStream_t s) {
     int dev = 0;
@@ -131,6 +132,7 @@ static void *big_cache_take(size_t bytes, cudaStream_t s) {
         if (best == v.size()) return nullptr;
         hit = v[best];
         v.erase(v.begin() + best);
+        g_big_cached_bytes[dev] -= hit.bytes;
         g_big_live[hit.p] = hit.bytes;
     }
     cudaStreamWaitEvent(s, hit.idle, 0);
@@ -157,14 +159,22 @@ static bool big_cache_put(void *p, cudaStream_t s) {
         cudaFreeAsync(p, s);
         return true;
     }
-    BigBlock evict{nullptr, 0, nullptr};
+    std::vector<BigBlock> evict;
     {
+        static size_t limit = 0;
+        if (!limit) { size_t free_b = 0, total_b = 0; limit = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? total_b / 3 : ((size_t)32 << 30); }
         std::lock_guard<std::mutex> g(g_pool_mutex);
         auto &v = g_big_cache[dev];
+        size_t &held = g_big_cached_bytes[dev];
         v.push_back(BigBlock{p, bytes, ev});
-        if (v.size() > BIG_CACHE_BLOCKS) { evict = v.front(); v.erase(v.begin()); }   // the oldest goes back to the pool
+        held += bytes;
+        while (v.size() > 1 && (v.size() > BIG_CACHE_BLOCKS || held > limit)) {   // the oldest go back to the pool
+            evict.push_back(v.front());
+            held -= v.front().bytes;
+            v.erase(v.begin());
+        }
     }
-    if (evict.p) { cudaStreamWaitEvent(s, evict.idle, 0); cudaEventDestroy(evict.idle); cudaFreeAsync(evict.p, s); }
+    for (auto &b : evict) { cudaStreamWaitEvent(s, b.idle, 0); cudaEventDestroy(b.idle); cudaFreeAsync(b.p, s); }
     return true;
 }
 
@@ -173,6 +183,7 @@ static void big_cache_drop(int dev) {
     {
         std::lock_guard<std::mutex> g(g_pool_mutex);
         v.swap(g_big_cache[dev]);
+        g_big_cached_bytes[dev] = 0;
     }
     for (auto &b : v) { cudaEventDestroy(b.idle); cudaFreeAsync(b.p, 0); }
 }
@@ -341,6 +352,8 @@ static int fail(int st, const char *msg) { g_error = msg; return st; }
 
 extern "C" {
 
+static void drop_kp_cache();   // defined with the cache, below
+
 const char *east_last_error(void) { return g_error.c_str(); }
 const char *east_version(void) { return "east_b200 0.1 (sm_100a)"; }
 
@@ -355,6 +368,10 @@ int east_set_option(const char *name, int64_t value) {
     if (!strcmp(name, "time_kernels")) {  // per-thread: events around every launch; value 0 also clears the table
         g_time_kernels = value ? 1 : 0;
         if (!value) g_kstats.clear();
+        return EAST_OK;
+    }
+    if (!strcmp(name, "drop_kp_cache")) {   // per-thread: forget the keyphrase preparation kept for the score calls
+        if (value) drop_kp_cache();
         return EAST_OK;
     }
     std::lock_guard<std::mutex> g(g_opt_mutex);
@@ -793,6 +810,15 @@ struct KpPrepared {
     KpDevice dev;                      // d_off, d_uniq_of, d_recs, d_q8: filled by kp_prep.cu (or by the host variant)
 };
 static thread_local std::unique_ptr<KpPrepared> g_kp_cache;
+static void drop_kp_cache() {
+    if (!g_kp_cache) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(g_kp_cache->device);
+    cudaDeviceSynchronize();
+    g_kp_cache.reset();
+    cudaSetDevice(cur);
+}
 
 static void check_keyphrases(const int64_t *kp_off, int32_t K) {
     if (kp_off[K] >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "keyphrase buffer too large");

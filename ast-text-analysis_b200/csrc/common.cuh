@@ -63,7 +63,10 @@ struct DevBuf {
     cudaStream_t s = 0;
     bool owned = true;   // false: a slice of an index arena (freed with the arena)
     DevBuf() {}
-    DevBuf(size_t n_, cudaStream_t s_) : n(n_), s(s_) { p = (T *)dev_alloc(sizeof(T) * (n_ ? n_ : 1), s_); }
+    DevBuf(size_t n_, cudaStream_t s_) : n(n_), s(s_) {
+        const size_t bytes = sizeof(T) * (n_ ? n_ : 1);
+        p = (T *)dev_alloc(bytes, s_, bytes >= ((size_t)32 << 20));   // large scratch: the library's own block cache
+    }
     DevBuf(T *slice, size_t n_) : p(slice), n(n_), owned(false) {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;

@@ -52,7 +52,9 @@ def parse_args():
     ap.add_argument("--gather-tiles", type=int, default=1,
                     help="config4: 1 = ONE all-gather after scoring (north_star); T > 1 = the table is scored in T document "
                          "tiles and the all-gather of tile t overlaps the scoring of tile t+1")
-    ap.add_argument("--workload", default="table", choices=["table", "single_doc", "config4"],
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the short runs of BASELINE configs[2] and [4] "
+                    "(single 200 MB document build; co-occurrence count at 10^4 x 10^5) reported under other_configs")
+    ap.add_argument("--workload", default="table", choices=["table", "single_doc", "config4", "graph"],
                     help="table = BASELINE configs[1] (headline); single_doc = configs[2]: SA+LCP+annotation build "
                          "throughput of ONE document of --doc-bytes (use 200000000), replicas only for N>1")
     ap.add_argument("--cpu-sample-docs", type=int, default=0, help="0 = 2 documents per host core (max 64)")
@@ -557,6 +559,9 @@ def run_b200(args):
                 "build_MB_per_s_per_core": r["build_MB_per_s"] / max(procs, 1)}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    if n_gpus == 1 and not args.no_extras:
+        del text_dev, out_dev
+        line["other_configs"] = extras_single_gpu(args, _capi, torch, np, synth, local_rank)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -645,16 +650,18 @@ def run_config4(args):
     # Document ids: with one all-gather rank r owns the contiguous range [r D, (r+1) D); with tiles the table is
     # tile-major -- tile t holds documents t W T + r T + j -- so that every tile's all-gather output is one contiguous
     # block AND the gathered table is in global document order.
-    packed, ms = [], []
+    texts, offs, doc_ms = [], [], []
     for t in range(tiles):
         cnt = min(T, D - t * T)
         first = (rank * D if tiles == 1 else t * world * T + rank * T)
-        p_t, m_t, _ = synth.packed_collection(cnt, doc_bytes, first_seed=1 + first)
-        packed += list(p_t); ms += list(m_t)
-    doc_m = np.array(ms, dtype=np.int32)
+        # numpy-only generator: the packed form of Zipf word documents without 10^5 rounds of Python tokenising
+        t_t, o_t, m_t = synth.packed_collection_fast(cnt, doc_bytes, first_seed=1000003 * (t + 1) + first)
+        texts.append(t_t); offs.append(np.diff(o_t)); doc_ms.append(m_t)
+    doc_m = np.concatenate(doc_ms).astype(np.int32)
     doc_off = np.zeros(D + 1, dtype=np.int64)
-    np.cumsum([len(p) for p in packed], out=doc_off[1:])
-    text_dev = torch.from_numpy(np.concatenate(packed).view(np.int32)).to(dev)
+    np.cumsum(np.concatenate(offs), out=doc_off[1:])
+    host_text = np.concatenate(texts)
+    text_dev = torch.from_numpy(host_text.view(np.int32)).to(dev)
     kps = [utils.prepare_text(k) for k in synth.keyphrases(K)]
     kp_codes, kp_off = _capi.pack_keyphrases(kps)
     kp_dev = torch.from_numpy(kp_codes.view(np.int32).copy()).to(dev)
@@ -665,6 +672,9 @@ def run_config4(args):
     stream = torch.cuda.current_stream()
 
     def step():
+        # every step prepares the keyphrases from scratch (suffix hashing / ordering / de-duplication on the device,
+        # kp_prep.cu): a real table call is made once per collection, there is nothing to reuse
+        _capi.set_option("drop_kp_cache", 1)
         idx = _capi.DeviceIndex.build_dev(text_dev.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream)
         score_ms = 0.0
         if tiles == 1:
@@ -711,6 +721,22 @@ def run_config4(args):
     ms_step = float(t.item())
     checksum = float((gathered if world > 1 else out_dev)[:: max(1, D * K // 4096)].sum().item())
     full_sum = float((gathered if world > 1 else out_dev).sum().item())
+    # untimed parity sample: rows of rank 0's own documents (the first rows of the table in both layouts) vs the oracle
+    parity = {"checked": False}
+    if rank == 0 and not os.environ.get("EAST_BENCH_NO_PARITY"):
+        try:
+            from oracle import oracle as oracle_mod
+            oracle_mod.build()
+            table = (gathered if world > 1 else out_dev)
+            first_tile = min(T, D)
+            bad, rows = 0, [0, 1, first_tile // 2, first_tile - 1]
+            for d in rows:
+                exp = oracle_mod.OracleEASA(text=host_text[doc_off[d]:doc_off[d + 1]], m=int(doc_m[d])).score_many(kp_codes, kp_off, True)
+                got = table[d * K:(d + 1) * K].cpu().numpy()
+                bad += int(not np.array_equal(exp.view(np.uint64), got.view(np.uint64)))
+            parity = {"checked": True, "rows_vs_oracle": len(rows), "scores_vs_oracle": len(rows) * K, "mismatching_rows": bad}
+        except Exception as e:  # noqa: BLE001
+            parity = {"checked": False, "error": repr(e)}
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": world * D * K / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -723,8 +749,180 @@ def run_config4(args):
                        "table_bytes": world * D * K * 8,
                        "gather": "one all-gather after scoring" if tiles == 1 else
                                  "%d document tiles, all-gather of tile t overlaps the scoring of tile t+1" % tiles},
+            "parity_checked": bool(parity.get("checked") and parity.get("mismatching_rows") == 0), "parity": parity,
             "breakdown": {"build_stages_ms": build_t, "score_ms": score_ms, "host_prep_s": prep_s, "checksum_sample": checksum,
-                          "table_sum": full_sum}}))
+                          "table_sum": full_sum,
+                          "keyphrase_preparation": "inside every timed step (device): the cache of the score calls is dropped first"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_cooc(_capi, torch, K, D, threshold=0.5, reps=3, device=0):
+    """Kernel-only time of the co-occurrence count C = B B^T (tcgen05, cooc_tc.cu) on a random [D, K] score table."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    S = torch.rand((D, K), dtype=torch.float64, device="cuda", generator=g)
+    C = torch.empty((K, K), dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        _capi.cooc_dev(S.data_ptr(), D, K, threshold, C.data_ptr(), device=device)
+    _capi.set_option("time_kernels", 0); _capi.set_option("time_kernels", 1)
+    for _ in range(reps):
+        _capi.cooc_dev(S.data_ptr(), D, K, threshold, C.data_ptr(), device=device)
+    ks = _capi.kernel_stats(); _capi.set_option("time_kernels", 0)
+    per = {k: v["ms"] / max(v["launches"], 1) for k, v in ks.items()}
+    gemm = per.get("k_cooc_umma_pipe") or per.get("k_cooc_umma")
+    # spot check against a dense fp32 product of a slab (exact in fp32: counts < 2^24)
+    Bs = (S[:, :256] >= threshold).to(torch.float32)
+    ref = (Bs.t() @ Bs).to(torch.int32)
+    ok = bool(torch.equal(ref, C[:256, :256]))
+    del S, C
+    return {"K": K, "D": D, "kernels_ms": per, "gemm_ms": gemm, "ops": 2.0 * K * K * D,
+            "TOPS_on_full_product": 2.0 * K * K * D / (gemm * 1e-3) / 1e12 if gemm else None,
+            "TOPS_executed": 2.0 * K * K * D * 0.5 * (1 + 256.0 / K) / (gemm * 1e-3) / 1e12 if gemm else None,
+            "slab_exact_vs_fp32_matmul": ok}
+
+
+def extras_single_gpu(args, _capi, torch, np, synth, local_rank):
+    """Short untimed-region extras for the N = 1 line: BASELINE configs[2] (one 200 MB document: SA + LCP + child table
+    + annotation build throughput) and the tensor-core half of configs[4] (co-occurrence count at 10^4 x 10^5)."""
+    out = {}
+    try:
+        packed, m, text_bytes, _ = synth.packed_big_document(200_000_000, seed=3)
+        n = int(packed.size)
+        doc_off = np.array([0, n], dtype=np.int64)
+        doc_m = np.array([m], dtype=np.int32)
+        dev_text = torch.from_numpy(packed.view(np.int32)).cuda()
+        stream = torch.cuda.current_stream()
+        for _ in range(2):
+            _capi.DeviceIndex.build_dev(dev_text.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream).close()
+        torch.cuda.synchronize()
+        _capi.set_option("time_kernels", 0); _capi.set_option("time_kernels", 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        reps = 3
+        for _ in range(reps):
+            _capi.DeviceIndex.build_dev(dev_text.data_ptr(), doc_off, doc_m, device=local_rank, stream=stream.cuda_stream).close()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        ks = _capi.kernel_stats(); _capi.set_option("time_kernels", 0)
+        peak, _ = load_peaks()
+        sweep = ks.get("k_rs_onesweep")
+        out["single_doc_200MB"] = {
+            "metric": "suffix_array_build_MB_per_sec", "value": text_bytes / 1e6 / (ms * 1e-3), "unit": "MB/s", "ms_per_build": ms,
+            "text_bytes": text_bytes, "n_codepoints": n, "strings": m, "codepoints_per_s": n / (ms * 1e-3),
+            "what": "BASELINE configs[2]: SA + LCP + child table + annotation of ONE document (global prefix-doubling sort), device-timed",
+            "k_rs_onesweep": ({"launches_per_build": sweep["launches"] / reps, "ms_per_build": sweep["ms"] / reps,
+                               "GBps": sweep["bytes"] / (sweep["ms"] * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": sweep["bytes"] / (sweep["ms"] * 1e-3) / 1e9 / peak} if sweep else None),
+            "kernels_ms": {k: v["ms"] / reps for k, v in sorted(ks.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
+        del dev_text
+    except Exception as e:  # noqa: BLE001
+        out["single_doc_200MB"] = {"error": repr(e)}
+    try:
+        _capi.trim(local_rank)
+        out["cooccurrence_1e4x1e5"] = time_cooc(_capi, torch, 10000, 100000, device=local_rank)
+        out["cooccurrence_1e4x1e5"]["what"] = ("BASELINE configs[4], tensor-core half: C = B B^T of 10^4 keyphrases x 10^5 documents "
+                                               "(tcgen05.mma kind::i8), kernel time from CUDA events")
+    except Exception as e:  # noqa: BLE001
+        out["cooccurrence_1e4x1e5"] = {"error": repr(e)}
+    _capi.trim(local_rank)
+    return out
+
+
+def run_graph(args):
+    """BASELINE configs[4]: keyphrases graph (-r 0.25 -c 0.6) over 10^4 keyphrases x 10^5 documents (~10 KB), documents
+    sharded over the GPUs.  A step = index + score this rank's documents (east_table_dev), count the co-occurrences of
+    its rows on the tensor cores (C_r = B_r B_r^T, east_cooc_dev), ONE all-reduce (int32 sum) of the K x K counts.
+    Device-timed, max over ranks.  The graph dict itself (K^2 confidences) is assembled on the host from C, untimed."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import synth
+    from east import _capi, utils
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join("/tmp", "nccl_%h_%p.log"))
+        dist.init_process_group("nccl", device_id=dev)
+    apply_env_options(_capi)
+    K = args.keyphrases if args.keyphrases != 1000 else 10000
+    doc_bytes = args.doc_bytes if args.doc_bytes != 50000 else 10000
+    D = args.docs_total // world
+    t0 = time.perf_counter()
+    host_text, doc_off, doc_m = synth.packed_collection_fast(D, doc_bytes, first_seed=77 + rank * 1009)
+    text_dev = torch.from_numpy(host_text.view(np.int32)).to(dev)
+    names = synth.keyphrases(K)
+    kp_codes, kp_off = _capi.pack_keyphrases([utils.prepare_text(k) for k in names])
+    kp_dev = torch.from_numpy(kp_codes.view(np.int32).copy()).to(dev)
+    prep_s = time.perf_counter() - t0
+    S = torch.empty(D * K, dtype=torch.float64, device=dev)
+    C = torch.empty((K, K), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    r_thr, c_conf = 0.25, 0.6
+
+    def step():
+        ev[0].record(stream)
+        _capi.DeviceIndex.build_dev_and_score(text_dev.data_ptr(), doc_off, doc_m, kp_dev.data_ptr(), kp_codes, kp_off,
+                                              S.data_ptr(), True, device=local_rank, stream=stream.cuda_stream).close()
+        ev[1].record(stream)
+        _capi.cooc_dev(S.data_ptr(), D, K, r_thr, C.data_ptr(), device=local_rank, stream=stream.cuda_stream)
+        ev[2].record(stream)
+        if world > 1:
+            dist.all_reduce(C, op=dist.ReduceOp.SUM)
+        ev[3].record(stream)
+        torch.cuda.synchronize()
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    parts = np.zeros(3)
+    for _ in range(args.steps):
+        parts += np.array(step())
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())
+    parts /= args.steps
+    # untimed: the graph itself + checks (support = diagonal; symmetric; a slab against a dense fp32 product of rank 0's rows
+    # is only exact at N = 1, so the check there is on the all-reduced diagonal instead)
+    support = torch.diagonal(C).to(torch.int64)
+    local_support = (S.view(D, K) >= r_thr).sum(dim=0).to(torch.int64)
+    if world > 1:
+        dist.all_reduce(local_support, op=dist.ReduceOp.SUM)
+    checks = {"support_equals_column_counts": bool(torch.equal(support, local_support)),
+              "symmetric": bool(torch.equal(C[:512, :512], C[:512, :512].t()))}
+    if rank == 0:
+        from east import applications
+        t1 = time.perf_counter()
+        graph = applications.graph_from_cooccurrence(names, names, C.cpu().numpy(), c_conf, r_thr, 1)
+        graph_s = time.perf_counter() - t1
+        print(json.dumps({
+            "metric": METRIC, "value": world * D * K / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 scores, u8 x u8 -> s32 co-occurrence", "data": "synthetic",
+            "config": {"workload": "keyphrases_graph -r %.2f -c %.2f (BASELINE configs[4]): %d keyphrases x %d synthetic Zipf docs x ~%d KB, "
+                                   "documents sharded over %d GPU(s); per rank build + score + tensor-core co-occurrence, one all-reduce "
+                                   "of the K x K int32 counts" % (r_thr, c_conf, K, world * D, doc_bytes // 1000, world),
+                       "keyphrases": K, "docs_total": world * D, "docs_per_gpu": D, "doc_bytes": doc_bytes},
+            "parity_checked": all(checks.values()), "parity": checks,
+            "breakdown": {"table_ms": parts[0], "cooc_ms": parts[1], "all_reduce_ms": parts[2],
+                          "cooc_TOPS_on_full_product": 2.0 * K * K * D / (parts[1] * 1e-3) / 1e12,
+                          "graph_nodes": len(graph["nodes"]), "graph_edges": len(graph["edges"]), "graph_assembly_host_s": graph_s,
+                          "host_prep_s": prep_s}}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -742,6 +940,8 @@ def main():
         return run_config4(args)
     if args.workload == "single_doc" and args.impl == "b200":
         return run_single_doc(args)
+    if args.workload == "graph" and args.impl == "b200":
+        return run_graph(args)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -100,3 +100,45 @@ def packed_big_document(n_bytes, seed=1, v=V):
     out[term_pos] = 0x0A00 + np.arange(m, dtype=np.uint32)
     text_bytes = total_chars + count - 1  # words joined by single spaces
     return out, int(m), int(text_bytes), ids
+
+
+def packed_collection_fast(n_docs, n_bytes, first_seed=1, v=V, chunk_docs=4096):
+    """n_docs synthetic documents of ~n_bytes each, already packed (uint32 code points + terminators), built with numpy
+    only: the same result as pack_strings_collection(text_to_strings_collection(" ".join(words))) for documents made
+    of whole vocabulary words (3..10 letters each: the token filter of utils.py:63 drops nothing).  Every document has
+    the same number of words (n_bytes / mean word length), drawn from the Zipf distribution with default_rng(first_seed
+    + chunk number).  Returns (text uint32 [N], doc_off int64 [n_docs + 1], doc_m int32 [n_docs])."""
+    words, cdf, lengths = vocabulary(v)
+    mean_len = float((lengths * np.diff(np.concatenate([[0.0], cdf]))).sum()) + 1.0
+    wpd = max(1, int(n_bytes / mean_len))
+    m_doc = (wpd + 2) // 3
+    vocab_codes = np.frombuffer("".join(words).upper().encode("ascii"), dtype=np.uint8)
+    vocab_off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    texts, sizes = [], []
+    for c0 in range(0, n_docs, chunk_docs):
+        nd = min(chunk_docs, n_docs - c0)
+        rng = np.random.default_rng(first_seed + c0 // chunk_docs)
+        count = nd * wpd
+        ids = np.searchsorted(cdf, rng.random(count), side="right")
+        wl = lengths[ids].astype(np.int64)
+        j = np.arange(count, dtype=np.int64) % wpd
+        ends_string = (j % 3 == 2) | (j == wpd - 1)
+        out_len = wl + ends_string
+        start = np.concatenate([[0], np.cumsum(out_len)[:-1]])
+        n = int(out_len.sum())
+        out = np.empty(n, dtype=np.uint32)
+        term_pos = (start + wl)[ends_string]
+        is_char = np.ones(n, dtype=bool)
+        is_char[term_pos] = False
+        total_chars = int(wl.sum())
+        word_of = np.repeat(np.arange(count, dtype=np.int64), wl)
+        char_start = np.concatenate([[0], np.cumsum(wl)[:-1]])
+        src = vocab_off[ids][word_of] + (np.arange(total_chars, dtype=np.int64) - char_start[word_of])
+        out[is_char] = vocab_codes[src]
+        out[term_pos] = 0x0A00 + (j[ends_string] // 3).astype(np.uint32)
+        texts.append(out)
+        sizes.append(np.add.reduceat(out_len, np.arange(0, count, wpd)))
+    sizes = np.concatenate(sizes)
+    doc_off = np.zeros(n_docs + 1, dtype=np.int64)
+    np.cumsum(sizes, out=doc_off[1:])
+    return np.concatenate(texts), doc_off, np.full(n_docs, m_doc, dtype=np.int32)
