@@ -774,7 +774,7 @@ static const int32_t *array_of(const east_index *idx, int which) {
 int east_index_copy(const east_index *idx, int32_t doc, int which, int32_t *dst_host) {
     EAST_API_BEGIN
     if (!idx || !dst_host || doc < 0 || doc >= idx->n_docs) throw Error(EAST_ERR_INVALID, "bad index/doc/destination");
-    const int32_t *src = array_of(idx, which);
+    const int32_t *src = which == EAST_PACKED_TEXT ? reinterpret_cast<const int32_t *>(idx->text) : array_of(idx, which);
     if (!src) throw Error(EAST_ERR_INVALID, "unknown array id");
     EAST_CUDA(cudaSetDevice(idx->device));
     wait_tables(idx);
@@ -1259,8 +1259,10 @@ static void table_run_done(void *vctx, const RunReady &r, int in_kernel) {
 
 static void table_host_impl(const void *text, int width, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
                             const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized, double *out_DxK,
-                            east_index **out_idx) {
+                            east_index **out_idx, double *own_rows_dev = nullptr, double *const *peer_rows = nullptr,
+                            int32_t n_peers = 0) {
     if (!kp || !kp_off || !out_DxK || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    if (n_peers < 0 || n_peers > DocScore::MAX_PEERS || (n_peers > 0 && !peer_rows)) throw Error(EAST_ERR_INVALID, "bad peer list");
     east_index *built = nullptr;
     check_build_args(text, doc_off, doc_m, n_docs, &built);
     check_keyphrases(kp_off, K);
@@ -1270,12 +1272,15 @@ static void table_host_impl(const void *text, int width, const int64_t *doc_off,
     // run there while the text is on its way
     cudaStream_t ps = prep_stream(device);
     DevBuf<uint32_t> d_kp((size_t)kp_off[K], ps);
-    DevBuf<double> d_out((size_t)n_docs * K, s);
+    DevBuf<double> d_out_own;
+    if (!own_rows_dev) d_out_own = DevBuf<double>((size_t)n_docs * K, s);
+    double *const d_out = own_rows_dev ? own_rows_dev : d_out_own.p;
     EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, ps));
     TableRun run;
     run.kp_own = kp_begin(device, d_kp.p, kp, kp_off, K, !get_option("score_no_dedup", 0), false, ps);
     run.kp_host = kp; run.d_kp = d_kp.p; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
-    run.d_out = d_out.p; run.host_out = out_DxK;
+    run.d_out = d_out; run.host_out = out_DxK;
+    run.peer_rows = peer_rows; run.n_peers = n_peers;
     RunHook hook;
     hook.begin = table_run_begin; hook.fn = table_run_done; hook.ctx = &run; hook.building = &run.building;
     build_host_impl(text, width, doc_off, doc_m, n_docs, device, &built, &hook);
@@ -1285,12 +1290,14 @@ static void table_host_impl(const void *text, int width, const int64_t *doc_off,
     // or the ordinary per-document pass (its copy is still in flight on stream s).
     const bool stands = !run.failed && run.docs_scored == n_docs &&
                         ((built->pipelined && !run.final_pass) || (built->doc_sorted && !built->pipelined && run.final_pass));
-    if (stands) {
-        EAST_CUDA(cudaStreamSynchronize(s));
-    } else {
-        score_common(built, d_kp.p, kp_off, K, normalized, d_out.p, 0, n_docs, s, nullptr, nullptr, kp);
-        EAST_CUDA(cudaMemcpy(out_DxK, d_out.p, sizeof(double) * (size_t)n_docs * K, cudaMemcpyDeviceToHost));
+    if (!stands) {
+        score_common(built, d_kp.p, kp_off, K, normalized, d_out, 0, n_docs, s, nullptr, nullptr, kp);
+        EAST_CUDA(cudaMemcpyAsync(out_DxK, d_out, sizeof(double) * (size_t)n_docs * K, cudaMemcpyDeviceToHost, s));
     }
+    if (n_peers > 0 && !(stands && run.docs_sent == n_docs))   // rows (also) produced by the batched scorer: plain peer copies
+        for (int32_t pi = 0; pi < n_peers; ++pi)
+            EAST_CUDA(cudaMemcpyAsync(peer_rows[pi], d_out, sizeof(double) * (size_t)n_docs * K, cudaMemcpyDefault, s));
+    EAST_CUDA(cudaStreamSynchronize(s));
     if (out_idx) *out_idx = guard.release();
 }
 
@@ -1346,6 +1353,16 @@ static void table_dev_impl(const uint32_t *text_dev, const int64_t *doc_off, con
     }
     EAST_CUDA(cudaStreamSynchronize(s));
     if (out_idx) *out_idx = guard.release();
+}
+
+int east_table_host_gather(const void *text, int32_t text_width, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs,
+                           int device, const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized, double *out_DxK,
+                           double *own_rows_dev, double *const *peer_rows, int32_t n_peers, east_index **out_idx) {
+    EAST_API_BEGIN
+    if (text_width != 1 && text_width != 4) throw Error(EAST_ERR_INVALID, "text_width must be 1 or 4");
+    table_host_impl(text, text_width, doc_off, doc_m, n_docs, device, kp, kp_off, K, normalized, out_DxK, out_idx, own_rows_dev,
+                    peer_rows, n_peers);
+    EAST_API_END
 }
 
 int east_table_dev(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
@@ -1411,6 +1428,129 @@ int east_cooc_host(const double *S_DxK, int64_t D, int32_t K, double threshold, 
     if (get_option("cooc_variant", 0) == 1) cooc_counts(d_S.p, D, K, threshold, d_C.p, s);
     else cooc_counts_tc(d_S.p, D, K, threshold, d_C.p, s, get_option("cooc_variant", 0) == 2);
     EAST_CUDA(cudaMemcpy(C_KxK, d_C.p, sizeof(int32_t) * (size_t)K * K, cudaMemcpyDeviceToHost));
+    EAST_API_END
+}
+
+// ---- persistence --------------------------------------------------------------------------
+// One file per index (= one device batch of documents): header, then the arrays in a fixed order.  The reference
+// rebuilds every AST on every run (relevance.py:38-47); a saved index is loaded at PCIe speed instead.
+namespace {
+struct IndexFileHeader {
+    char magic[8];
+    int32_t version, n_docs;
+    int64_t n, m_total;
+    int32_t sym_bits, term_code, fast_path, doc_sorted, rounds, key_chars, key_bits, tables_fused;
+    int32_t has_t8, has_bkt, has_sk, reserved;
+    uint8_t code_table[EAST_TERM_BASE];
+};
+const char INDEX_MAGIC[8] = {'E', 'A', 'S', 'T', 'I', 'D', 'X', '1'};
+
+struct FileCloser { FILE *f; ~FileCloser() { if (f) fclose(f); } };
+
+void write_dev_array(FILE *f, const void *dev, size_t bytes, std::vector<uint8_t> &stage) {
+    const uint8_t *src = static_cast<const uint8_t *>(dev);
+    for (size_t done = 0; done < bytes;) {
+        const size_t part = std::min(stage.size(), bytes - done);
+        EAST_CUDA(cudaMemcpy(stage.data(), src + done, part, cudaMemcpyDeviceToHost));
+        if (fwrite(stage.data(), 1, part, f) != part) throw Error(EAST_ERR_INVALID, "index file: short write");
+        done += part;
+    }
+}
+void read_dev_array(FILE *f, void *dev, size_t bytes, std::vector<uint8_t> &stage) {
+    uint8_t *dst = static_cast<uint8_t *>(dev);
+    for (size_t done = 0; done < bytes;) {
+        const size_t part = std::min(stage.size(), bytes - done);
+        if (fread(stage.data(), 1, part, f) != part) throw Error(EAST_ERR_INVALID, "index file: truncated");
+        EAST_CUDA(cudaMemcpy(dst + done, stage.data(), part, cudaMemcpyHostToDevice));
+        done += part;
+    }
+}
+}  // namespace
+
+int east_index_save(const east_index *idx, const char *path) {
+    EAST_API_BEGIN
+    if (!idx || !path) throw Error(EAST_ERR_INVALID, "NULL argument");
+    EAST_CUDA(cudaSetDevice(idx->device));
+    wait_tables(idx);
+    EAST_CUDA(cudaDeviceSynchronize());
+    FileCloser fc{fopen(path, "wb")};
+    if (!fc.f) throw Error(EAST_ERR_INVALID, std::string("cannot open ") + path + " for writing");
+    IndexFileHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, INDEX_MAGIC, 8);
+    h.version = 1; h.n_docs = idx->n_docs; h.n = idx->n; h.m_total = idx->m_total;
+    h.sym_bits = idx->sym_bits; h.term_code = idx->term_code; h.fast_path = idx->fast_path; h.doc_sorted = idx->doc_sorted;
+    h.rounds = idx->rounds; h.key_chars = idx->key_chars; h.key_bits = idx->key_bits; h.tables_fused = idx->tables_fused;
+    h.has_t8 = idx->t8 != nullptr; h.has_bkt = idx->bkt != nullptr; h.has_sk = idx->sk != nullptr;
+    if (idx->code_table.size() == EAST_TERM_BASE) memcpy(h.code_table, idx->code_table.data(), EAST_TERM_BASE);
+    if (fwrite(&h, sizeof(h), 1, fc.f) != 1) throw Error(EAST_ERR_INVALID, "index file: short write");
+    if (fwrite(idx->doc_off.data(), sizeof(int32_t), (size_t)idx->n_docs + 1, fc.f) != (size_t)idx->n_docs + 1 ||
+        fwrite(idx->doc_m.data(), sizeof(int32_t), (size_t)idx->n_docs, fc.f) != (size_t)idx->n_docs)
+        throw Error(EAST_ERR_INVALID, "index file: short write");
+    std::vector<uint8_t> stage((size_t)64 << 20);
+    const size_t words = sizeof(int32_t) * (size_t)idx->n;
+    write_dev_array(fc.f, idx->text, words, stage);
+    for (const int32_t *a : {idx->sa, idx->lcp, idx->up, idx->down, idx->next, idx->ann}) write_dev_array(fc.f, a, words, stage);
+    if (h.has_t8) write_dev_array(fc.f, idx->t8, (size_t)idx->n + 128, stage);
+    if (h.has_bkt) write_dev_array(fc.f, idx->bkt, sizeof(uint32_t) * (((size_t)idx->n_docs << (2 * idx->sym_bits)) + 1), stage);
+    if (h.has_sk) write_dev_array(fc.f, idx->sk, words, stage);
+    EAST_API_END
+}
+
+int east_index_load(const char *path, int device, east_index **out) {
+    EAST_API_BEGIN
+    if (!path || !out) throw Error(EAST_ERR_INVALID, "NULL argument");
+    use_device(device);
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) throw Error(EAST_ERR_INVALID, std::string("cannot open ") + path);
+    IndexFileHeader h;
+    if (fread(&h, sizeof(h), 1, fc.f) != 1 || memcmp(h.magic, INDEX_MAGIC, 8) != 0 || h.version != 1)
+        throw Error(EAST_ERR_INVALID, "not an east_b200 index file (or another version)");
+    if (h.n_docs <= 0 || h.n <= 0 || h.n >= (1ll << 30) || h.sym_bits < 0 || h.sym_bits > 7) throw Error(EAST_ERR_INVALID, "index file: bad header");
+    std::unique_ptr<east_index, void (*)(east_index *)> idx(new east_index(), free_index);
+    idx->device = device; idx->n_docs = h.n_docs; idx->n = (int32_t)h.n; idx->m_total = h.m_total;
+    idx->sym_bits = h.sym_bits; idx->term_code = h.term_code; idx->fast_path = h.fast_path; idx->doc_sorted = h.doc_sorted;
+    idx->rounds = h.rounds; idx->key_chars = h.key_chars; idx->key_bits = h.key_bits; idx->tables_fused = h.tables_fused;
+    idx->code_table.assign(h.code_table, h.code_table + EAST_TERM_BASE);
+    idx->doc_off.resize((size_t)h.n_docs + 1);
+    idx->doc_m.resize((size_t)h.n_docs);
+    if (fread(idx->doc_off.data(), sizeof(int32_t), idx->doc_off.size(), fc.f) != idx->doc_off.size() ||
+        fread(idx->doc_m.data(), sizeof(int32_t), idx->doc_m.size(), fc.f) != idx->doc_m.size())
+        throw Error(EAST_ERR_INVALID, "index file: truncated");
+    if (idx->doc_off.front() != 0 || idx->doc_off.back() != idx->n) throw Error(EAST_ERR_INVALID, "index file: bad document offsets");
+    const size_t words = sizeof(int32_t) * (size_t)idx->n;
+    const size_t bkt_entries = ((size_t)h.n_docs << (2 * h.sym_bits)) + 1;
+    size_t need = Arena::padded(sizeof(int32_t) * ((size_t)h.n_docs + 1)) + Arena::padded(sizeof(int32_t) * (size_t)h.n_docs) +
+                  (7 + (h.has_sk ? 1 : 0)) * Arena::padded(words) + (h.has_t8 ? Arena::padded((size_t)idx->n + 128) : 0) +
+                  (h.has_bkt ? Arena::padded(sizeof(uint32_t) * bkt_entries) : 0);
+    cudaStream_t s = 0;
+    idx->arena.base = (uint8_t *)dev_alloc(need, s, true);
+    idx->arena.cap = need;
+    auto take32 = [&](size_t count) { DevBuf<int32_t> b = idx->arena.take<int32_t>(count, s); int32_t *p = b.p; b.p = nullptr; return p; };
+    idx->d_doc_off = take32((size_t)h.n_docs + 1);
+    idx->d_doc_m = take32((size_t)h.n_docs);
+    idx->text = (uint32_t *)take32((size_t)idx->n);   // inside the arena: owns_text stays false
+    idx->sa = take32((size_t)idx->n); idx->lcp = take32((size_t)idx->n); idx->up = take32((size_t)idx->n);
+    idx->down = take32((size_t)idx->n); idx->next = take32((size_t)idx->n); idx->ann = take32((size_t)idx->n);
+    EAST_CUDA(cudaMemcpy(idx->d_doc_off, idx->doc_off.data(), sizeof(int32_t) * idx->doc_off.size(), cudaMemcpyHostToDevice));
+    EAST_CUDA(cudaMemcpy(idx->d_doc_m, idx->doc_m.data(), sizeof(int32_t) * idx->doc_m.size(), cudaMemcpyHostToDevice));
+    std::vector<uint8_t> stage((size_t)64 << 20);
+    read_dev_array(fc.f, idx->text, words, stage);
+    for (int32_t *a : {idx->sa, idx->lcp, idx->up, idx->down, idx->next, idx->ann}) read_dev_array(fc.f, a, words, stage);
+    if (h.has_t8) {
+        DevBuf<uint8_t> b = idx->arena.take<uint8_t>((size_t)idx->n + 128, s);
+        idx->t8 = b.p; b.p = nullptr;
+        read_dev_array(fc.f, idx->t8, (size_t)idx->n + 128, stage);
+    }
+    if (h.has_bkt) {
+        idx->bkt = (uint32_t *)take32(bkt_entries);
+        read_dev_array(fc.f, idx->bkt, sizeof(uint32_t) * bkt_entries, stage);
+    }
+    if (h.has_sk) {
+        idx->sk = (uint32_t *)take32((size_t)idx->n);
+        read_dev_array(fc.f, idx->sk, words, stage);
+    }
+    *out = idx.release();
     EAST_API_END
 }
 

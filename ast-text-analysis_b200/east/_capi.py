@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("EAST_B200_LIB",
                           os.path.join(os.path.dirname(_HERE), "lib", "libeast_b200.so"))
 
 # east_array ids (include/east_b200.h)
-SUFTAB, LCPTAB, CHILDTAB_UP, CHILDTAB_DOWN, CHILDTAB_NEXT_L_INDEX, ANNTAB = range(6)
+SUFTAB, LCPTAB, CHILDTAB_UP, CHILDTAB_DOWN, CHILDTAB_NEXT_L_INDEX, ANNTAB, PACKED_TEXT = range(7)
 TEXT_DEVPTR = 100
 
 EAST_ERR_ZERODIV = -4
@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
     "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
     "east_score_probes_dev", "east_index_stat", "east_score_range_dev", "east_table_host", "east_table_dev",
-    "east_build_host_u8", "east_table_host_u8", "east_table_dev_gather", "east_trim",
+    "east_build_host_u8", "east_table_host_u8", "east_table_dev_gather", "east_trim", "east_table_host_gather", "east_index_save", "east_index_load",
 ]
 
 _lib = None
@@ -74,6 +74,10 @@ def load():
                                  ctypes.c_int, _vp, _vp, ctypes.POINTER(_vp)]
     L.east_table_dev_gather.argtypes = [_vp, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _vp, _u32p, _i64p, ctypes.c_int32,
                                         ctypes.c_int, _vp, ctypes.POINTER(_vp), ctypes.c_int32, _vp, ctypes.POINTER(_vp)]
+    L.east_table_host_gather.argtypes = [_vp, ctypes.c_int32, _i64p, _i32p, ctypes.c_int32, ctypes.c_int, _u32p, _i64p, ctypes.c_int32,
+                                         ctypes.c_int, _f64p, _vp, ctypes.POINTER(_vp), ctypes.c_int32, ctypes.POINTER(_vp)]
+    L.east_index_save.argtypes = [_vp, ctypes.c_char_p]
+    L.east_index_load.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_vp)]
     L.east_score_range_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
     L.east_score_probes_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, _vp, _vp, _i64p]
     L.east_score_one.argtypes = [_vp, ctypes.c_int32, _u32p, ctypes.c_int32, ctypes.c_int, _f64p, _f64p]
@@ -215,7 +219,8 @@ class DeviceIndex(object):
         return cls.from_handle(h, doc_off, doc_m, int(device))
 
     @classmethod
-    def build_host_and_score(cls, text, doc_off, doc_m, kp_codes, kp_off, out, normalized=True, device=0):
+    def build_host_and_score(cls, text, doc_off, doc_m, kp_codes, kp_off, out, normalized=True, device=0, own_rows=None,
+                             peer_rows=None):
         """build_host() + score_table_into() as ONE engine call (east_table_host): on a large batch of small
         documents the runs of documents already sorted are scored, and their rows of `out` copied back, while
         the rest of the text is still on its way to the device.  Returns the index; `out` ([n_docs, K] float64,
@@ -229,6 +234,14 @@ class DeviceIndex(object):
         assert text.dtype in (np.uint32, np.uint8) and text.flags["C_CONTIGUOUS"]
         assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == len(doc_m) * K
         h = _vp()
+        if own_rows or peer_rows:   # sharded table: rows also to the gathered tables on the devices (east_table_host_gather)
+            peer_rows = list(peer_rows or [])
+            peers = (_vp * max(len(peer_rows), 1))(*[int(a) for a in peer_rows])
+            _check(L.east_table_host_gather(_vp(text.ctypes.data), int(text.itemsize), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p),
+                                            len(doc_m), int(device), _ptr(kp_codes, _u32p), _ptr(kp_off, _i64p), K,
+                                            1 if normalized else 0, _ptr(out, _f64p), _vp(own_rows or 0), peers, len(peer_rows),
+                                            ctypes.byref(h)))
+            return cls.from_handle(h, doc_off, doc_m, int(device))
         if text.dtype == np.uint8:   # one byte per code point, 0xFF ends a string (pack_strings_collection_u8)
             _check(L.east_table_host_u8(_ptr(text, _u8p), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m), int(device),
                                         _ptr(kp_codes, _u32p), _ptr(kp_off, _i64p), K, 1 if normalized else 0,
@@ -288,6 +301,36 @@ class DeviceIndex(object):
         _check(L.east_build_dev(_vp(text_devptr), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m),
                                 int(device), _vp(stream), ctypes.byref(h)))
         return cls.from_handle(h, doc_off, doc_m, int(device))
+
+    def save(self, path):
+        """Write the index (text, suffix array, tables, scorer side tables) to `path` (east_index_save)."""
+        _check(load().east_index_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path, device=0):
+        """Load an index written by save() onto `device`; scores and arrays equal the saved index's."""
+        L = load()
+        h = _vp()
+        _check(L.east_index_load(os.fsencode(path), int(device), ctypes.byref(h)))
+        n_docs = ctypes.c_int32()
+        _check(L.east_index_info(h, ctypes.byref(n_docs), None, None, None, None))
+        doc_off, doc_m = [0], []
+        off, n, m = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+        for d in range(n_docs.value):
+            _check(L.east_index_doc(h, d, ctypes.byref(off), ctypes.byref(n), ctypes.byref(m)))
+            doc_off.append(off.value + n.value)
+            doc_m.append(m.value)
+        return cls.from_handle(h, doc_off, doc_m, int(device))
+
+    def strings_collection(self, doc):
+        """The strings of a document, decoded from the packed text of the index (for indexes loaded from a file)."""
+        text = self.array(doc, PACKED_TEXT).view(np.uint32)
+        ends = np.nonzero(text >= 0x0A00)[0]
+        out, start = [], 0
+        for e in ends.tolist():
+            out.append(text[start:e].astype("<u4").tobytes().decode("utf-32-le", errors="surrogatepass"))
+            start = e + 1
+        return out
 
     def close(self):
         """Free the index (waits for its table kernels); afterwards build_timings holds the per-stage

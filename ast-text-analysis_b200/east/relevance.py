@@ -120,6 +120,41 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         if fused:
             self._table, self._table_keyphrases = table, list(prepared_keyphrases)
 
+    def save_index(self, directory):
+        """Write the indexed collection to `directory` (one file per device batch + the batch layout), so that a later
+        run loads it instead of rebuilding every structure (the reference rebuilds them on every run, relevance.py:38-47)."""
+        import json
+        import os
+        if not self._batches:
+            raise ValueError("no text collection has been indexed")
+        os.makedirs(directory, exist_ok=True)
+        layout = {"normalized": bool(self.normalized), "ast_algorithm": self.ast_algorithm, "n_texts": len(self.asts), "batches": []}
+        for b, (index, docs) in enumerate(self._batches):
+            name = "batch%04d.eastidx" % b
+            index.save(os.path.join(directory, name))
+            layout["batches"].append({"file": name, "docs": [int(j) for j in docs]})
+        with open(os.path.join(directory, "layout.json"), "w") as f:
+            json.dump(layout, f)
+
+    @classmethod
+    def load_index(cls, directory, device=0):
+        """A measure over the collection saved by save_index(): relevance(), relevance_table() and the asts' attributes
+        work as after set_text_collection()."""
+        import json
+        import os
+        with open(os.path.join(directory, "layout.json")) as f:
+            layout = json.load(f)
+        self = cls(layout["ast_algorithm"], layout["normalized"], device=device)
+        asts = [None] * layout["n_texts"]
+        batches = []
+        for entry in layout["batches"]:
+            index = _capi.DeviceIndex.load(os.path.join(directory, entry["file"]), device=device)
+            batches.append((index, entry["docs"]))
+            for local, j in enumerate(entry["docs"]):
+                asts[j] = easa.EnhancedAnnotatedSuffixArray(index.strings_collection(local), _index=index, _doc=local)
+        self.asts, self._batches, self._index = asts, batches, batches[0][0]
+        return self
+
     def relevance(self, keyphrase, text, synonimizer=None):
         return self.asts[text].score(keyphrase, normalized=self.normalized, synonimizer=synonimizer)
 

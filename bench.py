@@ -337,6 +337,11 @@ def run_b200(args):
             idx = _capi.DeviceIndex.build_host(host_text_np, doc_off, doc_m, device=local_rank)
             tb = time.perf_counter()
             idx.score_table_into(kp_codes, kp_off, host_out_np, True)
+        elif symm is not None:   # east_table_host_gather: the same call, rows also into every rank's gathered table
+            idx = _capi.DeviceIndex.build_host_and_score(host_text_np, doc_off, doc_m, kp_codes, kp_off, host_out_np,
+                                                         True, device=local_rank, own_rows=symm.own_rows(rank * D),
+                                                         peer_rows=symm.peer_rows(rank * D))
+            tb = time.perf_counter()
         else:   # east_table_host: the call behind applications.keyphrases_table (build + score, overlapped)
             idx = _capi.DeviceIndex.build_host_and_score(host_text_np, doc_off, doc_m, kp_codes, kp_off, host_out_np,
                                                          True, device=local_rank)
@@ -346,7 +351,10 @@ def run_b200(args):
         if debug:
             sys.stderr.write("e2e index: pipelined=%d miss=%d doc_sorted=%d overflow=%d\n" % (
                 pipelined, idx.stat("pipeline_miss"), idx.stat("doc_sorted"), idx.stat("doc_sort_overflow")))
-        if world > 1:
+        if symm is not None and not two_calls:
+            symm.barrier()
+            torch.cuda.synchronize()
+        elif world > 1:
             out_dev.copy_(host_out.view(-1), non_blocking=True)   # gather the table this step produced
             dist.all_gather_into_tensor(gathered, out_dev)
             torch.cuda.synchronize()
@@ -477,7 +485,7 @@ def run_b200(args):
             parity = {"checked": False, "error": repr(e)}
     if world > 1:
         gathered_sum = float(gathered.sum().item())
-        local = torch.tensor([float(out_dev.sum().item())], dtype=torch.float64, device=dev)
+        local = torch.tensor([float(host_out_np.sum())], dtype=torch.float64, device=dev)
         dist.all_reduce(local)
         parity["gathered_sum"] = gathered_sum
         parity["sum_of_rank_sums"] = float(local.item())

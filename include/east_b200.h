@@ -46,7 +46,8 @@ typedef enum east_array {
     EAST_CHILDTAB_UP = 2,        /* easa.py:268-287  _compute_childtab */
     EAST_CHILDTAB_DOWN = 3,      /* easa.py:268-287 */
     EAST_CHILDTAB_NEXT_L_INDEX = 4, /* easa.py:289-304 _compute_childtab_next_l_index */
-    EAST_ANNTAB = 5              /* easa.py:306-331  _compute_anntab */
+    EAST_ANNTAB = 5,             /* easa.py:306-331  _compute_anntab */
+    EAST_PACKED_TEXT = 6         /* easa.py:19  self.string as code points (terminators 0x0A00 + i) */
 } east_array;
 
 const char *east_last_error(void);
@@ -131,6 +132,13 @@ int east_table_dev_gather(const uint32_t *text_dev, const int64_t *doc_off, cons
                           int device, const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K,
                           int normalized, double *out_DxK_dev, double *const *peer_rows, int32_t n_peers, void *stream,
                           east_index **out_idx);
+/* The host-buffer entries (text_width 4: east_table_host, 1: east_table_host_u8) with the same fused all-gather: the
+ * rows go to out_DxK on the host AND to own_rows_dev (this rank's rows of its own gathered table on the device; may be
+ * NULL) AND to the other ranks' tables at peer_rows[i]. */
+int east_table_host_gather(const void *text, int32_t text_width, const int64_t *doc_off, const int32_t *doc_m,
+                           int32_t n_docs, int device, const uint32_t *kp, const int64_t *kp_off, int32_t K,
+                           int normalized, double *out_DxK, double *own_rows_dev, double *const *peer_rows,
+                           int32_t n_peers, east_index **out_idx);
 /* the rows of documents [doc_begin, doc_begin + doc_count) only: out[(d - doc_begin) * K + k].  Lets a caller
  * that shards documents over GPUs overlap the collective of one document tile with the scoring of the next. */
 int east_score_range_dev(const east_index *idx, const uint32_t *kp_dev, const int64_t *kp_off_host,
@@ -165,6 +173,12 @@ int east_kernel_stats(char *names, int32_t names_cap, double *ms, int64_t *launc
                       int32_t cap);
 /* number of kernel launches issued by the library on this thread since the last reset */
 int64_t east_launch_count(int reset);
+/* ---- persistence: the reference rebuilds every structure on every run (relevance.py:38-47); an index -- packed text,
+ * suffix array, LCP, child table, annotation and the scorer's side tables of one batch of documents -- can be written
+ * to a file and loaded back onto any device.  Scores and arrays of a loaded index are identical to the saved one's. */
+int east_index_save(const east_index *idx, const char *path);
+int east_index_load(const char *path, int device, east_index **out);
+
 /* The library allocates from two private stream-ordered memory pools per device (the device's default pool is not
  * touched) and keeps freed blocks for the next call, up to a quarter of the device memory.  east_trim waits for the
  * device and returns everything that is not in use to the driver (also drops the cached keyphrase preparation). */

@@ -249,3 +249,85 @@ def test_one_byte_text_entries_equal_the_uint32_entries(oracle_mod):
         table8(np.ascontiguousarray(t5, dtype=np.uint8), o5, [m_ + 1 for m_ in ms[:5]])
     # the Python layer takes the narrow form on its own when the text allows it
     assert au.pack_strings_collection_u8(["ÿ"]) is None and au.pack_strings_collection_u8(["Я"]) is None
+
+
+def test_saved_index_gives_identical_arrays_and_scores(tmp_path, oracle_mod):
+    # index persistence -- packed text, suffix array, LCP, child table, annotation and the scorer's
+    # side tables of a device batch go to a file and come back bit-identical; the measure saves / loads a collection
+    import synth
+    from east import applications, relevance, utils
+    capi = _capi()
+    packed, ms, cols = synth.packed_collection(6, 3000, first_seed=900)
+    codes, off = _keyphrases(40, extra=["QZX", "E"])
+    for opt in (0, 1):   # per-document kernel / global sort
+        try:
+            capi.set_option("no_doc_sort", opt)
+            idx = capi.DeviceIndex(packed, ms)
+        finally:
+            capi.set_option("no_doc_sort", 0)
+        exp = idx.score_table(codes, off, True)
+        path = str(tmp_path / ("idx%d.eastidx" % opt))
+        idx.save(path)
+        again = capi.DeviceIndex.load(path)
+        assert again.n_docs == 6 and list(again.doc_m) == list(ms)
+        for d in range(6):
+            for which in range(7):
+                assert np.array_equal(idx.array(d, which), again.array(d, which)), (opt, d, which)
+            assert again.strings_collection(d) == cols[d]
+        for normalized in (True, False):
+            assert np.array_equal(_bits(again.score_table(codes, off, normalized)), _bits(idx.score_table(codes, off, normalized)))
+        o = oracle_mod.OracleEASA(text=packed[3], m=ms[3])
+        assert np.array_equal(_bits(exp[3]), _bits(o.score_many(codes, off, True)))
+        idx.close(); again.close()
+    with pytest.raises(ValueError):
+        capi.DeviceIndex.load(str(tmp_path / "missing.eastidx"))
+    bad = tmp_path / "bad.eastidx"
+    bad.write_bytes(b"not an index")
+    with pytest.raises(ValueError):
+        capi.DeviceIndex.load(str(bad))
+    # through the measure: a mixed collection (two device batches), saved and loaded
+    docs = synth.documents(4, 3000, first_seed=300)
+    docs.insert(1, synth.documents(1, 90000, first_seed=400)[0])
+    texts = {"t%d" % i: d for i, d in enumerate(docs)}
+    kps = synth.keyphrases(10)
+    measure = relevance.ASTRelevanceMeasure("easa", True)
+    table = applications.keyphrases_table(kps, texts, measure)
+    measure.save_index(str(tmp_path / "collection"))
+    loaded = relevance.ASTRelevanceMeasure.load_index(str(tmp_path / "collection"))
+    prepared = [utils.prepare_text(k) for k in kps]
+    t2 = loaded.relevance_table(prepared)
+    for k, kp in enumerate(kps):
+        for j, name in enumerate(texts):
+            assert float(t2[j, k]).hex() == float(table[kp][name]).hex()
+    assert loaded.relevance(prepared[0], text=1) == measure.relevance(prepared[0], text=1)
+    assert loaded.asts[2].string == measure.asts[2].string
+    assert np.array_equal(loaded.asts[1].suftab, measure.asts[1].suftab)
+
+
+def test_synonym_expanded_scoring_is_the_best_variant(oracle_mod):
+    # easa.py:27-34: with a synonimizer the score is the maximum over all substitutions of the query words by their
+    # synonyms (always normalized); variants are generated on the host, each scored on the device
+    import collections
+    import itertools
+    from east import utils
+    from east.asts import base
+
+    class Synonimizer(object):
+        def get_synonyms(self):
+            d = collections.defaultdict(list)
+            d.update({"QUICK": ["FAST", "SPEEDY"], "FOX": ["VIXEN"], "LAZY": ["IDLE"]})
+            return d
+
+    strings = utils.text_to_strings_collection("the speedy brown vixen jumps over the idle dog while a fast fox sleeps")
+    ast = base.AST.get_ast(strings)
+    o = oracle_mod.OracleEASA(strings)
+    for query in ("QUICK FOX", "LAZY DOG", "QUICK BROWN FOX JUMPS", "NOTHING HERE"):
+        words = utils.tokenize(query)
+        syn = Synonimizer().get_synonyms()
+        variants = ["".join(w) for w in itertools.product(*[syn[x] + [x] for x in words])]
+        from east.asts.utils import codepoints
+        best = max(float(o.score_many(np.ascontiguousarray(codepoints(v), dtype=np.uint32), np.array([0, len(v)], dtype=np.int64), True)[0])
+                   for v in variants)
+        got = ast.score(query, synonimizer=Synonimizer())
+        assert float(got).hex() == float(best).hex(), query
+        assert float(got) >= float(ast.score(query))
