@@ -1319,7 +1319,12 @@ int east_table_host_u8(const uint8_t *text8, const int64_t *doc_off, const int32
 
 static void table_dev_impl(const uint32_t *text_dev, const int64_t *doc_off, const int32_t *doc_m, int32_t n_docs, int device,
                            const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, int normalized,
-                           double *out_DxK_dev, double *const *peer_rows, int32_t n_peers, void *stream, east_index **out_idx) {
+                           double *out_DxK_dev, double *const *peer_rows, int32_t n_peers, void *stream, east_index **out_idx,
+                           bool owns_text = false /* the index takes the text over (also when the call fails) */) {
+    struct TextGuard {   // an owned text that never reached an index
+        const uint32_t *p; bool armed;
+        ~TextGuard() { if (armed && p) dev_free(const_cast<uint32_t *>(p), 0); }
+    } text_guard{text_dev, owns_text};
     if (!kp_dev || !kp_off || !out_DxK_dev || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
     if (n_peers < 0 || n_peers > DocScore::MAX_PEERS || (n_peers > 0 && !peer_rows)) throw Error(EAST_ERR_INVALID, "bad peer list");
     east_index *built = nullptr;
@@ -1342,7 +1347,8 @@ static void table_dev_impl(const uint32_t *text_dev, const int64_t *doc_off, con
     run.peer_rows = peer_rows; run.n_peers = n_peers;
     RunHook hook;
     hook.begin = table_run_begin; hook.fn = table_run_done; hook.ctx = &run; hook.building = &run.building;
-    build_common(text_dev, false, doc_off, doc_m, n_docs, device, s, &built, nullptr, &hook);
+    text_guard.armed = false;   // build_common's index owns it from its first statement on
+    build_common(text_dev, owns_text, doc_off, doc_m, n_docs, device, s, &built, nullptr, &hook);
     std::unique_ptr<east_index, void (*)(east_index *)> guard(built, free_index);
     const bool stands = !run.failed && run.docs_scored == n_docs && built->doc_sorted && run.final_pass;
     if (!stands) score_common(built, kp_dev, kp_off, K, normalized, out_DxK_dev, 0, n_docs, s, nullptr, nullptr, kp_host);
@@ -1428,6 +1434,86 @@ int east_cooc_host(const double *S_DxK, int64_t D, int32_t K, double threshold, 
     if (get_option("cooc_variant", 0) == 1) cooc_counts(d_S.p, D, K, threshold, d_C.p, s);
     else cooc_counts_tc(d_S.p, D, K, threshold, d_C.p, s, get_option("cooc_variant", 0) == 2);
     EAST_CUDA(cudaMemcpy(C_KxK, d_C.p, sizeof(int32_t) * (size_t)K * K, cudaMemcpyDeviceToHost));
+    EAST_API_END
+}
+
+// ---- device preprocessing (tokenize.cu) -----------------------------------------------------
+namespace {
+struct PackedTexts {
+    uint32_t *text = nullptr;          // device, owned until released
+    std::vector<int64_t> doc_off;
+    std::vector<int32_t> doc_m;
+    ~PackedTexts() { if (text) dev_free(text, 0); }
+};
+
+// raw UTF-8 texts (host) -> packed documents on the device; throws EAST_ERR_UNSUPPORTED when a text needs the host path
+void texts_to_packed(const uint8_t *utf8, const int64_t *text_off, int32_t n_texts, cudaStream_t s, PackedTexts &out) {
+    if (!utf8 || !text_off || n_texts <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    if (text_off[0] != 0) throw Error(EAST_ERR_INVALID, "text_off[0] must be 0");
+    for (int32_t i = 0; i < n_texts; ++i)
+        if (text_off[i + 1] < text_off[i]) throw Error(EAST_ERR_INVALID, "text offsets must not decrease");
+    const int64_t bytes = text_off[n_texts];
+    if (bytes >= (1ll << 31)) throw Error(EAST_ERR_RANGE, "more than 2^31 bytes of text in one call; split the collection");
+    DevBuf<uint8_t> d_raw((size_t)bytes + 16, s);
+    DevBuf<int64_t> d_off((size_t)n_texts + 1, s), d_doc_off((size_t)n_texts + 1, s);
+    DevBuf<int32_t> d_sizes(3 * (size_t)n_texts, s);
+    if (bytes) EAST_CUDA(cudaMemcpyAsync(d_raw.p, utf8, (size_t)bytes, cudaMemcpyHostToDevice, s));
+    EAST_CUDA(cudaMemcpyAsync(d_off.p, text_off, sizeof(int64_t) * ((size_t)n_texts + 1), cudaMemcpyHostToDevice, s));
+    tokenize_texts(d_raw.p, d_off.p, n_texts, d_sizes.p, s);
+    std::vector<int32_t> sizes(3 * (size_t)n_texts);
+    EAST_CUDA(cudaMemcpyAsync(sizes.data(), d_sizes.p, sizeof(int32_t) * sizes.size(), cudaMemcpyDeviceToHost, s));
+    EAST_CUDA(cudaStreamSynchronize(s));
+    out.doc_off.assign((size_t)n_texts + 1, 0);
+    out.doc_m.resize((size_t)n_texts);
+    for (int32_t i = 0; i < n_texts; ++i) {
+        if (sizes[3 * (size_t)i + 2])
+            throw Error(EAST_ERR_UNSUPPORTED, "text " + std::to_string(i) + " has characters outside ASCII / U+0400-045F (or invalid UTF-8): "
+                                              "use the host preprocessing");
+        out.doc_off[(size_t)i + 1] = out.doc_off[(size_t)i] + sizes[3 * (size_t)i];
+        out.doc_m[(size_t)i] = sizes[3 * (size_t)i + 1];
+    }
+    if (out.doc_off.back() >= (1ll << 30)) throw Error(EAST_ERR_RANGE, "more than 2^30 code points in one index; split the batch");
+    EAST_CUDA(cudaMemcpyAsync(d_doc_off.p, out.doc_off.data(), sizeof(int64_t) * out.doc_off.size(), cudaMemcpyHostToDevice, s));
+    out.text = (uint32_t *)dev_alloc(sizeof(uint32_t) * (size_t)out.doc_off.back(), s, true);
+    tokenize_emit(d_raw.p, d_off.p, n_texts, d_doc_off.p, out.text, s);
+    EAST_CUDA(cudaStreamSynchronize(s));   // the staging buffers (and the pageable doc_off upload) end here
+}
+}  // namespace
+
+int east_texts_to_packed_host(const uint8_t *utf8, const int64_t *text_off, int32_t n_texts, int device, uint32_t *packed_out,
+                              int64_t packed_cap, int64_t *doc_off_out, int32_t *doc_m_out) {
+    EAST_API_BEGIN
+    if (!doc_off_out || !doc_m_out) throw Error(EAST_ERR_INVALID, "NULL argument");
+    use_device(device);
+    PackedTexts pt;
+    texts_to_packed(utf8, text_off, n_texts, 0, pt);
+    std::copy(pt.doc_off.begin(), pt.doc_off.end(), doc_off_out);
+    std::copy(pt.doc_m.begin(), pt.doc_m.end(), doc_m_out);
+    if (pt.doc_off.back() > packed_cap || !packed_out) throw Error(EAST_ERR_RANGE, "packed_out is too small (doc_off_out holds the sizes)");
+    EAST_CUDA(cudaMemcpy(packed_out, pt.text, sizeof(uint32_t) * (size_t)pt.doc_off.back(), cudaMemcpyDeviceToHost));
+    EAST_API_END
+}
+
+int east_table_texts_host(const uint8_t *utf8, const int64_t *text_off, int32_t n_texts, int device, const uint32_t *kp,
+                          const int64_t *kp_off, int32_t K, int normalized, double *out_DxK, int64_t *doc_off_out,
+                          int32_t *doc_m_out, east_index **out_idx) {
+    EAST_API_BEGIN
+    if (!kp || !kp_off || !out_DxK || K <= 0) throw Error(EAST_ERR_INVALID, "bad argument");
+    check_keyphrases(kp_off, K);
+    use_device(device);
+    cudaStream_t s = 0;
+    PackedTexts pt;
+    texts_to_packed(utf8, text_off, n_texts, s, pt);
+    if (doc_off_out) std::copy(pt.doc_off.begin(), pt.doc_off.end(), doc_off_out);
+    if (doc_m_out) std::copy(pt.doc_m.begin(), pt.doc_m.end(), doc_m_out);
+    DevBuf<uint32_t> d_kp((size_t)kp_off[K], s);
+    DevBuf<double> d_out((size_t)n_texts * K, s);
+    EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, s));
+    const uint32_t *text = pt.text;
+    pt.text = nullptr;   // the index owns it from here on
+    table_dev_impl(text, pt.doc_off.data(), pt.doc_m.data(), n_texts, device, d_kp.p, kp, kp_off, K, normalized, d_out.p, nullptr, 0,
+                   (void *)s, out_idx, true);
+    EAST_CUDA(cudaMemcpy(out_DxK, d_out.p, sizeof(double) * (size_t)n_texts * K, cudaMemcpyDeviceToHost));
     EAST_API_END
 }
 

@@ -132,6 +132,12 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
                      uint32_t *miss = nullptr, int64_t text_len = 0 /* code points of the whole batch */,
                      const uint8_t *text8 = nullptr /* with code_table: one byte per code point in, code points out to `text` */);
 
+// device preprocessing of raw UTF-8 texts (tokenize.cu): sizes[3 d] = code points of the packed document d, [3 d + 1] = its
+// strings, [3 d + 2] != 0 = the text has characters the device does not handle; then the packed documents themselves
+void tokenize_texts(const uint8_t *raw_dev, const int64_t *raw_off_dev, int32_t n_texts, int32_t *sizes_dev, cudaStream_t s);
+void tokenize_emit(const uint8_t *raw_dev, const int64_t *raw_off_dev, int32_t n_texts, const int64_t *doc_off_dev, uint32_t *text_dev,
+                   cudaStream_t s);
+
 // Kasai-equivalent LCP (easa.py:247-266), child table (easa.py:268-304) and annotation
 // (easa.py:306-331) of the whole batch
 void build_lcp_tables(const uint32_t *text, const uint8_t *t8 /*or null*/, int term_code, const int32_t *sa, const int32_t *doc_off, const int32_t *doc_m,

@@ -20,6 +20,12 @@ SUFTAB, LCPTAB, CHILDTAB_UP, CHILDTAB_DOWN, CHILDTAB_NEXT_L_INDEX, ANNTAB, PACKE
 TEXT_DEVPTR = 100
 
 EAST_ERR_ZERODIV = -4
+EAST_ERR_UNSUPPORTED = -6
+
+
+class UnsupportedText(ValueError):
+    """The device preprocessing met a character outside ASCII / U+0400-045F: use the host preprocessing."""
+
 
 EXPORTED_SYMBOLS = [
     "east_last_error", "east_device_count", "east_version", "east_build_host", "east_build_dev",
@@ -27,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "east_score_table_host", "east_score_table_dev", "east_score_one", "east_cooc_dev",
     "east_cooc_host", "east_last_timings", "east_launch_count", "east_set_option", "east_kernel_stats",
     "east_score_probes_dev", "east_index_stat", "east_score_range_dev", "east_table_host", "east_table_dev",
-    "east_build_host_u8", "east_table_host_u8", "east_table_dev_gather", "east_trim", "east_table_host_gather", "east_index_save", "east_index_load",
+    "east_build_host_u8", "east_table_host_u8", "east_table_dev_gather", "east_trim", "east_table_host_gather", "east_index_save", "east_index_load", "east_texts_to_packed_host", "east_table_texts_host",
 ]
 
 _lib = None
@@ -78,6 +84,9 @@ def load():
                                          ctypes.c_int, _f64p, _vp, ctypes.POINTER(_vp), ctypes.c_int32, ctypes.POINTER(_vp)]
     L.east_index_save.argtypes = [_vp, ctypes.c_char_p]
     L.east_index_load.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_vp)]
+    L.east_texts_to_packed_host.argtypes = [_u8p, _i64p, ctypes.c_int32, ctypes.c_int, _u32p, ctypes.c_int64, _i64p, _i32p]
+    L.east_table_texts_host.argtypes = [_u8p, _i64p, ctypes.c_int32, ctypes.c_int, _u32p, _i64p, ctypes.c_int32, ctypes.c_int, _f64p,
+                                        _i64p, _i32p, ctypes.POINTER(_vp)]
     L.east_score_range_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32, _vp, _vp]
     L.east_score_probes_dev.argtypes = [_vp, _vp, _i64p, ctypes.c_int32, _vp, _vp, _i64p]
     L.east_score_one.argtypes = [_vp, ctypes.c_int32, _u32p, ctypes.c_int32, ctypes.c_int, _f64p, _f64p]
@@ -100,6 +109,8 @@ def _check(rc):
         raise ZeroDivisionError(msg or "float division by zero")  # easa.py:134 on an empty query
     if rc == -3:
         raise MemoryError(msg)
+    if rc == EAST_ERR_UNSUPPORTED:
+        raise UnsupportedText(msg)
     if rc == -1 or rc == -5:
         raise ValueError(msg)
     raise exceptions.DeviceError(reason=msg)
@@ -162,6 +173,31 @@ def pack_keyphrases(queries):
     return codes, off
 
 
+def concat_utf8(texts):
+    """list of str / bytes -> (uint8 buffer of the UTF-8 texts back to back, int64 offsets [n + 1])"""
+    raws = [t if isinstance(t, (bytes, bytearray)) else t.encode("utf-8", errors="surrogatepass") for t in texts]
+    off = np.zeros(len(raws) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in raws], out=off[1:])
+    buf = np.frombuffer(b"".join(raws), dtype=np.uint8) if off[-1] else np.zeros(1, dtype=np.uint8)
+    return buf, off
+
+
+def texts_to_packed(texts, device=0):
+    """utils.text_to_strings_collection + pack_strings_collection of every text ON THE DEVICE (east_texts_to_packed_host).
+    texts: list of str or UTF-8 bytes.  Returns (uint32 packed text, int64 doc_off [n + 1], int32 doc_m [n]); raises
+    UnsupportedText when a text has characters outside ASCII / U+0400-045F."""
+    L = load()
+    buf, off = concat_utf8(texts)
+    n = len(texts)
+    doc_off = np.zeros(n + 1, dtype=np.int64)
+    doc_m = np.zeros(n, dtype=np.int32)
+    cap = int(off[-1]) + 2 * n + 2     # a packed document never has more entries than its text has bytes, + 2
+    packed = np.empty(cap, dtype=np.uint32)
+    _check(L.east_texts_to_packed_host(_ptr(buf, _u8p), _ptr(off, _i64p), n, int(device), _ptr(packed, _u32p), cap,
+                                       _ptr(doc_off, _i64p), _ptr(doc_m, _i32p)))
+    return packed[: int(doc_off[-1])], doc_off, doc_m
+
+
 class DeviceIndex(object):
     """A batch of documents indexed on one GPU (opaque east_index handle)."""
 
@@ -204,6 +240,27 @@ class DeviceIndex(object):
         h = _vp()
         _check(L.east_build_host(_ptr(text, _u32p), _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), len(doc_m),
                                  int(device), ctypes.byref(h)))
+        return cls.from_handle(h, doc_off, doc_m, int(device))
+
+    @classmethod
+    def table_from_texts(cls, texts, kp_codes, kp_off, out, normalized=True, device=0):
+        """Raw texts in, score table out, in ONE engine call (east_table_texts_host): the texts are upper-cased,
+        tokenised, grouped and packed on the device (tokenize.cu), indexed and scored.  texts: list of str / UTF-8
+        bytes (ASCII and Cyrillic; anything else raises UnsupportedText).  Returns the index."""
+        L = load()
+        # texts may also be (uint8 buffer, int64 offsets): texts already laid out back to back (e.g. in pinned memory)
+        buf, off = texts if isinstance(texts, tuple) else concat_utf8(texts)
+        n = len(off) - 1
+        kp_codes = np.ascontiguousarray(kp_codes, dtype=np.uint32)
+        kp_off = np.ascontiguousarray(kp_off, dtype=np.int64)
+        K = len(kp_off) - 1
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == n * K
+        doc_off = np.zeros(n + 1, dtype=np.int64)
+        doc_m = np.zeros(n, dtype=np.int32)
+        h = _vp()
+        _check(L.east_table_texts_host(_ptr(buf, _u8p), _ptr(off, _i64p), n, int(device), _ptr(kp_codes, _u32p),
+                                       _ptr(kp_off, _i64p), K, 1 if normalized else 0, _ptr(out, _f64p),
+                                       _ptr(doc_off, _i64p), _ptr(doc_m, _i32p), ctypes.byref(h)))
         return cls.from_handle(h, doc_off, doc_m, int(device))
 
     @classmethod

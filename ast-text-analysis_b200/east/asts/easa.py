@@ -25,8 +25,12 @@ class EnhancedAnnotatedSuffixArray(base.AST):
     __algorithm__ = consts.ASTAlgorithm.EASA
 
     def __init__(self, strings_collection, _index=None, _doc=0, device=0):
-        super(EnhancedAnnotatedSuffixArray, self).__init__(strings_collection)
-        self.strings_collection = strings_collection
+        if strings_collection is None and _index is not None:
+            # indexed from raw text on the device (or loaded from a file): the strings are decoded on first use
+            self._strings_collection = None
+        else:
+            super(EnhancedAnnotatedSuffixArray, self).__init__(strings_collection)
+            self._strings_collection = strings_collection
         if _index is None:
             packed = utils.pack_strings_collection(strings_collection)
             _index = _capi.DeviceIndex([packed], [len(strings_collection)], device=device)
@@ -34,6 +38,12 @@ class EnhancedAnnotatedSuffixArray(base.AST):
         self._index = _index
         self._doc = _doc
         self._cache = {}
+
+    @property
+    def strings_collection(self):
+        if self._strings_collection is None:
+            self._strings_collection = self._index.strings_collection(self._doc)
+        return self._strings_collection
 
     # ---- the reference's attributes, materialised lazily from device memory ----
     def _array(self, which):

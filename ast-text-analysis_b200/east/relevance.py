@@ -17,6 +17,9 @@ from east.asts import easa
 from east.asts import utils as asts_utils
 
 
+import re
+
+_DEVICE_TEXT_RE = re.compile(r"[\x00-\x7f\u0400-\u045f]*\Z")   # what csrc/tokenize.cu handles
 SMALL_DOCUMENT_LIMIT = 65535   # code points: the per-document shared-memory kernel (csrc/doc_sort.cu) takes these
 MAX_BATCH_CODE_POINTS = 1 << 29   # one device index addresses < 2^30 code points (int32 ranks)
 
@@ -52,8 +55,9 @@ class RelevanceMeasure(object):
 
 class ASTRelevanceMeasure(RelevanceMeasure):
 
-    def __init__(self, ast_algorithm=consts.ASTAlgorithm.EASA, normalized=True, device=0):
+    def __init__(self, ast_algorithm=consts.ASTAlgorithm.EASA, normalized=True, device=0, device_preprocessing=True):
         super(ASTRelevanceMeasure, self).__init__()
+        self.device_preprocessing = device_preprocessing
         self.ast_algorithm = ast_algorithm
         self.normalized = normalized
         self.device = device
@@ -85,9 +89,11 @@ class ASTRelevanceMeasure(RelevanceMeasure):
                 logging.progress("Indexing texts with ASTs", i + 1, total_texts)
             logging.clear()
             return
-        collections = [utils.text_to_strings_collection(text) for text in texts]
-        if not collections:
+        if not texts:
             return
+        if prepared_keyphrases and self.device_preprocessing and self._set_text_collection_on_device(texts, prepared_keyphrases):
+            return
+        collections = [utils.text_to_strings_collection(text) for text in texts]
         # one byte per code point where the text allows it (ASCII / Latin-1: a quarter of the bytes over the host link),
         # uint32 code points otherwise; both have one entry per code point + one per string
         packed = [asts_utils.pack_strings_collection_u8(c) for c in collections]
@@ -119,6 +125,39 @@ class ASTRelevanceMeasure(RelevanceMeasure):
         self.asts, self._batches, self._index = asts, batches, batches[0][0]
         if fused:
             self._table, self._table_keyphrases = table, list(prepared_keyphrases)
+
+    def _set_text_collection_on_device(self, texts, prepared_keyphrases):
+        """keyphrases_table for a collection of small ASCII / Cyrillic texts: ONE engine call takes the raw texts,
+        does the preprocessing of utils.text_to_strings_collection on the device (csrc/tokenize.cu), indexes and scores
+        (east_table_texts_host).  Returns False when the collection needs the host preprocessing (other scripts --
+        Python's Unicode tables --, a text too large for the per-document kernel, several device batches)."""
+        total = 0
+        for t in texts:
+            if isinstance(t, (bytes, bytearray)):
+                size = len(t)
+            elif t.isascii():
+                size = len(t)
+            elif _DEVICE_TEXT_RE.match(t):
+                size = 2 * len(t)
+            else:
+                return False
+            if size > SMALL_DOCUMENT_LIMIT - 2:
+                return False
+            total += size
+        if total >= MAX_BATCH_CODE_POINTS:
+            return False
+        fused = _capi.pack_keyphrases(prepared_keyphrases)
+        table = np.empty((len(texts), len(prepared_keyphrases)), dtype=np.float64)
+        try:
+            index = _capi.DeviceIndex.table_from_texts(texts, fused[0], fused[1], table, normalized=self.normalized,
+                                                       device=self.device)
+        except _capi.UnsupportedText:
+            return False
+        docs = list(range(len(texts)))
+        self.asts = [easa.EnhancedAnnotatedSuffixArray(None, _index=index, _doc=j) for j in docs]
+        self._batches, self._index = [(index, docs)], index
+        self._table, self._table_keyphrases = table, list(prepared_keyphrases)
+        return True
 
     def save_index(self, directory):
         """Write the indexed collection to `directory` (one file per device batch + the batch layout), so that a later

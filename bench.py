@@ -450,6 +450,25 @@ def run_b200(args):
         e2e_other_ms = (time.perf_counter() - w1) * 1e3 / max(3, args.steps // 4)
         e2e_text[0] = host_text8_np if e2e_width == 1 else host_text_np
         step_e2e()   # the table the parity check reads comes from the headline variant
+    # ---- from RAW TEXT: east_table_texts_host does the reference's host preprocessing (upper / tokenise / filter / group /
+    # pack, utils.text_to_strings_collection) on the device too: the UTF-8 bytes of the documents go in, the table comes out
+    raw_ms = None
+    if not two_calls:
+        raw_buf, raw_off = _capi.concat_utf8(docs)
+        raw_pinned = torch.empty(raw_buf.size, dtype=torch.uint8).pin_memory()
+        raw_np = raw_pinned.numpy()
+        raw_np[:] = raw_buf
+        raw_out = np.empty((D, K), dtype=np.float64)
+        for _ in range(2):
+            _capi.DeviceIndex.table_from_texts((raw_np, raw_off), kp_codes, kp_off, raw_out, True, device=local_rank).close()
+        barrier()
+        w2 = time.perf_counter()
+        raw_steps = max(3, args.steps // 2)
+        for _ in range(raw_steps):
+            _capi.DeviceIndex.table_from_texts((raw_np, raw_off), kp_codes, kp_off, raw_out, True, device=local_rank).close()
+        barrier()
+        raw_ms = (time.perf_counter() - w2) * 1e3 / raw_steps
+        raw_equal = bool(np.array_equal(raw_out.view(np.uint64), host_out_np.view(np.uint64)))
     # clocks under load: samples taken between the start of the device-timed region and the end of the e2e one
     clocks = sampler.stop(t_timed0, time.perf_counter())
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
@@ -526,6 +545,10 @@ def run_b200(args):
         "e2e": {"value": n_gpus * D * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_total * e2e_width + doc_off.nbytes + doc_m.nbytes + kp_codes.nbytes + kp_off.nbytes),
                 "text_bytes_per_code_point": e2e_width,
+                "from_raw_text": ({"call": "east_table_texts_host", "ms_per_step": raw_ms, "value": n_gpus * D * K / (raw_ms * 1e-3),
+                                   "h2d_bytes_per_step": int(raw_off[-1]), "table_equals_e2e_table": raw_equal,
+                                   "what": "UTF-8 documents in, table out: preprocessing (east/utils.py:31-79) on the device as well; "
+                                           "the same preprocessing on the host costs host_prep_s.tokenize_pack"} if raw_ms else None),
                 "other_width": {"text_bytes_per_code_point": 5 - e2e_width, "ms_per_step": e2e_other_ms,
                                 "value": (n_gpus * D * K / (e2e_other_ms * 1e-3)) if e2e_other_ms else None},
                 "d2h_bytes_per_step": int(D * K * 8),
@@ -552,6 +575,7 @@ def run_b200(args):
                       "kernels": kernel_table, "scorer_algorithmic_bytes": probes,
                       "index": info0, "n_codepoints": n_total, "checksum": checksum, "kp_prep_ms": kp_prep_ms,
                       "host_prep_s": {"generate": t1 - t0, "tokenize_pack": t2 - t1}},
+        "host_prep_s": {"generate": t1 - t0, "tokenize_pack": t2 - t1},
     }
     if not args.no_cpu_baseline and n_gpus == 1:
         try:

@@ -36,7 +36,8 @@ typedef enum east_status {
     EAST_ERR_CUDA = -2,    /* CUDA runtime error or no device */
     EAST_ERR_NOMEM = -3,
     EAST_ERR_ZERODIV = -4, /* empty query: the reference raises ZeroDivisionError (easa.py:134) */
-    EAST_ERR_RANGE = -5    /* size exceeds the int32/2^30 limits of one index */
+    EAST_ERR_RANGE = -5,   /* size exceeds the int32/2^30 limits of one index */
+    EAST_ERR_UNSUPPORTED = -6 /* device preprocessing: a text has characters outside ASCII / U+0400-045F */
 } east_status;
 
 /* which array east_index_copy() exports; names follow east/asts/easa.py:18-24 */
@@ -173,6 +174,21 @@ int east_kernel_stats(char *names, int32_t names_cap, double *ms, int64_t *launc
                       int32_t cap);
 /* number of kernel launches issued by the library on this thread since the last reset */
 int64_t east_launch_count(int reset);
+/* ---- preprocessing on the device: replaces utils.text_to_strings_collection (east/utils.py:31-79: utf-8 decode, upper(),
+ * [\w']+ tokens, tokens of <= 2 characters and all-digit tokens dropped, every 3 consecutive tokens joined, [" "] for a text
+ * without tokens) + make_unique_endings (east/asts/utils.py:25-40) for raw UTF-8 texts of ASCII and Cyrillic (U+0400-045F)
+ * characters.  utf8: the texts concatenated, text_off: n_texts + 1 byte offsets.  A text with any other character (or
+ * invalid UTF-8) makes the call fail with EAST_ERR_UNSUPPORTED: the caller then uses the host preprocessing (Python's
+ * full Unicode tables), which stays the reference behaviour.
+ * east_texts_to_packed_host returns the packed documents (uint32 code points, what east_build_host takes), their
+ * offsets (n_texts + 1) and string counts; EAST_ERR_RANGE when packed_cap is too small (doc_off_out is valid then).
+ * east_table_texts_host = that + east_table_dev + the table back on the host: raw text in, scores out, one call. */
+int east_texts_to_packed_host(const uint8_t *utf8, const int64_t *text_off, int32_t n_texts, int device,
+                              uint32_t *packed_out, int64_t packed_cap, int64_t *doc_off_out, int32_t *doc_m_out);
+int east_table_texts_host(const uint8_t *utf8, const int64_t *text_off, int32_t n_texts, int device,
+                          const uint32_t *kp, const int64_t *kp_off, int32_t K, int normalized, double *out_DxK,
+                          int64_t *doc_off_out /* optional */, int32_t *doc_m_out /* optional */, east_index **out_idx);
+
 /* ---- persistence: the reference rebuilds every structure on every run (relevance.py:38-47); an index -- packed text,
  * suffix array, LCP, child table, annotation and the scorer's side tables of one batch of documents -- can be written
  * to a file and loaded back onto any device.  Scores and arrays of a loaded index are identical to the saved one's. */

@@ -246,11 +246,13 @@ def test_hse_table_and_graph(golden):
         for g in hse["graphs"]:
             graph = applications.keyphrases_graph(kps, marker_texts, referral_confidence=g["c"], relevance_threshold=g["r"],
                                                   support_threshold=g["p"],
-                                                  similarity_measure=relevance.ASTRelevanceMeasure("easa", normalized=True))
+                                                  similarity_measure=relevance.ASTRelevanceMeasure("easa", normalized=True,
+                                                                                                   device_preprocessing=False))
             assert graph["nodes"] == g["nodes"], (g["c"], g["r"], g["p"])
             assert [(e["source"], e["target"], float(e["confidence"]).hex()) for e in graph["edges"]] == \
                    [(e["source"], e["target"], e["confidence"]) for e in g["edges"]]
-        tab = applications.keyphrases_table(kps, marker_texts, relevance.ASTRelevanceMeasure("easa", normalized=True))
+        tab = applications.keyphrases_table(kps, marker_texts, relevance.ASTRelevanceMeasure("easa", normalized=True,
+                                                                                             device_preprocessing=False))
         for kp in kps:
             for d in hse["docs"]:
                 assert float(tab[kp][d["name"]]).hex() == hse["table_norm"][kp][d["name"]]

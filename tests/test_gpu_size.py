@@ -331,3 +331,84 @@ def test_synonym_expanded_scoring_is_the_best_variant(oracle_mod):
         got = ast.score(query, synonimizer=Synonimizer())
         assert float(got).hex() == float(best).hex(), query
         assert float(got) >= float(ast.score(query))
+
+
+def _host_packed(texts):
+    from east import utils
+    from east.asts import utils as au
+    cols = [utils.text_to_strings_collection(t) for t in texts]
+    return cols, [au.pack_strings_collection(c) for c in cols]
+
+
+def test_device_preprocessing_equals_text_to_strings_collection(golden):
+    # utils.text_to_strings_collection + packing on the device (csrc/tokenize.cu) for ASCII and
+    # Cyrillic texts: the packed documents must equal the host path's code point for code point -- on the reference's
+    # own preprocessing goldens, on hand-made edge cases and on random texts
+    import synth
+    capi = _capi()
+    texts = [c["in"] for c in golden["prep"]["collections"]]
+    packed, doc_off, doc_m = capi.texts_to_packed(texts)
+    for d, c in enumerate(golden["prep"]["collections"]):
+        seg = packed[doc_off[d]:doc_off[d + 1]]
+        strs = "".join(chr(x) if x < 0x0A00 else "\n" for x in seg).split("\n")[:-1]
+        assert strs == c["out"], (c["in"], strs)
+        assert doc_m[d] == len(c["out"])
+    edge = ["", " ", "a", "ab", "abc", "abc ", " abc", "ab cd ef", "123 4567 89", "12a 34' ''' ___ _1_", "x" * 5000, "7" * 5000 + "x",
+            "7" * 5000, "ab " * 3000, "abc " * 3000, "one two", "one two three", "one two three four",
+            "Tabs\tand\nnew\r\nlines\x00nul\x7fdel", "it's o'clock 'quoted' rock'n'roll", "UPPER lower MiXeD",
+            "привет мир ёжик Ёлка ѐѝџ ЀЍЏ як", "mixed смесь text текст 123 ab аб абв", "ёё ё ёёё", "q" * 65000,
+            synth.document(50000, 5), synth.document(777, 6).replace(" ", ", "), "a" * 511 + " " + "b" * 513 + " cc dd eee"]
+    rng = np.random.default_rng(11)
+    alphabet = list("abcXYZ019_' .,;-\n\t") + list("яЖё")
+    for _ in range(300):
+        n = int(rng.integers(0, 400)) if rng.random() < 0.8 else int(rng.integers(400, 6000))
+        edge.append("".join(rng.choice(alphabet, size=n)))
+    cols, exp = _host_packed(edge)
+    packed, doc_off, doc_m = capi.texts_to_packed(edge)
+    for d in range(len(edge)):
+        got = packed[doc_off[d]:doc_off[d + 1]]
+        assert np.array_equal(got, exp[d]), (d, edge[d][:60], got[:20], exp[d][:20])
+        assert doc_m[d] == len(cols[d])
+    # bytes go in as they are
+    p2, o2, m2 = capi.texts_to_packed([t.encode("utf-8") for t in edge[:30]])
+    assert np.array_equal(p2, packed[: doc_off[30]]) and np.array_equal(o2, doc_off[:31])
+    # what the device does not handle is refused, never approximated
+    for bad in ("café au lait", "中文 text", "emoji \U0001F600 here", b"broken \xff\xfe utf8", b"cut \xd0", "Ѡ beyond the block",
+                b"stray \x80 continuation"):
+        with pytest.raises(capi.UnsupportedText):
+            capi.texts_to_packed(["fine text here", bad])
+
+
+def test_keyphrases_table_from_raw_texts_in_one_call(oracle_mod):
+    # east_table_texts_host: raw texts in, scores out; and the public API takes that path on its own for ASCII / Cyrillic
+    import synth
+    from east import applications, relevance, utils
+    capi = _capi()
+    docs = synth.documents(40, 20000, first_seed=2100) + ["", "12 ab", "привет мир привет ёжик " * 50]
+    codes, off = _keyphrases(300, extra=["ПРИВЕТ", "ЁЖИК МИР"])
+    out = np.full((len(docs), len(off) - 1), -1.0)
+    idx = capi.DeviceIndex.table_from_texts(docs, codes, off, out, True)
+    cols, packed = _host_packed(docs)
+    for d in (0, 17, 39, 40, 41, 42):
+        o = oracle_mod.OracleEASA(text=packed[d], m=len(cols[d]))
+        assert np.array_equal(_bits(out[d]), _bits(o.score_many(codes, off, True))), d
+        _check_arrays(idx, d, o, ("texts", d))
+        assert idx.strings_collection(d) == cols[d]
+    idx.close()
+    texts = {"t%d" % i: t for i, t in enumerate(docs)}
+    kps = synth.keyphrases(25) + ["привет", "ёжик мир"]
+    on_device = relevance.ASTRelevanceMeasure("easa", True)
+    on_host = relevance.ASTRelevanceMeasure("easa", True, device_preprocessing=False)
+    t_dev = applications.keyphrases_table(kps, texts, on_device)
+    t_host = applications.keyphrases_table(kps, texts, on_host)
+    assert on_device.asts[0]._strings_collection is None    # indexed from raw text: nothing was tokenised on the host
+    for kp in kps:
+        for name in texts:
+            assert float(t_dev[kp][name]).hex() == float(t_host[kp][name]).hex(), (kp, name)
+    assert on_device.asts[42].string == on_host.asts[42].string
+    assert on_device.relevance(utils.prepare_text(kps[0]), text=3) == on_host.relevance(utils.prepare_text(kps[0]), text=3)
+    # a collection the device does not handle falls back to the host preprocessing, silently and exactly
+    texts["latin1"] = "café crème brûlée " * 20
+    t_mixed = applications.keyphrases_table(kps, texts, relevance.ASTRelevanceMeasure("easa", True))
+    for kp in kps:
+        assert float(t_mixed[kp]["t5"]).hex() == float(t_host[kp]["t5"]).hex()
