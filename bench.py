@@ -565,7 +565,17 @@ def run_b200(args):
                      "peak_source": peak_kind,
                      "launches_per_step": dom["launches"] / args.steps, "ms_per_launch": per_launch_ms,
                      "algorithmic_bytes_per_launch": per_launch_bytes,
-                     "share_of_step": dom["ms"] / args.steps / dev_ms},
+                     "share_of_step": dom["ms"] / args.steps / dev_ms,
+                     # the roofline that actually bounds this kernel: warp instructions issued per second against the issue
+                     # peak (148 SMs x 4 schedulers x SM clock); instructions per code point from the committed ncu capture
+                     "issue": ({"warp_instructions_per_code_point": tinfo["warp_instructions_per_code_point"],
+                                "achieved_Ginst_per_s": tinfo["warp_instructions_per_code_point"] * n_total / (per_launch_ms * 1e-3) / 1e9,
+                                "peak_Ginst_per_s": 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                                "frac": tinfo["warp_instructions_per_code_point"] * n_total / (per_launch_ms * 1e-3) /
+                                        (148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                                "active_threads_per_instruction": tinfo.get("thread_instructions_per_warp_instruction"),
+                                "source": tinfo.get("instruction_source")}
+                               if "warp_instructions_per_code_point" in tinfo and dom["launches"] == args.steps else None)},
         "breakdown": {"device_call": "east_build_dev+east_score_table_dev" if two_calls else "east_table_dev",
                       "build_ms": build_ms, "score_ms": score_ms,
                       "sa_build_MB_per_s": text_mb / (build_ms * 1e-3) if build_ms > 0 else None,
