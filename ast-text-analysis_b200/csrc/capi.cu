@@ -1416,7 +1416,7 @@ int east_cooc_dev(const double *S_DxK_dev, int64_t D, int32_t K, double threshol
     StageTimer tm(s);
     tm.mark("cooc");
     if (get_option("cooc_variant", 0) == 1) cooc_counts(S_DxK_dev, D, K, threshold, C_KxK_dev, s);
-    else cooc_counts_tc(S_DxK_dev, D, K, threshold, C_KxK_dev, s, get_option("cooc_variant", 0) == 2);
+    else cooc_counts_tc(S_DxK_dev, D, K, threshold, C_KxK_dev, s, get_option("cooc_variant", 0) == 2 ? 1 : (get_option("cooc_variant", 0) == 3 ? 2 : 0));
     tm.finish();
     EAST_CUDA(cudaStreamSynchronize(s));
     tm.collect();
@@ -1432,7 +1432,7 @@ int east_cooc_host(const double *S_DxK, int64_t D, int32_t K, double threshold, 
     DevBuf<int32_t> d_C((size_t)K * K, s);
     EAST_CUDA(cudaMemcpyAsync(d_S.p, S_DxK, sizeof(double) * (size_t)D * K, cudaMemcpyHostToDevice, s));
     if (get_option("cooc_variant", 0) == 1) cooc_counts(d_S.p, D, K, threshold, d_C.p, s);
-    else cooc_counts_tc(d_S.p, D, K, threshold, d_C.p, s, get_option("cooc_variant", 0) == 2);
+    else cooc_counts_tc(d_S.p, D, K, threshold, d_C.p, s, get_option("cooc_variant", 0) == 2 ? 1 : (get_option("cooc_variant", 0) == 3 ? 2 : 0));
     EAST_CUDA(cudaMemcpy(C_KxK, d_C.p, sizeof(int32_t) * (size_t)K * K, cudaMemcpyDeviceToHost));
     EAST_API_END
 }

@@ -18,6 +18,7 @@
 //                          Epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> int32 stores.
 // C = B * B^T is symmetric: the CTAs below the diagonal exit at once, the others store their tile and its transpose.
 // Counts are exact: u8 products accumulated in int32 (D < 2^31).
+#include <cuda.h>   // CUtensorMap and the enums of cuTensorMapEncodeTiled (types only: libcuda is not linked)
 #include "sa_build.h"
 
 namespace east {
@@ -55,24 +56,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
-// S[d][k] >= thr  ->  Bm[k][d] (uint8), 32 x 32 transposing tiles through shared memory
+// S[d][k] >= thr  ->  Bm[k][d] (uint8): 128 (documents) x 32 (keyphrases) transposing tiles through shared memory.
+// Reads: a warp takes 32 consecutive doubles of a row of S (256 bytes), four rows in flight per thread; writes: every
+// keyphrase row of the tile leaves as 128 contiguous bytes (eight 16-byte stores).  HBM-bound: 8 D K bytes in, D K out.
+constexpr int TB_D = 128, TB_K = 32;
 __global__ void __launch_bounds__(256)
 k_threshold_bytes(const double *__restrict__ S, int64_t D, int32_t K, double thr, uint8_t *__restrict__ Bm,
                   int64_t Dp) {
-    __shared__ uint8_t tile[32][33];
+    __shared__ __align__(16) uint8_t tile[TB_K][TB_D + 16];    // [k][d]: the store phase reads 16 consecutive d of one k
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-    const int64_t d0 = (int64_t)blockIdx.x * 32;
-    const int32_t k0 = blockIdx.y * 32;
-    for (int r = ty; r < 32; r += 8) {
-        const int64_t d = d0 + r;
-        const int32_t k = k0 + tx;
-        tile[r][tx] = (d < D && k < K && S[d * K + k] >= thr) ? 1 : 0;
+    const int64_t d0 = (int64_t)blockIdx.x * TB_D;
+    const int32_t k0 = blockIdx.y * TB_K;
+    const int32_t k = k0 + tx;
+#pragma unroll
+    for (int r0 = 0; r0 < TB_D; r0 += 32) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t d = d0 + r0 + ty + 8 * u;
+            v[u] = (d < D && k < K) ? __ldcs(S + d * K + k) : -1.0;   // streamed: S is read once
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t d = d0 + r0 + ty + 8 * u;
+            tile[tx][r0 + ty + 8 * u] = (d < D && k < K && v[u] >= thr) ? 1 : 0;
+        }
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int32_t k = k0 + r;
-        const int64_t d = d0 + tx;
-        if (k < K && d < Dp) Bm[(int64_t)k * Dp + d] = tile[tx][r];
+    // thread t: keyphrase row t >> 3 of the tile, 16-byte piece t & 7 of its 128 bytes
+    const int kr = threadIdx.x >> 3, piece = threadIdx.x & 7;
+    const int32_t ko = k0 + kr;
+    const int64_t dd = d0 + 16 * piece;
+    if (ko < K && dd < Dp) {   // Dp is a multiple of 128: a piece is inside or outside as a whole
+        const uint4 out = *reinterpret_cast<const uint4 *>(&tile[kr][16 * piece]);
+        *reinterpret_cast<uint4 *>(Bm + (int64_t)ko * Dp + dd) = out;
     }
 }
 
@@ -324,18 +341,209 @@ k_cooc_umma_pipe(const uint8_t *__restrict__ Bm, int64_t Dp, int32_t K, int32_t 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA-fed cluster version (default): the same 128 x 256 tile per CTA, but
+//   * the operands arrive by TMA (cp.async.bulk.tensor.2d, SASS UTMALDG) as 128-row x 128-byte boxes in the 128-byte
+//     swizzled K-major layout the tensor cores read directly (UMMA descriptors with SWIZZLE_128B, 32-byte steps
+//     along K inside the swizzle atom): ONE thread issues the loads, nobody computes addresses;
+//   * two CTAs that own vertically adjacent tiles (same 256 columns of C = the same rows of B as their N-side operand)
+//     form a thread-block cluster: each loads ONE half of that operand and multicasts it into both CTAs' shared
+//     memory, so the pair pulls 512 operand rows per K-slab out of L2 instead of 768.  The profile of the cp.async
+//     kernel (profiles/r2): tensor pipe 15 % active, L2 -> SM traffic 126 GB per launch at 8.2 TB/s -- operand feed
+//     from L2 is the limit, not the tensor cores;
+//   * a stage is released to BOTH producers by the tcgen05.commit of both consumers (multicast commit on the
+//     stage's "empty" barriers, arrival count 2), since each producer writes into both CTAs.
+// Warps: 0 = TMA producer (one lane), 1 = MMA issuer (one lane), 2-5 = epilogue (TMEM quarter = warp & 3).
+// ------------------------------------------------------------------------------------------
+constexpr int CQ_TM = 128, CQ_TN = 256, CQ_BK = 128, CQ_STAGES = 4;
+constexpr int CQ_BOX_BYTES = 128 * CQ_BK;                          // one TMA box: 128 rows x 128 bytes = 16 KB
+constexpr int CQ_STAGE_BYTES = (CQ_TM + CQ_TN) * CQ_BK;            // A box + two B boxes = 48 KB
+constexpr int CQ_THREADS = 192;
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor: 8-row x 128-byte atoms, 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3ffffu) >> 4)        // start address, 16-byte units
+           | ((uint64_t)1 << 16)                       // leading byte offset: unused for swizzled K-major layouts
+           | ((uint64_t)(1024 >> 4) << 32)             // stride byte offset: next 8-row group
+           | (1ull << 46)                              // descriptor version 1 (sm_100)
+           | (2ull << 61);                             // layout type SWIZZLE_128B
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(CQ_THREADS, 1)
+k_cooc_umma_tma(const __grid_constant__ CUtensorMap tmap, int64_t Dp, int32_t K, int32_t *__restrict__ C) {
+    extern __shared__ __align__(1024) uint8_t cq_smem_raw[];
+    __shared__ __align__(8) uint64_t s_full[CQ_STAGES], s_empty[CQ_STAGES], s_done;
+    __shared__ uint32_t s_tmem;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t rank = cluster_ctarank();                 // 0 / 1: upper / lower tile of the pair
+    const int32_t i0 = blockIdx.y * CQ_TM, j0 = blockIdx.x * CQ_TN;
+    const int32_t pair_i0 = (int32_t)(blockIdx.y & ~1u) * CQ_TM;
+    // symmetric result: a PAIR whose columns all lie left of its rows is covered by the transposed stores of other tiles
+    // (the decision must be the same for both CTAs of a cluster: they synchronise with each other)
+    if (j0 + CQ_TN <= pair_i0) return;
+    // dynamic shared memory: the swizzle atoms need 1024-byte alignment
+    uint8_t *cq_smem = reinterpret_cast<uint8_t *>(((uintptr_t)cq_smem_raw + 1023) & ~(uintptr_t)1023);
+
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (t == 0) {
+        for (int i = 0; i < CQ_STAGES; ++i) {
+            mbar_init(smem_u32(&s_full[i]), 1);     // the producer's arrive.expect_tx; the bytes of both CTAs' loads complete it
+            mbar_init(smem_u32(&s_empty[i]), 2);    // one tcgen05.commit from each CTA of the pair
+        }
+        mbar_init(smem_u32(&s_done), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();     // the peer's barriers exist before anything of ours can land there
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem;
+    const int chunks = (int)(Dp / CQ_BK);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer
+            const uint64_t tm = reinterpret_cast<uint64_t>(&tmap);
+            for (int c = 0; c < chunks; ++c) {
+                const int st = c % CQ_STAGES, round = c / CQ_STAGES;
+                if (round > 0) mbar_wait(smem_u32(&s_empty[st]), (uint32_t)((round - 1) & 1));
+                const uint32_t full = smem_u32(&s_full[st]);
+                const uint32_t sa = smem_u32(cq_smem + st * CQ_STAGE_BYTES), sb = sa + CQ_BOX_BYTES;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"((uint32_t)CQ_STAGE_BYTES) : "memory");
+                const int32_t x = c * CQ_BK;
+                // own M-side operand: rows i0 .. i0 + 127
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(sa), "l"(tm), "r"(x), "r"(i0), "r"(full) : "memory");
+                // this CTA's half of the shared N-side operand (rows j0 + 128 rank ..), into both CTAs of the pair
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+                             "[%0], [%1, {%2, %3}], [%4], %5;"
+                             ::"r"(sb + rank * CQ_BOX_BYTES), "l"(tm), "r"(x), "r"(j0 + (int32_t)rank * 128), "r"(full), "h"((uint16_t)3)
+                             : "memory");
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(CQ_TN >> 3) << 17) | ((uint32_t)(CQ_TM >> 4) << 24);
+            for (int c = 0; c < chunks; ++c) {
+                const int st = c % CQ_STAGES, round = c / CQ_STAGES;
+                mbar_wait(smem_u32(&s_full[st]), (uint32_t)(round & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t a_base = smem_u32(cq_smem + st * CQ_STAGE_BYTES), b_base = a_base + CQ_BOX_BYTES;
+#pragma unroll
+                for (int k = 0; k < CQ_BK / 32; ++k) {
+                    const uint64_t da = umma_desc_sw128(a_base + k * 32), db = umma_desc_sw128(b_base + k * 32);
+                    const uint32_t accumulate = (c > 0 || k > 0) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+                        "}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                        : "memory");
+                }
+                // the slot goes back to BOTH producers: each of them writes into both CTAs
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                             ::"r"(smem_u32(&s_empty[st])), "h"((uint16_t)3) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_done)) : "memory");
+        }
+    } else {
+        // ---- epilogue (warps 2-5): TMEM lanes 32 q .. 32 q + 31 = rows i0 + 32 q .. of the tile, q = warp & 3
+        const int q4 = warp & 3;
+        mbar_wait(smem_u32(&s_done), 0u);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int32_t row = i0 + q4 * 32 + lane;
+#pragma unroll 1
+        for (int cb = 0; cb < CQ_TN; cb += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)cb;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < K) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int32_t colj = j0 + cb + q;
+                    if (colj < K) {
+                        C[(int64_t)row * K + colj] = (int32_t)v[q];
+                        C[(int64_t)colj * K + row] = (int32_t)v[q];   // the transposed element (same value where tiles overlap)
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    cluster_sync_all();     // nobody leaves while the peer may still signal its barriers
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+}
+
+// the tensor map of B (uint8 [Kp][Dp], 128-row x 128-byte boxes, 128-byte swizzle) through the driver entry point
+// (libcuda is not linked: the runtime hands the function out); false = no TMA on this driver, use the cp.async kernel
+static bool make_b_tensor_map(const uint8_t *Bm, int64_t Dp, int32_t Kp, CUtensorMap *out) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    static bool looked = false;
+    if (!looked) {
+        looked = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            encode = (EncodeTiled)fn;
+        else
+            cudaGetLastError();
+    }
+    if (!encode) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)Dp, (cuuint64_t)Kp};
+    const cuuint64_t gstride[1] = {(cuuint64_t)Dp};
+    const cuuint32_t box[2] = {(cuuint32_t)CQ_BK, 128u};
+    const cuuint32_t estride[2] = {1u, 1u};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(Bm), gdim, gstride, box, estride,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 void cooc_counts_tc(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s, int simple) {
     const int64_t Dp = (D + CT_BK - 1) / CT_BK * CT_BK;
     const int32_t Kp = (K + CP_TN - 1) / CP_TN * CP_TN;   // rows padded to the larger tile edge (256)
     DevBuf<uint8_t> Bm((size_t)Kp * (size_t)Dp, s);
     EAST_CUDA(cudaMemsetAsync(Bm.p, 0, (size_t)Kp * (size_t)Dp, s));  // padding rows / columns are zero
-    dim3 tg((unsigned)((Dp + 31) / 32), (unsigned)((K + 31) / 32));
+    dim3 tg((unsigned)((Dp + TB_D - 1) / TB_D), (unsigned)((K + TB_K - 1) / TB_K));
     EAST_BYTES(8.0 * (double)D * K + (double)K * Dp);
     EAST_LAUNCH(k_threshold_bytes, tg, 256, 0, s, S_DxK, D, K, threshold, Bm.p, Dp);
     const int smem = 2 * CT_STAGE_BYTES + 1024, smem_pipe = CP_STAGES * CP_STAGE_BYTES + 1024;
     ensure_dynamic_smem((const void *)k_cooc_umma, smem);
     ensure_dynamic_smem((const void *)k_cooc_umma_pipe, smem_pipe);
-    if (simple) {
+    CUtensorMap tmap;
+    if (simple == 0 && make_b_tensor_map(Bm.p, Dp, Kp, &tmap)) {
+        const int smem_tma = CQ_STAGES * CQ_STAGE_BYTES + 1024;
+        ensure_dynamic_smem((const void *)k_cooc_umma_tma, smem_tma);
+        dim3 grid(Kp / CQ_TN, Kp / CQ_TM);   // Kp is a multiple of 256: an even number of tile rows, clusters of (1, 2)
+        EAST_LAUNCH(k_cooc_umma_tma, grid, CQ_THREADS, smem_tma, s, tmap, Dp, K, C);
+    } else if (simple == 1) {
         dim3 grid(Kp / CT_TILE, Kp / CT_TILE);
         EAST_LAUNCH(k_cooc_umma, grid, CT_THREADS, smem, s, Bm.p, Dp, Kp, K, C);
     } else {

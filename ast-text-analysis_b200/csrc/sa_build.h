@@ -188,6 +188,6 @@ void fill_suffix_keys(const uint8_t *t8, const int32_t *sa, int32_t n, uint32_t 
 
 void cooc_counts(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s);     // AND + POPC
 void cooc_counts_tc(const double *S_DxK, int64_t D, int32_t K, double threshold, int32_t *C, cudaStream_t s,
-                    int simple = 0 /* 1: the non-pipelined 128 x 128 kernel */);  // tcgen05
+                    int simple = 0 /* 0: TMA-fed cluster kernel, 1: the non-pipelined 128 x 128 kernel, 2: the cp.async pipeline */);  // tcgen05
 
 }  // namespace east

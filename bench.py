@@ -811,7 +811,7 @@ def time_cooc(_capi, torch, K, D, threshold=0.5, reps=3, device=0):
         _capi.cooc_dev(S.data_ptr(), D, K, threshold, C.data_ptr(), device=device)
     ks = _capi.kernel_stats(); _capi.set_option("time_kernels", 0)
     per = {k: v["ms"] / max(v["launches"], 1) for k, v in ks.items()}
-    gemm = per.get("k_cooc_umma_pipe") or per.get("k_cooc_umma")
+    gemm = per.get("k_cooc_umma_tma") or per.get("k_cooc_umma_pipe") or per.get("k_cooc_umma")
     # spot check against a dense fp32 product of a slab (exact in fp32: counts < 2^24)
     Bs = (S[:, :256] >= threshold).to(torch.float32)
     ref = (Bs.t() @ Bs).to(torch.int32)

@@ -12,7 +12,7 @@ g = torch.Generator(device="cuda").manual_seed(1)
 S = torch.rand((D, K), dtype=torch.float64, device="cuda", generator=g)
 C = torch.empty((K, K), dtype=torch.int32, device="cuda")
 res = {}
-for variant, name in ((0, "tcgen05"), (2, "tcgen05_simple"), (1, "and_popc")):
+for variant, name in ((0, "tcgen05"), (3, "tcgen05_cp_async"), (2, "tcgen05_simple"), (1, "and_popc")):
     _capi.set_option("cooc_variant", variant)
     for _ in range(2):
         _capi.cooc_dev(S.data_ptr(), D, K, 0.5, C.data_ptr())
@@ -22,10 +22,12 @@ for variant, name in ((0, "tcgen05"), (2, "tcgen05_simple"), (1, "and_popc")):
     ks = _capi.kernel_stats(); _capi.set_option("time_kernels", 0)
     res[name] = {k: v["ms"] / v["launches"] for k, v in ks.items()}
     res[name + "_checksum"] = int(C.to(torch.int64).sum().item())
-main = res["tcgen05"].get("k_cooc_umma_pipe")
+main = res["tcgen05"].get("k_cooc_umma_tma") or res["tcgen05"].get("k_cooc_umma_pipe")
+cpa = res["tcgen05_cp_async"].get("k_cooc_umma_pipe")
 simple = res["tcgen05_simple"].get("k_cooc_umma")
 flops = 2.0 * K * K * D
 print(json.dumps({"K": K, "D": D, "ms": res, "tcgen05_TOPS": flops / (main * 1e-3) / 1e12 if main else None,
+                  "tcgen05_cp_async_TOPS": flops / (cpa * 1e-3) / 1e12 if cpa else None,
                   "tcgen05_simple_TOPS": flops / (simple * 1e-3) / 1e12 if simple else None,
                   "and_popc_equiv_TOPS": flops / (res["and_popc"]["k_cooc_popc"] * 1e-3) / 1e12,
-                  "checksums_equal": res["tcgen05_checksum"] == res["and_popc_checksum"]}))
+                  "checksums_equal": res["tcgen05_checksum"] == res["and_popc_checksum"] == res["tcgen05_cp_async_checksum"]}))
