@@ -332,6 +332,10 @@ static cudaStream_t copy_stream(int device) {
 
 // block until the tables of `idx` are complete; publishes the build's stage timings once
 static void wait_tables(const east_index *cidx) {
+    // an index is immutable for its users, but "the tables are complete" is published here, once: concurrent
+    // east_index_copy / east_index_devptr / score calls on one index take turns
+    static std::mutex m;
+    std::lock_guard<std::mutex> g(m);
     east_index *idx = const_cast<east_index *>(cidx);
     if (!idx->tables_pending) return;
     EAST_CUDA(cudaEventSynchronize(idx->ev_tables));
