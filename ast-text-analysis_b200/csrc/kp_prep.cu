@@ -9,10 +9,10 @@
 //
 //   k_kp_suffix_keys   one thread per keyphrase, backwards: 64-bit hash of every suffix, "contains a code point
 //                      >= 0x0A00" flag, end of the suffix
-//   k_kp_lexkeys       one thread per suffix: its first symbols as one 64-bit word (9 symbols of 7 bits for A-Z) or,
-//                      for wide alphabets, two (12 bits per code point: 2 x 5 symbols)
-//   radix sort x 2-3   the library's own onesweep LSD sort, stable: by 32 hash bits, then by the symbol word(s)
-//                      -> lexicographic by the first symbols, identical suffixes adjacent (equal hash)
+//   k_kp_sortkeys      one thread per suffix: ONE 64-bit key = its first symbols (42 bits: 6 symbols of 7 bits for A-Z,
+//                      3 of 12 bits for wide alphabets) above 22 hash bits
+//   radix sort         the library's own onesweep LSD sort (8 passes) -> lexicographic by the first symbols, identical
+//                      suffixes adjacent (equal key)
 //   k_kp_mark          a suffix that equals its predecessor code point by code point (hash, length and a full
 //                      comparison: a hash collision only costs a redundant walk, never a wrong twin) is a
 //                      duplicate; every other one is the head of a group of identical suffixes
@@ -43,7 +43,7 @@ k_kp_suffix_keys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ of
             h = h * 0x100000001b3ull + (uint64_t)cp + 0x632be59bd9b4e019ull;
             h ^= h >> 29;
             if (cp >= EAST_TERM_BASE) w = 1;
-            hash[p] = h >> 32;     // 32 bits order the groups; identity is decided by comparing the code points
+            hash[p] = h;
             vals[p] = (uint32_t)p;
             send[p] = e;
             weird[p] = w;
@@ -51,30 +51,20 @@ k_kp_suffix_keys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ of
     }
 }
 
-// the first 2 * per_word symbols of every suffix as two words of per_word symbols, sym_bits bits each (symbol = code
-// point + 1, clamped; 0 = past the end of the keyphrase)
+// ONE 64-bit sort key per suffix: its first symbols (sym_bits bits each: code point + 1, clamped; 0 = past the end of the
+// keyphrase) in the high lex_bits, hash bits below.  Sorted by it the suffixes are lexicographic by their first symbols
+// and identical suffixes are adjacent; different suffixes that share the key only cost a redundant walk.
 __global__ void __launch_bounds__(256)
-k_kp_lexkeys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ send, int32_t total, int sym_bits, int per_word,
-             uint64_t *__restrict__ lex0, uint64_t *__restrict__ lex1) {
+k_kp_sortkeys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ send, const uint64_t *__restrict__ hash, int32_t total,
+              int sym_bits, int n_sym, uint64_t *__restrict__ keys) {
     const uint32_t top = (1u << sym_bits) - 1u;
+    const int hash_bits = 64 - n_sym * sym_bits;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
         const int32_t e = send[p];
-        uint64_t w0 = 0ull, w1 = 0ull;
-        for (int q = 0; q < per_word; ++q) w0 = (w0 << sym_bits) | (uint64_t)((p + q < e) ? min(kp[p + q] + 1u, top) : 0u);
-        if (lex1) for (int q = per_word; q < 2 * per_word; ++q) w1 = (w1 << sym_bits) | (uint64_t)((p + q < e) ? min(kp[p + q] + 1u, top) : 0u);
-        lex0[p] = w0;
-        if (lex1) lex1[p] = w1;
+        uint64_t w = 0ull;
+        for (int q = 0; q < n_sym; ++q) w = (w << sym_bits) | (uint64_t)((p + q < e) ? min(kp[p + q] + 1u, top) : 0u);
+        keys[p] = (w << hash_bits) | (hash[p] >> (64 - hash_bits));
     }
-}
-
-__global__ void __launch_bounds__(256)
-k_kp_gather(const uint64_t *__restrict__ src, const uint32_t *__restrict__ vals, int32_t total, uint64_t *__restrict__ keys) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) keys[i] = src[vals[i]];
-}
-
-__global__ void __launch_bounds__(256)
-k_kp_identity(uint32_t *__restrict__ vals, int32_t total) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) vals[i] = (uint32_t)i;
 }
 
 // block-wide inclusive scan of one 0/1 flag per thread (KP_THREADS threads); returns the inclusive count, *total = block sum
@@ -201,7 +191,7 @@ void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, co
     kp.d_n_uniq = DevBuf<uint32_t>(1, s);
     EAST_CUDA(cudaMemcpyAsync(kp.d_off.p, kp.off32.data(), sizeof(int32_t) * ((size_t)K + 1), cudaMemcpyHostToDevice, s));
 
-    DevBuf<uint64_t> hash((size_t)total, s), lex0, lex1, keys_a, keys_b;
+    DevBuf<uint64_t> hash((size_t)total, s), keys_a, keys_b;
     DevBuf<uint32_t> vals_a((size_t)total, s), vals_b;
     DevBuf<int32_t> send((size_t)total, s);
     DevBuf<uint8_t> weird((size_t)total, s), flags((size_t)total, s);
@@ -210,33 +200,22 @@ void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, co
     EAST_LAUNCH(k_kp_suffix_keys, grid_for(K, 256, 8), 256, 0, s, kp_dev, kp.d_off.p, K, hash.p, vals_a.p, send.p, weird.p);
     const uint32_t *order = vals_a.p;
     if (dedup) {
-        // symbol width from the largest code point (the host has the keyphrases; without a host copy: the full 12 bits).
-        // Narrow symbols (7 bits for A-Z) put 9 of them into ONE 64-bit word: two sorts instead of three.
+        // symbol width from the largest code point (the host has the keyphrases; without a host copy: the full 12 bits);
+        // 42 bits of symbols (6 seven-bit symbols for A-Z) + 22 hash bits: one 8-pass sort
         int sym_bits = KP_MAX_SYM_BITS;
         if (kp_host) {
             uint32_t mx = 0;
             for (int32_t p = 0; p < total; ++p) mx = std::max(mx, kp_host[p]);
             sym_bits = std::min(KP_MAX_SYM_BITS, std::max(1, bits_for((uint64_t)mx + 1)));
         }
-        const int per_word = 64 / sym_bits;
-        const bool two_words = per_word < 8;
-        lex0 = DevBuf<uint64_t>((size_t)total, s);
-        if (two_words) lex1 = DevBuf<uint64_t>((size_t)total, s);
+        const int n_sym = std::max(1, 42 / sym_bits);
         keys_a = DevBuf<uint64_t>((size_t)total, s); keys_b = DevBuf<uint64_t>((size_t)total, s);
         vals_b = DevBuf<uint32_t>((size_t)total, s);
         DevBuf<uint32_t> hist(256 * RS_MAX_PASSES, s);
         DevBuf<uint8_t> scratch(rs_scratch_bytes(total, RS_MAX_PASSES), s);
-        EAST_LAUNCH(k_kp_lexkeys, grid_for(total, 256, 8), 256, 0, s, kp_dev, send.p, total, sym_bits, per_word, lex0.p, lex1.p);
-        uint32_t *va = vals_a.p, *vb = vals_b.p;
-        const uint64_t *srcs[3] = {hash.p, lex1.p, lex0.p};
-        const int bits[3] = {32, per_word * sym_bits, per_word * sym_bits};
-        for (int round = 0; round < 3; ++round) {
-            if (!srcs[round]) continue;
-            EAST_LAUNCH(k_kp_gather, grid_for(total, 256, 8), 256, 0, s, srcs[round], va, total, keys_a.p);
-            const int cur = radix_sort_pairs(keys_a.p, keys_b.p, va, vb, total, bits[round], hist.p, false, scratch.p, s);
-            if (cur) std::swap(va, vb);
-        }
-        order = va;
+        EAST_LAUNCH(k_kp_sortkeys, grid_for(total, 256, 8), 256, 0, s, kp_dev, send.p, hash.p, total, sym_bits, n_sym, keys_a.p);
+        const int cur = radix_sort_pairs(keys_a.p, keys_b.p, vals_a.p, vals_b.p, total, 64, hist.p, false, scratch.p, s);
+        order = cur ? vals_b.p : vals_a.p;
     }
     EAST_LAUNCH(k_kp_mark, nb, KP_THREADS, 0, s, kp_dev, hash.p, send.p, order, total, dedup ? 1 : 0, flags.p, bsum.p);
     EAST_LAUNCH(k_kp_scan_blocks, 1, KP_THREADS, 0, s, bsum.p, nb, kp.d_n_uniq.p);
