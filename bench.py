@@ -89,6 +89,24 @@ def cpu_sample(n_docs, doc_bytes, n_kps, procs):
     return json.loads(out.decode().strip().splitlines()[-1])
 
 
+def oracle_check(sample, kp_codes, kp_off, normalized):
+    """Rows of a score table against the CPU oracle, in a subprocess (oracle/check_rows.py): the benchmark process
+    itself loads nothing from oracle/.  sample: [(packed uint32 document, m, float64 row)]."""
+    import tempfile
+    import numpy as np
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "rows.npz")
+        arrays = {"kp_codes": kp_codes, "kp_off": kp_off, "normalized": np.array(bool(normalized)), "n_rows": np.array(len(sample))}
+        for i, (text, m, row) in enumerate(sample):
+            arrays["text_%d" % i] = np.ascontiguousarray(text, dtype=np.uint32)
+            arrays["m_%d" % i] = np.array(int(m))
+            arrays["row_%d" % i] = np.ascontiguousarray(row, dtype=np.float64)
+        np.savez(path, **arrays)
+        out = subprocess.check_output([sys.executable, os.path.join(ROOT, "oracle", "check_rows.py"), path],
+                                      stderr=subprocess.DEVNULL, timeout=1500)
+    return json.loads(out.decode().strip().splitlines()[-1])
+
+
 def cpu_sample_size(args):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
@@ -482,24 +500,21 @@ def run_b200(args):
     parity = {"checked": False}
     if rank == 0 and not os.environ.get("EAST_BENCH_NO_PARITY"):
         try:
-            from oracle import oracle as oracle_mod
-            oracle_mod.build()
             rows = sorted(set([0, 1, D // 2, D - 1] + list(range(3, D, max(1, D // 14)))))[:18]
-            bad = 0
-            for d in rows:
-                exp = oracle_mod.OracleEASA(text=packed[d], m=int(doc_m[d])).score_many(kp_codes, kp_off, True)
-                bad += int(not np.array_equal(exp.view(np.uint64), host_out_np[d].view(np.uint64)))
+            sample = [(packed[d], int(doc_m[d]), host_out_np[d]) for d in rows]
             other = 0
             if world > 1:
                 g = gathered.view(world, D, K)
                 for r in sorted(set([1, world - 1])):
                     for j in (0, D - 1):
                         col = utils.text_to_strings_collection(synth.documents(1, args.doc_bytes, first_seed=1 + r * args.docs + j)[0])
-                        exp = oracle_mod.OracleEASA(col).score_many(kp_codes, kp_off, True)
-                        bad += int(not np.array_equal(exp.view(np.uint64), g[r, j].cpu().numpy().view(np.uint64)))
+                        sample.append((asts_utils.pack_strings_collection(col), len(col), g[r, j].cpu().numpy()))
                         other += 1
-            parity = {"checked": True, "rows_vs_oracle": len(rows), "rows_of_other_ranks": other, "mismatching_rows": bad,
-                      "how": "bit-exact comparison of fp64 rows with oracle/east_oracle.c after the timed region"}
+            res = oracle_check(sample, kp_codes, kp_off, True)
+            parity = {"checked": True, "rows_vs_oracle": len(rows), "rows_of_other_ranks": other,
+                      "mismatching_rows": res["mismatching_rows"],
+                      "how": "bit-exact comparison of fp64 rows with oracle/east_oracle.c (oracle/check_rows.py, a subprocess) "
+                             "after the timed region"}
         except Exception as e:  # noqa: BLE001
             parity = {"checked": False, "error": repr(e)}
     if world > 1:
@@ -767,16 +782,13 @@ def run_config4(args):
     parity = {"checked": False}
     if rank == 0 and not os.environ.get("EAST_BENCH_NO_PARITY"):
         try:
-            from oracle import oracle as oracle_mod
-            oracle_mod.build()
             table = (gathered if world > 1 else out_dev)
             first_tile = min(T, D)
-            bad, rows = 0, [0, 1, first_tile // 2, first_tile - 1]
-            for d in rows:
-                exp = oracle_mod.OracleEASA(text=host_text[doc_off[d]:doc_off[d + 1]], m=int(doc_m[d])).score_many(kp_codes, kp_off, True)
-                got = table[d * K:(d + 1) * K].cpu().numpy()
-                bad += int(not np.array_equal(exp.view(np.uint64), got.view(np.uint64)))
-            parity = {"checked": True, "rows_vs_oracle": len(rows), "scores_vs_oracle": len(rows) * K, "mismatching_rows": bad}
+            rows = [0, 1, first_tile // 2, first_tile - 1]
+            sample = [(host_text[doc_off[d]:doc_off[d + 1]], int(doc_m[d]), table[d * K:(d + 1) * K].cpu().numpy()) for d in rows]
+            res = oracle_check(sample, kp_codes, kp_off, True)
+            parity = {"checked": True, "rows_vs_oracle": len(rows), "scores_vs_oracle": len(rows) * K,
+                      "mismatching_rows": res["mismatching_rows"]}
         except Exception as e:  # noqa: BLE001
             parity = {"checked": False, "error": repr(e)}
     if rank == 0:
