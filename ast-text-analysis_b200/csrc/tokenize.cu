@@ -11,6 +11,10 @@
 //   word characters   0-9 A-Z a-z _ ' and every Cyrillic letter of the block
 //   upper()           a-z -> A-Z;  U+0430-044F -> U+0410-042F;  U+0450-045F -> U+0400-040F  (all 1:1)
 //   isdigit()         0-9
+// plus, as separators only (not word characters, no case mapping): the controls and signs of U+0080-00BF that Python does
+// not count as alphanumeric (no-break space, guillemets, section / degree / copyright signs ...), General Punctuation
+// U+2000-206F (dashes, typographic quotation marks, ellipsis), the numero sign U+2116 and the byte order mark U+FEFF --
+// what Russian and English running text actually contains besides letters.
 // Any other byte (another lead byte, a stray continuation byte, invalid UTF-8) flags the text: the caller sends the
 // collection through the host preprocessing instead (Python's full Unicode tables).
 //
@@ -30,6 +34,12 @@ constexpr int TK_THREADS = 512;
 
 struct TkChar { uint32_t cp; int len; bool word, digit, bad; };
 
+// U+0080 + i, i = 0 .. 63: bit i set = the character is NOT a word character and has no case mapping (controls, no-break
+// space, currency and typographic signs, the guillemets ...); clear = ª ² ³ µ ¹ º ¼ ½ ¾, which Python counts as
+// alphanumeric (or upper-cases into another block): those flag the text.  Checked against Python's re / str.upper for
+// every code point in tests/test_gpu_size.py.
+constexpr uint64_t TK_LATIN1_SEPARATORS = 0x89d3fbffffffffffull;
+
 // the code point that starts at byte i (i is not a continuation byte), upper-cased
 __device__ __forceinline__ TkChar tk_decode(const uint8_t *__restrict__ p, int64_t i, int64_t end) {
     TkChar c;
@@ -42,8 +52,9 @@ __device__ __forceinline__ TkChar tk_decode(const uint8_t *__restrict__ p, int64
         c.cp = lower ? b - 32u : b;
         return c;
     }
-    if ((b == 0xd0u || b == 0xd1u) && i + 1 < end && (p[i + 1] & 0xc0u) == 0x80u) {
-        uint32_t cp = ((b & 0x1fu) << 6) | (p[i + 1] & 0x3fu);
+    const uint32_t b1 = (i + 1 < end) ? p[i + 1] : 0u;
+    if ((b == 0xd0u || b == 0xd1u) && (b1 & 0xc0u) == 0x80u) {          // U+0400 .. 047F: the Cyrillic block up to 045F
+        uint32_t cp = ((b & 0x1fu) << 6) | (b1 & 0x3fu);
         c.len = 2;
         c.word = true;
         if (cp > 0x45fu) c.bad = true;
@@ -52,15 +63,41 @@ __device__ __forceinline__ TkChar tk_decode(const uint8_t *__restrict__ p, int64
         c.cp = cp;
         return c;
     }
+    if (b == 0xc2u && (b1 & 0xc0u) == 0x80u) {                           // U+0080 .. 00BF: separators only
+        c.len = 2; c.word = false; c.cp = 0x80u + (b1 & 0x3fu);
+        c.bad = ((TK_LATIN1_SEPARATORS >> (b1 & 0x3fu)) & 1ull) == 0ull;
+        return c;
+    }
+    const uint32_t b2 = (i + 2 < end) ? p[i + 2] : 0u;
+    if ((b == 0xe2u || b == 0xefu) && (b1 & 0xc0u) == 0x80u && (b2 & 0xc0u) == 0x80u) {
+        // three bytes: General Punctuation U+2000 .. 206F (dashes, quotation marks, ellipsis, spaces), the numero sign
+        // U+2116 and the byte order mark U+FEFF -- none of them a word character, none with a case mapping
+        const uint32_t cp = ((b & 0x0fu) << 12) | ((b1 & 0x3fu) << 6) | (b2 & 0x3fu);
+        c.len = 3; c.word = false; c.cp = cp;
+        c.bad = !((cp >= 0x2000u && cp <= 0x206fu) || cp == 0x2116u || cp == 0xfeffu);
+        return c;
+    }
     c.bad = true; c.word = false; c.cp = 0xfffdu;
     return c;
 }
 
 // is the code point that ENDS at byte i - 1 a word character (i > begin)
-__device__ __forceinline__ bool tk_prev_is_word(const uint8_t *__restrict__ p, int64_t i) {
+__device__ __forceinline__ bool tk_prev_is_word(const uint8_t *__restrict__ p, int64_t i, int64_t begin) {
     const uint32_t b = p[i - 1];
-    if (b >= 0x80u) return true;   // second byte of a Cyrillic letter (anything else flags the text anyway)
-    return (b >= 'a' && b <= 'z') || (b >= '0' && b <= '9') || (b >= 'A' && b <= 'Z') || b == '_' || b == '\'';
+    if (b < 0x80u) return (b >= 'a' && b <= 'z') || (b >= '0' && b <= '9') || (b >= 'A' && b <= 'Z') || b == '_' || b == '\'';
+    // the last byte of a multi-byte character: only the Cyrillic letters (lead bytes D0 / D1, two bytes) are word characters
+    if (i - 2 < begin) return false;
+    const uint32_t lead = p[i - 2];
+    return lead == 0xd0u || lead == 0xd1u;
+}
+
+// a continuation byte at i: does a lead byte the tokenizer accepts claim it (anything else flags the text)
+__device__ __forceinline__ bool tk_continuation_ok(const uint8_t *__restrict__ p, int64_t i, int64_t begin) {
+    if (i - 1 < begin) return false;
+    const uint32_t a = p[i - 1];
+    if (a >= 0xc0u) return true;                                         // second byte of a 2- or 3-byte sequence
+    if ((a & 0xc0u) != 0x80u || i - 2 < begin) return false;
+    return p[i - 2] >= 0xe0u;                                            // third byte of a 3-byte sequence
 }
 
 // block-wide exclusive scan of two counters per thread; totals to everybody
@@ -102,13 +139,13 @@ k_tokenize(const uint8_t *__restrict__ raw, const int64_t *__restrict__ raw_off,
     bool bad = false;
     for (int64_t i = c0; i < c1;) {
         if ((p[i] & 0xc0u) == 0x80u) {   // continuation byte: belongs to the code point before it
-            if (i == begin || p[i - 1] < 0xc0u) bad = true;   // ... which must be a lead byte right before
+            if (!tk_continuation_ok(p, i, begin)) bad = true;
             ++i;
             continue;
         }
         TkChar c = tk_decode(p, i, end);
         bad = bad || c.bad;
-        if (!c.word || (i > begin && tk_prev_is_word(p, i))) { i += c.len; continue; }
+        if (!c.word || (i > begin && tk_prev_is_word(p, i, begin))) { i += c.len; continue; }
         // a token starts here: walk it to its end
         uint32_t tl = 0;
         bool all_digits = true;
@@ -145,7 +182,7 @@ k_tokenize(const uint8_t *__restrict__ raw, const int64_t *__restrict__ raw_off,
     for (int64_t i = c0; i < c1;) {
         if ((p[i] & 0xc0u) == 0x80u) { ++i; continue; }
         TkChar c = tk_decode(p, i, end);
-        if (!c.word || (i > begin && tk_prev_is_word(p, i))) { i += c.len; continue; }
+        if (!c.word || (i > begin && tk_prev_is_word(p, i, begin))) { i += c.len; continue; }
         uint32_t tl = 0;
         bool all_digits = true;
         int64_t e = i;

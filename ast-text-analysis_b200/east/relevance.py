@@ -19,7 +19,11 @@ from east.asts import utils as asts_utils
 
 import re
 
-_DEVICE_TEXT_RE = re.compile(r"[\x00-\x7f\u0400-\u045f]*\Z")   # what csrc/tokenize.cu handles
+# what csrc/tokenize.cu handles: ASCII, the Cyrillic block up to U+045F and -- as separators -- the non-alphanumeric signs of
+# U+0080-00BF (mask TK_LATIN1_SEPARATORS), General Punctuation, the numero sign and the byte order mark
+_LATIN1_SEPARATORS = 0x89d3fbffffffffff
+_DEVICE_TEXT_RE = re.compile("[\\x00-\\x7f\\u0400-\\u045f\\u2000-\\u206f\\u2116\\ufeff%s]*\\Z" % "".join(
+    "\\x%02x" % (0x80 + i) for i in range(64) if (_LATIN1_SEPARATORS >> i) & 1))
 SMALL_DOCUMENT_LIMIT = 65535   # code points: the per-document shared-memory kernel (csrc/doc_sort.cu) takes these
 MAX_BATCH_CODE_POINTS = 1 << 29   # one device index addresses < 2^30 code points (int32 ranks)
 
@@ -138,7 +142,7 @@ class ASTRelevanceMeasure(RelevanceMeasure):
             elif t.isascii():
                 size = len(t)
             elif _DEVICE_TEXT_RE.match(t):
-                size = 2 * len(t)
+                size = 3 * len(t)   # bound on the UTF-8 size
             else:
                 return False
             if size > SMALL_DOCUMENT_LIMIT - 2:

@@ -369,12 +369,27 @@ def test_device_preprocessing_equals_text_to_strings_collection(golden):
         got = packed[doc_off[d]:doc_off[d + 1]]
         assert np.array_equal(got, exp[d]), (d, edge[d][:60], got[:20], exp[d][:20])
         assert doc_m[d] == len(cols[d])
+    # every code point the device accepts, against Python's own tables: between letters, doubled, next to digits, at both ends
+    from east import relevance
+    accepted = [c for c in list(range(0x80)) + list(range(0x80, 0xC0)) + list(range(0x400, 0x460)) + list(range(0x2000, 0x2070)) +
+                [0x2116, 0xFEFF] if relevance._DEVICE_TEXT_RE.match(chr(c))]
+    assert len(accepted) == 128 + 55 + 96 + 112 + 2
+    per_cp = ["%sab%scd%s%sxyz 12%s3 %sэюя%sABC%s" % ((chr(c),) * 8) for c in accepted]
+    cols_cp, exp_cp = _host_packed(per_cp)
+    packed_cp, off_cp, m_cp = capi.texts_to_packed(per_cp)
+    for d, c in enumerate(accepted):
+        assert np.array_equal(packed_cp[off_cp[d]:off_cp[d + 1]], exp_cp[d]), (hex(c), cols_cp[d])
+    russian = "«Положение о зачётах» – документ №5… утверждён 12.03.2014 г. (см. п. 3.1–3.4); «ёлки-палки», it's ok"
+    cols_r, exp_r = _host_packed([russian])
+    packed_r, off_r, m_r = capi.texts_to_packed([russian])
+    assert np.array_equal(packed_r, exp_r[0]) and m_r[0] == len(cols_r[0])
     # bytes go in as they are
     p2, o2, m2 = capi.texts_to_packed([t.encode("utf-8") for t in edge[:30]])
     assert np.array_equal(p2, packed[: doc_off[30]]) and np.array_equal(o2, doc_off[:31])
     # what the device does not handle is refused, never approximated
     for bad in ("café au lait", "中文 text", "emoji \U0001F600 here", b"broken \xff\xfe utf8", b"cut \xd0", "Ѡ beyond the block",
-                b"stray \x80 continuation"):
+                b"stray \x80 continuation", "x² squared", "µm", "½ cup", "ª", b"cut \xe2\x80", b"\xe2\x80\x93\x93 one continuation too many",
+                "superscript \u2070", "\u20ac euro", b"overlong \xc0\x80", b"\xc2 alone"):
         with pytest.raises(capi.UnsupportedText):
             capi.texts_to_packed(["fine text here", bad])
 
@@ -412,3 +427,38 @@ def test_keyphrases_table_from_raw_texts_in_one_call(oracle_mod):
     t_mixed = applications.keyphrases_table(kps, texts, relevance.ASTRelevanceMeasure("easa", True))
     for kp in kps:
         assert float(t_mixed[kp]["t5"]).hex() == float(t_host[kp]["t5"]).hex()
+
+
+def test_reference_sample_corpus_from_raw_text(golden):
+    # the reference's own sample corpus (doc/samples: 30 Russian texts x 17 keyphrases), from RAW text: the device
+    # preprocessing must give the strings collections the reference produced, and applications.keyphrases_table /
+    # keyphrases_graph -- which now take the raw-text engine call on their own -- the reference's tables and graphs
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    from east import applications, relevance
+    capi = _capi()
+    hse = golden["hse"]
+    with open(os.path.join(GOLDEN_DIR, "hse_texts.json"), encoding="utf-8") as f:
+        raw = json.load(f)
+    names = [d["name"] for d in hse["docs"]]
+    packed, doc_off, doc_m = capi.texts_to_packed([raw[n] for n in names])
+    for j, d in enumerate(hse["docs"]):
+        seg = packed[doc_off[j]:doc_off[j + 1]]
+        strs = "".join(chr(x) if x < 0x0A00 else "\n" for x in seg).split("\n")[:-1]
+        assert strs == d["strings"], d["name"]
+    texts = {n: raw[n] for n in names}
+    kps = hse["keyphrases"]
+    for normalized, key in ((True, "table_norm"), (False, "table_denorm")):
+        measure = relevance.ASTRelevanceMeasure("easa", normalized)
+        table = applications.keyphrases_table(kps, texts, measure)
+        assert measure.asts[0]._strings_collection is None     # the raw-text path was taken
+        for kp in kps:
+            for n in names:
+                assert float(table[kp][n]).hex() == hse[key][kp][n], (kp, n)
+    for g in hse["graphs"]:
+        graph = applications.keyphrases_graph(kps, texts, referral_confidence=g["c"], relevance_threshold=g["r"],
+                                              support_threshold=g["p"], similarity_measure=relevance.ASTRelevanceMeasure("easa", True))
+        assert graph["nodes"] == g["nodes"]
+        assert [(e["source"], e["target"], float(e["confidence"]).hex()) for e in graph["edges"]] == \
+               [(e["source"], e["target"], e["confidence"]) for e in g["edges"]]

@@ -132,3 +132,52 @@ def test_plan_batches_separates_large_documents_and_bounds_the_batch():
     assert plan_batches([]) == []
     flat = sorted(j for b in plan_batches(list(range(1, 200)), small_limit=50, max_batch=300) for j in b)
     assert flat == list(range(199))
+
+
+def test_host_preprocessing_reproduces_the_reference_on_its_sample_corpus(golden):
+    # raw texts of doc/samples (tests/golden/hse_texts.json) -> the strings collections the REFERENCE produced (golden.json)
+    import json
+    from east import utils
+    with open(os.path.join(ROOT, "tests", "golden", "hse_texts.json"), encoding="utf-8") as f:
+        texts = json.load(f)
+    assert len(texts) == len(golden["hse"]["docs"]) == 30
+    for d in golden["hse"]["docs"]:
+        assert utils.text_to_strings_collection(texts[d["name"]]) == d["strings"], d["name"]
+
+
+def test_narrow_packing_and_batch_planning():
+    from east import relevance
+    from east.asts import utils as au
+    col = ["AB", "C D", "XYZ"]
+    p8, p32 = au.pack_strings_collection_u8(col), au.pack_strings_collection(col)
+    assert p8.dtype == np.uint8 and p8.size == p32.size
+    assert p8.tolist() == [65, 66, 255, 67, 32, 68, 255, 88, 89, 90, 255]
+    assert [int(x) for x in p32[p32 >= 0x0A00]] == [0x0A00, 0x0A01, 0x0A02]
+    assert np.array_equal(np.where(p8 == 255, 0, p8), np.where(p32 >= 0x0A00, 0, p32))
+    assert au.pack_strings_collection_u8(["ÿ"]) is None and au.pack_strings_collection_u8(["Ж"]) is None
+    assert au.pack_strings_collection_u8(["été"]) is not None      # Latin-1 fits one byte per code point
+    # small and large documents go to separate device batches; no batch exceeds the limit
+    assert relevance.plan_batches([10, 70000, 20, 30]) == [[0, 2, 3], [1]]
+    assert relevance.plan_batches([5, 5, 5], small_limit=10, max_batch=10) == [[0, 1], [2]]
+    assert relevance.plan_batches([]) == []
+    # what the device preprocessing accepts (mirror of csrc/tokenize.cu)
+    ok = relevance._DEVICE_TEXT_RE.match
+    assert ok("plain ASCII, it's 100% fine_") and ok("«Привет» – №5…") and ok("﻿BOM first")
+    assert not ok("café") and not ok("x²") and not ok("中文") and not ok("Ѡ")
+
+
+def test_graph_from_cooccurrence_matches_the_reference_graphs(golden):
+    # the graph assembly (applications.py:115-149) from exact co-occurrence counts computed on the host from the golden table
+    from east import applications
+    hse = golden["hse"]
+    kps = hse["keyphrases"]
+    names = [d["name"] for d in hse["docs"]]
+    table = np.array([[float.fromhex(hse["table_norm"][kp][n]) for kp in kps] for n in names])
+    for g in hse["graphs"]:
+        B = (table >= g["r"]).astype(np.int64)
+        graph = applications.graph_from_cooccurrence(kps, kps, (B.T @ B).astype(np.int32), g["c"], g["r"], g["p"])
+        assert graph["nodes"] == g["nodes"]
+        assert [(e["source"], e["target"], float(e["confidence"]).hex()) for e in graph["edges"]] == \
+               [(e["source"], e["target"], e["confidence"]) for e in g["edges"]]
+    with pytest.raises(KeyError):
+        applications.graph_from_cooccurrence(["a", ""], ["a"], np.zeros((1, 1), dtype=np.int32), 0.5, 0.5, 1)
