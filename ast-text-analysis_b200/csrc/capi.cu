@@ -285,7 +285,7 @@ struct east_index {
     uint32_t *sk = nullptr;         // fast path: text bytes at offsets 2..5 of every suffix, in rank order
     std::vector<uint8_t> code_table;
     int sym_bits = 0, term_code = 0;
-    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0, tables_fused = 0, pipelined = 0, pipeline_miss = 0;
+    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0, tables_fused = 0, pipelined = 0, pipeline_miss = 0, alphabet_miss = 0;
     uint32_t active_after_round0 = 0;
     // LCP / child / annotation tables are produced on an auxiliary stream after the suffix array is
     // final, so a score call (which needs only SA + text) overlaps them; readers wait on ev_tables
@@ -541,6 +541,8 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
                        !in.segmented_sort || !in.local_group_sort) ? 0 : 1;
         in.want_bkt3 = get_option("no_bkt3", 0) ? 0 : 1;
         in.light_scan = get_option("no_light_scan", 0) ? 0 : 1;
+        // device-resident batches: alphabet from the first 2 M code points (option alphabet_sample; -1 = the whole text)
+        { const int64_t smp = get_option("alphabet_sample", (int64_t)1 << 21); in.alphabet_sample = smp < 0 ? 0 : smp; }
         in.fused_encode = get_option("no_fused_encode", 0) ? 0 : 1;
         if (!get_option("no_suffix_keys", 0)) {
             idx->sk = (uint32_t *)take32((size_t)n);
@@ -570,7 +572,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         SaOutput so;
         so.sa = idx->sa;
         build_suffix_array(in, so, tm, s);
-        idx->pipelined = so.pipelined; idx->pipeline_miss = so.pipeline_miss;
+        idx->pipelined = so.pipelined; idx->pipeline_miss = so.pipeline_miss; idx->alphabet_miss = so.alphabet_miss;
         idx->rounds = so.rounds; idx->fast_path = so.fast_path; idx->key_chars = so.key_chars;
         idx->key_bits = so.key_bits; idx->active_after_round0 = so.active_after_round0;
         idx->doc_sorted = so.doc_sorted; idx->doc_sort_overflow = so.doc_sort_overflow;
@@ -759,6 +761,7 @@ int east_index_stat(const east_index *idx, const char *name, int64_t *value) {
     else if (!strcmp(name, "bkt3")) *value = idx->bkt3 != nullptr;
     else if (!strcmp(name, "pipelined")) *value = idx->pipelined;
     else if (!strcmp(name, "pipeline_miss")) *value = idx->pipeline_miss;
+    else if (!strcmp(name, "alphabet_miss")) *value = idx->alphabet_miss;
     else if (!strcmp(name, "key_chars")) *value = idx->key_chars;
     else if (!strcmp(name, "key_bits")) *value = idx->key_bits;
     else if (!strcmp(name, "rounds")) *value = idx->rounds;

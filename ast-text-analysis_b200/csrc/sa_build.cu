@@ -991,6 +991,27 @@ static DevBuf<T> take(const SaInput &in, size_t count, cudaStream_t s) {
     return in.arena ? in.arena->take<T>(count, s) : DevBuf<T>(count, s);
 }
 
+// An alphabet taken from PART of the text (run 0 of a pipelined build, the sampled prefix of a device-resident one) may
+// lack a rare letter or digit that the rest uses, and a miss costs a second build.  A code that the text never uses costs
+// nothing as long as the symbol width stays the same: a class of ASCII symbols (A-Z, a-z, 0-9) that the part has met at all
+// is completed when that fits.  present: bitmap of the code points seen (updated); extra: what was added (code points < 128).
+static void complete_symbol_classes(uint32_t *present, uint32_t extra[4]) {
+    int seen = 0;
+    for (int w = 0; w < (int)(EAST_TERM_BASE / 32); ++w) seen += __builtin_popcount(present[w]);
+    const int width = bits_for((uint64_t)seen + 1);
+    int room = (1 << width) - 1 - (seen + 1);   // codes 1..sigma and sigma + 1 for the terminators must fit `width` bits
+    const int classes[3][2] = {{'A', 'Z'}, {'a', 'z'}, {'0', '9'}};
+    for (auto &cl : classes) {
+        int have = 0, lack = 0;
+        for (int c = cl[0]; c <= cl[1]; ++c) (present[c >> 5] & (1u << (c & 31))) ? ++have : ++lack;
+        if (have == 0 || lack == 0 || lack > room) continue;
+        for (int c = cl[0]; c <= cl[1]; ++c)
+            if (!(present[c >> 5] & (1u << (c & 31)))) extra[c >> 5] |= 1u << (c & 31);
+        room -= lack;
+    }
+    for (int w = 0; w < 4; ++w) present[w] |= extra[w];
+}
+
 static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s, uint32_t &doc_sort_flags) {
     const int32_t n = in.n;
     const int D = in.n_docs;
@@ -1006,27 +1027,10 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     ScanResult first;
     EAST_CUDA(cudaMemcpyAsync(&first, d_first.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
     EAST_CUDA(cudaStreamSynchronize(s));
-    // The alphabet of run 0 (a few dozen documents) may lack a rare letter or digit that later runs use, and a miss
-    // costs a second, ordinary build.  A code that the text never uses costs nothing as long as the symbol width
-    // stays the same: a class of ASCII symbols (A-Z, a-z, 0-9) that run 0 has met at all is completed when that fits.
+    // the alphabet of run 0 (a few dozen documents), with the ASCII classes it has met completed
     uint32_t *present = first.present;
     uint32_t extra[4] = {0u, 0u, 0u, 0u};
-    {
-        int seen = 0;
-        for (int w = 0; w < (int)(EAST_TERM_BASE / 32); ++w) seen += __builtin_popcount(present[w]);
-        const int width = bits_for((uint64_t)seen + 1);
-        int room = (1 << width) - 1 - (seen + 1);   // codes 1..sigma and sigma + 1 for the terminators must fit `width` bits
-        const int classes[3][2] = {{'A', 'Z'}, {'a', 'z'}, {'0', '9'}};
-        for (auto &cl : classes) {
-            int have = 0, lack = 0;
-            for (int c = cl[0]; c <= cl[1]; ++c) (present[c >> 5] & (1u << (c & 31))) ? ++have : ++lack;
-            if (have == 0 || lack == 0 || lack > room) continue;
-            for (int c = cl[0]; c <= cl[1]; ++c)
-                if (!(present[c >> 5] & (1u << (c & 31)))) extra[c >> 5] |= 1u << (c & 31);
-            room -= lack;
-        }
-        for (int w = 0; w < 4; ++w) present[w] |= extra[w];
-    }
+    complete_symbol_classes(present, extra);
     int sigma = 0;
     std::vector<uint8_t> table(EAST_TERM_BASE, 0);
     for (uint32_t c = 0; c < EAST_TERM_BASE; ++c)
@@ -1175,8 +1179,13 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     tm.mark("scan_text");
     EAST_CUDA(cudaMemsetAsync(d_scan.p, 0, sizeof(ScanResult), s));
     EAST_BYTES(4.0 * n);
+    // Device-resident batches of small documents: the alphabet comes from a PREFIX of the text (speculation, as in the
+    // pipelined host build: the rest uses no other code point below 0x0A00); the per-document kernel reports a code point
+    // the table lacks and the batch is then redone with the alphabet of the whole text.  Saves the pass over the text.
+    const int32_t n_scan = (light && in.fused_encode && in.alphabet_sample > 0 && in.alphabet_sample < n) ? (int32_t)in.alphabet_sample : n;
+    const bool sampled = n_scan < n;
     if (light) {
-        EAST_LAUNCH(k_alphabet, grid_for(n, 256 * 4 * 4, 4), 256, 0, s, in.text, n, d_scan.p);
+        EAST_LAUNCH(k_alphabet, grid_for(n_scan, 256 * 4 * 4, 4), 256, 0, s, in.text, n_scan, d_scan.p);
     } else {
         EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p, 0,
                     (n + ST_TILE - 1) / ST_TILE, 1);
@@ -1184,6 +1193,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
     EAST_CUDA(cudaStreamSynchronize(s));
 
+    uint32_t extra[4] = {0u, 0u, 0u, 0u};
+    if (sampled) complete_symbol_classes(scan.present, extra);
     int sigma = 0;
     std::vector<uint8_t> table(EAST_TERM_BASE, 0);
     for (uint32_t c = 0; c < EAST_TERM_BASE; ++c)
@@ -1191,7 +1202,8 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             ++sigma;
             table[c] = (uint8_t)(sigma & 0xff);
         }
-    bool fast = !scan.bad && scan.n_term == (uint32_t)in.m_total && sigma <= 253 && !in.force_general;
+    // (a sampled scan has not counted the terminators of the whole text: the per-document kernel validates the layout)
+    bool fast = !scan.bad && (sampled || scan.n_term == (uint32_t)in.m_total) && sigma <= 253 && !in.force_general;
     out.fast_path = fast ? 1 : 0;
     out.sigma = sigma;
 
@@ -1237,7 +1249,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     };
     if (fast) {
         d_table = DevBuf<uint8_t>(EAST_TERM_BASE, s);
-        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p, make_uint4(0u, 0u, 0u, 0u));
+        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p, make_uint4(extra[0], extra[1], extra[2], extra[3]));
         t8 = take<uint8_t>(in, (size_t)n + 128, s);
         arena_after_t8 = in.arena ? in.arena->used : 0;
         if (!(try_doc_sort && in.fused_encode)) encode_all();
@@ -1245,6 +1257,14 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     out.code_table = table;
     out.term_code = fast ? (int)kp.term : 0;
 
+    if (sampled && !try_doc_sort) {   // the sample does not lead to the per-document kernel: decide on the whole text
+        t8.release();
+        if (in.arena) in.arena->used = arena_mark;
+        SaInput again = in;
+        again.alphabet_sample = 0;
+        build_suffix_array(again, out, tm, s);
+        return;
+    }
     // ---- small documents: one CTA per document, everything in shared memory (doc_sort.cu)
     uint32_t doc_sort_flags = 0;   // bit 0: a bucket too large, bit 1: bad terminator layout
     if (try_doc_sort) {
@@ -1280,9 +1300,11 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             if (hooks && in.run_begin) in.run_begin(in.run_ctx, run, score);
             doc_sort_launch(plan, t8.p, in.text, in.doc_off, in.doc_m, 0, D, n, kp.term, out.sa, out.bkt.p, out.bkt3.p, flag.p, s, clk.p,
                             fuse ? &tables : nullptr, in.sk, &score, coded ? nullptr : d_table.p, flag.p + 1, n);
-            uint32_t overflow = 0;
-            EAST_CUDA(cudaMemcpyAsync(&overflow, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            uint32_t h_flag[2] = {0u, 0u};
+            EAST_CUDA(cudaMemcpyAsync(h_flag, flag.p, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
             EAST_CUDA(cudaStreamSynchronize(s));
+            const uint32_t overflow = h_flag[0];
+            const bool missed = sampled && h_flag[1] != 0u;   // the sampled alphabet lacks a code point of the text
             if (profile) {
                 unsigned long long h[16];
                 EAST_CUDA(cudaMemcpy(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost));
@@ -1290,6 +1312,19 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 fprintf(stderr, "[east] doc_sort phases, kilo-cycles per document:");
                 for (int k = 0; k < 10; ++k) fprintf(stderr, " %s %.1f", names[k], (double)h[k] / D / 1e3);
                 fprintf(stderr, "\n");
+            }
+            if (missed) {
+                // nothing of this pass is kept: the same build with the alphabet of the whole text
+                out.bkt = DevBuf<uint32_t>();
+                out.bkt3 = DevBuf<uint32_t>();
+                out.sym_bits = 0;
+                t8.release();
+                if (in.arena) in.arena->used = arena_mark;
+                SaInput again = in;
+                again.alphabet_sample = 0;
+                build_suffix_array(again, out, tm, s);
+                out.alphabet_miss = 1;
+                return;
             }
             if (!overflow) {
                 if (hooks && in.run_hook) in.run_hook(in.run_ctx, run, score.recs != nullptr ? 1 : 0);
@@ -1315,6 +1350,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         // the global sort relies on the validated layout: start over with the full scan
         SaInput again = in;
         again.light_scan = 0;
+        again.alphabet_sample = 0;
         if (doc_sort_flags & 1u) again.doc_sort = 0;
         t8.release();
         if (in.arena) in.arena->used = arena_mark;

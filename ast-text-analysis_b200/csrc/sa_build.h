@@ -63,6 +63,7 @@ struct SaInput {
     int32_t *lcp = nullptr, *up = nullptr, *down = nullptr, *next = nullptr, *ann = nullptr;
     uint32_t *sk = nullptr;                 // destination of the scorer's per-rank key bytes (fast path only)
     int light_scan = 1;                     // small documents: alphabet-only scan first (the per-document kernel validates)
+    int64_t alphabet_sample = 0;            // ... over this many leading code points only (speculation, checked by the kernel); 0 = all
     int want_bkt3 = 1;                      // per-document kernel: also keep its 3-gram bucket starts for the scorer
     int fused_encode = 1;                   // per-document kernel: byte-code the text itself (no separate k_encode_text pass)
     // pipelined host build: the text arrives in n_chunks runs of whole documents; chunk c = documents
@@ -104,6 +105,7 @@ struct SaOutput {
     int sk_done = 0;                 // the scorer's per-rank key bytes were produced
     int pipelined = 0;               // the build overlapped the host-to-device copy (speculative alphabet held)
     int pipeline_miss = 0;           // it did not hold (later chunks brought new symbols / bad layout): redone
+    int alphabet_miss = 0;           // the alphabet sampled from a prefix of a device-resident text did not hold: redone
 };
 
 void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s);

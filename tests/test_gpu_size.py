@@ -462,3 +462,43 @@ def test_reference_sample_corpus_from_raw_text(golden):
         assert graph["nodes"] == g["nodes"]
         assert [(e["source"], e["target"], float(e["confidence"]).hex()) for e in graph["edges"]] == \
                [(e["source"], e["target"], e["confidence"]) for e in g["edges"]]
+
+
+def test_sampled_alphabet_of_device_resident_batches_recovers(oracle_mod):
+    # east_table_dev / east_build_dev take the alphabet of a batch of small documents from a PREFIX of the text (2 M code
+    # points by default) and let the per-document kernel report a code point the table lacks; a miss redoes the batch with
+    # the alphabet of the whole text.  Forced here with a tiny sample.
+    import synth
+    from east.asts import utils as au
+    capi = _capi()
+    packed, ms, _ = synth.packed_collection(40, 3000, first_seed=3100)
+    codes, off = _keyphrases(60, extra=["QUIZ7", "E"])
+    try:
+        capi.set_option("alphabet_sample", 2000)
+        idx, out = _table_dev(packed, ms, codes, off)
+        assert idx.stat("alphabet_miss") == 0 and idx.info()["doc_sorted"]
+        exp = _oracle_rows(oracle_mod, packed, ms, (0, 39), codes, off)
+        for d in (0, 39):
+            assert np.array_equal(_bits(out[d]), _bits(exp[d]))
+            _check_arrays(idx, d, oracle_mod.OracleEASA(text=packed[d], m=ms[d]), ("sampled", d))
+        idx.close()
+        # digits and a rare letter first appear in the last document, far behind the sample
+        late = au.pack_strings_collection(["0123456789 QUIZ", "ZEBRA9 J"])
+        packed2, ms2 = list(packed) + [late], list(ms) + [2]
+        idx, out = _table_dev(packed2, ms2, codes, off)
+        assert idx.stat("alphabet_miss") == 1 and idx.info()["doc_sorted"]
+        exp = _oracle_rows(oracle_mod, packed2, ms2, (0, 40), codes, off)
+        for d in (0, 40):
+            assert np.array_equal(_bits(out[d]), _bits(exp[d])), d
+            _check_arrays(idx, d, oracle_mod.OracleEASA(text=packed2[d], m=ms2[d]), ("miss", d))
+        assert np.array_equal(_bits(idx.score_table(codes, off, True)), _bits(out))
+        idx.close()
+        # a text that collides with the terminator range behind the sample: the general path takes over
+        weird = au.pack_strings_collection(["中文", "AB"])
+        idx, out = _table_dev(list(packed) + [weird], list(ms) + [2], codes, off)
+        assert not idx.info()["fast_path"]
+        o = oracle_mod.OracleEASA(text=weird, m=2)
+        assert np.array_equal(_bits(out[40]), _bits(o.score_many(codes, off, True)))
+        idx.close()
+    finally:
+        capi.set_option("alphabet_sample", 0)
