@@ -455,6 +455,7 @@ struct ChunkPlan {   // pipelined host build: runs of whole documents and the ev
 struct RunHook {
     void (*begin)(void *ctx, const RunReady &run, DocScore &score) = nullptr;
     void (*fn)(void *ctx, const RunReady &run, int in_kernel) = nullptr;
+    void (*scan_queued)(void *ctx) = nullptr;
     void *ctx = nullptr;
     const east_index **building = nullptr;
 };
@@ -555,7 +556,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.helper_stream = aux_stream(device);
         if (!get_option("no_prep_stream", 0)) in.prep_stream = prep_stream(device);
         if (hook && hook->fn) {
-            in.run_begin = hook->begin; in.run_hook = hook->fn; in.run_ctx = hook->ctx;
+            in.run_begin = hook->begin; in.run_hook = hook->fn; in.run_ctx = hook->ctx; in.scan_queued = hook->scan_queued;
             if (hook->building) *hook->building = idx.get();
         }
         if (chunks && text8_dev) {
@@ -1174,6 +1175,11 @@ struct TableRun {
     int32_t n_peers = 0;
     int32_t docs_sent = 0;                          // documents whose rows have reached the peers (current pass)
     std::unique_ptr<KpPrepared> kp_own;   // prepared for this call only (a table call is made once per collection)
+    // east_table_dev: stage 1 of the preparation is queued from the build's scan_queued hook (its ~15 launches are host
+    // time that hides under the round trip of the alphabet scan); everything it needs:
+    int device = 0;
+    bool dedup = true;
+    cudaStream_t kp_stream = nullptr, caller_stream = nullptr;
     cudaEvent_t kp_ready = nullptr;       // dense codes of the current pass queued
     KpPrepared *kp = nullptr;
     east_index view;                 // non-owning: the pointers of the index under construction + the run's tables
@@ -1186,6 +1192,21 @@ struct TableRun {
     bool failed = false;
     ~TableRun() { if (kp_ready) cudaEventDestroy(kp_ready); }
 };
+
+static void table_kp_begin(void *vctx) {
+    TableRun &t = *static_cast<TableRun *>(vctx);
+    if (t.kp_own) return;
+    try {
+        cudaEvent_t inputs_ready;   // the keyphrases may have been produced on the caller's stream
+        EAST_CUDA(cudaEventCreateWithFlags(&inputs_ready, cudaEventDisableTiming));
+        EAST_CUDA(cudaEventRecord(inputs_ready, t.caller_stream));
+        EAST_CUDA(cudaStreamWaitEvent(t.kp_stream, inputs_ready, 0));
+        EAST_CUDA(cudaEventDestroy(inputs_ready));
+        t.kp_own = kp_begin(t.device, t.d_kp, t.kp_host, t.kp_off, t.K, t.dedup, false, t.kp_stream);
+    } catch (...) {
+        t.failed = true;
+    }
+}
 
 static int table_lane(TableRun &t, cudaStream_t s) {
     for (int i = 0; i < 2; ++i)
@@ -1214,6 +1235,8 @@ static void table_run_begin(void *vctx, const RunReady &r, DocScore &score) {
             v.sym_bits = r.sym_bits;
             v.code_table = *r.code_table;
             const bool fast = v.bkt && v.t8 && !get_option("score_generic", 0);
+            table_kp_begin(&t);   // (the builds that do not scan first -- pipelined host build -- have queued it long ago)
+            if (!t.kp_own) return;
             host_debug_mark("kp_finish begin");
             kp_finish(t.kp_own.get(), t.d_kp, fast, v.sym_bits, v.code_table, r.stream);
             t.kp = t.kp_own.get();
@@ -1345,20 +1368,15 @@ static void table_dev_impl(const uint32_t *text_dev, const int64_t *doc_off, con
     use_device(device);
     cudaStream_t s = (cudaStream_t)stream;
     TableRun run;
-    {   // keyphrase preparation on a side stream, under the alphabet scan of the text and its round trip to the host
-        cudaStream_t ps = prep_stream(device);
-        cudaEvent_t inputs_ready;
-        EAST_CUDA(cudaEventCreateWithFlags(&inputs_ready, cudaEventDisableTiming));
-        EAST_CUDA(cudaEventRecord(inputs_ready, s));
-        EAST_CUDA(cudaStreamWaitEvent(ps, inputs_ready, 0));
-        EAST_CUDA(cudaEventDestroy(inputs_ready));
-        run.kp_own = kp_begin(device, kp_dev, kp_host, kp_off, K, !get_option("score_no_dedup", 0), false, ps);
-    }
+    // keyphrase preparation on a side stream, queued from the build once its alphabet scan is on its way
+    run.device = device; run.dedup = !get_option("score_no_dedup", 0); run.kp_stream = prep_stream(device); run.caller_stream = s;
     run.kp_host = kp_host; run.d_kp = kp_dev; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
     run.d_out = out_DxK_dev; run.host_out = nullptr;
     run.peer_rows = peer_rows; run.n_peers = n_peers;
     RunHook hook;
     hook.begin = table_run_begin; hook.fn = table_run_done; hook.ctx = &run; hook.building = &run.building;
+    hook.scan_queued = table_kp_begin;
+    if (get_option("kp_upfront", 0)) table_kp_begin(&run);   // A/B: queue the preparation before the build starts
     text_guard.armed = false;   // build_common's index owns it from its first statement on
     build_common(text_dev, owns_text, doc_off, doc_m, n_docs, device, s, &built, nullptr, &hook);
     std::unique_ptr<east_index, void (*)(east_index *)> guard(built, free_index);

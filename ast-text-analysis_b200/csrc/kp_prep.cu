@@ -23,6 +23,7 @@
 //
 // Stage 1 (all but the last kernel) does not depend on the index: east_table_host runs it on a side stream while
 // the text is still on its way to the device.
+#include <cstdlib>
 #include "kp_prep.h"
 #include "radix_sort.cuh"
 
@@ -56,9 +57,9 @@ k_kp_suffix_keys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ of
 // and identical suffixes are adjacent; different suffixes that share the key only cost a redundant walk.
 __global__ void __launch_bounds__(256)
 k_kp_sortkeys(const uint32_t *__restrict__ kp, const int32_t *__restrict__ send, const uint64_t *__restrict__ hash, int32_t total,
-              int sym_bits, int n_sym, uint64_t *__restrict__ keys) {
+              int sym_bits, int n_sym, int key_bits, uint64_t *__restrict__ keys) {
     const uint32_t top = (1u << sym_bits) - 1u;
-    const int hash_bits = 64 - n_sym * sym_bits;
+    const int hash_bits = key_bits - n_sym * sym_bits;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
         const int32_t e = send[p];
         uint64_t w = 0ull;
@@ -208,13 +209,14 @@ void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, co
             for (int32_t p = 0; p < total; ++p) mx = std::max(mx, kp_host[p]);
             sym_bits = std::min(KP_MAX_SYM_BITS, std::max(1, bits_for((uint64_t)mx + 1)));
         }
-        const int n_sym = std::max(1, 42 / sym_bits);
+        static const int key_bits = getenv("EAST_KP_KEY_BITS") ? atoi(getenv("EAST_KP_KEY_BITS")) : 64;
+        const int n_sym = std::max(1, (key_bits - 20) / sym_bits);
         keys_a = DevBuf<uint64_t>((size_t)total, s); keys_b = DevBuf<uint64_t>((size_t)total, s);
         vals_b = DevBuf<uint32_t>((size_t)total, s);
         DevBuf<uint32_t> hist(256 * RS_MAX_PASSES, s);
         DevBuf<uint8_t> scratch(rs_scratch_bytes(total, RS_MAX_PASSES), s);
-        EAST_LAUNCH(k_kp_sortkeys, grid_for(total, 256, 8), 256, 0, s, kp_dev, send.p, hash.p, total, sym_bits, n_sym, keys_a.p);
-        const int cur = radix_sort_pairs(keys_a.p, keys_b.p, vals_a.p, vals_b.p, total, 64, hist.p, false, scratch.p, s);
+        EAST_LAUNCH(k_kp_sortkeys, grid_for(total, 256, 8), 256, 0, s, kp_dev, send.p, hash.p, total, sym_bits, n_sym, key_bits, keys_a.p);
+        const int cur = radix_sort_pairs(keys_a.p, keys_b.p, vals_a.p, vals_b.p, total, key_bits, hist.p, false, scratch.p, s);
         order = cur ? vals_b.p : vals_a.p;
     }
     EAST_LAUNCH(k_kp_mark, nb, KP_THREADS, 0, s, kp_dev, hash.p, send.p, order, total, dedup ? 1 : 0, flags.p, bsum.p);

@@ -1191,6 +1191,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                     (n + ST_TILE - 1) / ST_TILE, 1);
     }
     EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
+    if (in.scan_queued) in.scan_queued(in.run_ctx);
     EAST_CUDA(cudaStreamSynchronize(s));
 
     uint32_t extra[4] = {0u, 0u, 0u, 0u};

@@ -80,6 +80,9 @@ struct SaInput {
     void (*run_begin)(void *ctx, const RunReady &run, DocScore &score) = nullptr;
     void (*run_hook)(void *ctx, const RunReady &run, int in_kernel) = nullptr;
     void *run_ctx = nullptr;
+    // called once the text scan has been queued, before the host waits for its result: host work (launches on other
+    // streams) that does not depend on the alphabet hides under the scan's round trip
+    void (*scan_queued)(void *ctx) = nullptr;
     Arena *arena = nullptr;   // where the arrays that stay with the index (byte text, bucket tables) are taken from
 };
 
