@@ -1051,7 +1051,9 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
 // scratch tmp[tile_docs][n_uniq]) into out_dev[(d - doc_begin) * K + k]; nothing here waits for the device.
 static void score_enqueue(const east_index *idx, const KpPrepared *kp, const uint32_t *kp_dev, int64_t total, int32_t K,
                           int normalized, double *out_dev, int32_t doc_begin, int32_t doc_count, cudaStream_t s,
-                          double *tmp, int32_t tile_docs, unsigned long long *probe_count) {
+                          double *tmp, int32_t tile_docs, unsigned long long *probe_count,
+                          double *const *peer_rows = nullptr /* sharded table: rows of document doc_begin in the peers' tables */,
+                          int32_t n_peers = 0) {
     ScoreInput in;
     in.text = idx->text; in.sa = idx->sa;
     in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
@@ -1065,15 +1067,52 @@ static void score_enqueue(const east_index *idx, const KpPrepared *kp, const uin
     }
     in.algorithmic_bytes = (double)get_option("score_bytes", 0);
     in.probe_count = probe_count;
-    for (int32_t d0 = 0; d0 < doc_count; d0 += tile_docs) {
+    auto tile = [&](int32_t d0, int32_t cnt) {
         ScoreInput part = in;
-        part.n_docs = std::min(tile_docs, doc_count - d0);
+        part.n_docs = cnt;
         part.doc_off = in.doc_off + d0;
         part.doc_m = in.doc_m + d0;
         if (in.bkt) part.bkt = in.bkt + ((size_t)d0 << (2 * in.sym_bits));
         if (in.bkt3) part.bkt3 = in.bkt3 + ((size_t)d0 << (3 * in.sym_bits));
         part.algorithmic_bytes = in.algorithmic_bytes * ((double)part.n_docs / (double)doc_count);
-        score_table(part, tmp, out_dev + (size_t)d0 * K, s);
+        part.n_peers = n_peers;
+        for (int32_t pi = 0; pi < n_peers; ++pi) part.peer_out[pi] = peer_rows[pi] + (size_t)d0 * K;
+        return part;
+    };
+    const int32_t n_tiles = (doc_count + tile_docs - 1) / tile_docs;
+    if (n_tiles <= 2 || tile_docs < 2 || probe_count || get_option("score_no_overlap", 0)) {
+        for (int32_t d0 = 0; d0 < doc_count; d0 += tile_docs) {
+            const ScoreInput part = tile(d0, std::min(tile_docs, doc_count - d0));
+            score_table(part, tmp, out_dev + (size_t)d0 * K, s);
+        }
+        return;
+    }
+    // Many tiles (large K: the scratch holds a few hundred documents at a time): the keyphrase sums of tile t -- and, in a
+    // sharded run, the peer stores of its rows, bound by NVLink, not by the SMs -- run on the auxiliary stream while the
+    // walks of tile t + 1 keep the SMs busy; the scratch is used in two halves.
+    const int32_t half = tile_docs / 2;
+    cudaStream_t aux = aux_stream(idx->device);
+    cudaEvent_t walked[2], summed[2];
+    for (int i = 0; i < 2; ++i) {
+        EAST_CUDA(cudaEventCreateWithFlags(&walked[i], cudaEventDisableTiming));
+        EAST_CUDA(cudaEventCreateWithFlags(&summed[i], cudaEventDisableTiming));
+    }
+    int t = 0;
+    for (int32_t d0 = 0; d0 < doc_count; d0 += half, ++t) {
+        const int b = t & 1;
+        const ScoreInput part = tile(d0, std::min(half, doc_count - d0));
+        double *buf = tmp + (size_t)b * (size_t)half * (size_t)in.n_uniq;
+        if (t >= 2) EAST_CUDA(cudaStreamWaitEvent(s, summed[b], 0));   // the sums that read this half two tiles ago
+        score_suffixes(part, buf, s);
+        EAST_CUDA(cudaEventRecord(walked[b], s));
+        EAST_CUDA(cudaStreamWaitEvent(aux, walked[b], 0));
+        score_combine(part, buf, out_dev + (size_t)d0 * K, aux);
+        EAST_CUDA(cudaEventRecord(summed[b], aux));
+    }
+    for (int i = 0; i < 2; ++i) {
+        EAST_CUDA(cudaStreamWaitEvent(s, summed[i], 0));
+        EAST_CUDA(cudaEventDestroy(walked[i]));     // released once they have fired
+        EAST_CUDA(cudaEventDestroy(summed[i]));
     }
 }
 
@@ -1278,11 +1317,12 @@ static void table_run_done(void *vctx, const RunReady &r, int in_kernel) {
         const int li = table_lane(t, r.stream);
         double *rows = t.d_out + (size_t)r.doc_begin * t.K;
         if (!in_kernel) {
+            std::vector<double *> peers((size_t)t.n_peers);
+            for (int32_t pi = 0; pi < t.n_peers; ++pi) peers[(size_t)pi] = t.peer_rows[pi] + (size_t)r.doc_begin * t.K;
             score_enqueue(&t.view, t.kp, t.d_kp, t.kp_off[t.K], t.K, t.normalized, rows, r.doc_begin, r.doc_count, r.stream,
-                          t.tmp[li].p, (int32_t)t.tmp_docs[li], nullptr);
-        } else {
-            t.docs_sent += r.doc_count;   // the kernel stores its rows to the peers itself
+                          t.tmp[li].p, (int32_t)t.tmp_docs[li], nullptr, peers.data(), t.n_peers);
         }
+        t.docs_sent += r.doc_count;   // the rows reach the peers from the kernels that produce them, on either path
         if (t.host_out)
             EAST_CUDA(cudaMemcpyAsync(t.host_out + (size_t)r.doc_begin * t.K, rows, sizeof(double) * (size_t)r.doc_count * t.K,
                                       cudaMemcpyDeviceToHost, r.stream));

@@ -182,11 +182,17 @@ struct ScoreInput {
     int sym_bits = 0;
     unsigned long long *probe_count = nullptr;  // device counter: run the probe-counting variant
     double algorithmic_bytes = 0.0;             // 8 B x probes of this workload, if known (roofline numerator)
+    // sharded table: k_score_combine also stores every cell into the gathered tables of the other ranks (mapped peer
+    // memory, same offset as out_DxK): the all-gather of the batched scorer path
+    double *peer_out[DocScore::MAX_PEERS] = {};
+    int32_t n_peers = 0;
 };
 // the second half of score_table alone: tmp[doc][distinct suffix] (here: written by the per-document kernel) -> out[doc][k]
 void score_combine(const ScoreInput &in, const double *suffix_tmp, double *out_DxK, cudaStream_t s);
 void score_table(const ScoreInput &in, double *suffix_tmp /*n_docs x n_uniq*/, double *out_DxK,
                  cudaStream_t s);
+// the first half alone: the walks of every (document, distinct suffix) -> suffix_tmp
+void score_suffixes(const ScoreInput &in, double *suffix_tmp, cudaStream_t s);
 
 // sk[r] = the 4 byte codes at offsets 2..5 of suffix sa[r] (for indexes built by the global sort)
 void fill_suffix_keys(const uint8_t *t8, const int32_t *sa, int32_t n, uint32_t *sk, cudaStream_t s);

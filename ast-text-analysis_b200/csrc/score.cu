@@ -70,8 +70,11 @@ k_score_combine(ScoreInput in, const double *__restrict__ tmp, double *__restric
         const double *row = tmp + (int64_t)doc * in.n_uniq;
         double result = 0.0;
         for (int32_t s = b; s < e; ++s) result = result + row[__ldg(in.uniq_of + s)];
-        out[idx] = result / (double)(e - b);
+        const double v = result / (double)(e - b);
+        out[idx] = v;
+        for (int pi = 0; pi < in.n_peers; ++pi) in.peer_out[pi][idx] = v;   // NVLink peer stores: the fused all-gather
     }
+    if (in.n_peers > 0) __threadfence_system();
 }
 
 __global__ void __launch_bounds__(256)
@@ -95,6 +98,11 @@ void score_combine(const ScoreInput &in, const double *suffix_tmp, double *out_D
 }
 
 void score_table(const ScoreInput &in, double *suffix_tmp, double *out_DxK, cudaStream_t s) {
+    score_suffixes(in, suffix_tmp, s);
+    score_combine(in, suffix_tmp, out_DxK, s);
+}
+
+void score_suffixes(const ScoreInput &in, double *suffix_tmp, cudaStream_t s) {
     const int64_t work = (int64_t)in.n_docs * in.n_uniq;
     if (work > 0) {
         if (in.probe_count) {
@@ -106,7 +114,6 @@ void score_table(const ScoreInput &in, double *suffix_tmp, double *out_DxK, cuda
                         (unsigned long long *)nullptr);
         }
     }
-    score_combine(in, suffix_tmp, out_DxK, s);
 }
 
 // ------------------------------------------------------------------------------------------

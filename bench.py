@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--keyphrases", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--docs-total", type=int, default=100000, help="config4: documents of the whole job (sharded over the GPUs)")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "fused"],
+                    help="config4: nccl = all_gather_into_tensor (north_star); fused = the rows are stored into the other ranks' "
+                         "tables by the scorer's own kernels (east_table_dev_gather, symmetric memory), one barrier ends the step")
     ap.add_argument("--gather-tiles", type=int, default=1,
                     help="config4: 1 = ONE all-gather after scoring (north_star); T > 1 = the table is scored in T document "
                          "tiles and the all-gather of tile t overlaps the scoring of tile t+1")
@@ -731,12 +734,29 @@ def run_config4(args):
     kp_codes, kp_off = _capi.pack_keyphrases(kps)
     kp_dev = torch.from_numpy(kp_codes.view(np.int32).copy()).to(dev)
     prep_s = time.perf_counter() - t0
-    out_dev = torch.empty(D * K, dtype=torch.float64, device=dev) if tiles == 1 else None
+    fused = args.gather == "fused" and world > 1 and tiles == 1
+    symm = None
+    if fused:
+        from east import distributed as east_dist
+        symm = east_dist.SymmetricTable(world * D, K, local_rank)
+    out_dev = torch.empty(D * K, dtype=torch.float64, device=dev) if (tiles == 1 and not fused) else None
     bufs = [torch.empty(T * K, dtype=torch.float64, device=dev) for _ in range(2)] if tiles > 1 else None
-    gathered = torch.empty(world * D * K, dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = (symm.tensor.view(-1) if fused else torch.empty(world * D * K, dtype=torch.float64, device=dev)) if world > 1 else None
     stream = torch.cuda.current_stream()
 
+    def step_fused():
+        # ONE engine call: index, score, and the all-gather inside the scorer's kernels (peer stores over NVLink)
+        idx = _capi.DeviceIndex.build_dev_and_score(text_dev.data_ptr(), doc_off, doc_m, kp_dev.data_ptr(), kp_codes, kp_off,
+                                                    symm.own_rows(rank * D), True, device=local_rank, stream=stream.cuda_stream,
+                                                    peer_rows=symm.peer_rows(rank * D))
+        symm.barrier()
+        torch.cuda.synchronize()
+        idx.close()
+        return dict(idx.build_timings), 0.0
+
     def step():
+        if fused:
+            return step_fused()
         # every step prepares the keyphrases from scratch (suffix hashing / ordering / de-duplication on the device,
         # kp_prep.cu): a real table call is made once per collection, there is nothing to reuse
         _capi.set_option("drop_kp_cache", 1)
@@ -809,7 +829,8 @@ def run_config4(args):
                                        K, world * D, doc_bytes // 1000, world),
                        "keyphrases": K, "docs_total": world * D, "docs_per_gpu": D, "doc_bytes": doc_bytes,
                        "table_bytes": world * D * K * 8,
-                       "gather": "one all-gather after scoring" if tiles == 1 else
+                       "gather": "fused: rows stored into the peers' tables by the scorer's kernels, one barrier" if fused else
+                                 "one all-gather after scoring" if tiles == 1 else
                                  "%d document tiles, all-gather of tile t overlaps the scoring of tile t+1" % tiles},
             "parity_checked": bool(parity.get("checked") and parity.get("mismatching_rows") == 0), "parity": parity,
             "breakdown": {"build_stages_ms": build_t, "score_ms": score_ms, "host_prep_s": prep_s, "checksum_sample": checksum,

@@ -349,6 +349,15 @@ def _nccl_worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, "rank%d.npy" % rank), full.cpu().numpy())
         plain = distributed.relevance_table_sharded(docs, kps, True, device=rank, fused_gather=False)
         np.save(os.path.join(out_dir, "plain%d.npy" % rank), plain.cpu().numpy())
+        # the batched scorer path (scratch too small for in-kernel scoring, many document tiles): the keyphrase sums
+        # store the rows to the peers
+        from east import _capi
+        try:
+            _capi.set_option("score_tmp_doubles", 150)
+            tiled = distributed.relevance_table_sharded(docs, kps, True, device=rank)
+        finally:
+            _capi.set_option("score_tmp_doubles", 0)
+        np.save(os.path.join(out_dir, "tiled%d.npy" % rank), tiled.cpu().numpy())
         # a ragged collection (one document the per-document kernel cannot take): several device batches per rank
         ragged = docs[:3] + [synth.document(90000, 999)] + docs[3:]
         rag = distributed.relevance_table_sharded(ragged, kps, True, device=rank)
@@ -393,6 +402,8 @@ def test_multi_gpu_sharded_table_is_bit_identical(tmp_path):
         got = np.load(str(tmp_path / ("rank%d.npy" % r)))
         assert np.array_equal(got.view(np.uint64), expect.view(np.uint64))
         got = np.load(str(tmp_path / ("plain%d.npy" % r)))
+        assert np.array_equal(got.view(np.uint64), expect.view(np.uint64))
+        got = np.load(str(tmp_path / ("tiled%d.npy" % r)))
         assert np.array_equal(got.view(np.uint64), expect.view(np.uint64))
         got = np.load(str(tmp_path / ("ragged%d.npy" % r)))
         assert np.array_equal(got.view(np.uint64), expect_ragged.view(np.uint64))
