@@ -178,7 +178,11 @@ k_kp_encode(const uint32_t *__restrict__ kp, int32_t total, const uint8_t *__res
     }
 }
 
-static thread_local uint32_t *g_pinned_word = nullptr;
+// pinned words the distinct-suffix counts are copied to: a small ring per thread, so that two preparations in flight on
+// one thread (a table call's own + the cached one of a score call) never share a word
+static thread_local uint32_t *g_pinned_words = nullptr;
+static thread_local unsigned g_pinned_next = 0;
+constexpr unsigned KP_PINNED_WORDS = 64;
 
 void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s) {
     const int64_t total64 = kp_off[K];
@@ -222,8 +226,8 @@ void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, co
     EAST_LAUNCH(k_kp_mark, nb, KP_THREADS, 0, s, kp_dev, hash.p, send.p, order, total, dedup ? 1 : 0, flags.p, bsum.p);
     EAST_LAUNCH(k_kp_scan_blocks, 1, KP_THREADS, 0, s, bsum.p, nb, kp.d_n_uniq.p);
     EAST_LAUNCH(k_kp_emit, nb, KP_THREADS, 0, s, send.p, weird.p, order, flags.p, bsum.p, total, kp.d_uniq_of.p, kp.d_recs.p);
-    if (!g_pinned_word) EAST_CUDA(cudaHostAlloc((void **)&g_pinned_word, 64, cudaHostAllocDefault));
-    kp.n_uniq_host = g_pinned_word;
+    if (!g_pinned_words) EAST_CUDA(cudaHostAlloc((void **)&g_pinned_words, sizeof(uint32_t) * KP_PINNED_WORDS, cudaHostAllocDefault));
+    kp.n_uniq_host = g_pinned_words + (g_pinned_next++ % KP_PINNED_WORDS);
     EAST_CUDA(cudaMemcpyAsync(kp.n_uniq_host, kp.d_n_uniq.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     if (!kp.done) EAST_CUDA(cudaEventCreateWithFlags(&kp.done, cudaEventDisableTiming));
     EAST_CUDA(cudaEventRecord(kp.done, s));

@@ -40,16 +40,33 @@ struct TkChar { uint32_t cp; int len; bool word, digit, bad; };
 // every code point in tests/test_gpu_size.py.
 constexpr uint64_t TK_LATIN1_SEPARATORS = 0x89d3fbffffffffffull;
 
+// class of a byte: 1 word character, 2 digit, 4 lower-case letter (ASCII); 0x80 = part of a multi-byte sequence.
+// One shared-memory lookup instead of a dozen comparisons per byte (the walks decode every kept character three times).
+constexpr uint32_t TKC_WORD = 1u, TKC_DIGIT = 2u, TKC_LOWER = 4u, TKC_MULTI = 0x80u;
+__device__ __forceinline__ void tk_fill_classes(uint8_t *lut) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+        uint32_t cls = 0;
+        if (b >= 0x80) cls = TKC_MULTI;
+        else {
+            const bool lower = b >= 'a' && b <= 'z', digit = b >= '0' && b <= '9';
+            if (lower || digit || (b >= 'A' && b <= 'Z') || b == '_' || b == '\'') cls |= TKC_WORD;
+            if (digit) cls |= TKC_DIGIT;
+            if (lower) cls |= TKC_LOWER;
+        }
+        lut[b] = (uint8_t)cls;
+    }
+}
+
 // the code point that starts at byte i (i is not a continuation byte), upper-cased
-__device__ __forceinline__ TkChar tk_decode(const uint8_t *__restrict__ p, int64_t i, int64_t end) {
+__device__ __forceinline__ TkChar tk_decode(const uint8_t *__restrict__ p, int64_t i, int64_t end, const uint8_t *lut) {
     TkChar c;
     const uint32_t b = p[i];
     c.len = 1; c.bad = false; c.digit = false;
-    if (b < 0x80u) {
-        const bool lower = b >= 'a' && b <= 'z';
-        c.digit = b >= '0' && b <= '9';
-        c.word = lower || c.digit || (b >= 'A' && b <= 'Z') || b == '_' || b == '\'';
-        c.cp = lower ? b - 32u : b;
+    const uint32_t cls = lut[b];
+    if (!(cls & TKC_MULTI)) {
+        c.digit = (cls & TKC_DIGIT) != 0u;
+        c.word = (cls & TKC_WORD) != 0u;
+        c.cp = b - ((cls & TKC_LOWER) << 3);   // lower case: - 32
         return c;
     }
     const uint32_t b1 = (i + 1 < end) ? p[i + 1] : 0u;
@@ -82,9 +99,10 @@ __device__ __forceinline__ TkChar tk_decode(const uint8_t *__restrict__ p, int64
 }
 
 // is the code point that ENDS at byte i - 1 a word character (i > begin)
-__device__ __forceinline__ bool tk_prev_is_word(const uint8_t *__restrict__ p, int64_t i, int64_t begin) {
+__device__ __forceinline__ bool tk_prev_is_word(const uint8_t *__restrict__ p, int64_t i, int64_t begin, const uint8_t *lut) {
     const uint32_t b = p[i - 1];
-    if (b < 0x80u) return (b >= 'a' && b <= 'z') || (b >= '0' && b <= '9') || (b >= 'A' && b <= 'Z') || b == '_' || b == '\'';
+    const uint32_t cls = lut[b];
+    if (!(cls & TKC_MULTI)) return (cls & TKC_WORD) != 0u;
     // the last byte of a multi-byte character: only the Cyrillic letters (lead bytes D0 / D1, two bytes) are word characters
     if (i - 2 < begin) return false;
     const uint32_t lead = p[i - 2];
@@ -127,6 +145,9 @@ k_tokenize(const uint8_t *__restrict__ raw, const int64_t *__restrict__ raw_off,
            int32_t *__restrict__ sizes /* [n_texts][3]: n, m, unsupported */, const int64_t *__restrict__ doc_off,
            uint32_t *__restrict__ text) {
     __shared__ uint32_t s_wa[TK_THREADS / 32], s_wb[TK_THREADS / 32];
+    __shared__ uint8_t s_cls[256];
+    tk_fill_classes(s_cls);
+    __syncthreads();
     const int d = blockIdx.x;
     const int64_t begin = raw_off[d], end = raw_off[d + 1];
     const int64_t len = end - begin;
@@ -143,15 +164,15 @@ k_tokenize(const uint8_t *__restrict__ raw, const int64_t *__restrict__ raw_off,
             ++i;
             continue;
         }
-        TkChar c = tk_decode(p, i, end);
+        TkChar c = tk_decode(p, i, end, s_cls);
         bad = bad || c.bad;
-        if (!c.word || (i > begin && tk_prev_is_word(p, i, begin))) { i += c.len; continue; }
+        if (!c.word || (i > begin && tk_prev_is_word(p, i, begin, s_cls))) { i += c.len; continue; }
         // a token starts here: walk it to its end
         uint32_t tl = 0;
         bool all_digits = true;
         int64_t e = i;
         while (e < end) {
-            c = tk_decode(p, e, end);
+            c = tk_decode(p, e, end, s_cls);
             if (!c.word) break;
             bad = bad || c.bad;
             ++tl;
@@ -181,13 +202,13 @@ k_tokenize(const uint8_t *__restrict__ raw, const int64_t *__restrict__ raw_off,
     uint32_t j = j0, ch = ch0;
     for (int64_t i = c0; i < c1;) {
         if ((p[i] & 0xc0u) == 0x80u) { ++i; continue; }
-        TkChar c = tk_decode(p, i, end);
-        if (!c.word || (i > begin && tk_prev_is_word(p, i, begin))) { i += c.len; continue; }
+        TkChar c = tk_decode(p, i, end, s_cls);
+        if (!c.word || (i > begin && tk_prev_is_word(p, i, begin, s_cls))) { i += c.len; continue; }
         uint32_t tl = 0;
         bool all_digits = true;
         int64_t e = i;
         while (e < end) {
-            c = tk_decode(p, e, end);
+            c = tk_decode(p, e, end, s_cls);
             if (!c.word) break;
             ++tl;
             all_digits = all_digits && c.digit;
@@ -197,7 +218,7 @@ k_tokenize(const uint8_t *__restrict__ raw, const int64_t *__restrict__ raw_off,
             uint32_t *dst = out + ch + j / 3u;
             int64_t q = i;
             for (uint32_t x = 0; x < tl; ++x) {
-                c = tk_decode(p, q, end);
+                c = tk_decode(p, q, end, s_cls);
                 dst[x] = c.cp;
                 q += c.len;
             }

@@ -75,3 +75,26 @@ def test_oracle_root_annotation_and_leaf_counts(oracle_mod):
         o = oracle_mod.OracleEASA(strings)
         assert o.anntab[0] == o.n - o.m
         assert sorted(o.suftab.tolist()) == list(range(o.n))
+
+
+def test_bench_row_checker_subprocess(oracle_mod):
+    # bench.py checks rows of its table in a subprocess (oracle/check_rows.py): right rows pass, a flipped bit is caught
+    import importlib.util
+    import os
+    import synth
+    from conftest import ROOT
+    from east import _capi, utils
+    from east.asts import utils as au
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cols = [utils.text_to_strings_collection(d) for d in synth.documents(3, 2000, first_seed=11)]
+    packed = [au.pack_strings_collection(c) for c in cols]
+    codes, off = _capi.pack_keyphrases([utils.prepare_text(k) for k in synth.keyphrases(15)])
+    rows = [oracle_mod.OracleEASA(text=p, m=len(c)).score_many(codes, off, True) for p, c in zip(packed, cols)]
+    sample = [(p, len(c), r) for p, c, r in zip(packed, cols, rows)]
+    assert bench.oracle_check(sample, codes, off, True) == {"rows": 3, "mismatching_rows": 0}
+    rows[2] = rows[2].copy()
+    rows[2][4] = np.nextafter(rows[2][4], 1.0)
+    sample[2] = (packed[2], len(cols[2]), rows[2])
+    assert bench.oracle_check(sample, codes, off, True)["mismatching_rows"] == 1
