@@ -292,6 +292,7 @@ struct east_index {
     std::unique_ptr<StageTimer> build_timer;
     cudaEvent_t ev_tables = nullptr;
     bool tables_pending = false;
+    bool sk_pending = false;          // sk is allocated but not filled yet (indexes built by the global sort)
 };
 
 // per-device auxiliary (non-blocking) stream for the table kernels
@@ -346,6 +347,17 @@ static void wait_tables(const east_index *cidx) {
     EAST_CUDA(cudaEventSynchronize(idx->ev_tables));
     idx->tables_pending = false;
     if (idx->build_timer) idx->build_timer->collect();
+}
+
+// the scorer's per-rank key words of an index built by the global sort: filled by the first scoring call (on its stream)
+static void ensure_suffix_keys(const east_index *cidx, cudaStream_t s) {
+    static std::mutex m;
+    std::lock_guard<std::mutex> g(m);
+    east_index *idx = const_cast<east_index *>(cidx);
+    if (!idx->sk_pending) return;
+    fill_suffix_keys(idx->t8, idx->sa, idx->n, idx->sk, s);
+    EAST_CUDA(cudaStreamSynchronize(s));   // later calls may use other streams
+    idx->sk_pending = false;
 }
 
 static int fail(const Error &e) { g_error = e.what(); return e.status; }
@@ -583,7 +595,9 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
         idx->tables_fused = so.tables_done;
         if (idx->sk && !so.sk_done) {
-            if (idx->t8) fill_suffix_keys(idx->t8, idx->sa, n, idx->sk, s);    // global sort, fast path
+            // global sort: the scorer's per-rank key words are not part of the structure (SA, LCP, child table, annotation):
+            // they are made by the first call that scores against the index (ensure_suffix_keys), not by the build
+            if (idx->t8) idx->sk_pending = true;
             else { if (!idx->arena.holds(idx->sk)) dev_free(idx->sk, s); idx->sk = nullptr; }   // general path: no byte text
         }
         if (so.tables_done) {
@@ -1054,6 +1068,7 @@ static void score_enqueue(const east_index *idx, const KpPrepared *kp, const uin
                           double *tmp, int32_t tile_docs, unsigned long long *probe_count,
                           double *const *peer_rows = nullptr /* sharded table: rows of document doc_begin in the peers' tables */,
                           int32_t n_peers = 0) {
+    ensure_suffix_keys(idx, s);
     ScoreInput in;
     in.text = idx->text; in.sa = idx->sa;
     in.doc_off = idx->d_doc_off + doc_begin; in.doc_m = idx->d_doc_m + doc_begin; in.n_docs = doc_count;
@@ -1628,6 +1643,7 @@ int east_index_save(const east_index *idx, const char *path) {
     if (!idx || !path) throw Error(EAST_ERR_INVALID, "NULL argument");
     EAST_CUDA(cudaSetDevice(idx->device));
     wait_tables(idx);
+    ensure_suffix_keys(idx, 0);
     EAST_CUDA(cudaDeviceSynchronize());
     FileCloser fc{fopen(path, "wb")};
     if (!fc.f) throw Error(EAST_ERR_INVALID, std::string("cannot open ") + path + " for writing");
