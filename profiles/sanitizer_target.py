@@ -30,3 +30,35 @@ idx4 = _capi.DeviceIndex.build_host_and_score(text, doc_off, mm, codes, off, out
 print("pipelined:", idx4.stat("pipelined"), "miss:", idx4.stat("pipeline_miss"), float(out.sum()))
 idx5 = _capi.DeviceIndex.build_host_and_score(text[:doc_off[300]].copy(), doc_off[:301], mm[:300], codes, off, out[:300])
 print("pipelined:", idx5.stat("pipelined"), float(out[:300].sum()))
+# ---- round 2 paths: one byte per code point (pipelined in-kernel decode + device expansion), raw texts (tokenizer),
+# device keyphrase preparation with odd keyphrases, sampled alphabet with a miss, persistence, co-occurrence (TMA cluster kernel)
+cols300 = [utils.text_to_strings_collection(d) for d in synth.documents(300, 700, first_seed=9)]
+p8 = [au.pack_strings_collection_u8(c) for c in cols300]
+m8 = [len(c) for c in cols300]
+off8 = np.zeros(len(p8) + 1, dtype=np.int64); np.cumsum([len(p) for p in p8], out=off8[1:])
+t8 = np.ascontiguousarray(np.concatenate(p8), dtype=np.uint8)
+out8 = np.zeros((300, len(kps)))
+idx6 = _capi.DeviceIndex.build_host_and_score(t8, off8, m8, codes, off, out8)
+print("u8 pipelined:", idx6.stat("pipelined"), bool(np.array_equal(out8.view(np.uint64), out[:300].view(np.uint64))))
+idx7 = _capi.DeviceIndex.build_host_u8(t8[:off8[7]].copy(), off8[:8], m8[:7]); print("u8 small:", idx7.info()["doc_sorted"])
+odd = kps + ["E", "E", "Q" * 300, "中文A", "ABਁC"]
+c2, o2 = _capi.pack_keyphrases(odd)
+raw_out = np.zeros((302, len(odd)))
+texts = synth.documents(300, 700, first_seed=9) + ["", "привет мир – «ёжик» №5 привет"]
+idx8 = _capi.DeviceIndex.table_from_texts(texts, c2, o2, raw_out)
+print("raw texts:", idx8.info()["doc_sorted"], float(raw_out.sum()), idx8.strings_collection(301))
+_capi.set_option("alphabet_sample", 3000)
+import torch
+late = many[:300] + [au.pack_strings_collection(["0123456789 QUIZ", "ZEBRA9 J"])]
+doc_off = np.zeros(len(late) + 1, dtype=np.int64); np.cumsum([len(p) for p in late], out=doc_off[1:])
+td = torch.from_numpy(np.concatenate(late).astype(np.uint32).view(np.int32)).cuda()
+kd = torch.from_numpy(c2.view(np.int32).copy()).cuda()
+od = torch.zeros((301, len(odd)), dtype=torch.float64, device="cuda")
+idx9 = _capi.DeviceIndex.build_dev_and_score(td.data_ptr(), doc_off, mm[:300] + [2], kd.data_ptr(), c2, o2, od.data_ptr(), True)
+print("sampled alphabet miss:", idx9.stat("alphabet_miss"), float(od.sum().item()))
+_capi.set_option("alphabet_sample", 0)
+idx9.save("/tmp/east_sanitizer.idx"); idx10 = _capi.DeviceIndex.load("/tmp/east_sanitizer.idx")
+print("loaded:", bool(np.array_equal(idx10.array(300, _capi.SUFTAB), idx9.array(300, _capi.SUFTAB))))
+S = np.random.default_rng(1).random((700, 300))
+C = _capi.cooc_host(S, 0.5); B = S >= 0.5
+print("cooc exact:", bool(np.array_equal(C, (B.T.astype(np.int64) @ B.astype(np.int64)).astype(np.int32))))
