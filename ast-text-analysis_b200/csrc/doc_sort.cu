@@ -29,17 +29,19 @@
 //   6  buckets of <= 32 suffixes: a warp takes a window of 32 ranks and every suffix ranks itself inside its
 //      own bucket by counting the smaller members; keys are the next 8 symbols (raw bytes, byte-reversed),
 //      ties go to a byte-wise SWAR comparison of the shared-memory text (or to the position)
-//   7  zero-fill the document's slices of the child / annotation arrays (phase 8 stores sparsely); LCP of
-//      neighbouring suffixes (SWAR on the staged text), 16-bit copy + min-pyramid in the freed scratch,
+//   7  LCP of neighbouring suffixes (SWAR on the staged text), 16-bit copy + min-pyramid in the freed scratch,
 //      per-rank key bytes for the scorer
-//   8  child table and annotation: per-thread chunks walked with the reference's stack discipline, what lies
-//      outside a chunk searched in the pyramid (farthest first, so that the lanes' long searches coincide)
+//   8  child table and annotation: every warp zero-fills the slices of its 32 chunks (phase 8 stores sparsely; filled
+//      right before they are walked the lines reach HBM once), per-thread chunks walked with the reference's stack
+//      discipline, what lies outside a chunk searched in the pyramid afterwards (farthest first, so that the lanes' long
+//      searches coincide)
 //   9  (optional: east_table_host / east_table_dev) score every distinct query suffix against the document
 //      (easa.py:91-139; walks of score_walk.cuh) from a copy of text + suffix array in the freed shared memory,
 //      then add the results up per keyphrase: the CTA writes its row of the score table.
 // A bucket of more than 4096 suffixes raises flag bit 0: the host redoes the batch with the global sort.  A
 // document the kernel gives up on gets empty bucket rows (and, for a bad layout, an in-range suffix array), so
 // that a caller that scores speculatively stays inside the arrays.
+#include <cstdlib>
 #include "sa_build.h"
 #include "score_walk.cuh"
 
@@ -92,6 +94,7 @@ struct DocSortParams {
     // the document becomes the terminator 0x0A00 + k -- to text_out (= text) for the later readers of the index
     const uint8_t *text8;
     uint32_t *text_out;
+    int fill_early;           // tuning / A-B: zero-fill the child and annotation slices at the start of phase 7 (round 1)
 };
 
 // 8 bytes of shared memory at an arbitrary byte offset from a 16-byte aligned base: three aligned
@@ -1035,7 +1038,10 @@ k_doc_suffix_sort(DocSortParams p) {
     // child table and annotation are stored sparsely in phase 8: their slices of this document are zero-filled
     // here, by the CTA itself -- the stores drain under the LCP computation and the sparse stores that follow find
     // the lines in L2 (host-side fills of the whole batch made the kernel wait for them and went to HBM twice)
-    {
+    // (option fill_early, round 1: here, for the whole document -- 120 k cycles before the walk dirties the lines again, with
+    // 108 MB of such lines in flight over the 148 CTAs most of them were written back twice.  Default: every warp fills the
+    // slices of its own 32 chunks right before it walks them, see phase 8.)
+    if (p.fill_early) {
         int32_t *const up_doc = p.up + base, *const down_doc = p.down + base, *const next_doc = p.next + base, *const ann_doc = p.ann + base;
         for (int r = tid; r < n; r += DS_THREADS) { up_doc[r] = 0; down_doc[r] = 0; next_doc[r] = 0; ann_doc[r] = 0; }
     }
@@ -1094,7 +1100,7 @@ k_doc_suffix_sort(DocSortParams p) {
     // stack, e of the ranks still stacked at the end -- comes from the min-pyramid.  Closed forms as
     // in tables.cu: lcp[q] == l -> next[q] = r; else r is the first l-index of [q .. e-1]:
     // ann[r] = e - q, up[e] = r if lcp[q] <= lcp[e], down[q] = r if lcp[e] <= lcp[q] (e inside the
-    // document).  Values are ranks local to the document, 0 = none (the arrays were zero-filled at the start of phase 7).
+    // document).  Values are ranks local to the document, 0 = none (every warp zero-fills the slices of its 32 chunks right before it walks them).
     // The stacks (one byte per entry: offset in the chunk | 0x80 = first l-index) reuse the text area.
     {
         const int m = p.doc_m[doc];
@@ -1133,6 +1139,16 @@ k_doc_suffix_sort(DocSortParams p) {
         // empty stack (PSE unknown).
         // The top entry and its LCP value live in registers: shared memory is read only when a pop
         // uncovers the entry below (which is also the popped rank's PSE).
+        if (!p.fill_early) {
+            // zero-fill, warp by warp: the 32 chunks of a warp are 32 C consecutive ranks -- coalesced stores --, and the walk
+            // that follows at once stores into these very lines (it never leaves its chunk): they are still in L2, so they
+            // reach HBM once.  What is stored outside a chunk comes after the block-wide barrier below.
+            const int w0 = min(n, warp * 32 * C), w1 = min(n, w0 + 32 * C);
+            int32_t *const up_w = p.up + base, *const down_w = p.down + base, *const next_w = p.next + base, *const ann_w = p.ann + base;
+            for (int x = w0 + lane; x < w1; x += 32) { up_w[x] = 0; down_w[x] = 0; next_w[x] = 0; ann_w[x] = 0; }
+            __syncwarp();
+        }
+        uint64_t lost = 0ull;   // chunk offsets of the ranks pushed on an empty stack whose record did not fit
         int r = c0;
         uint32_t l = (r < c1) ? s_lcp[r] : 0u;
         uint32_t top = 0, top_l = 0;   // valid while depth > 0
@@ -1148,7 +1164,7 @@ k_doc_suffix_sort(DocSortParams p) {
                 if (depth > 0) { below = stk[depth - 1]; below_l = s_lcp[c0 + (int)(below & 0x3fu)]; }
                 if (popped & 0x40u) {
                     if (nrec < R) { rec[2 * nrec] = (uint8_t)(popped & 0x3fu); rec[2 * nrec + 1] = (uint8_t)(r - c0); ++nrec; }
-                    else resolve_outside(t, r);
+                    else lost |= 1ull << (popped & 0x3fu);   // no room for the record: both neighbours are searched for later
                 } else if (popped & 0x80u) {   // first l-index of [q .. r-1], q = the entry below (not the bottom: it exists)
                     const int q = c0 + (int)(below & 0x3fu);
                     ann_doc[t] = r - q;
@@ -1173,7 +1189,8 @@ k_doc_suffix_sort(DocSortParams p) {
                 if (r < c1) l = s_lcp[r];
             }
         }
-        if (p.phase_clk) { __syncthreads(); DS_STAMP(7); }   // profiling only: split the phase
+        __syncthreads();   // every slice is filled and walked: from here on the stores may land in other threads' chunks
+        DS_STAMP(7);
         // ---- what lies outside the chunk, from the min-pyramid.  Farthest first in every lane: the
         // bottom of the stack and the LAST record have the smallest LCP values, whose neighbours are
         // thousands of ranks away (the ends of a first-letter block); met in the same iterations by all
@@ -1188,6 +1205,11 @@ k_doc_suffix_sort(DocSortParams p) {
             }
         }
         for (int i = nrec - 1; i >= 0; --i) resolve_outside(c0 + (int)rec[2 * i], c0 + (int)rec[2 * i + 1]);
+        while (lost) {   // (rare) popped inside the chunk, record dropped: its next smaller value is searched for from the rank itself
+            const int t = c0 + (__ffsll((long long)lost) - 1);
+            lost &= lost - 1ull;
+            resolve_outside(t, ds_next_lt(M, t, s_lcp[t], n));
+        }
     }
     if (p.phase_clk) __syncthreads();
     DS_STAMP(8);
@@ -1237,6 +1259,8 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     p.code_table = (code_table && miss) ? code_table : nullptr;
     p.t8_out = const_cast<uint8_t *>(t8); p.miss = miss; p.text_len = text_len;
     p.text8 = p.code_table ? text8 : nullptr; p.text_out = const_cast<uint32_t *>(text);
+    static const bool fill_early = getenv("EAST_DOC_SORT_FILL_EARLY") != nullptr;
+    p.fill_early = fill_early ? 1 : 0;
     p.lcp = p.up = p.down = p.next = p.ann = nullptr;
     if (tables && plan.tables_fit) { p.lcp = tables->lcp; p.up = tables->up; p.down = tables->down; p.next = tables->next; p.ann = tables->ann; }
     // algorithmic bytes per code point: 1 (byte text in) + 4 (suffix array out), with the fused tables + 5 x 4
