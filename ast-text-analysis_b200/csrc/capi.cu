@@ -292,7 +292,8 @@ struct east_index {
     std::unique_ptr<StageTimer> build_timer;
     cudaEvent_t ev_tables = nullptr;
     bool tables_pending = false;
-    bool sk_pending = false;          // sk is allocated but not filled yet (indexes built by the global sort)
+    bool sk_pending = false;          // sk is allocated but not (completely) filled yet: indexes built by the global sort, and
+                                      // documents the per-document kernel scored itself; ensure_suffix_keys() makes it
 };
 
 // per-device auxiliary (non-blocking) stream for the table kernels
@@ -594,6 +595,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         idx->bkt3 = so.bkt3.p; so.bkt3.p = nullptr;
         idx->code_table = so.code_table; idx->sym_bits = so.sym_bits; idx->term_code = so.term_code;
         idx->tables_fused = so.tables_done;
+        if (idx->sk && so.sk_done && so.sk_skipped && idx->t8) idx->sk_pending = true;   // made by the first later score call
         if (idx->sk && !so.sk_done) {
             // global sort: the scorer's per-rank key words are not part of the structure (SA, LCP, child table, annotation):
             // they are made by the first call that scores against the index (ensure_suffix_keys), not by the build
@@ -1314,6 +1316,7 @@ static void table_run_begin(void *vctx, const RunReady &r, DocScore &score) {
             score.tmp = t.tmp[li].p; score.normalized = t.normalized ? 1 : 0;
             score.kp_off = t.kp->dev.d_off.p; score.uniq_of = t.kp->dev.d_uniq_of.p; score.K = t.K;
             score.out = t.d_out + (size_t)r.doc_begin * t.K;
+            score.skip_suffix_keys = get_option("eager_suffix_keys", 0) ? 0 : 1;
             score.n_peers = t.n_peers;
             for (int32_t pi = 0; pi < t.n_peers; ++pi) score.peer_out[pi] = t.peer_rows[pi] + (size_t)r.doc_begin * t.K;
             score.algorithmic_bytes = (double)get_option("score_bytes", 0) * ((double)r.doc_count / (double)t.view.n_docs);

@@ -1255,7 +1255,8 @@ void doc_sort_launch(const DocSortPlan &plan, const uint8_t *t8, const uint32_t 
     p.phase_clk = phase_clk;
     p.doc_begin = doc_begin;
     p.sk = sk;
-    if (score && score->recs && bkt && sk) p.score = *score;
+    if (score && score->recs && bkt) p.score = *score;
+    if (p.score.recs && p.score.skip_suffix_keys) p.sk = nullptr;
     p.code_table = (code_table && miss) ? code_table : nullptr;
     p.t8_out = const_cast<uint8_t *>(t8); p.miss = miss; p.text_len = text_len;
     p.text8 = p.code_table ? text8 : nullptr; p.text_out = const_cast<uint32_t *>(text);

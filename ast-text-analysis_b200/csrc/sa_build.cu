@@ -1096,7 +1096,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
                 EAST_CUDA(cudaStreamWaitEvent(ls, coded, 0));
                 EAST_CUDA(cudaEventDestroy(coded));   // released once it has fired
             }
-            const bool hooks = out.bkt.p && in.sk;
+            const bool hooks = out.bkt.p != nullptr;
             const RunReady run{d0, d1 - d0, ls, t8.p, out.bkt.p, out.bkt3.p, out.sym_bits, &table, 1};
             DocScore score;
             host_debug_mark("run begin");
@@ -1106,6 +1106,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
                             out.bkt3.p, flags.p, ls, nullptr, fuse ? &tables : nullptr, in.sk, &score,
                             in.fused_encode ? d_table.p : nullptr, flags.p + 1, n, in.text8);
             if (hooks && in.run_hook) in.run_hook(in.run_ctx, run, score.recs != nullptr ? 1 : 0);
+            if (score.recs && score.skip_suffix_keys) out.sk_skipped = 1;
         }
         if (lanes[1] != s) {
             EAST_CUDA(cudaEventRecord(helper_done, lanes[1]));
@@ -1295,7 +1296,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             }
             DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
             const bool fuse = in.lcp != nullptr && plan.tables_fit;
-            const bool hooks = out.bkt.p && in.sk;
+            const bool hooks = out.bkt.p != nullptr;
             const RunReady run{0, D, s, t8.p, out.bkt.p, out.bkt3.p, out.sym_bits, &table, 0};
             DocScore score;
             if (hooks && in.run_begin) in.run_begin(in.run_ctx, run, score);
@@ -1329,6 +1330,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             }
             if (!overflow) {
                 if (hooks && in.run_hook) in.run_hook(in.run_ctx, run, score.recs != nullptr ? 1 : 0);
+                if (score.recs && score.skip_suffix_keys) out.sk_skipped = 1;
                 out.doc_sorted = 1;
                 out.tables_done = fuse ? 1 : 0;
                 out.sk_done = in.sk ? 1 : 0;

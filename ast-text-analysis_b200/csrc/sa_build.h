@@ -26,6 +26,9 @@ struct DocScore {
     double *peer_out[MAX_PEERS] = {};
     int32_t n_peers = 0;
     double algorithmic_bytes = 0.0;   // of the walks of this launch (measurement only: added to the kernel's byte count)
+    // the per-rank key words (sk) only serve LATER score calls on the index (the in-kernel walks read the staged text): a
+    // launch that scores its documents itself may leave them to the first such call (ensure_suffix_keys in capi.cu)
+    int skip_suffix_keys = 0;
 };
 
 // What a caller-supplied hook sees once the per-document kernel of one run of
@@ -106,6 +109,7 @@ struct SaOutput {
     int doc_sort_overflow = 0;       // it met a bucket it cannot sort and the global sort took over
     int tables_done = 0;             // LCP / child / annotation tables were produced by the per-document kernel
     int sk_done = 0;                 // the scorer's per-rank key bytes were produced
+    int sk_skipped = 0;              // ... except by launches that scored their documents themselves (made on first use)
     int pipelined = 0;               // the build overlapped the host-to-device copy (speculative alphabet held)
     int pipeline_miss = 0;           // it did not hold (later chunks brought new symbols / bad layout): redone
     int alphabet_miss = 0;           // the alphabet sampled from a prefix of a device-resident text did not hold: redone
