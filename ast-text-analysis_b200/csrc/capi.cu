@@ -1016,7 +1016,7 @@ static std::unique_ptr<KpPrepared> kp_begin(int device, const uint32_t *kp_dev, 
             EAST_CUDA(cudaStreamSynchronize(s));
         }
     }
-    if (!host_prep) kp_stage1(c->dev, kp_dev, kp_host_in, kp_off, K, dedup, s);
+    if (!host_prep) kp_stage1(c->dev, kp_dev, kp_host_in, kp_off, K, dedup, s, (int32_t)get_option("kp_small_max", 1 << 30));
     return c;
 }
 

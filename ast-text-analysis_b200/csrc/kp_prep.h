@@ -24,8 +24,9 @@ struct KpDevice {
 // Stage 1 (independent of any index): hashes, lexicographic order, groups of identical suffixes -> d_off, d_uniq_of,
 // d_recs (without dense codes), the distinct count on its way to the host.  Everything is queued on `s`; nothing waits.
 // dedup = false: every suffix is its own group, in suffix order (per-suffix results wanted).
+// Up to small_max suffixes (at most 64 Ki) the whole stage is one kernel (a cluster of 8 CTAs).
 void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host /* optional */, const int64_t *kp_off_host, int32_t K, bool dedup,
-               cudaStream_t s);
+               cudaStream_t s, int32_t small_max = 1 << 30);
 // Stage 2 (per index alphabet; may be repeated): dense byte codes.  code_table_host = NULL: the index has no fast
 // path, every suffix takes the generic walk.  Queued on `s` behind stage 1; returns with kp.n_uniq known.
 void kp_stage2(KpDevice &kp, const uint32_t *kp_dev, const uint8_t *code_table_host, cudaStream_t s);

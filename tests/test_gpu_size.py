@@ -162,20 +162,23 @@ def test_keyphrase_preparation_on_the_device_equals_the_host_variant(oracle_mod)
     packed, ms, _ = synth.packed_collection(5, 4000, first_seed=31)
     extra = ["E", "E", "THE", "THETHE", "ATHE", "中文A", "A中", "਀", "ABਁC", "Q" * 300, "Q" * 299, "ABCDEFGHIJKLMNOPQRSTUVWXYZ" * 9,
              "ABCDEFGHIJKLMNOPQRSTUVWXYZ" * 9 + "A", "XYZABCDEFGHIJ", "WXYZABCDEFGHIJ", "ZABCDEFGHIJK"]
-    for K in (1, 7, 1000):
+    for K in (1, 7, 1000, 4000):   # 4000: ~60 thousand suffixes, just below the one-kernel limit
         codes, off = _keyphrases(K, extra=extra if K > 1 else ())
         exp = _oracle_rows(oracle_mod, packed, ms, range(5), codes, off)
-        for host_prep in (0, 1):
+        # the device preparation in one CTA (few suffixes), as the chain of kernels (many), and the host variant
+        for host_prep, small_max in ((0, 0), (0, 1), (1, 0)):
             try:
                 capi.set_option("kp_prep_host", host_prep)
+                capi.set_option("kp_small_max", small_max)
                 idx, out = _table_host(packed, ms, codes, off)
                 two = idx.score_table(codes, off, True)
                 idx.close()
             finally:
                 capi.set_option("kp_prep_host", 0)
+                capi.set_option("kp_small_max", 0)
             for d in range(5):
-                assert np.array_equal(_bits(out[d]), _bits(exp[d])), (K, host_prep, d)
-            assert np.array_equal(_bits(two), _bits(out)), (K, host_prep)
+                assert np.array_equal(_bits(out[d]), _bits(exp[d])), (K, host_prep, small_max, d)
+            assert np.array_equal(_bits(two), _bits(out)), (K, host_prep, small_max)
     # per-suffix results (return_suffix_scores): every suffix is its own group, in suffix order
     from east.asts import base
     ast = base.AST.get_ast(["XABXAC", "HI"])
