@@ -285,7 +285,7 @@ struct east_index {
     uint32_t *sk = nullptr;         // fast path: text bytes at offsets 2..5 of every suffix, in rank order
     std::vector<uint8_t> code_table;
     int sym_bits = 0, term_code = 0;
-    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0, tables_fused = 0, pipelined = 0, pipeline_miss = 0, alphabet_miss = 0;
+    int rounds = 0, fast_path = 0, key_chars = 0, key_bits = 0, doc_sorted = 0, doc_sort_overflow = 0, tables_fused = 0, pipelined = 0, pipeline_miss = 0, alphabet_miss = 0, alphabet_guessed = 0;
     uint32_t active_after_round0 = 0;
     // LCP / child / annotation tables are produced on an auxiliary stream after the suffix array is
     // final, so a score call (which needs only SA + text) overlaps them; readers wait on ev_tables
@@ -557,6 +557,8 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         in.light_scan = get_option("no_light_scan", 0) ? 0 : 1;
         // device-resident batches: alphabet from the first 2 M code points (option alphabet_sample; -1 = the whole text)
         { const int64_t smp = get_option("alphabet_sample", (int64_t)1 << 21); in.alphabet_sample = smp < 0 ? 0 : smp; }
+        // ... or from the thread's previous batch on this device (option no_alphabet_guess = 1: always scan)
+        in.alphabet_guess = get_option("no_alphabet_guess", 0) ? 0 : 1;
         in.fused_encode = get_option("no_fused_encode", 0) ? 0 : 1;
         if (!get_option("no_suffix_keys", 0)) {
             idx->sk = (uint32_t *)take32((size_t)n);
@@ -586,7 +588,7 @@ static int build_common(const uint32_t *text_dev, bool owns_text, const int64_t 
         SaOutput so;
         so.sa = idx->sa;
         build_suffix_array(in, so, tm, s);
-        idx->pipelined = so.pipelined; idx->pipeline_miss = so.pipeline_miss; idx->alphabet_miss = so.alphabet_miss;
+        idx->pipelined = so.pipelined; idx->pipeline_miss = so.pipeline_miss; idx->alphabet_miss = so.alphabet_miss; idx->alphabet_guessed = so.alphabet_guessed;
         idx->rounds = so.rounds; idx->fast_path = so.fast_path; idx->key_chars = so.key_chars;
         idx->key_bits = so.key_bits; idx->active_after_round0 = so.active_after_round0;
         idx->doc_sorted = so.doc_sorted; idx->doc_sort_overflow = so.doc_sort_overflow;
@@ -779,6 +781,7 @@ int east_index_stat(const east_index *idx, const char *name, int64_t *value) {
     else if (!strcmp(name, "pipelined")) *value = idx->pipelined;
     else if (!strcmp(name, "pipeline_miss")) *value = idx->pipeline_miss;
     else if (!strcmp(name, "alphabet_miss")) *value = idx->alphabet_miss;
+    else if (!strcmp(name, "alphabet_guessed")) *value = idx->alphabet_guessed;
     else if (!strcmp(name, "key_chars")) *value = idx->key_chars;
     else if (!strcmp(name, "key_bits")) *value = idx->key_bits;
     else if (!strcmp(name, "rounds")) *value = idx->rounds;
@@ -1059,7 +1062,7 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
     kp_finish(c, kp_dev, fast, idx->sym_bits, idx->code_table, s);
     EAST_CUDA(cudaStreamSynchronize(s));
     // the entry outlives this call: whoever drops it frees on the legacy stream of its device, after a device sync
-    for (cudaStream_t *ps : {&c->dev.d_off.s, &c->dev.d_uniq_of.s, &c->dev.d_recs.s, &c->dev.d_q8.s, &c->dev.d_table.s, &c->dev.d_n_uniq.s}) *ps = 0;
+    for (cudaStream_t *ps : {&c->dev.d_off.s, &c->dev.d_uniq_of.s, &c->dev.d_recs.s, &c->dev.d_q8.s, &c->dev.d_n_uniq.s}) *ps = 0;
     return c;
 }
 

@@ -31,6 +31,7 @@
 // shared memory.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "kp_prep.h"
 #include "radix_sort.cuh"
 #include <cooperative_groups.h>
@@ -388,13 +389,21 @@ k_kp_small(const uint32_t *__restrict__ kp, const int32_t *__restrict__ off, int
 #undef KP_STAMP
 }
 
-// index-dependent part: dense byte codes (0 = the code point does not occur in the batch, or is >= 0x0A00)
+// index-dependent part: dense byte codes (0 = the code point does not occur in the batch, or is >= 0x0A00).  The code
+// table of the index comes BY VALUE (2.5 KB of kernel parameters, staged in shared memory): an upload would be one more
+// operation in the chain the first wave of the per-document kernel waits for, behind the text on the host link.
+struct KpCodeTable { uint32_t w[EAST_TERM_BASE / 4]; };
+
 __global__ void __launch_bounds__(256)
-k_kp_encode(const uint32_t *__restrict__ kp, int32_t total, const uint8_t *__restrict__ table /* NULL: no fast path */,
+k_kp_encode(const uint32_t *__restrict__ kp, int32_t total, KpCodeTable tab, int fast /* 0: the index has no fast path */,
             const uint32_t *__restrict__ n_uniq, SufRec *__restrict__ recs, uint8_t *__restrict__ q8) {
+    __shared__ uint32_t s_tab[EAST_TERM_BASE / 4];
+    if (fast) for (int i = threadIdx.x; i < (int)(EAST_TERM_BASE / 4); i += blockDim.x) s_tab[i] = tab.w[i];
+    __syncthreads();
+    const uint8_t *table = reinterpret_cast<const uint8_t *>(s_tab);
     const int32_t nu = (int32_t)*n_uniq;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < max(total + 16, nu); i += gridDim.x * blockDim.x) {
-        if (table && i < total + 16) {
+        if (fast && i < total + 16) {
             uint8_t c = 0;
             if (i < total) { const uint32_t cp = kp[i]; if (cp < EAST_TERM_BASE) c = table[cp]; }
             q8[i] = c;   // the scorer reads the queries 8 bytes at a time: 16 zero bytes of slack
@@ -402,7 +411,7 @@ k_kp_encode(const uint32_t *__restrict__ kp, int32_t total, const uint8_t *__res
         if (i < nu) {
             SufRec r = recs[i];
             r.q8_first = 0ull;
-            if (table) {
+            if (fast) {
                 for (int q = 0; q < 8 && q < (int)r.len; ++q) {
                     const uint32_t cp = kp[r.sidx + q];
                     r.q8_first |= (uint64_t)(cp < EAST_TERM_BASE ? table[cp] : 0) << (8 * q);
@@ -517,13 +526,12 @@ void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, co
 void kp_stage2(KpDevice &kp, const uint32_t *kp_dev, const uint8_t *code_table_host, cudaStream_t s) {
     EAST_CUDA(cudaStreamWaitEvent(s, kp.done, 0));
     const bool fast = code_table_host != nullptr;
+    KpCodeTable tab;
     if (fast) {
-        if (!kp.d_table.p) kp.d_table = DevBuf<uint8_t>(EAST_TERM_BASE, s);
         if (!kp.d_q8.p) kp.d_q8 = DevBuf<uint8_t>((size_t)kp.total + 16, s);
-        EAST_CUDA(cudaMemcpyAsync(kp.d_table.p, code_table_host, EAST_TERM_BASE, cudaMemcpyHostToDevice, s));
+        memcpy(tab.w, code_table_host, EAST_TERM_BASE);
     }
-    EAST_LAUNCH(k_kp_encode, grid_for(kp.total + 16, 256, 8), 256, 0, s, kp_dev, kp.total, fast ? kp.d_table.p : (const uint8_t *)nullptr,
-                kp.d_n_uniq.p, kp.d_recs.p, kp.d_q8.p);
+    EAST_LAUNCH(k_kp_encode, grid_for(kp.total + 16, 256, 8), 256, 0, s, kp_dev, kp.total, tab, fast ? 1 : 0, kp.d_n_uniq.p, kp.d_recs.p, kp.d_q8.p);
     if (kp.n_uniq < 0) {
         EAST_CUDA(cudaEventSynchronize(kp.done));
         kp.n_uniq = (int64_t)*kp.n_uniq_host;

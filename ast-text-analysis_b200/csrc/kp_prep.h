@@ -11,7 +11,7 @@ struct KpDevice {
     std::vector<int32_t> off32;        // K + 1 (source of the upload)
     DevBuf<int32_t> d_off, d_uniq_of;  // K + 1 offsets; per suffix: position of its distinct twin in visiting order
     DevBuf<SufRec> d_recs;             // one record per distinct suffix in visiting order (n_uniq of `total` used)
-    DevBuf<uint8_t> d_q8, d_table;     // dense codes of the keyphrases / the alphabet they were made for
+    DevBuf<uint8_t> d_q8;              // dense codes of the keyphrases
     DevBuf<uint32_t> d_n_uniq;
     uint32_t *n_uniq_host = nullptr;   // pinned word the count is copied to
     cudaEvent_t done = nullptr;        // stage 1 complete (recorded on its stream)

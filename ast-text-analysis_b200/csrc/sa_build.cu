@@ -380,6 +380,47 @@ k_code_table(const ScanResult *__restrict__ res, uint8_t *__restrict__ table, ui
 
 __global__ void k_store_u32(uint32_t *dst, uint32_t value) { *dst = value; }
 
+// Everything a batch of per-document kernels needs before its first wave, in ONE launch: the code table (from the scan
+// result, or from a bitmap handed over by value when the alphabet is a guess), the cleared flag words, the closing entries of
+// the bucket tables.  Every launch of a dependent chain costs its latency; with the text of a pipelined build on the host
+// link that is 30-50 us apiece (the command fetch shares the link with the copies), and the chain used to be five long.
+struct PresentBits { uint32_t w[EAST_TERM_BASE / 32]; };
+
+__device__ __forceinline__ void code_table_from_bits(uint32_t *s_bits, uint32_t *s_before, uint8_t *__restrict__ table) {
+    constexpr int W = EAST_TERM_BASE / 32;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int w = 0; w < W; ++w) { s_before[w] = run; run += __popc(s_bits[w]); }
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        const uint32_t bits = s_bits[w];
+        uint32_t code = s_before[w];
+        for (int k = 0; k < 32; ++k) {
+            const bool on = (bits >> k) & 1u;
+            if (on) ++code;
+            table[32 * w + k] = on ? (uint8_t)(code & 0xffu) : (uint8_t)0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_doc_sort_prologue(const ScanResult *__restrict__ res /* or NULL: bits */, PresentBits bits, uint4 extra, uint8_t *__restrict__ table,
+                    uint32_t *flags2, uint32_t *end0, uint32_t *end1, uint32_t n) {
+    constexpr int W = EAST_TERM_BASE / 32;
+    __shared__ uint32_t s_bits[W];
+    __shared__ uint32_t s_before[W];
+    const uint32_t ex[4] = {extra.x, extra.y, extra.z, extra.w};
+    for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = (res ? res->present[w] : bits.w[w]) | (w < 4 ? ex[w] : 0u);
+    code_table_from_bits(s_bits, s_before, table);
+    if (threadIdx.x == 0) {
+        if (flags2) { flags2[0] = 0u; flags2[1] = 0u; }
+        if (end0) *end0 = n;
+        if (end1) *end1 = n;
+    }
+}
+
 // Light text scan: bitmap of the code points below 0x0A00 that occur in T[0, n), number of code points
 // >= 0x0A00 and the maximum code point -- everything k_scan_text reports except the validation of the
 // terminator layout, which the per-document kernel does itself.  Streams at HBM speed.
@@ -424,7 +465,9 @@ k_alphabet8(const uint8_t *__restrict__ T8, int32_t n, ScanResult *res) {
     __shared__ uint32_t s_present[8];
     if (threadIdx.x < 8) s_present[threadIdx.x] = 0;
     __syncthreads();
-    uint32_t seen[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    // a code point costs one look at the CTA's bitmap in shared memory; the atomic only follows for the first few
+    // occurrences of a symbol (a per-thread bitmap in registers cost ~25 instructions per byte)
+    volatile uint32_t *seen = s_present;
     uint32_t nt = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
     for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; i0 < n; i0 += stride) {
@@ -437,15 +480,10 @@ k_alphabet8(const uint8_t *__restrict__ T8, int32_t n, ScanResult *res) {
             if (i0 + 15 >= n) { if (i0 + j >= n) continue; c = T8[i0 + j]; }
             if (c == 0xffu) ++nt;
             else {
-#pragma unroll
-                for (int q = 0; q < 8; ++q) if ((int)(c >> 5) == q) seen[q] |= 1u << (c & 31);
+                const uint32_t bit = 1u << (c & 31);
+                if (!(seen[c >> 5] & bit)) atomicOr(&s_present[c >> 5], bit);
             }
         }
-    }
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const uint32_t s = __reduce_or_sync(0xffffffffu, seen[q]);
-        if ((threadIdx.x & 31) == 0 && s) atomicOr(&s_present[q], s);
     }
     nt = __reduce_add_sync(0xffffffffu, nt);
     if ((threadIdx.x & 31) == 0 && nt) atomicAdd(&res->n_term, nt);
@@ -1012,6 +1050,51 @@ static void complete_symbol_classes(uint32_t *present, uint32_t extra[4]) {
     for (int w = 0; w < 4; ++w) present[w] |= extra[w];
 }
 
+// The alphabet of run 0 goes to the host through a store into pinned memory, not through a device-to-host copy: with
+// the text of the later runs in flight, a copy -- small as it is -- waits for its turn on a copy engine (measured: the
+// host had the 332 bytes ~80 us after the scan had ended).
+static thread_local ScanResult *g_scan_pinned = nullptr;
+
+__global__ void __launch_bounds__(128)
+k_publish_scan(const ScanResult *__restrict__ src, ScanResult *dst_pinned) {
+    const uint32_t *a = reinterpret_cast<const uint32_t *>(src);
+    volatile uint32_t *b = reinterpret_cast<volatile uint32_t *>(dst_pinned);
+    for (int i = threadIdx.x; i < (int)(sizeof(ScanResult) / sizeof(uint32_t)); i += blockDim.x) b[i] = a[i];
+    __threadfence_system();
+}
+
+// The alphabet a thread's last batch of small documents was indexed with, as a guess for its next batch on the same
+// device (collections come in batches of one language).  It is the same speculation as the alphabet of run 0 / of a
+// sampled prefix -- phase 1 of the per-document kernel reports every code point the table lacks, and the batch is then
+// redone from a scan -- but it needs no scan kernel and, above all, no host round trip before the first wave: with the
+// text of the later runs in flight the answer of the scan took 0.1-0.2 ms to reach the host.
+struct AlphabetGuess {
+    bool valid = false;
+    int device = -1;
+    uint32_t present[EAST_TERM_BASE / 32];
+};
+static thread_local AlphabetGuess g_alphabet_guess;
+
+__global__ void __launch_bounds__(128)
+k_set_present(ScanResult *res, PresentBits bits) {
+    for (int i = threadIdx.x; i < (int)(EAST_TERM_BASE / 32); i += blockDim.x) res->present[i] = bits.w[i];
+}
+
+static bool alphabet_guess_for(const SaInput &in, PresentBits &bits) {
+    int dev = -1;
+    if (!in.alphabet_guess || !g_alphabet_guess.valid || cudaGetDevice(&dev) != cudaSuccess || dev != g_alphabet_guess.device) return false;
+    memcpy(bits.w, g_alphabet_guess.present, sizeof(bits.w));
+    return true;
+}
+
+static void alphabet_guess_keep(const uint32_t *present) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    g_alphabet_guess.valid = true;
+    g_alphabet_guess.device = dev;
+    memcpy(g_alphabet_guess.present, present, sizeof(g_alphabet_guess.present));
+}
+
 static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s, uint32_t &doc_sort_flags) {
     const int32_t n = in.n;
     const int D = in.n_docs;
@@ -1019,14 +1102,24 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     for (int d = 0; d < D; ++d) max_doc_n = std::max(max_doc_n, in.doc_off_host[d + 1] - in.doc_off_host[d]);
     tm.mark("alphabet");
     DevBuf<ScanResult> d_first(1, s);
-    EAST_CUDA(cudaMemsetAsync(d_first.p, 0, sizeof(ScanResult), s));
-    EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
     const int32_t n0 = in.doc_off_host[in.chunk_doc[1]];
-    if (in.text8) EAST_LAUNCH(k_alphabet8, grid_for(n0, 256 * 16, 4), 256, 0, s, in.text8, n0, d_first.p);
-    else EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_first.p);
     ScanResult first;
-    EAST_CUDA(cudaMemcpyAsync(&first, d_first.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
-    EAST_CUDA(cudaStreamSynchronize(s));
+    PresentBits guess;
+    const bool guessed = alphabet_guess_for(in, guess);
+    if (guessed) {
+        memset(&first, 0, sizeof(first));
+        memcpy(first.present, guess.w, sizeof(guess.w));
+    } else {
+        EAST_CUDA(cudaMemsetAsync(d_first.p, 0, sizeof(ScanResult), s));
+        EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
+        if (in.text8) EAST_LAUNCH(k_alphabet8, grid_for(n0, 256 * 16, 4), 256, 0, s, in.text8, n0, d_first.p);
+        else EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_first.p);
+        if (!g_scan_pinned) EAST_CUDA(cudaHostAlloc((void **)&g_scan_pinned, sizeof(ScanResult), cudaHostAllocDefault));
+        EAST_LAUNCH(k_publish_scan, 1, 128, 0, s, d_first.p, g_scan_pinned);
+        EAST_CUDA(cudaStreamSynchronize(s));
+        host_debug_mark("scan back");
+        first = *g_scan_pinned;
+    }
     // the alphabet of run 0 (a few dozen documents), with the ASCII classes it has met completed
     uint32_t *present = first.present;
     uint32_t extra[4] = {0u, 0u, 0u, 0u};
@@ -1044,21 +1137,27 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     if (eligible) {
         tm.mark("doc_sort");
         DevBuf<uint8_t> d_table(EAST_TERM_BASE, s);
-        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_first.p, d_table.p, make_uint4(extra[0], extra[1], extra[2], extra[3]));
         t8 = take<uint8_t>(in, (size_t)n + 128, s);
-        EAST_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(uint32_t), s));
+        uint32_t *end0 = nullptr, *end1 = nullptr;
         if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
             const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
             out.bkt = take<uint32_t>(in, entries, s);
-            EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt.p + entries - 1, (uint32_t)n);
+            end0 = out.bkt.p + entries - 1;
             out.sym_bits = plan.b;
             if (in.want_bkt3 && plan.G == 3 && ((size_t)D << (3 * plan.b)) * sizeof(uint32_t) <= ((size_t)8 << 30)) {
                 // the kernel's buckets ARE the 3-grams: their first ranks cost one more coalesced store and turn
                 // the scorer's depth-2 narrowing (a binary search over the largest intervals) into a lookup
                 const size_t e3 = ((size_t)D << (3 * plan.b)) + 1;
                 out.bkt3 = take<uint32_t>(in, e3, s);
-                EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt3.p + e3 - 1, (uint32_t)n);
+                end1 = out.bkt3.p + e3 - 1;
             }
+        }
+        {   // code table, cleared flags, closing entries of the bucket tables: one launch
+            PresentBits bits;
+            memcpy(bits.w, present, sizeof(bits.w));   // (completed; only read when the alphabet is a guess)
+            EAST_LAUNCH(k_doc_sort_prologue, 1, 128, 0, s, guessed ? (const ScanResult *)nullptr : d_first.p, bits,
+                        make_uint4(extra[0], extra[1], extra[2], extra[3]), d_table.p, flags.p, end0, end1, (uint32_t)n);
+            if (guessed) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));   // (a scan has waited for the lead run already)
         }
         DocSortTables tables{in.lcp, in.up, in.down, in.next, in.ann};
         const bool fuse = in.lcp != nullptr && plan.tables_fit;
@@ -1116,7 +1215,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
         }
         out.tables_done = fuse ? 1 : 0;
     } else {
-        for (int c = 1; c < in.n_chunks; ++c) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
+        for (int c = guessed ? 0 : 1; c < in.n_chunks; ++c) EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[c], 0));
     }
     tm.mark("validate");
     uint32_t h_flags[2] = {0u, 0u};
@@ -1124,7 +1223,9 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
     EAST_CUDA(cudaStreamSynchronize(s));
     const bool ok = eligible && !h_flags[0] && !h_flags[1];
     doc_sort_flags = h_flags[0];
+    out.alphabet_guessed = guessed ? 1 : 0;
     if (!ok) {
+        if (guessed) g_alphabet_guess.valid = false;   // whatever went wrong: the next batch starts from a scan
         out.pipeline_miss = eligible ? 1 : 0;
         out.doc_sort_overflow = (h_flags[0] & 1u) ? 1 : 0;
         out.tables_done = 0;
@@ -1133,6 +1234,7 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
         out.sym_bits = 0;
         return false;
     }
+    alphabet_guess_keep(present);
     out.pipelined = 1;
     out.sk_done = in.sk ? 1 : 0;
     out.fast_path = 1;
@@ -1185,15 +1287,25 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
     // the table lacks and the batch is then redone with the alphabet of the whole text.  Saves the pass over the text.
     const int32_t n_scan = (light && in.fused_encode && in.alphabet_sample > 0 && in.alphabet_sample < n) ? (int32_t)in.alphabet_sample : n;
     const bool sampled = n_scan < n;
-    if (light) {
-        EAST_LAUNCH(k_alphabet, grid_for(n_scan, 256 * 4 * 4, 4), 256, 0, s, in.text, n_scan, d_scan.p);
+    // ... or, where a sample would do, from the alphabet of this thread's previous batch (g_alphabet_guess): no scan, no wait
+    PresentBits guess;
+    const bool guessed = sampled && alphabet_guess_for(in, guess);
+    if (guessed) {
+        memset(&scan, 0, sizeof(scan));
+        memcpy(scan.present, guess.w, sizeof(guess.w));
+        if (in.scan_queued) in.scan_queued(in.run_ctx);
     } else {
-        EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p, 0,
-                    (n + ST_TILE - 1) / ST_TILE, 1);
+        if (light) {
+            EAST_LAUNCH(k_alphabet, grid_for(n_scan, 256 * 4 * 4, 4), 256, 0, s, in.text, n_scan, d_scan.p);
+        } else {
+            EAST_LAUNCH(k_scan_text, grid_for(n, ST_TILE, 4), 256, 0, s, in.text, n, in.doc_off, in.doc_m, D, d_scan.p, 0,
+                        (n + ST_TILE - 1) / ST_TILE, 1);
+        }
+        EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
+        if (in.scan_queued) in.scan_queued(in.run_ctx);
+        EAST_CUDA(cudaStreamSynchronize(s));
     }
-    EAST_CUDA(cudaMemcpyAsync(&scan, d_scan.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
-    if (in.scan_queued) in.scan_queued(in.run_ctx);
-    EAST_CUDA(cudaStreamSynchronize(s));
+    out.alphabet_guessed = guessed ? 1 : 0;
 
     uint32_t extra[4] = {0u, 0u, 0u, 0u};
     if (sampled) complete_symbol_classes(scan.present, extra);
@@ -1249,17 +1361,27 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                     (uint8_t)kp.term, t8.p, (uint32_t *)nullptr);
         coded = true;
     };
+    // the per-document kernel that byte-codes its documents itself gets the code table from its one-launch prologue below
+    const bool table_in_prologue = try_doc_sort && in.fused_encode;
     if (fast) {
         d_table = DevBuf<uint8_t>(EAST_TERM_BASE, s);
-        EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p, make_uint4(extra[0], extra[1], extra[2], extra[3]));
+        if (!table_in_prologue) {
+            if (guessed) {   // (the bitmap only exists on the host so far)
+                PresentBits bits;
+                memcpy(bits.w, scan.present, sizeof(bits.w));
+                EAST_LAUNCH(k_set_present, 1, 128, 0, s, d_scan.p, bits);
+            }
+            EAST_LAUNCH(k_code_table, 1, 128, 0, s, d_scan.p, d_table.p, make_uint4(extra[0], extra[1], extra[2], extra[3]));
+        }
         t8 = take<uint8_t>(in, (size_t)n + 128, s);
         arena_after_t8 = in.arena ? in.arena->used : 0;
-        if (!(try_doc_sort && in.fused_encode)) encode_all();
+        if (!table_in_prologue) encode_all();
     }
     out.code_table = table;
     out.term_code = fast ? (int)kp.term : 0;
 
     if (sampled && !try_doc_sort) {   // the sample does not lead to the per-document kernel: decide on the whole text
+        if (guessed) g_alphabet_guess.valid = false;
         t8.release();
         if (in.arena) in.arena->used = arena_mark;
         SaInput again = in;
@@ -1273,20 +1395,30 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
         const DocSortPlan &plan = doc_plan;
         {
             tm.mark("doc_sort");
-            DevBuf<uint32_t> flag(2, s);   // [0] the kernel's flags, [1] encoder miss (cannot happen here: the alphabet is complete)
-            EAST_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(uint32_t), s));
+            DevBuf<uint32_t> flag(2, s);   // [0] the kernel's flags, [1] encoder miss (a sampled or guessed alphabet lacks a code point)
+            uint32_t *end0 = nullptr, *end1 = nullptr;
             if (((size_t)D << (2 * plan.b)) <= (size_t)2 * n + 4096) {
                 const size_t entries = ((size_t)D << (2 * plan.b)) + 1;
                 out.bkt = take<uint32_t>(in, entries, s);
-                EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt.p + entries - 1, (uint32_t)n);
+                end0 = out.bkt.p + entries - 1;
                 out.sym_bits = plan.b;
                 if (in.want_bkt3 && plan.G == 3 && ((size_t)D << (3 * plan.b)) * sizeof(uint32_t) <= ((size_t)8 << 30)) {
                     // the kernel's buckets ARE the 3-grams: their first ranks cost one more coalesced store and turn
                     // the scorer's depth-2 narrowing (a binary search over the largest intervals) into a lookup
                     const size_t e3 = ((size_t)D << (3 * plan.b)) + 1;
                     out.bkt3 = take<uint32_t>(in, e3, s);
-                    EAST_LAUNCH(k_store_u32, 1, 1, 0, s, out.bkt3.p + e3 - 1, (uint32_t)n);
+                    end1 = out.bkt3.p + e3 - 1;
                 }
+            }
+            if (table_in_prologue) {   // code table, cleared flags, closing entries of the bucket tables: one launch
+                PresentBits bits;
+                memcpy(bits.w, scan.present, sizeof(bits.w));
+                EAST_LAUNCH(k_doc_sort_prologue, 1, 128, 0, s, guessed ? (const ScanResult *)nullptr : d_scan.p, bits,
+                            make_uint4(extra[0], extra[1], extra[2], extra[3]), d_table.p, flag.p, end0, end1, (uint32_t)n);
+            } else {
+                EAST_CUDA(cudaMemsetAsync(flag.p, 0, 2 * sizeof(uint32_t), s));
+                if (end0) EAST_LAUNCH(k_store_u32, 1, 1, 0, s, end0, (uint32_t)n);
+                if (end1) EAST_LAUNCH(k_store_u32, 1, 1, 0, s, end1, (uint32_t)n);
             }
             static const bool profile = getenv("EAST_DOC_SORT_PROFILE") != nullptr;
             DevBuf<unsigned long long> clk;
@@ -1317,6 +1449,7 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
             }
             if (missed) {
                 // nothing of this pass is kept: the same build with the alphabet of the whole text
+                if (guessed) g_alphabet_guess.valid = false;
                 out.bkt = DevBuf<uint32_t>();
                 out.bkt3 = DevBuf<uint32_t>();
                 out.sym_bits = 0;
@@ -1326,9 +1459,11 @@ void build_suffix_array(const SaInput &in, SaOutput &out, StageTimer &tm, cudaSt
                 again.alphabet_sample = 0;
                 build_suffix_array(again, out, tm, s);
                 out.alphabet_miss = 1;
+                out.alphabet_guessed = guessed ? 1 : 0;
                 return;
             }
             if (!overflow) {
+                alphabet_guess_keep(scan.present);
                 if (hooks && in.run_hook) in.run_hook(in.run_ctx, run, score.recs != nullptr ? 1 : 0);
                 if (score.recs && score.skip_suffix_keys) out.sk_skipped = 1;
                 out.doc_sorted = 1;

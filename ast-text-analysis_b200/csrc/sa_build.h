@@ -67,6 +67,8 @@ struct SaInput {
     uint32_t *sk = nullptr;                 // destination of the scorer's per-rank key bytes (fast path only)
     int light_scan = 1;                     // small documents: alphabet-only scan first (the per-document kernel validates)
     int64_t alphabet_sample = 0;            // ... over this many leading code points only (speculation, checked by the kernel); 0 = all
+    int alphabet_guess = 0;                 // batches of small documents may start from the alphabet of this thread's previous batch
+                                            // (the same speculation without the scan and its host round trip; checked by the kernel)
     int want_bkt3 = 1;                      // per-document kernel: also keep its 3-gram bucket starts for the scorer
     int fused_encode = 1;                   // per-document kernel: byte-code the text itself (no separate k_encode_text pass)
     // pipelined host build: the text arrives in n_chunks runs of whole documents; chunk c = documents
@@ -112,6 +114,7 @@ struct SaOutput {
     int sk_skipped = 0;              // ... except by launches that scored their documents themselves (made on first use)
     int pipelined = 0;               // the build overlapped the host-to-device copy (speculative alphabet held)
     int pipeline_miss = 0;           // it did not hold (later chunks brought new symbols / bad layout): redone
+    int alphabet_guessed = 0;        // the build started from the alphabet of the thread's previous batch (and it held, or see the misses)
     int alphabet_miss = 0;           // the alphabet sampled from a prefix of a device-resident text did not hold: redone
 };
 

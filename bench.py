@@ -500,6 +500,26 @@ def run_b200(args):
         raw_equal = bool(np.array_equal(raw_out.view(np.uint64), host_out_np.view(np.uint64)))
     # clocks under load: samples taken between the start of the device-timed region and the end of the e2e one
     clocks = sampler.stop(t_timed0, time.perf_counter())
+    # ---- the same two arms when every call scans for its alphabet (option no_alphabet_guess): by default a batch starts
+    # from the alphabet of the thread's previous batch -- a guess the per-document kernel checks code point by code point
+    scanned = None
+    if world == 1 and not two_calls:
+        _capi.set_option("no_alphabet_guess", 1)
+        try:
+            n_ab = max(5, args.steps // 3)
+            out_ab = {}
+            for name, fn in (("device_ms_per_step", step_device), ("e2e_ms_per_step", step_e2e)):
+                fn()
+                barrier()
+                w3 = time.perf_counter()
+                for _ in range(n_ab):
+                    fn()
+                barrier()
+                out_ab[name] = (time.perf_counter() - w3) * 1e3 / n_ab
+            scanned = out_ab
+        finally:
+            _capi.set_option("no_alphabet_guess", 0)
+        step_e2e()   # the table the parity check reads comes from the headline variant
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -579,8 +599,13 @@ def run_b200(args):
                                 "value": (n_gpus * D * K / (e2e_other_ms * 1e-3)) if e2e_other_ms else None},
                 "d2h_bytes_per_step": int(D * K * 8),
                 "call": "east_build_host+east_score_table_host" if two_calls else ("east_table_host_u8" if e2e_width == 1 else "east_table_host"),
-                "keyphrase_preparation": "inside every call (device, kp_prep.cu): nothing is cached between table calls",
-                "kp_prep_ms": kp_prep_ms},
+                "keyphrase_preparation": "inside every call (device, kp_prep.cu): nothing derived from the keyphrases is cached between table calls",
+                "kp_prep_ms": kp_prep_ms,
+                "alphabet": "guessed: a batch starts from the alphabet of the thread's previous batch; the per-document kernel checks "
+                            "every code point against it and a miss redoes the batch from a scan (tests: "
+                            "test_alphabet_of_the_previous_batch_is_only_a_guess); alphabet_scanned = both arms with the guess "
+                            "switched off (host wall clock per step, fewer steps)",
+                "alphabet_scanned": scanned},
         "parity_checked": bool(parity.get("checked") and parity.get("mismatching_rows") == 0),
         "parity": parity,
         "gpu_launches": launches,

@@ -478,6 +478,7 @@ def test_sampled_alphabet_of_device_resident_batches_recovers(oracle_mod):
     codes, off = _keyphrases(60, extra=["QUIZ7", "E"])
     try:
         capi.set_option("alphabet_sample", 2000)
+        capi.set_option("no_alphabet_guess", 1)   # this test is about the sample; the guess has its own below
         idx, out = _table_dev(packed, ms, codes, off)
         assert idx.stat("alphabet_miss") == 0 and idx.info()["doc_sorted"]
         exp = _oracle_rows(oracle_mod, packed, ms, (0, 39), codes, off)
@@ -505,3 +506,68 @@ def test_sampled_alphabet_of_device_resident_batches_recovers(oracle_mod):
         idx.close()
     finally:
         capi.set_option("alphabet_sample", 0)
+        capi.set_option("no_alphabet_guess", 0)
+
+
+def test_alphabet_of_the_previous_batch_is_only_a_guess(oracle_mod):
+    # A batch of small documents may start from the alphabet of the thread's previous batch instead of a scan and its host
+    # round trip; the per-document kernel reports every code point the guess lacks and the batch is redone from a scan.
+    # Hit, miss (new symbols anywhere), a narrower alphabet after a wider one, option off -- pipelined host build and
+    # device-resident build; the tables never depend on it.
+    import synth
+    from east.asts import utils as au
+    capi = _capi()
+    codes, off = _keyphrases(200, extra=["QUIZ7", "E", "Я"])
+    packed, ms, cols = synth.packed_collection(300, 30000, first_seed=4100)
+    digits = au.pack_strings_collection(["0123456789 QUIZ7", "ZEBRA9 J"])
+    cyr = au.pack_strings_collection(["ЯБЛОКО И ГРУША", "ABC"])
+    with_digits = (list(packed[:200]) + [digits] + list(packed[200:]), list(ms[:200]) + [2] + list(ms[200:]))
+    with_cyr = (list(packed) + [cyr], list(ms) + [2])
+
+    def check(idx, out, batch, rows, what):
+        exp = _oracle_rows(oracle_mod, batch[0], batch[1], rows, codes, off)
+        for d in rows:
+            assert np.array_equal(_bits(out[d]), _bits(exp[d])), (what, d)
+        _check_arrays(idx, rows[-1], oracle_mod.OracleEASA(text=batch[0][rows[-1]], m=batch[1][rows[-1]]), what)
+
+    try:
+        capi.set_option("alphabet_sample", 100000)   # device-resident batches above this size sample / guess
+        for fn in (_table_host, _table_dev):
+            name = fn.__name__
+            capi.set_option("no_alphabet_guess", 1)
+            idx, ref = fn(packed, ms, codes, off)
+            assert idx.stat("alphabet_guessed") == 0
+            idx.close()
+            capi.set_option("no_alphabet_guess", 0)
+            idx, out = fn(packed, ms, codes, off)          # whatever the guess was (an earlier test's batch), the table stands
+            assert np.array_equal(_bits(out), _bits(ref)), name
+            idx.close()
+            idx, out = fn(packed, ms, codes, off)          # now the guess is this batch's own alphabet: a hit
+            assert idx.stat("alphabet_guessed") == 1 and idx.stat("alphabet_miss") == 0 and idx.stat("pipeline_miss") == 0, name
+            assert np.array_equal(_bits(out), _bits(ref)), name
+            check(idx, out, (packed, ms), (0, 299), (name, "hit"))
+            idx.close()
+            for batch, rows, what in ((with_digits, (0, 200, 300), "digits in the middle"), (with_cyr, (5, 300), "cyrillic at the end")):
+                idx, out = fn(batch[0], batch[1], codes, off)
+                assert idx.stat("alphabet_guessed") + idx.stat("pipeline_miss") + idx.stat("alphabet_miss") >= 1, (name, what)
+                assert idx.stat("pipeline_miss") == 1 or idx.stat("alphabet_miss") == 1, (name, what)   # the guess lacked them
+                check(idx, out, batch, rows, (name, what))
+                idx.close()
+                idx, out2 = fn(batch[0], batch[1], codes, off)   # the redone batch left its own alphabet behind: a hit
+                assert idx.stat("alphabet_guessed") == 1 and idx.stat("alphabet_miss") == 0 and idx.stat("pipeline_miss") == 0, (name, what)
+                assert np.array_equal(_bits(out2), _bits(out)), (name, what)
+                idx.close()
+            weird = au.pack_strings_collection(["中文", "AB"])   # collides with the terminator range: the general path
+            idx, out = fn(list(packed) + [weird], list(ms) + [2], codes, off)
+            assert not idx.info()["fast_path"], name
+            assert np.array_equal(_bits(out[300]), _bits(oracle_mod.OracleEASA(text=weird, m=2).score_many(codes, off, True))), name
+            assert np.array_equal(_bits(out[:300]), _bits(ref)), name
+            idx.close()
+            idx, out = fn(packed, ms, codes, off)          # narrower than the guess: codes the batch never uses cost nothing
+            assert idx.stat("alphabet_miss") == 0 and idx.stat("pipeline_miss") == 0, name
+            assert np.array_equal(_bits(out), _bits(ref)), name
+            check(idx, out, (packed, ms), (17, 299), (name, "narrower"))
+            idx.close()
+    finally:
+        capi.set_option("alphabet_sample", 0)
+        capi.set_option("no_alphabet_guess", 0)
