@@ -1004,7 +1004,8 @@ static void prepare_keyphrases_host(KpPrepared *c, bool fast, int sym_bits, cons
 // waits: east_table_host runs it on a side stream under the transfer of the text).  kp_finish: the dense codes for the
 // alphabet of an index, queued on `s`; returns with n_uniq known.  kp_finish may be repeated for another alphabet.
 static std::unique_ptr<KpPrepared> kp_begin(int device, const uint32_t *kp_dev, const uint32_t *kp_host_in, const int64_t *kp_off,
-                                            int32_t K, bool dedup, bool keep_host_copy, cudaStream_t s) {
+                                            int32_t K, bool dedup, bool keep_host_copy, cudaStream_t s,
+                                            const uint8_t *likely_code_table = nullptr /* of the index to come, if anyone knows */) {
     std::unique_ptr<KpPrepared> c(new KpPrepared());
     const int64_t total = kp_off[K];
     const bool host_prep = get_option("kp_prep_host", 0) != 0;
@@ -1019,7 +1020,7 @@ static std::unique_ptr<KpPrepared> kp_begin(int device, const uint32_t *kp_dev, 
             EAST_CUDA(cudaStreamSynchronize(s));
         }
     }
-    if (!host_prep) kp_stage1(c->dev, kp_dev, kp_host_in, kp_off, K, dedup, s, (int32_t)get_option("kp_small_max", 1 << 30));
+    if (!host_prep) kp_stage1(c->dev, kp_dev, kp_host_in, kp_off, K, dedup, s, (int32_t)get_option("kp_small_max", 1 << 30), likely_code_table);
     return c;
 }
 
@@ -1057,7 +1058,7 @@ static KpPrepared *prepare_keyphrases(const east_index *idx, const uint32_t *kp_
         (!fast || (c->sym_bits == idx->sym_bits && c->code_table == idx->code_table)))
         return c;
     if (c) { cudaSetDevice(c->device); cudaDeviceSynchronize(); g_kp_cache.reset(); cudaSetDevice(idx->device); }
-    g_kp_cache = kp_begin(idx->device, kp_dev, kh, kp_off, K, dedup, true, s);
+    g_kp_cache = kp_begin(idx->device, kp_dev, kh, kp_off, K, dedup, true, s, fast ? idx->code_table.data() : nullptr);
     c = g_kp_cache.get();
     kp_finish(c, kp_dev, fast, idx->sym_bits, idx->code_table, s);
     EAST_CUDA(cudaStreamSynchronize(s));
@@ -1252,6 +1253,13 @@ struct TableRun {
     ~TableRun() { if (kp_ready) cudaEventDestroy(kp_ready); }
 };
 
+// the code table a table call's build is expected to end up with: that of the guessed alphabet (sa_build.cu), if any
+static const uint8_t *likely_code_table() {
+    static thread_local uint8_t table[EAST_TERM_BASE];
+    if (get_option("no_alphabet_guess", 0)) return nullptr;
+    return alphabet_guess_code_table(table) ? table : nullptr;
+}
+
 static void table_kp_begin(void *vctx) {
     TableRun &t = *static_cast<TableRun *>(vctx);
     if (t.kp_own) return;
@@ -1261,7 +1269,7 @@ static void table_kp_begin(void *vctx) {
         EAST_CUDA(cudaEventRecord(inputs_ready, t.caller_stream));
         EAST_CUDA(cudaStreamWaitEvent(t.kp_stream, inputs_ready, 0));
         EAST_CUDA(cudaEventDestroy(inputs_ready));
-        t.kp_own = kp_begin(t.device, t.d_kp, t.kp_host, t.kp_off, t.K, t.dedup, false, t.kp_stream);
+        t.kp_own = kp_begin(t.device, t.d_kp, t.kp_host, t.kp_off, t.K, t.dedup, false, t.kp_stream, likely_code_table());
     } catch (...) {
         t.failed = true;
     }
@@ -1373,7 +1381,7 @@ static void table_host_impl(const void *text, int width, const int64_t *doc_off,
     double *const d_out = own_rows_dev ? own_rows_dev : d_out_own.p;
     EAST_CUDA(cudaMemcpyAsync(d_kp.p, kp, sizeof(uint32_t) * (size_t)kp_off[K], cudaMemcpyHostToDevice, ps));
     TableRun run;
-    run.kp_own = kp_begin(device, d_kp.p, kp, kp_off, K, !get_option("score_no_dedup", 0), false, ps);
+    run.kp_own = kp_begin(device, d_kp.p, kp, kp_off, K, !get_option("score_no_dedup", 0), false, ps, likely_code_table());
     run.kp_host = kp; run.d_kp = d_kp.p; run.kp_off = kp_off; run.K = K; run.normalized = normalized;
     run.d_out = d_out; run.host_out = out_DxK;
     run.peer_rows = peer_rows; run.n_peers = n_peers;

@@ -164,6 +164,8 @@ k_kp_emit(const int32_t *__restrict__ send, const uint8_t *__restrict__ weird, c
     }
 }
 
+struct KpCodeTable { uint32_t w[EAST_TERM_BASE / 4]; };   // the code table of an index as a kernel parameter
+
 // ---- stage 1 in one kernel: a cluster of 8 CTAs (total <= KP_SMALL_MAX)
 constexpr int KP_CL_CTAS = 8;
 constexpr int KP_SMALL_MAX = 65536;
@@ -177,7 +179,8 @@ constexpr int KP_CARRY = 2;                                // rounds of 32 a war
 __global__ void __cluster_dims__(KP_CL_CTAS, 1, 1) __launch_bounds__(KP_THREADS, 1)
 k_kp_small(const uint32_t *__restrict__ kp, const int32_t *__restrict__ off, int32_t K, int32_t total, int dedup, int sym_bits, uint32_t sym_min,
            int n_sym, int key_bits, uint64_t *hash, int32_t *send, uint8_t *weird, uint8_t *planes, uint32_t *idx_a, uint32_t *idx_b,
-           int32_t *__restrict__ uniq_of, SufRec *__restrict__ recs, uint32_t *__restrict__ n_uniq, unsigned long long *phase_clk) {
+           int32_t *__restrict__ uniq_of, SufRec *recs, uint32_t *__restrict__ n_uniq, unsigned long long *phase_clk,
+           KpCodeTable tab, uint8_t *__restrict__ q8 /* NULL: no dense codes yet (k_kp_encode follows) */) {
     cg::cluster_group cluster = cg::this_cluster();
     long long t_prev = clock64();
 #define KP_STAMP(k)                                                                     \
@@ -353,9 +356,13 @@ k_kp_small(const uint32_t *__restrict__ kp, const int32_t *__restrict__ off, int
     cluster.sync();
     KP_STAMP(7);
     // positions in visiting order, one record per group (k_kp_scan_blocks, k_kp_emit)
-    uint32_t running = 0;
-    for (int c = 0; c < cta; ++c) running += *cluster.map_shared_rank(&s_heads, c);
-    if (cta == KP_CL_CTAS - 1 && tid == 0) *n_uniq = running + heads;
+    uint32_t running = 0, n_all = 0;
+    for (int c = 0; c < KP_CL_CTAS; ++c) {
+        const uint32_t v = *cluster.map_shared_rank(&s_heads, c);
+        if (c < cta) running += v;
+        n_all += v;
+    }
+    if (cta == KP_CL_CTAS - 1 && tid == 0) *n_uniq = n_all;
     chunk = 0;
     for (int i0 = r0; i0 < r1; i0 += KP_THREADS, ++chunk) {
         const int i = i0 + tid;
@@ -384,16 +391,40 @@ k_kp_small(const uint32_t *__restrict__ kp, const int32_t *__restrict__ off, int
         running += sum;
         __syncthreads();
     }
-    cluster.sync();   // no CTA leaves while another may still read its shared memory
+    cluster.sync();   // no CTA leaves while another may still read its shared memory; every record is in global memory
     KP_STAMP(8);
+    // the dense codes for the code table the index is expected to have (k_kp_encode's work, one launch less on the way
+    // to the first wave of the per-document kernel); shared memory from here on is this CTA's own
+    if (q8) {
+        uint32_t *s_tab = cursor;
+        for (int i = tid; i < (int)(EAST_TERM_BASE / 4); i += KP_THREADS) s_tab[i] = tab.w[i];
+        __syncthreads();
+        const uint8_t *table = reinterpret_cast<const uint8_t *>(s_tab);
+        for (int i = gtid; i < total + 16; i += KP_CL_THREADS) {
+            uint8_t c = 0;
+            if (i < total) { const uint32_t cp = kp[i]; if (cp < EAST_TERM_BASE) c = table[cp]; }
+            q8[i] = c;
+        }
+        for (int i = gtid; i < (int)n_all; i += KP_CL_THREADS) {
+            uint4 raw = __ldcg(reinterpret_cast<const uint4 *>(recs) + i);
+            const int32_t sidx = (int32_t)raw.z;
+            const int len = (int)(raw.w & 0xffffu);
+            uint64_t first = 0ull;
+            for (int q = 0; q < 8 && q < len; ++q) {
+                const uint32_t cp = kp[sidx + q];
+                first |= (uint64_t)(cp < EAST_TERM_BASE ? table[cp] : 0) << (8 * q);
+            }
+            raw.x = (uint32_t)first; raw.y = (uint32_t)(first >> 32);
+            reinterpret_cast<uint4 *>(recs)[i] = raw;
+        }
+        KP_STAMP(9);
+    }
 #undef KP_STAMP
 }
 
 // index-dependent part: dense byte codes (0 = the code point does not occur in the batch, or is >= 0x0A00).  The code
 // table of the index comes BY VALUE (2.5 KB of kernel parameters, staged in shared memory): an upload would be one more
 // operation in the chain the first wave of the per-document kernel waits for, behind the text on the host link.
-struct KpCodeTable { uint32_t w[EAST_TERM_BASE / 4]; };
-
 __global__ void __launch_bounds__(256)
 k_kp_encode(const uint32_t *__restrict__ kp, int32_t total, KpCodeTable tab, int fast /* 0: the index has no fast path */,
             const uint32_t *__restrict__ n_uniq, SufRec *__restrict__ recs, uint8_t *__restrict__ q8) {
@@ -451,7 +482,7 @@ static void kp_stage1_done(KpDevice &kp, cudaStream_t s) {
 }
 
 void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, const int64_t *kp_off, int32_t K, bool dedup, cudaStream_t s,
-               int32_t small_max) {
+               int32_t small_max, const uint8_t *likely_code_table) {
     const int64_t total64 = kp_off[K];
     const int32_t total = (int32_t)total64;
     kp.total = total; kp.K = K; kp.dedup = dedup; kp.n_uniq = -1;
@@ -484,18 +515,27 @@ void kp_stage1(KpDevice &kp, const uint32_t *kp_dev, const uint32_t *kp_host, co
         static const bool stamps = getenv("EAST_KP_STAMPS") != nullptr;
         DevBuf<unsigned long long> clk;
         if (stamps) { clk = DevBuf<unsigned long long>(16, s); EAST_CUDA(cudaMemsetAsync(clk.p, 0, 16 * sizeof(unsigned long long), s)); }
+        KpCodeTable tab;
+        kp.encoded_for.clear();
+        if (likely_code_table) {
+            memcpy(tab.w, likely_code_table, EAST_TERM_BASE);
+            kp.encoded_for.assign(likely_code_table, likely_code_table + EAST_TERM_BASE);
+            if (!kp.d_q8.p) kp.d_q8 = DevBuf<uint8_t>((size_t)total + 16, s);
+        }
         EAST_LAUNCH(k_kp_small, KP_CL_CTAS, KP_THREADS, 0, s, kp_dev, kp.d_off.p, K, total, dedup ? 1 : 0, sym_bits, sym_min, n_sym, small_key_bits, hash, send,
-                    weird, planes, idx_a, idx_b, kp.d_uniq_of.p, kp.d_recs.p, kp.d_n_uniq.p, clk.p);
+                    weird, planes, idx_a, idx_b, kp.d_uniq_of.p, kp.d_recs.p, kp.d_n_uniq.p, clk.p, tab,
+                    likely_code_table ? kp.d_q8.p : (uint8_t *)nullptr);
         if (stamps) {
             unsigned long long h[16];
             EAST_CUDA(cudaMemcpyAsync(h, clk.p, sizeof(h), cudaMemcpyDeviceToHost, s));
             EAST_CUDA(cudaStreamSynchronize(s));
-            fprintf(stderr, "[east] k_kp_small clocks: hash %llu keys %llu | hist %llu sync %llu scan %llu scatter %llu sync %llu | mark %llu emit %llu\n",
-                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+            fprintf(stderr, "[east] k_kp_small clocks: hash %llu keys %llu | hist %llu sync %llu scan %llu scatter %llu sync %llu | mark %llu emit %llu encode %llu\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
         }
         kp_stage1_done(kp, s);
         return;
     }
+    kp.encoded_for.clear();
     DevBuf<uint64_t> hash((size_t)total, s), keys_a, keys_b;
     DevBuf<uint32_t> vals_a((size_t)total, s), vals_b;
     DevBuf<int32_t> send((size_t)total, s);
@@ -531,7 +571,9 @@ void kp_stage2(KpDevice &kp, const uint32_t *kp_dev, const uint8_t *code_table_h
         if (!kp.d_q8.p) kp.d_q8 = DevBuf<uint8_t>((size_t)kp.total + 16, s);
         memcpy(tab.w, code_table_host, EAST_TERM_BASE);
     }
-    EAST_LAUNCH(k_kp_encode, grid_for(kp.total + 16, 256, 8), 256, 0, s, kp_dev, kp.total, tab, fast ? 1 : 0, kp.d_n_uniq.p, kp.d_recs.p, kp.d_q8.p);
+    const bool encoded = fast && kp.encoded_for.size() == (size_t)EAST_TERM_BASE && memcmp(kp.encoded_for.data(), code_table_host, EAST_TERM_BASE) == 0;
+    if (fast) kp.encoded_for.assign(code_table_host, code_table_host + EAST_TERM_BASE); else kp.encoded_for.clear();
+    if (!encoded) EAST_LAUNCH(k_kp_encode, grid_for(kp.total + 16, 256, 8), 256, 0, s, kp_dev, kp.total, tab, fast ? 1 : 0, kp.d_n_uniq.p, kp.d_recs.p, kp.d_q8.p);
     if (kp.n_uniq < 0) {
         EAST_CUDA(cudaEventSynchronize(kp.done));
         kp.n_uniq = (int64_t)*kp.n_uniq_host;

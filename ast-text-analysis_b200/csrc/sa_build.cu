@@ -1093,6 +1093,22 @@ static void alphabet_guess_keep(const uint32_t *present) {
     g_alphabet_guess.valid = true;
     g_alphabet_guess.device = dev;
     memcpy(g_alphabet_guess.present, present, sizeof(g_alphabet_guess.present));
+    uint32_t extra[4] = {0u, 0u, 0u, 0u};   // kept with its ASCII classes completed (idempotent): what a build makes of it
+    complete_symbol_classes(g_alphabet_guess.present, extra);
+}
+
+// The code table a build on this thread and device would derive from the guess (codes 1..sigma in code point order), for
+// callers that prepare something for that table before the build runs (the keyphrases' dense codes); false: no guess.
+bool alphabet_guess_code_table(uint8_t *table /* EAST_TERM_BASE entries */) {
+    int dev = -1;
+    if (!g_alphabet_guess.valid || cudaGetDevice(&dev) != cudaSuccess || dev != g_alphabet_guess.device) return false;
+    int sigma = 0;
+    for (uint32_t c = 0; c < EAST_TERM_BASE; ++c) {
+        const bool on = (g_alphabet_guess.present[c >> 5] >> (c & 31)) & 1u;
+        if (on) ++sigma;
+        table[c] = on ? (uint8_t)(sigma & 0xff) : (uint8_t)0;
+    }
+    return sigma <= 253;
 }
 
 static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cudaStream_t s, uint32_t &doc_sort_flags) {

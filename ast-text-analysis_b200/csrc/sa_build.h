@@ -158,6 +158,8 @@ void build_lcp_tables(const uint32_t *text, const uint8_t *t8 /*or null*/, int t
 
 // batched scorer (easa.py:91-139)
 // one record per DISTINCT query suffix, in visiting order (thread order): everything a walk needs to start
+bool alphabet_guess_code_table(uint8_t *table /* EAST_TERM_BASE entries */);   // sa_build.cu: see AlphabetGuess
+
 struct SufRec {
     uint64_t q8_first;   // dense codes of the first 8 symbols (fast path; symbol d in byte d)
     int32_t sidx;        // index of (one of) the suffix(es) in the concatenated keyphrases
