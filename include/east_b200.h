@@ -199,7 +199,18 @@ int east_index_load(const char *path, int device, east_index **out);
  * touched) and keeps freed blocks for the next call, up to a quarter of the device memory.  east_trim waits for the
  * device and returns everything that is not in use to the driver (also drops the cached keyphrase preparation). */
 int east_trim(int device);
-/* tuning knobs (0 = default): "key_chars" (round-0 window), "score_block", ... */
+/* Process-wide switches and tuning knobs (0 = default), mostly for A/B measurements and tests.  The ones that change what a
+ * call does rather than how fast:
+ *   "no_alphabet_guess" = 1   batches of small documents always scan for their alphabet.  Default: a batch starts from the
+ *                             alphabet of the calling thread's previous batch on the device -- a guess the per-document
+ *                             kernel checks against every code point; a miss redoes the batch from a scan (index stats
+ *                             "alphabet_guessed", "alphabet_miss", "pipeline_miss").  Results never depend on it.
+ *   "alphabet_sample"   = n   device-resident batches take their alphabet from the first n code points (default 2 M;
+ *                             -1: the whole text); checked and redone the same way.
+ *   "kp_prep_host"      = 1   keyphrase preparation on the host (round 1; cross-check of the device variants);
+ *   "kp_small_max"      = n   largest number of query suffixes the one-kernel preparation takes (default and limit 65 536).
+ *   "drop_kp_cache"     = 1   forget the keyphrase preparation kept for score calls on an existing index.
+ * Others ("key_chars", "rs_variant", "cooc_variant", "time_kernels", ...) are described where they are read (csrc/capi.cu). */
 int east_set_option(const char *name, int64_t value);
 
 #ifdef __cplusplus
