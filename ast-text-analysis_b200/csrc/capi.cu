@@ -396,6 +396,10 @@ int east_set_option(const char *name, int64_t value) {
         if (value) drop_kp_cache();
         return EAST_OK;
     }
+    if (!strcmp(name, "forget_alphabet_guess")) {   // per-thread: the next batch of small documents scans for its alphabet
+        if (value) alphabet_guess_forget();
+        return EAST_OK;
+    }
     std::lock_guard<std::mutex> g(g_opt_mutex);
     g_options[name] = value;
     return EAST_OK;

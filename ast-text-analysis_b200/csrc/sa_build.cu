@@ -1097,6 +1097,8 @@ static void alphabet_guess_keep(const uint32_t *present) {
     complete_symbol_classes(g_alphabet_guess.present, extra);
 }
 
+void alphabet_guess_forget() { g_alphabet_guess.valid = false; }
+
 // The code table a build on this thread and device would derive from the guess (codes 1..sigma in code point order), for
 // callers that prepare something for that table before the build runs (the keyphrases' dense codes); false: no guess.
 bool alphabet_guess_code_table(uint8_t *table /* EAST_TERM_BASE entries */) {

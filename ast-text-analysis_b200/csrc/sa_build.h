@@ -159,6 +159,7 @@ void build_lcp_tables(const uint32_t *text, const uint8_t *t8 /*or null*/, int t
 // batched scorer (easa.py:91-139)
 // one record per DISTINCT query suffix, in visiting order (thread order): everything a walk needs to start
 bool alphabet_guess_code_table(uint8_t *table /* EAST_TERM_BASE entries */);   // sa_build.cu: see AlphabetGuess
+void alphabet_guess_forget();                                                  // the calling thread's guess
 
 struct SufRec {
     uint64_t q8_first;   // dense codes of the first 8 symbols (fast path; symbol d in byte d)

@@ -205,6 +205,7 @@ int east_trim(int device);
  *                             alphabet of the calling thread's previous batch on the device -- a guess the per-document
  *                             kernel checks against every code point; a miss redoes the batch from a scan (index stats
  *                             "alphabet_guessed", "alphabet_miss", "pipeline_miss").  Results never depend on it.
+ *   "forget_alphabet_guess" = 1  (an action, per thread) the calling thread's next batch scans.
  *   "alphabet_sample"   = n   device-resident batches take their alphabet from the first n code points (default 2 M;
  *                             -1: the whole text); checked and redone the same way.
  *   "kp_prep_host"      = 1   keyphrase preparation on the host (round 1; cross-check of the device variants);

@@ -40,3 +40,14 @@ def have_gpu():
         return _capi.device_count() > 0
     except Exception:
         return False
+
+
+@pytest.fixture(autouse=True)
+def _no_alphabet_guess_across_tests(request):
+    """A batch of small documents starts from the alphabet of the thread's previous batch (a guess, see
+    test_alphabet_of_the_previous_batch_is_only_a_guess).  Tests that look at the miss statistics of an index must
+    not depend on which test ran before them: every GPU test starts without a guess."""
+    if request.node.get_closest_marker("gpu") is not None:
+        from east import _capi
+        _capi.set_option("forget_alphabet_guess", 1)
+    yield
