@@ -353,39 +353,6 @@ k_encode_text(const uint32_t *__restrict__ T, int32_t begin, int32_t end, const 
 // The dense-code table (code point < 0x0A00 -> 1..sigma in code point order, 0 = absent) from the scan's
 // presence bitmap, on the device: the host derives the same table for itself, and a host-to-device upload here
 // would queue behind the bulk text copies of a pipelined build (one copy engine per direction).
-__global__ void __launch_bounds__(128)
-k_code_table(const ScanResult *__restrict__ res, uint8_t *__restrict__ table, uint4 extra) {
-    // extra: code points below 128 that get a code although the scan did not meet them (pipelined build)
-    constexpr int W = EAST_TERM_BASE / 32;
-    __shared__ uint32_t s_bits[W];
-    __shared__ uint32_t s_before[W];
-    const uint32_t ex[4] = {extra.x, extra.y, extra.z, extra.w};
-    for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = res->present[w] | (w < 4 ? ex[w] : 0u);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int w = 0; w < W; ++w) { s_before[w] = run; run += __popc(s_bits[w]); }
-    }
-    __syncthreads();
-    for (int w = threadIdx.x; w < W; w += blockDim.x) {
-        const uint32_t bits = s_bits[w];
-        uint32_t code = s_before[w];
-        for (int k = 0; k < 32; ++k) {
-            const bool on = (bits >> k) & 1u;
-            if (on) ++code;
-            table[32 * w + k] = on ? (uint8_t)(code & 0xffu) : (uint8_t)0;
-        }
-    }
-}
-
-__global__ void k_store_u32(uint32_t *dst, uint32_t value) { *dst = value; }
-
-// Everything a batch of per-document kernels needs before its first wave, in ONE launch: the code table (from the scan
-// result, or from a bitmap handed over by value when the alphabet is a guess), the cleared flag words, the closing entries of
-// the bucket tables.  Every launch of a dependent chain costs its latency; with the text of a pipelined build on the host
-// link that is 30-50 us apiece (the command fetch shares the link with the copies), and the chain used to be five long.
-struct PresentBits { uint32_t w[EAST_TERM_BASE / 32]; };
-
 __device__ __forceinline__ void code_table_from_bits(uint32_t *s_bits, uint32_t *s_before, uint8_t *__restrict__ table) {
     constexpr int W = EAST_TERM_BASE / 32;
     __syncthreads();
@@ -404,6 +371,25 @@ __device__ __forceinline__ void code_table_from_bits(uint32_t *s_bits, uint32_t 
         }
     }
 }
+
+__global__ void __launch_bounds__(128)
+k_code_table(const ScanResult *__restrict__ res, uint8_t *__restrict__ table, uint4 extra) {
+    // extra: code points below 128 that get a code although the scan did not meet them (pipelined build)
+    constexpr int W = EAST_TERM_BASE / 32;
+    __shared__ uint32_t s_bits[W];
+    __shared__ uint32_t s_before[W];
+    const uint32_t ex[4] = {extra.x, extra.y, extra.z, extra.w};
+    for (int w = threadIdx.x; w < W; w += blockDim.x) s_bits[w] = res->present[w] | (w < 4 ? ex[w] : 0u);
+    code_table_from_bits(s_bits, s_before, table);
+}
+
+__global__ void k_store_u32(uint32_t *dst, uint32_t value) { *dst = value; }
+
+// Everything a batch of per-document kernels needs before its first wave, in ONE launch: the code table (from the scan
+// result, or from a bitmap handed over by value when the alphabet is a guess), the cleared flag words, the closing entries of
+// the bucket tables.  Every launch of a dependent chain costs its latency; with the text of a pipelined build on the host
+// link that is 30-50 us apiece (the command fetch shares the link with the copies), and the chain used to be five long.
+struct PresentBits { uint32_t w[EAST_TERM_BASE / 32]; };
 
 __global__ void __launch_bounds__(128)
 k_doc_sort_prologue(const ScanResult *__restrict__ res /* or NULL: bits */, PresentBits bits, uint4 extra, uint8_t *__restrict__ table,
@@ -1050,19 +1036,6 @@ static void complete_symbol_classes(uint32_t *present, uint32_t extra[4]) {
     for (int w = 0; w < 4; ++w) present[w] |= extra[w];
 }
 
-// The alphabet of run 0 goes to the host through a store into pinned memory, not through a device-to-host copy: with
-// the text of the later runs in flight, a copy -- small as it is -- waits for its turn on a copy engine (measured: the
-// host had the 332 bytes ~80 us after the scan had ended).
-static thread_local ScanResult *g_scan_pinned = nullptr;
-
-__global__ void __launch_bounds__(128)
-k_publish_scan(const ScanResult *__restrict__ src, ScanResult *dst_pinned) {
-    const uint32_t *a = reinterpret_cast<const uint32_t *>(src);
-    volatile uint32_t *b = reinterpret_cast<volatile uint32_t *>(dst_pinned);
-    for (int i = threadIdx.x; i < (int)(sizeof(ScanResult) / sizeof(uint32_t)); i += blockDim.x) b[i] = a[i];
-    __threadfence_system();
-}
-
 // The alphabet a thread's last batch of small documents was indexed with, as a guess for its next batch on the same
 // device (collections come in batches of one language).  It is the same speculation as the alphabet of run 0 / of a
 // sampled prefix -- phase 1 of the per-document kernel reports every code point the table lacks, and the batch is then
@@ -1132,11 +1105,9 @@ static bool build_pipelined(const SaInput &in, SaOutput &out, StageTimer &tm, cu
         EAST_CUDA(cudaStreamWaitEvent(s, in.chunk_ready[0], 0));
         if (in.text8) EAST_LAUNCH(k_alphabet8, grid_for(n0, 256 * 16, 4), 256, 0, s, in.text8, n0, d_first.p);
         else EAST_LAUNCH(k_alphabet, grid_for(n0, 256 * 4 * 4, 4), 256, 0, s, in.text, n0, d_first.p);
-        if (!g_scan_pinned) EAST_CUDA(cudaHostAlloc((void **)&g_scan_pinned, sizeof(ScanResult), cudaHostAllocDefault));
-        EAST_LAUNCH(k_publish_scan, 1, 128, 0, s, d_first.p, g_scan_pinned);
+        EAST_CUDA(cudaMemcpyAsync(&first, d_first.p, sizeof(ScanResult), cudaMemcpyDeviceToHost, s));
         EAST_CUDA(cudaStreamSynchronize(s));
         host_debug_mark("scan back");
-        first = *g_scan_pinned;
     }
     // the alphabet of run 0 (a few dozen documents), with the ASCII classes it has met completed
     uint32_t *present = first.present;
