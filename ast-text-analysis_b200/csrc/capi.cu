@@ -1749,6 +1749,7 @@ int east_trim(int device) {
     use_device(device);
     EAST_CUDA(cudaDeviceSynchronize());
     g_kp_cache.reset();
+    alphabet_guess_forget();
     big_cache_drop(device);
     EAST_CUDA(cudaDeviceSynchronize());
     std::lock_guard<std::mutex> g(g_pool_mutex);

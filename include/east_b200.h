@@ -197,7 +197,8 @@ int east_index_load(const char *path, int device, east_index **out);
 
 /* The library allocates from two private stream-ordered memory pools per device (the device's default pool is not
  * touched) and keeps freed blocks for the next call, up to a quarter of the device memory.  east_trim waits for the
- * device and returns everything that is not in use to the driver (also drops the cached keyphrase preparation). */
+ * device and returns everything that is not in use to the driver (also drops the calling thread's cached keyphrase
+ * preparation and alphabet guess). */
 int east_trim(int device);
 /* Process-wide switches and tuning knobs (0 = default), mostly for A/B measurements and tests.  The ones that change what a
  * call does rather than how fast:
