@@ -24,11 +24,12 @@
 // Stage 1 (all but the last kernel) does not depend on the index: east_table_host runs it on a side stream while
 // the text is still on its way to the device.
 //
-// Up to 64 Ki suffixes (10^3 keyphrases: 14 thousand) all of stage 1 is ONE kernel, k_kp_small, a cluster of 8 CTAs: the chain
-// above is 15 launches of ~13 us each for 3 us of work, and the per-document kernel of a table call cannot start its
-// first wave before the records exist.  The sort moves positions between two arrays in global memory (L2); the key
-// bytes stay where they were written (one byte plane per pass); per-digit counts cross CTAs through distributed
-// shared memory.
+// Up to 64 Ki suffixes (10^3 keyphrases: 14 thousand) all of stage 1 is ONE kernel, k_kp_small, a cluster of 8 CTAs:
+// the chain above is 17 launches of ~13 us each for 3 us of work, and the per-document kernel of a table call cannot
+// start its first wave before the records exist.  The sort moves positions between two arrays in global memory (L2);
+// the key bytes stay where they were written (one byte plane per pass); per-digit counts cross CTAs through
+// distributed shared memory.  When the caller can tell which code table the index will have (a guessed alphabet, an
+// existing index), the same kernel writes the dense codes as well and k_kp_encode has nothing left to do.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
