@@ -457,7 +457,7 @@ def run_b200(args):
     dev_ms = float(t.item())
 
     # ---- end-to-end arm (host buffers through the C ABI)
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(3, args.warmup)):   # the first host-buffer calls after a series of device-resident ones run slower
         step_e2e()
     barrier()
     w0 = time.perf_counter()
@@ -505,13 +505,14 @@ def run_b200(args):
     scanned = None
     if world == 1 and not two_calls:
         try:
-            n_ab = max(5, args.steps // 3)
+            n_ab = max(8, args.steps // 2)
             scanned = {}
             for label, off_ in (("guessed", 0), ("scanned", 1)):   # both measured the same way: host wall clock, no event pairs
                 _capi.set_option("no_alphabet_guess", off_)
                 scanned[label] = {}
                 for name, fn in (("device_ms_per_step", step_device), ("e2e_ms_per_step", step_e2e)):
-                    fn()
+                    for _ in range(3):
+                        fn()
                     barrier()
                     w3 = time.perf_counter()
                     for _ in range(n_ab):
